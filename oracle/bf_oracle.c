@@ -1,0 +1,279 @@
+/*
+ * oracle/bf_oracle.c -- TEST INFRASTRUCTURE (CPU oracle), not product code.  See bf_oracle.h.
+ *
+ * Non-generic part of the restatement: global sizes (fftw_convolver.c:36-49, 784-851), the two FFT
+ * wrappers (196-214, 391-409), raw2cbuf / cbuf2raw (170-194, 482-518), convolve_eval (411-433),
+ * runtime_coeffs2cbuf (575-596), verify_cbuf (598-622) and the realsize dispatch.
+ */
+#define _GNU_SOURCE
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "bf_oracle.h"
+#include "shim/fftw3.h"
+
+static int g_realsize, g_n_fft, g_n_fft2;
+static double g_safety_limit;
+static void *g_plan_fwd, *g_plan_inv;
+static void (*g_fail_handler)(int);
+
+static void
+orc_fail(int code)
+{
+    if (g_fail_handler != NULL) {
+        g_fail_handler(code);
+        return;
+    }
+    abort();
+}
+
+void
+orc_set_fail_handler(void (*handler)(int code))
+{
+    g_fail_handler = handler;
+}
+
+static void *
+orc_alloc(size_t size)
+{
+    void *p = NULL;
+    if (posix_memalign(&p, 64, size < 64 ? 64 : size) != 0) {
+        fprintf(stderr, "oracle: out of memory\n");
+        abort();
+    }
+    return p;
+}
+
+#define REAL float
+#define SFX f
+#define ORC_REAL_IS_FLOAT 1
+#include "bf_oracle_funs.inc"
+#undef REAL
+#undef SFX
+#undef ORC_REAL_IS_FLOAT
+
+#define REAL double
+#define SFX d
+#define ORC_REAL_IS_FLOAT 0
+#include "bf_oracle_funs.inc"
+#undef REAL
+#undef SFX
+#undef ORC_REAL_IS_FLOAT
+
+/* fftw_convolver.c:784-851: L must be a power of two, realsize 4 or 8; n_fft = 2 L. */
+int
+orc_init(const char *unused_config, int length, int realsize)
+{
+    (void)unused_config;
+    if (realsize != 4 && realsize != 8) {
+        fprintf(stderr, "Invalid real size %d.\n", realsize);
+        return 0;
+    }
+    if (length < 1 || (length & (length - 1)) != 0) {
+        fprintf(stderr, "Invalid length %d.\n", length);
+        return 0;
+    }
+    g_realsize = realsize;
+    g_n_fft2 = length;
+    g_n_fft = 2 * length;
+    if (realsize == 4) {
+        g_plan_fwd = fftwf_plan_r2r_1d(g_n_fft, NULL, NULL, FFTW_R2HC, FFTW_MEASURE);
+        g_plan_inv = fftwf_plan_r2r_1d(g_n_fft, NULL, NULL, FFTW_HC2R, FFTW_MEASURE);
+    } else {
+        g_plan_fwd = fftw_plan_r2r_1d(g_n_fft, NULL, NULL, FFTW_R2HC, FFTW_MEASURE);
+        g_plan_inv = fftw_plan_r2r_1d(g_n_fft, NULL, NULL, FFTW_HC2R, FFTW_MEASURE);
+    }
+    return 1;
+}
+
+int
+orc_cbufsize(void)
+{
+    return g_n_fft * g_realsize;      /* fftw_convolver.c:520-524 */
+}
+
+void
+orc_set_safety_limit(double limit)
+{
+    g_safety_limit = limit;           /* bfconf->safety_limit, read at real2raw.h:32 */
+}
+
+void
+orc_time2freq(void *in, void *out)
+{
+    if (g_realsize == 4) {
+        fftwf_execute_r2r(g_plan_fwd, in, out);
+    } else {
+        fftw_execute_r2r(g_plan_fwd, in, out);
+    }
+}
+
+void
+orc_freq2time(void *in, void *out)
+{
+    if (g_realsize == 4) {
+        fftwf_execute_r2r(g_plan_inv, in, out);
+    } else {
+        fftw_execute_r2r(g_plan_inv, in, out);
+    }
+}
+
+/* fftw_convolver.c:170-194: convert L new samples into next_cbuf[0..L), copy to cbuf[L..2L). */
+void
+orc_raw2cbuf(void *rawbuf, void *cbuf, void *next_cbuf, struct orc_buffer_format *bf,
+             void (*postprocess)(void *, int, void *), void *pp_arg)
+{
+    const uint8_t *raw = (const uint8_t *)rawbuf + bf->byte_offset;
+    if (g_realsize == 4) {
+        orc_raw2realf(next_cbuf, raw, bf->sf.bytes, bf->sf.isfloat, bf->sample_spacing, bf->sf.swap,
+                      g_n_fft2);
+    } else {
+        orc_raw2reald(next_cbuf, raw, bf->sf.bytes, bf->sf.isfloat, bf->sample_spacing, bf->sf.swap,
+                      g_n_fft2);
+    }
+    if (postprocess != NULL) {
+        postprocess(next_cbuf, g_n_fft2, pp_arg);
+    }
+    memcpy((uint8_t *)cbuf + (size_t)g_n_fft2 * g_realsize, next_cbuf, (size_t)g_n_fft2 * g_realsize);
+}
+
+/* fftw_convolver.c:482-518, dither-off branches only (north_star: dither off). */
+void
+orc_cbuf2raw(void *cbuf, void *outbuf, struct orc_buffer_format *bf, int apply_dither,
+             void *dither_state, struct orc_overflow *overflow)
+{
+    uint8_t *raw = (uint8_t *)outbuf + bf->byte_offset;
+    (void)dither_state;
+    if (apply_dither && !bf->sf.isfloat) {
+        fprintf(stderr, "oracle: dither is outside the restated path\n");
+        orc_fail(1);
+        return;
+    }
+    if (g_realsize == 4) {
+        orc_real2rawf(raw, cbuf, bf->sf.sbytes << 3, bf->sf.bytes, bf->sf.isfloat,
+                      bf->sample_spacing, bf->sf.swap, g_n_fft2, overflow);
+    } else {
+        orc_real2rawd(raw, cbuf, bf->sf.sbytes << 3, bf->sf.bytes, bf->sf.isfloat,
+                      bf->sample_spacing, bf->sf.swap, g_n_fft2, overflow);
+    }
+}
+
+void
+orc_mixnscale(void *inputs[], void *out, double scales[], int n_bufs, int mixmode)
+{
+    if (g_realsize == 4) {
+        orc_mixnscalef(inputs, out, scales, n_bufs, mixmode);
+    } else {
+        orc_mixnscaled(inputs, out, scales, n_bufs, mixmode);
+    }
+}
+
+void
+orc_convolve(void *in, void *coeffs, void *out)
+{
+    if (g_realsize == 4) {
+        orc_convolvef(in, coeffs, out);
+    } else {
+        orc_convolved(in, coeffs, out);
+    }
+}
+
+void
+orc_convolve_inplace(void *cbuf, void *coeffs)
+{
+    /* fftw_convfuns.h:503-532: same arithmetic as convolve with out == in (each chunk reads its
+       operands before writing them) */
+    orc_convolve(cbuf, coeffs, cbuf);
+}
+
+void
+orc_convolve_add(void *in, void *coeffs, void *out)
+{
+    if (g_realsize == 4) {
+        orc_convolve_addf(in, coeffs, out);
+    } else {
+        orc_convolve_addd(in, coeffs, out);
+    }
+}
+
+void
+orc_dirac_convolve(void *in, void *out)
+{
+    if (g_realsize == 4) {
+        orc_dirac_convolvef(in, out);
+    } else {
+        orc_dirac_convolved(in, out);
+    }
+}
+
+void
+orc_dirac_convolve_inplace(void *cbuf)
+{
+    orc_dirac_convolve(cbuf, cbuf);
+}
+
+void
+orc_crossfade_inplace(void *input_cbuf, void *crossfade_cbuf, void *buffer_cbuf)
+{
+    if (g_realsize == 4) {
+        orc_crossfade_inplacef(input_cbuf, crossfade_cbuf, buffer_cbuf);
+    } else {
+        orc_crossfade_inplaced(input_cbuf, crossfade_cbuf, buffer_cbuf);
+    }
+}
+
+/* fftw_convolver.c:411-433: IFFT into the upper N of a 1.5 N buffer whose lower L holds the
+   previous block's second half, FFT the lower N, then slide. */
+void
+orc_convolve_eval(void *input_cbuf, void *buffer_cbuf, void *output_cbuf)
+{
+    uint8_t *buf = buffer_cbuf;
+    const size_t half = (size_t)g_n_fft2 * g_realsize;
+    orc_freq2time(input_cbuf, buf + half);
+    orc_time2freq(buf, output_cbuf);
+    memcpy(buf, buf + half, half);
+}
+
+void *
+orc_coeffs2cbuf(void *coeffs, int n_coeffs, double scale, void *optional_dest)
+{
+    if (g_realsize == 4) {
+        return orc_coeffs2cbuff(coeffs, n_coeffs, scale, optional_dest);
+    }
+    return orc_coeffs2cbufd(coeffs, n_coeffs, scale, optional_dest);
+}
+
+/* fftw_convolver.c:575-596 */
+void
+orc_runtime_coeffs2cbuf(void *src, void *dest)
+{
+    const size_t half = (size_t)g_n_fft2 * g_realsize;
+    void *tmp = orc_alloc(2 * half), *in[1];
+    double scale = 1.0 / (double)g_n_fft;
+
+    memset(dest, 0, half);
+    memcpy((uint8_t *)dest + half, src, half);
+    orc_time2freq(dest, tmp);
+    in[0] = tmp;
+    orc_mixnscale(in, dest, &scale, 1, ORC_MIXMODE_INPUT);
+    free(tmp);
+}
+
+/* fftw_convolver.c:598-622 */
+int
+orc_verify_cbuf(void *cbufs[], int n_cbufs)
+{
+    int n, i;
+    for (n = 0; n < n_cbufs; n++) {
+        for (i = 0; i < g_n_fft; i++) {
+            const double v = g_realsize == 4 ? (double)((float *)cbufs[n])[i] : ((double *)cbufs[n])[i];
+            if (!isfinite(v)) {
+                fprintf(stderr, "NaN or Inf value among coefficients.\n");
+                return 0;
+            }
+        }
+    }
+    return 1;
+}
