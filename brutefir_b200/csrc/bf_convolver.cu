@@ -1,0 +1,514 @@
+// bf_convolver.cu -- the reference's per-call interface (include/bfcuda_convolver.h == convolver.h) on
+// the GPU: host pointers in, one or a few kernel launches, host pointers out.  See the header for why
+// this exists next to the block-level engine.  One process-wide context, like the reference's file-scope
+// statics (fftw_convolver.c:36-49); not re-entrant, like the reference.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/bfcuda_convolver.h"
+#include "bf_kernels.h"
+
+using namespace bf;
+
+namespace {
+
+struct CvContext {
+    bool ready;
+    int L, N, rs;
+    FftPlan plan;
+    cudaStream_t stream;
+    char *d_a, *d_b, *d_c;      // three cbuf-sized (x2) work buffers
+    void **d_ptrs;              // mixnscale input pointer table
+    double *d_scales;
+    char *d_mix;                // mixnscale input staging, grown on demand
+    size_t mix_cap;
+    uint8_t *d_raw;             // raw sample staging, grown on demand
+    size_t raw_cap;
+    Overflow *d_of;
+    unsigned int *d_status;
+};
+
+CvContext g_cv;
+void (*g_exit_hook)(int) = nullptr;
+int g_quiet = 0;
+double g_safety_limit = 0.0;
+char g_cv_err[512] = "";
+
+void cv_exit(int status)
+{
+    if (g_exit_hook != nullptr) {
+        g_exit_hook(status);
+    } else {
+        exit(status);       // stands in for bf_exit(), bfrun.c:2790-2820
+    }
+}
+
+bool cv_fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_cv_err, sizeof(g_cv_err), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "%s\n", g_cv_err);
+    return false;
+}
+
+// CUDA failures have no counterpart in the reference: report and leave through the exit hook
+bool cu_ok(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) {
+        return true;
+    }
+    cv_fail("bfcuda convolver: %s failed: %s", what, cudaGetErrorString(e));
+    cv_exit(1 /* BF_EXIT_OTHER */);
+    return false;
+}
+#define CVCU(call)                    \
+    do {                              \
+        if (!cu_ok((call), #call)) {  \
+            return;                   \
+        }                             \
+    } while (0)
+
+size_t cbytes() { return (size_t)g_cv.N * g_cv.rs; }
+
+bool need_ready()
+{
+    if (!g_cv.ready) {
+        cv_fail("bfcuda convolver: convolver_init() has not been called");
+        cv_exit(1);
+        return false;
+    }
+    return true;
+}
+
+bool grow(char **p, size_t *cap, size_t want)
+{
+    if (*cap >= want) {
+        return true;
+    }
+    if (*p != nullptr) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (!cu_ok(cudaMalloc((void **)p, want), "cudaMalloc")) {
+        *cap = 0;
+        return false;
+    }
+    *cap = want;
+    return true;
+}
+
+SampleFormat dev_format(const bfcuda_buffer_format *bf, int byte_offset)
+{
+    SampleFormat f;
+    f.isfloat = bf->sf.isfloat;
+    f.swap = bf->sf.swap;
+    f.bytes = bf->sf.bytes;
+    f.sbytes = bf->sf.sbytes;
+    f.sample_spacing = bf->sample_spacing;
+    f.byte_offset = byte_offset;
+    return f;
+}
+
+// bytes from the first to the last byte this channel touches inside a raw block
+size_t raw_span(const bfcuda_buffer_format *bf)
+{
+    return ((size_t)(g_cv.L - 1) * bf->sample_spacing + 1) * bf->sf.bytes;
+}
+
+void h2d(void *dst, const void *src, size_t n) { cu_ok(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, g_cv.stream), "H2D"); }
+void d2h(void *dst, const void *src, size_t n) { cu_ok(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, g_cv.stream), "D2H"); }
+void sync() { cu_ok(cudaStreamSynchronize(g_cv.stream), "cudaStreamSynchronize"); }
+
+// device-side mixnscale over device-resident inputs
+bool dev_mixnscale(char *const in[], const double scales[], int n, char *out, int mode)
+{
+    std::vector<void *> ptrs(in, in + n);
+    if (!cu_ok(cudaMemcpyAsync(g_cv.d_ptrs, ptrs.data(), sizeof(void *) * n, cudaMemcpyHostToDevice, g_cv.stream), "H2D")) return false;
+    if (!cu_ok(cudaMemcpyAsync(g_cv.d_scales, scales, sizeof(double) * n, cudaMemcpyHostToDevice, g_cv.stream), "H2D")) return false;
+    return cu_ok(launch_cv_mixnscale(g_cv.plan, (const void *const *)g_cv.d_ptrs, g_cv.d_scales, n, out, mode, g_cv.stream), "mixnscale");
+}
+
+}  // namespace
+
+extern "C" {
+
+void bfcuda_convolver_set_host(void (*bf_exit_hook)(int), int quiet, double safety_limit)
+{
+    g_exit_hook = bf_exit_hook;
+    g_quiet = quiet;
+    g_safety_limit = safety_limit;
+}
+
+const char *bfcuda_convolver_last_error(void)
+{
+    return g_cv_err;
+}
+
+bool_t convolver_init(const char config_filename[], int length, int realsize)
+{
+    (void)config_filename;  // FFTW wisdom: "Some convolvers may ignore 'config_filename'" (convolver.h:147)
+    if (realsize != 4 && realsize != 8) {
+        fprintf(stderr, "Invalid real size %d.\n", realsize);       // fftw_convolver.c:796-799
+        return 0;
+    }
+    if (length < 1 || (length & (length - 1)) != 0) {
+        fprintf(stderr, "Invalid length %d.\n", length);           // fftw_convolver.c:800-803
+        return 0;
+    }
+    if (!fft_size_supported(2 * length, realsize)) {
+        fprintf(stderr, "Invalid length %d (single-block FFT supports 4..%d at realsize %d).\n", length,
+                realsize == 4 ? 16384 : 8192, realsize);
+        return 0;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fprintf(stderr, "No CUDA device available (there is no CPU fallback).\n");
+        return 0;
+    }
+    if (g_cv.ready) {
+        cudaStreamSynchronize(g_cv.stream);
+        fft_plan_destroy(&g_cv.plan);
+        cudaFree(g_cv.d_a); cudaFree(g_cv.d_b); cudaFree(g_cv.d_c); cudaFree(g_cv.d_ptrs); cudaFree(g_cv.d_scales);
+        cudaFree(g_cv.d_of); cudaFree(g_cv.d_status);
+        if (g_cv.d_mix) cudaFree(g_cv.d_mix);
+        if (g_cv.d_raw) cudaFree(g_cv.d_raw);
+        cudaStreamDestroy(g_cv.stream);
+        memset(&g_cv, 0, sizeof(g_cv));
+    }
+    g_cv.L = length;
+    g_cv.N = 2 * length;
+    g_cv.rs = realsize;
+    const size_t cb = 2 * cbytes();
+    if (cudaStreamCreateWithFlags(&g_cv.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        fft_plan_create(&g_cv.plan, g_cv.N, realsize) != cudaSuccess ||
+        cudaMalloc((void **)&g_cv.d_a, cb) != cudaSuccess || cudaMalloc((void **)&g_cv.d_b, cb) != cudaSuccess ||
+        cudaMalloc((void **)&g_cv.d_c, cb) != cudaSuccess ||
+        cudaMalloc((void **)&g_cv.d_ptrs, sizeof(void *) * (BFCUDA_MAXCHANNELS + BFCUDA_MAXFILTERS)) != cudaSuccess ||
+        cudaMalloc((void **)&g_cv.d_scales, sizeof(double) * (BFCUDA_MAXCHANNELS + BFCUDA_MAXFILTERS)) != cudaSuccess ||
+        cudaMalloc((void **)&g_cv.d_of, sizeof(Overflow)) != cudaSuccess ||
+        cudaMalloc((void **)&g_cv.d_status, sizeof(unsigned int)) != cudaSuccess) {
+        fprintf(stderr, "CUDA initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    g_cv.ready = true;
+    return 1;
+}
+
+int convolver_cbufsize(void)
+{
+    return g_cv.N * g_cv.rs;    // fftw_convolver.c:520-524
+}
+
+void convolver_raw2cbuf(void *rawbuf, void *cbuf, void *next_cbuf, struct bfcuda_buffer_format *bf,
+                        void (*postprocess)(void *, int, void *), void *pp_arg)
+{
+    if (!need_ready()) return;
+    const bool okf = bf->sf.isfloat ? (bf->sf.bytes == 4 || bf->sf.bytes == 8) : (bf->sf.bytes >= 1 && bf->sf.bytes <= 4);
+    if (!okf) {
+        fprintf(stderr, "Sample byte size %d is not supported.\n", bf->sf.bytes);   // raw2real.h:154-158
+        cv_exit(1);
+        return;
+    }
+    const size_t span = raw_span(bf), half = (size_t)g_cv.L * g_cv.rs;
+    if (!grow((char **)&g_cv.d_raw, &g_cv.raw_cap, span)) return;
+    h2d(g_cv.d_raw, (const uint8_t *)rawbuf + bf->byte_offset, span);
+    CVCU(launch_cv_raw2real(g_cv.plan, g_cv.d_raw, dev_format(bf, 0), g_cv.d_a, g_cv.stream));
+    d2h(next_cbuf, g_cv.d_a, half);
+    sync();
+    if (postprocess != nullptr) {
+        postprocess(next_cbuf, g_cv.L, pp_arg);
+    }
+    memcpy((uint8_t *)cbuf + half, next_cbuf, half);    // fftw_convolver.c:193
+}
+
+void convolver_time2freq(void *input_cbuf, void *output_cbuf)
+{
+    if (!need_ready()) return;
+    h2d(g_cv.d_a, input_cbuf, cbytes());
+    CVCU(launch_r2hc(g_cv.plan, g_cv.d_a, g_cv.d_b, 1, g_cv.stream));
+    d2h(output_cbuf, g_cv.d_b, cbytes());
+    sync();
+}
+
+void convolver_freq2time(void *input_cbuf, void *output_cbuf)
+{
+    if (!need_ready()) return;
+    h2d(g_cv.d_a, input_cbuf, cbytes());
+    CVCU(launch_hc2r(g_cv.plan, g_cv.d_a, g_cv.d_b, 1, g_cv.stream));
+    d2h(output_cbuf, g_cv.d_b, cbytes());
+    sync();
+}
+
+void convolver_mixnscale(void *input_cbufs[], void *output_cbuf, double scales[], int n_bufs, int mixmode)
+{
+    if (!need_ready()) return;
+    if (mixmode != CONVOLVER_MIXMODE_INPUT && mixmode != CONVOLVER_MIXMODE_OUTPUT) {
+        fprintf(stderr, "Invalid mixmode: %d.\n", mixmode);     // fftw_convfuns.h:496-499
+        cv_exit(1);
+        return;
+    }
+    if (n_bufs < 1 || n_bufs > BFCUDA_MAXCHANNELS + BFCUDA_MAXFILTERS) {
+        cv_fail("bfcuda convolver: mixnscale with %d buffers", n_bufs);
+        cv_exit(1);
+        return;
+    }
+    if (!grow(&g_cv.d_mix, &g_cv.mix_cap, (size_t)n_bufs * cbytes())) return;
+    std::vector<char *> in(n_bufs);
+    for (int i = 0; i < n_bufs; i++) {
+        in[i] = g_cv.d_mix + (size_t)i * cbytes();
+        h2d(in[i], input_cbufs[i], cbytes());
+    }
+    if (!dev_mixnscale(in.data(), scales, n_bufs, g_cv.d_a, mixmode)) return;
+    d2h(output_cbuf, g_cv.d_a, cbytes());
+    sync();
+}
+
+static void cv_convolve(void *input_cbuf, void *coeffs, void *output_cbuf, int op)
+{
+    if (!need_ready()) return;
+    h2d(g_cv.d_a, input_cbuf, cbytes());
+    h2d(g_cv.d_b, coeffs, cbytes());
+    if (op) {
+        h2d(g_cv.d_c, output_cbuf, cbytes());
+    }
+    CVCU(launch_cv_convolve(g_cv.plan, g_cv.d_a, g_cv.d_b, g_cv.d_c, op, g_cv.stream));
+    d2h(output_cbuf, g_cv.d_c, cbytes());
+    sync();
+}
+
+void convolver_convolve(void *input_cbuf, void *coeffs, void *output_cbuf)
+{
+    cv_convolve(input_cbuf, coeffs, output_cbuf, 0);
+}
+
+void convolver_convolve_inplace(void *cbuf, void *coeffs)
+{
+    cv_convolve(cbuf, coeffs, cbuf, 0);     // fftw_convfuns.h:503-532: same arithmetic, result over the input
+}
+
+void convolver_convolve_add(void *input_cbuf, void *coeffs, void *output_cbuf)
+{
+    cv_convolve(input_cbuf, coeffs, output_cbuf, 1);
+}
+
+void convolver_dirac_convolve(void *input_cbuf, void *output_cbuf)
+{
+    if (!need_ready()) return;
+    h2d(g_cv.d_a, input_cbuf, cbytes());
+    CVCU(launch_cv_dirac(g_cv.plan, g_cv.d_a, g_cv.d_b, g_cv.stream));
+    d2h(output_cbuf, g_cv.d_b, cbytes());
+    sync();
+}
+
+void convolver_dirac_convolve_inplace(void *cbuf)
+{
+    convolver_dirac_convolve(cbuf, cbuf);
+}
+
+// fftw_convolver.c:330-368, float branch semantics for both precisions (see DESIGN.md on the reference's
+// broken double branch).  All five transforms stay on the device.
+void convolver_crossfade_inplace(void *input_cbuf, void *crossfade_cbuf, void *buffer_cbuf)
+{
+    if (!need_ready()) return;
+    const size_t cb = cbytes();
+    const double one = 1.0, inv_n = 1.0 / (double)g_cv.N;
+    char *d_new = g_cv.d_a, *d_old = g_cv.d_b, *d_tmp = g_cv.d_c;
+    char *d_old_t = g_cv.d_b + cb, *d_new_t = g_cv.d_a + cb;
+    h2d(d_new, input_cbuf, cb);
+    h2d(d_old, crossfade_cbuf, cb);
+    char *in[1];
+    in[0] = d_old;
+    if (!dev_mixnscale(in, &one, 1, d_tmp, CONVOLVER_MIXMODE_OUTPUT)) return;
+    CVCU(launch_hc2r(g_cv.plan, d_tmp, d_old_t, 1, g_cv.stream));
+    in[0] = d_new;
+    if (!dev_mixnscale(in, &one, 1, d_tmp, CONVOLVER_MIXMODE_OUTPUT)) return;
+    CVCU(launch_hc2r(g_cv.plan, d_tmp, d_new_t, 1, g_cv.stream));
+    CVCU(launch_cv_xfade_blend(g_cv.plan, d_old_t, d_new_t, g_cv.stream));
+    CVCU(launch_r2hc(g_cv.plan, d_new_t, d_tmp, 1, g_cv.stream));
+    in[0] = d_tmp;
+    if (!dev_mixnscale(in, &inv_n, 1, d_new, CONVOLVER_MIXMODE_INPUT)) return;
+    d2h(input_cbuf, d_new, cb);
+    d2h(crossfade_cbuf, d_old_t, cb);   // the reference leaves the old signal's time domain here (l.345)
+    d2h(buffer_cbuf, d_tmp, cb);        // and the blended spectrum, half-complex, here (l.364)
+    sync();
+}
+
+// fftw_convolver.c:411-433
+void convolver_convolve_eval(void *input_cbuf, void *buffer_cbuf, void *output_cbuf)
+{
+    if (!need_ready()) return;
+    const size_t cb = cbytes(), half = cb / 2;
+    // d_b holds the 1.5 x cbuf state
+    h2d(g_cv.d_a, input_cbuf, cb);
+    h2d(g_cv.d_b, buffer_cbuf, half);
+    CVCU(launch_hc2r(g_cv.plan, g_cv.d_a, g_cv.d_b + half, 1, g_cv.stream));
+    CVCU(launch_r2hc(g_cv.plan, g_cv.d_b, g_cv.d_c, 1, g_cv.stream));
+    d2h(output_cbuf, g_cv.d_c, cb);
+    d2h((char *)buffer_cbuf + half, g_cv.d_b + half, cb);
+    sync();
+    memcpy(buffer_cbuf, (char *)buffer_cbuf + half, half);
+}
+
+void convolver_cbuf2raw(void *cbuf, void *outbuf, struct bfcuda_buffer_format *bf, bool_t apply_dither,
+                        void *dither_state, struct bfcuda_overflow *overflow)
+{
+    (void)dither_state;
+    if (!need_ready()) return;
+    if (apply_dither && !bf->sf.isfloat) {
+        cv_fail("bfcuda convolver: dither is outside the accelerated path (north_star: dither off)");
+        cv_exit(1);
+        return;
+    }
+    const bool okf = bf->sf.isfloat ? (bf->sf.bytes == 4 || bf->sf.bytes == 8) : (bf->sf.bytes >= 1 && bf->sf.bytes <= 4);
+    if (!okf) {
+        fprintf(stderr, "Sample byte size %d is not supported.\n", bf->sf.bytes);   // real2raw.h:245-249
+        cv_exit(1);
+        return;
+    }
+    const size_t span = raw_span(bf);
+    uint8_t *host_raw = (uint8_t *)outbuf + bf->byte_offset;
+    if (!grow((char **)&g_cv.d_raw, &g_cv.raw_cap, span)) return;
+    Overflow of;
+    of.n_overflows = overflow->n_overflows;
+    of.intlargest = overflow->intlargest;
+    of.largest = overflow->largest;
+    of.max = overflow->max;
+    unsigned int status = 0;
+    h2d(g_cv.d_raw, host_raw, span);    // neighbouring channels' bytes inside the span must survive
+    h2d(g_cv.d_a, cbuf, (size_t)g_cv.L * g_cv.rs);
+    h2d(g_cv.d_of, &of, sizeof(of));
+    h2d(g_cv.d_status, &status, sizeof(status));
+    CVCU(launch_cv_real2raw(g_cv.plan, g_cv.d_a, g_cv.d_raw, dev_format(bf, 0), g_cv.d_of, g_cv.d_status,
+                            g_safety_limit, g_cv.stream));
+    d2h(host_raw, g_cv.d_raw, span);
+    d2h(&of, g_cv.d_of, sizeof(of));
+    d2h(&status, g_cv.d_status, sizeof(status));
+    sync();
+    overflow->n_overflows = of.n_overflows;
+    overflow->intlargest = of.intlargest;
+    overflow->largest = of.largest;
+    if (status & 1u) {
+        fprintf(stderr, "NaN or Inf values in the output! Bad output. Aborting.\n");    // real2raw.h:27-31
+        cv_exit(-5);
+    } else if (status & 2u) {
+        fprintf(stderr, "Safety limit exceeded on output. Aborting.\n");                // real2raw.h:32-41
+        cv_exit(1);
+    }
+}
+
+void *convolver_coeffs2cbuf(void *coeffs, int n_coeffs, double scale, void *optional_dest)
+{
+    if (!need_ready()) return nullptr;
+    const int len = n_coeffs > g_cv.L ? g_cv.L : n_coeffs;
+    std::vector<unsigned char> padded((size_t)g_cv.L * g_cv.rs, 0);
+    // fftw_convolver.c:539-557: reject NaN/Inf among the scaled taps
+    for (int n = 0; n < len; n++) {
+        const double v = g_cv.rs == 4 ? (double)(((float *)coeffs)[n] * (float)scale) : ((double *)coeffs)[n] * scale;
+        if (!std::isfinite(v)) {
+            fprintf(stderr, "NaN or Inf value among coefficients.\n");
+            return nullptr;
+        }
+    }
+    memcpy(padded.data(), coeffs, (size_t)len * g_cv.rs);
+    h2d(g_cv.d_a, padded.data(), padded.size());
+    if (!cu_ok(launch_coeff_fft(g_cv.plan, g_cv.d_a, 1, scale, g_cv.d_b, 0, g_cv.stream), "coeff_fft")) return nullptr;
+    if (!cu_ok(launch_permute(g_cv.plan, g_cv.d_b, g_cv.d_c, 1, PLANAR_TO_BLOCKED, g_cv.stream), "permute")) return nullptr;
+    void *dest = optional_dest;
+    if (dest == nullptr && posix_memalign(&dest, 32, cbytes()) != 0) {     // emallocaligned, sysarch.h:10
+        return nullptr;
+    }
+    d2h(dest, g_cv.d_c, cbytes());
+    sync();
+    return dest;
+}
+
+void convolver_runtime_coeffs2cbuf(void *src, void *dest)
+{
+    convolver_coeffs2cbuf(src, g_cv.L, 1.0, dest);  // fftw_convolver.c:575-596: same transform, scale 1, no check
+}
+
+bool_t convolver_verify_cbuf(void *cbufs[], int n_cbufs)
+{
+    // fftw_convolver.c:598-622; a scan of host memory, nothing to accelerate
+    for (int n = 0; n < n_cbufs; n++) {
+        for (int i = 0; i < g_cv.N; i++) {
+            const double v = g_cv.rs == 4 ? (double)((float *)cbufs[n])[i] : ((double *)cbufs[n])[i];
+            if (!std::isfinite(v)) {
+                fprintf(stderr, "NaN or Inf value among coefficients.\n");
+                return 0;
+            }
+        }
+    }
+    return 1;
+}
+
+void convolver_debug_dump_cbuf(const char filename[], void *cbufs[], int n_cbufs)
+{
+    // fftw_convolver.c:624-660: back to taps (second half of the inverse transform), one per line
+    if (!need_ready()) return;
+    FILE *stream = fopen(filename, "wt");
+    if (stream == nullptr) {
+        fprintf(stderr, "Could not open \"%s\" for writing.", filename);
+        return;
+    }
+    std::vector<unsigned char> host(cbytes());
+    const double one = 1.0;
+    for (int n = 0; n < n_cbufs; n++) {
+        char *in[1] = { g_cv.d_a };
+        h2d(g_cv.d_a, cbufs[n], cbytes());
+        if (!dev_mixnscale(in, &one, 1, g_cv.d_b, CONVOLVER_MIXMODE_OUTPUT)) break;
+        if (!cu_ok(launch_hc2r(g_cv.plan, g_cv.d_b, g_cv.d_c, 1, g_cv.stream), "hc2r")) break;
+        d2h(host.data(), g_cv.d_c, cbytes());
+        sync();
+        for (int i = 0; i < g_cv.L; i++) {
+            const double v = g_cv.rs == 4 ? (double)((float *)host.data())[g_cv.L + i] : ((double *)host.data())[g_cv.L + i];
+            fprintf(stream, "%.16e\n", v);
+        }
+    }
+    fclose(stream);
+}
+
+void *convolver_fftplan(int order, int invert, int inplace)
+{
+    (void)order; (void)invert; (void)inplace;
+    cv_fail("bfcuda convolver: convolver_fftplan() hands out FFTW plans (fftw_convolver.c:662-680); there is no "
+            "FFTW behind this convolver");
+    return nullptr;
+}
+
+int convolver_td_block_length(int n_coeffs)
+{
+    // fftw_convolver.c:689-696 / log2.h:28-43: next power of two
+    if (n_coeffs < 1) {
+        return -1;
+    }
+    int len = 1;
+    while (len < n_coeffs) {
+        len <<= 1;
+    }
+    return len;
+}
+
+td_conv_t *convolver_td_new(void *coeffs, int n_coeffs)
+{
+    (void)coeffs; (void)n_coeffs;
+    cv_fail("bfcuda convolver: the sub-sample-delay convolver (convolver_td_*) is outside the accelerated path");
+    return nullptr;
+}
+
+void convolver_td_convolve(td_conv_t *tdc, void *overlap_block)
+{
+    (void)tdc; (void)overlap_block;
+    cv_fail("bfcuda convolver: the sub-sample-delay convolver (convolver_td_*) is outside the accelerated path");
+}
+
+}  // extern "C"

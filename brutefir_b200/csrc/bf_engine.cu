@@ -1,0 +1,1187 @@
+// bf_engine.cu -- the block-level engine behind include/bfcuda.h.
+//
+// Host-side state machine that replaces the per-block body of filter_process()
+// (/root/reference/bfrun.c:1420-2083): it keeps the frequency-domain delay lines, coefficient spectra,
+// the run-time control snapshot and the overflow counters in HBM, and turns each audio block into
+// three kernel launches (forward, multiply-accumulate, inverse; see bf_kernels.cu).
+//
+// HBM layout (all "planar" spectra, bf_common.cuh):
+//   H    [sum of coeff blocks][N]      coefficient spectra, pre-scaled by 1/N  (bfconf->coeffs_data)
+//   FDL  [n_streams][P][N]             delay-line rings, slot (t + delay) % P written per block
+//                                      (cbuf[n][n_blocks], bfrun.c:1045, 1273-1287)
+//   Y    [split][2 F][N]               filter outputs (ocbuf[n]); slots F.. hold the "old coefficient"
+//                                      outputs while a crossfade is in progress (crossfadebuf[0])
+//   prev [n_in][L]                     previous input block per channel (input_timecbuf, fftw_convolver.c:180-193)
+//   xin  [n_in][N]                     unscaled input spectra, only for inputs feeding a multi-input mix
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/bfcuda.h"
+#include "bf_kernels.h"
+
+namespace bf {
+bool mac_tma_applicable(const FftPlan &plan);
+}
+
+using namespace bf;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            return fail(BFCUDA_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                       \
+        }                                                                                                \
+    } while (0)
+
+// ---- NCCL, bound lazily so that single-GPU use has no NCCL dependency --------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void *nccl_comm_t;
+struct NcclApi {
+    void *handle;
+    int (*GetUniqueId)(nccl_uid_t *);
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int);
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
+    int (*CommDestroy)(nccl_comm_t);
+    const char *(*GetErrorString)(int);
+};
+static NcclApi g_nccl;
+
+static int nccl_load(void)
+{
+    if (g_nccl.handle != nullptr) {
+        return 0;
+    }
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) {
+        h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (h == nullptr) {
+        return fail(BFCUDA_ECOMM, "cannot load libnccl.so.2: %s", dlerror());
+    }
+    g_nccl.GetUniqueId = (int (*)(nccl_uid_t *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm_t *, int, nccl_uid_t, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce =
+        (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.GroupStart = (int (*)(void))dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)(void))dlsym(h, "ncclGroupEnd");
+    g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.GroupStart ||
+        !g_nccl.GroupEnd || !g_nccl.CommDestroy) {
+        return fail(BFCUDA_ECOMM, "libnccl.so.2 lacks required symbols");
+    }
+    g_nccl.handle = h;
+    return 0;
+}
+
+// ---- engine state ------------------------------------------------------------------------------------
+
+struct FilterState {
+    int crossfade;
+    std::vector<int> ch[2];
+    std::vector<double> scale[2];
+    int coeff, prevcoeff, delayblocks;
+};
+
+#define TIMING_RING 64
+
+struct bfcuda_engine {
+    int L, P, N, rs;
+    int n_ch[2], n_bytes[2];
+    int n_filters, n_coeffs;
+    int device;
+    unsigned int flags;
+    double safety_limit;
+    int split, mac_variant;
+    int sm_count;
+    char device_name[64];
+    std::vector<bfcuda_buffer_format> fmt[2];
+    std::vector<FilterState> filters;
+    std::vector<int> coeff_n_blocks, coeff_hbase;
+    int total_coeff_blocks;
+
+    cudaStream_t stream;
+    FftPlan plan;
+    uint8_t *d_raw[2];
+    SampleFormat *d_fmt[2];
+    void *d_prev, *d_fdl, *d_xin, *d_H, *d_Y, *d_out_time, *d_scratch;
+    Overflow *d_overflow;
+    unsigned int *d_status;
+    unsigned int *h_status;     // pinned
+    size_t device_bytes;
+
+    // tables: host mirrors and device copies
+    std::vector<FwdDest> h_dests;
+    std::vector<int> h_dest_first;
+    std::vector<uint8_t> h_need_xin;
+    std::vector<MixStream> h_mix_streams;
+    std::vector<MixTerm> h_mix_terms;
+    std::vector<MacJob> h_jobs;
+    std::vector<OutChan> h_chans;
+    std::vector<MixTerm> h_out_terms;
+    std::vector<int> shared_out;
+    FwdDest *d_dests;
+    int *d_dest_first;
+    uint8_t *d_need_xin;
+    MixStream *d_mix_streams;
+    MixTerm *d_mix_terms;
+    MacJob *d_jobs;
+    OutChan *d_chans;
+    MixTerm *d_out_terms;
+    bool dirty, xfade_active;
+    size_t mac_bytes;
+
+    unsigned int t;
+    // measurement
+    cudaEvent_t timer[2];
+    cudaEvent_t ring[TIMING_RING][4];
+    int ring_fill;
+    double stage_ms[BFCUDA_N_STAGES];
+    long stage_blocks, launches;
+    // multi-GPU
+    nccl_comm_t comm;
+    int n_ranks;
+};
+
+static size_t rs_bytes(const bfcuda_engine *e, size_t n_reals) { return n_reals * (size_t)e->rs; }
+
+template <typename T>
+static int dev_alloc(bfcuda_engine *e, T **p, size_t bytes, bool zero = true)
+{
+    *p = nullptr;
+    if (bytes == 0) {
+        bytes = 16;
+    }
+    cudaError_t err = cudaMalloc((void **)p, bytes);
+    if (err != cudaSuccess) {
+        return fail(BFCUDA_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+    }
+    e->device_bytes += bytes;
+    if (zero) {
+        err = cudaMemset(*p, 0, bytes);
+        if (err != cudaSuccess) {
+            return fail(BFCUDA_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(err));
+        }
+    }
+    return 0;
+}
+
+static SampleFormat to_dev_format(const bfcuda_buffer_format &b)
+{
+    SampleFormat f;
+    f.isfloat = b.sf.isfloat;
+    f.swap = b.sf.swap;
+    f.bytes = b.sf.bytes;
+    f.sbytes = b.sf.sbytes;
+    f.sample_spacing = b.sample_spacing;
+    f.byte_offset = b.byte_offset;
+    return f;
+}
+
+static double round_to_real(const bfcuda_engine *e, double v)
+{
+    return e->rs == 4 ? (double)(float)v : v;   // (real_t)scale, fftw_convfuns.h:18-20
+}
+
+static int clamp_delay(const bfcuda_engine *e, int delay)
+{
+    if (delay < 0) return 0;                    // bfrun.c:1579-1584
+    if (delay > e->P - 1) return e->P - 1;
+    return delay;
+}
+
+static int coeff_blocks_used(const bfcuda_engine *e, int coeff, int delay)
+{
+    // bfrun.c:1585-1598
+    if (coeff < 0 || e->coeff_n_blocks[coeff] > e->P - delay) {
+        return e->P - delay;
+    }
+    return e->coeff_n_blocks[coeff];
+}
+
+// Rebuild every per-block table from the control snapshot: the analogue of bfrun.c:1460-1484 plus the
+// scale / slot / coefficient bookkeeping spread over bfrun.c:1566-1600, 1663-1675, 1726-1777, 1847-1854.
+static void build_tables(bfcuda_engine *e)
+{
+    const int F = e->n_filters;
+    std::vector<std::vector<FwdDest>> per_ch(e->n_ch[0]);
+    e->h_mix_streams.clear();
+    e->h_mix_terms.clear();
+    e->h_jobs.clear();
+    std::fill(e->h_need_xin.begin(), e->h_need_xin.end(), (e->flags & 4u) ? 1 : 0);
+    e->xfade_active = false;
+    size_t blocks_h = 0, blocks_x = 0;
+
+    for (int f = 0; f < F; f++) {
+        const FilterState &fs = e->filters[f];
+        const int delay = clamp_delay(e, fs.delayblocks);
+        const int nin = (int)fs.ch[0].size();
+        if (nin == 1) {
+            FwdDest d;
+            d.stream = f;
+            d.delay = delay;
+            d.scale = round_to_real(e, fs.scale[0][0] * e->fmt[0][fs.ch[0][0]].sf.scale);
+            per_ch[fs.ch[0][0]].push_back(d);
+        } else if (nin > 1) {
+            MixStream ms;
+            ms.stream = f;
+            ms.delay = delay;
+            ms.n_inputs = nin;
+            ms.first = (int)e->h_mix_terms.size();
+            for (int i = 0; i < nin; i++) {
+                MixTerm tm;
+                tm.index = fs.ch[0][i];
+                tm.scale = round_to_real(e, fs.scale[0][i] * e->fmt[0][fs.ch[0][i]].sf.scale);
+                e->h_mix_terms.push_back(tm);
+                e->h_need_xin[fs.ch[0][i]] = 1;
+            }
+            e->h_mix_streams.push_back(ms);
+        }
+        MacJob jb;
+        jb.stream = f;
+        jb.hbase = fs.coeff < 0 ? -1 : e->coeff_hbase[fs.coeff];
+        jb.n_parts = fs.coeff < 0 ? 1 : coeff_blocks_used(e, fs.coeff, delay);
+        jb.out = f;
+        e->h_jobs.push_back(jb);
+        blocks_h += fs.coeff < 0 ? 0 : jb.n_parts;
+        blocks_x += jb.n_parts;
+        if (fs.crossfade && fs.prevcoeff != fs.coeff) {
+            // bfrun.c:1726-1736, 1755-1769: the same delay line through the previous coefficients
+            MacJob old = jb;
+            old.hbase = fs.prevcoeff < 0 ? -1 : e->coeff_hbase[fs.prevcoeff];
+            old.n_parts = fs.prevcoeff < 0 ? 1 : coeff_blocks_used(e, fs.prevcoeff, delay);
+            old.out = F + f;
+            e->h_jobs.push_back(old);
+            blocks_h += fs.prevcoeff < 0 ? 0 : old.n_parts;
+            blocks_x += old.n_parts;
+            e->xfade_active = true;
+        }
+    }
+    e->h_dests.clear();
+    for (int c = 0; c < e->n_ch[0]; c++) {
+        e->h_dest_first[c] = (int)e->h_dests.size();
+        e->h_dests.insert(e->h_dests.end(), per_ch[c].begin(), per_ch[c].end());
+    }
+    e->h_dest_first[e->n_ch[0]] = (int)e->h_dests.size();
+
+    // output mixes, filters in index order (bfrun.c:1351-1365, 1847-1868)
+    e->h_out_terms.clear();
+    for (int o = 0; o < e->n_ch[1]; o++) {
+        OutChan oc;
+        oc.first = (int)e->h_out_terms.size();
+        oc.n = 0;
+        oc.xf_first = -1;
+        oc.shared = std::find(e->shared_out.begin(), e->shared_out.end(), o) != e->shared_out.end() ? 1 : 0;
+        bool any_xf = false;
+        for (int f = 0; f < F; f++) {
+            const FilterState &fs = e->filters[f];
+            for (size_t j = 0; j < fs.ch[1].size(); j++) {
+                if (fs.ch[1][j] == o) {
+                    MixTerm tm;
+                    tm.index = f;
+                    tm.scale = round_to_real(e, fs.scale[1][j] / e->fmt[1][o].sf.scale);
+                    e->h_out_terms.push_back(tm);
+                    oc.n++;
+                    any_xf |= fs.crossfade && fs.prevcoeff != fs.coeff;
+                    break;      // "output exists only once per filter", bfrun.c:1360
+                }
+            }
+        }
+        if (any_xf) {
+            oc.xf_first = (int)e->h_out_terms.size();
+            for (int j = 0; j < oc.n; j++) {
+                MixTerm tm = e->h_out_terms[oc.first + j];
+                const FilterState &fs = e->filters[tm.index];
+                if (fs.crossfade && fs.prevcoeff != fs.coeff) {
+                    tm.index = F + tm.index;
+                }
+                e->h_out_terms.push_back(tm);
+            }
+        }
+        e->h_chans[o] = oc;
+    }
+    // algorithmic MAC traffic, SURVEY.md 8(d): rs * N * (coefficient blocks + delay-line blocks + outputs)
+    e->mac_bytes = (size_t)e->rs * e->N * (blocks_h + blocks_x + e->h_jobs.size());
+    e->dirty = false;
+}
+
+template <typename T>
+static cudaError_t upload_vec(T *dst, const std::vector<T> &v, cudaStream_t s)
+{
+    if (v.empty()) {
+        return cudaSuccess;
+    }
+    return cudaMemcpyAsync(dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+static int upload_tables(bfcuda_engine *e)
+{
+    CU(upload_vec(e->d_dests, e->h_dests, e->stream));
+    CU(upload_vec(e->d_dest_first, e->h_dest_first, e->stream));
+    CU(upload_vec(e->d_need_xin, e->h_need_xin, e->stream));
+    CU(upload_vec(e->d_mix_streams, e->h_mix_streams, e->stream));
+    CU(upload_vec(e->d_mix_terms, e->h_mix_terms, e->stream));
+    CU(upload_vec(e->d_jobs, e->h_jobs, e->stream));
+    CU(upload_vec(e->d_chans, e->h_chans, e->stream));
+    CU(upload_vec(e->d_out_terms, e->h_out_terms, e->stream));
+    return 0;
+}
+
+static int choose_split(const bfcuda_engine *e, int requested)
+{
+    if (requested >= 1) {
+        return std::min(requested, std::max(1, e->P));
+    }
+    // Automatic: keep the reference's summation order (split 1) whenever the (filter, bin) space alone
+    // fills the machine; otherwise split the partition sum so that ~512 threads per SM have work.
+    const long threads = (long)std::max(1, e->n_filters) * (e->N / 2 / (16 / e->rs));
+    const long target = (long)e->sm_count * 512;
+    long s = (target + threads - 1) / threads;
+    s = std::min<long>(s, std::max(1, e->P / 8));
+    return (int)std::max<long>(1, s);
+}
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+
+extern "C" {
+
+const char *bfcuda_strerror(void)
+{
+    return g_err;
+}
+
+int bfcuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void bfcuda_destroy(bfcuda_engine *e)
+{
+    if (e == nullptr) {
+        return;
+    }
+    cudaSetDevice(e->device);
+    if (e->stream) {
+        cudaStreamSynchronize(e->stream);
+    }
+    if (e->comm != nullptr && g_nccl.handle != nullptr) {
+        g_nccl.CommDestroy(e->comm);
+    }
+    void *ptrs[] = { e->d_raw[0], e->d_raw[1], e->d_fmt[0], e->d_fmt[1], e->d_prev, e->d_fdl, e->d_xin, e->d_H,
+                     e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
+                     e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms };
+    for (void *p : ptrs) {
+        if (p != nullptr) {
+            cudaFree(p);
+        }
+    }
+    if (e->h_status) cudaFreeHost(e->h_status);
+    fft_plan_destroy(&e->plan);
+    for (int i = 0; i < 2; i++) {
+        if (e->timer[i]) cudaEventDestroy(e->timer[i]);
+    }
+    for (int i = 0; i < TIMING_RING; i++) {
+        for (int j = 0; j < 4; j++) {
+            if (e->ring[i][j]) cudaEventDestroy(e->ring[i][j]);
+        }
+    }
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
+{
+    if (c == nullptr || out == nullptr) {
+        return fail(BFCUDA_EINVAL, "null argument");
+    }
+    *out = nullptr;
+    // convolver_init's checks (fftw_convolver.c:796-803) + bfconf's limits (bfconf.c:1495-1520, bfmod.h:22-23)
+    if (c->realsize != 4 && c->realsize != 8) {
+        return fail(BFCUDA_EINVAL, "Invalid real size %d.", c->realsize);
+    }
+    if (c->filter_length < 4 || (c->filter_length & (c->filter_length - 1)) != 0) {
+        return fail(BFCUDA_EINVAL, "Invalid length %d.", c->filter_length);
+    }
+    if (c->n_blocks < 1) {
+        return fail(BFCUDA_EINVAL, "Invalid number of blocks %d.", c->n_blocks);
+    }
+    if (c->n_channels[0] < 0 || c->n_channels[0] > BFCUDA_MAXCHANNELS || c->n_channels[1] < 0 ||
+        c->n_channels[1] > BFCUDA_MAXCHANNELS || c->n_filters < 0 || c->n_filters > BFCUDA_MAXFILTERS) {
+        return fail(BFCUDA_EINVAL, "channel or filter count out of range");
+    }
+    if (!fft_size_supported(2 * c->filter_length, c->realsize)) {
+        return fail(BFCUDA_ENOTSUP, "filter_length %d at realsize %d exceeds the single-block FFT (max %d)",
+                    c->filter_length, c->realsize, c->realsize == 4 ? 16384 : 8192);
+    }
+    for (int io = 0; io < 2; io++) {
+        for (int n = 0; n < c->n_channels[io]; n++) {
+            const bfcuda_buffer_format &b = c->formats[io][n];
+            const bool okf = b.sf.isfloat ? (b.sf.bytes == 4 || b.sf.bytes == 8) : (b.sf.bytes >= 1 && b.sf.bytes <= 4);
+            if (!okf || b.sample_spacing < 1 || b.byte_offset < 0 ||
+                (long)b.byte_offset + ((long)(c->filter_length - 1) * b.sample_spacing + 1) * b.sf.bytes >
+                    c->n_bytes[io]) {
+                // raw2real.h:154-158 / real2raw.h:245-249 ("Sample byte size %d is not supported.")
+                return fail(BFCUDA_EINVAL, "%s channel %d: unsupported sample format or layout (bytes %d)",
+                            io ? "output" : "input", n, b.sf.bytes);
+            }
+        }
+    }
+    for (int f = 0; f < c->n_filters; f++) {
+        const bfcuda_filter &s = c->filters[f];
+        if (s.n_filters_in != 0) {
+            return fail(BFCUDA_ENOTSUP, "filter %d: filter-to-filter inputs (convolver_convolve_eval) are not on "
+                                        "the accelerated path yet", f);
+        }
+        if (s.coeff >= c->n_coeffs) {
+            return fail(BFCUDA_EINVAL, "filter %d: coefficient index %d out of range", f, s.coeff);
+        }
+        for (int io = 0; io < 2; io++) {
+            for (int i = 0; i < s.n_channels[io]; i++) {
+                if (s.channels[io][i] < 0 || s.channels[io][i] >= c->n_channels[io]) {
+                    return fail(BFCUDA_EINVAL, "filter %d: channel index out of range", f);
+                }
+            }
+        }
+    }
+    for (int n = 0; n < c->n_coeffs; n++) {
+        if (c->coeff_n_blocks[n] < 1 || c->coeff_n_blocks[n] > c->n_blocks) {
+            return fail(BFCUDA_EINVAL, "coefficient set %d: %d blocks (must be 1..%d)", n, c->coeff_n_blocks[n],
+                        c->n_blocks);
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BFCUDA_ENODEV, "no CUDA device available (and there is no CPU fallback)");
+    }
+    if (c->device < 0 || c->device >= ndev) {
+        return fail(BFCUDA_EINVAL, "device %d out of range (%d devices)", c->device, ndev);
+    }
+    CU(cudaSetDevice(c->device));
+
+    bfcuda_engine *e = new bfcuda_engine();
+    memset(&e->plan, 0, sizeof(e->plan));
+    e->L = c->filter_length;
+    e->P = c->n_blocks;
+    e->N = 2 * e->L;
+    e->rs = c->realsize;
+    e->device = c->device;
+    e->flags = c->flags;
+    e->safety_limit = c->safety_limit;
+    e->n_filters = c->n_filters;
+    e->n_coeffs = c->n_coeffs;
+    e->stream = nullptr;
+    e->comm = nullptr;
+    e->n_ranks = 1;
+    e->device_bytes = 0;
+    e->t = 0;
+    e->ring_fill = 0;
+    e->stage_blocks = e->launches = 0;
+    e->h_status = nullptr;
+    memset(e->stage_ms, 0, sizeof(e->stage_ms));
+    memset(e->timer, 0, sizeof(e->timer));
+    memset(e->ring, 0, sizeof(e->ring));
+    void **zero[] = { (void **)&e->d_raw[0], (void **)&e->d_raw[1], (void **)&e->d_fmt[0], (void **)&e->d_fmt[1],
+                      &e->d_prev, &e->d_fdl, &e->d_xin, &e->d_H, &e->d_Y, &e->d_out_time, &e->d_scratch,
+                      (void **)&e->d_overflow, (void **)&e->d_status, (void **)&e->d_dests, (void **)&e->d_dest_first,
+                      (void **)&e->d_need_xin, (void **)&e->d_mix_streams, (void **)&e->d_mix_terms,
+                      (void **)&e->d_jobs, (void **)&e->d_chans, (void **)&e->d_out_terms };
+    for (void **p : zero) {
+        *p = nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess) {
+        e->sm_count = prop.multiProcessorCount;
+        snprintf(e->device_name, sizeof(e->device_name), "%s", prop.name);
+    } else {
+        e->sm_count = 148;
+        e->device_name[0] = '\0';
+    }
+    for (int io = 0; io < 2; io++) {
+        e->n_ch[io] = c->n_channels[io];
+        e->n_bytes[io] = c->n_bytes[io];
+        e->fmt[io].assign(c->formats[io], c->formats[io] + c->n_channels[io]);
+    }
+    e->filters.resize(e->n_filters);
+    for (int f = 0; f < e->n_filters; f++) {
+        const bfcuda_filter &s = c->filters[f];
+        FilterState &fs = e->filters[f];
+        fs.crossfade = s.crossfade;
+        for (int io = 0; io < 2; io++) {
+            fs.ch[io].assign(s.channels[io], s.channels[io] + s.n_channels[io]);
+            fs.scale[io].assign(s.scale[io], s.scale[io] + s.n_channels[io]);
+        }
+        fs.coeff = fs.prevcoeff = s.coeff;      // bfrun.c:1326
+        fs.delayblocks = s.delayblocks;
+    }
+    e->coeff_n_blocks.assign(c->coeff_n_blocks, c->coeff_n_blocks + c->n_coeffs);
+    e->coeff_hbase.resize(e->n_coeffs);
+    e->total_coeff_blocks = 0;
+    for (int n = 0; n < e->n_coeffs; n++) {
+        e->coeff_hbase[n] = e->total_coeff_blocks;
+        e->total_coeff_blocks += e->coeff_n_blocks[n];
+    }
+    e->split = choose_split(e, c->mac_split);
+    const char *variant = getenv("BFCUDA_MAC_VARIANT");
+    e->mac_variant = variant != nullptr ? atoi(variant) : 0;
+
+    int rc = 0;
+#define TRY(x)                    \
+    do {                          \
+        rc = (x);                 \
+        if (rc != 0) goto error;  \
+    } while (0)
+#define TRYCU(call)                                                                                \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            rc = fail(BFCUDA_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__));               \
+            goto error;                                                                            \
+        }                                                                                          \
+    } while (0)
+    {
+        const size_t N = e->N, L = e->L, P = e->P, F = std::max(1, e->n_filters);
+        TRYCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        TRYCU(fft_plan_create(&e->plan, e->N, e->rs));
+        TRYCU(cudaEventCreate(&e->timer[0]));
+        TRYCU(cudaEventCreate(&e->timer[1]));
+        if (e->flags & BFCUDA_FLAG_STAGE_TIMING) {
+            for (int i = 0; i < TIMING_RING; i++) {
+                for (int j = 0; j < 4; j++) {
+                    TRYCU(cudaEventCreate(&e->ring[i][j]));
+                }
+            }
+        }
+        TRYCU(cudaMallocHost((void **)&e->h_status, sizeof(unsigned int)));
+        *e->h_status = 0;
+        TRY(dev_alloc(e, &e->d_raw[0], (size_t)e->n_bytes[0]));
+        TRY(dev_alloc(e, &e->d_raw[1], (size_t)e->n_bytes[1]));
+        TRY(dev_alloc(e, &e->d_fmt[0], sizeof(SampleFormat) * std::max(1, e->n_ch[0])));
+        TRY(dev_alloc(e, &e->d_fmt[1], sizeof(SampleFormat) * std::max(1, e->n_ch[1])));
+        TRY(dev_alloc(e, &e->d_prev, rs_bytes(e, (size_t)e->n_ch[0] * L)));
+        TRY(dev_alloc(e, &e->d_fdl, rs_bytes(e, F * P * N)));
+        TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, (size_t)std::max(1, e->n_ch[0]) * N)));
+        TRY(dev_alloc(e, &e->d_H, rs_bytes(e, (size_t)std::max(1, e->total_coeff_blocks) * N)));
+        TRY(dev_alloc(e, &e->d_Y, rs_bytes(e, (size_t)e->split * 2 * F * N)));
+        TRY(dev_alloc(e, &e->d_out_time, rs_bytes(e, (size_t)std::max(1, e->n_ch[1]) * L)));
+        TRY(dev_alloc(e, &e->d_scratch, rs_bytes(e, 4 * N)));
+        TRY(dev_alloc(e, &e->d_overflow, sizeof(Overflow) * std::max(1, e->n_ch[1])));
+        TRY(dev_alloc(e, &e->d_status, sizeof(unsigned int)));
+        TRY(dev_alloc(e, &e->d_dests, sizeof(FwdDest) * F));
+        TRY(dev_alloc(e, &e->d_dest_first, sizeof(int) * (e->n_ch[0] + 1)));
+        TRY(dev_alloc(e, &e->d_need_xin, (size_t)std::max(1, e->n_ch[0])));
+        TRY(dev_alloc(e, &e->d_mix_streams, sizeof(MixStream) * F));
+        {
+            size_t terms = 1;
+            for (const FilterState &fs : e->filters) {
+                terms += fs.ch[0].size();
+            }
+            TRY(dev_alloc(e, &e->d_mix_terms, sizeof(MixTerm) * terms));
+            terms = 1;
+            for (const FilterState &fs : e->filters) {
+                terms += 2 * fs.ch[1].size();
+            }
+            TRY(dev_alloc(e, &e->d_out_terms, sizeof(MixTerm) * terms));
+        }
+        TRY(dev_alloc(e, &e->d_jobs, sizeof(MacJob) * 2 * F));
+        TRY(dev_alloc(e, &e->d_chans, sizeof(OutChan) * std::max(1, e->n_ch[1])));
+        e->h_dest_first.assign(e->n_ch[0] + 1, 0);
+        e->h_need_xin.assign(std::max(1, e->n_ch[0]), 0);
+        e->h_chans.assign(e->n_ch[1], OutChan());
+
+        for (int io = 0; io < 2; io++) {
+            std::vector<SampleFormat> f(e->n_ch[io]);
+            for (int n = 0; n < e->n_ch[io]; n++) {
+                f[n] = to_dev_format(e->fmt[io][n]);
+            }
+            if (!f.empty()) {
+                TRYCU(cudaMemcpy(e->d_fmt[io], f.data(), sizeof(SampleFormat) * f.size(), cudaMemcpyHostToDevice));
+            }
+        }
+        TRY(bfcuda_reset_overflow(e));
+        e->dirty = true;
+        e->xfade_active = false;
+        build_tables(e);
+        e->dirty = true;    // tables still have to be uploaded by the first block
+    }
+    *out = e;
+    return 0;
+error:
+    bfcuda_destroy(e);
+    return rc;
+#undef TRY
+#undef TRYCU
+}
+
+int bfcuda_reset_overflow(bfcuda_engine *e)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    std::vector<Overflow> of(e->n_ch[1]);
+    for (int n = 0; n < e->n_ch[1]; n++) {
+        of[n].n_overflows = 0;
+        of[n].intlargest = 0;
+        of[n].largest = 0.0;
+        // bfrun.c:2264-2279
+        if (e->fmt[1][n].sf.isfloat) {
+            of[n].max = 1.0;
+        } else {
+            of[n].max = (double)((uint64_t)1 << ((e->fmt[1][n].sf.sbytes << 3) - 1)) - 1;
+        }
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    if (!of.empty()) {
+        CU(cudaMemcpy(e->d_overflow, of.data(), sizeof(Overflow) * of.size(), cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemset(e->d_status, 0, sizeof(unsigned int)));
+    return 0;
+}
+
+int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflow *overflow)
+{
+    if (e == nullptr || overflow == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    if (out_channel < 0 || out_channel >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    Overflow of;
+    CU(cudaMemcpy(&of, e->d_overflow + out_channel, sizeof(of), cudaMemcpyDeviceToHost));
+    overflow->n_overflows = of.n_overflows;
+    overflow->intlargest = of.intlargest;
+    overflow->largest = of.largest;
+    overflow->max = of.max;
+    return 0;
+}
+
+// ---- coefficients ------------------------------------------------------------------------------------
+
+static int check_coeff(bfcuda_engine *e, int coeff, int block)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    if (coeff < 0 || coeff >= e->n_coeffs) return fail(BFCUDA_EINVAL, "coefficient index %d out of range", coeff);
+    if (block < 0 || block >= e->coeff_n_blocks[coeff]) {
+        return fail(BFCUDA_EINVAL, "coefficient block %d out of range", block);
+    }
+    return 0;
+}
+
+int bfcuda_coeff_from_taps(bfcuda_engine *e, int coeff, const void *taps, int n_taps, double scale)
+{
+    int rc = check_coeff(e, coeff, 0);
+    if (rc != 0) return rc;
+    if (taps == nullptr || n_taps < 0) return fail(BFCUDA_EINVAL, "bad taps");
+    CU(cudaSetDevice(e->device));
+    const int nb = e->coeff_n_blocks[coeff];
+    const size_t total = (size_t)nb * e->L;
+    const size_t n = std::min<size_t>((size_t)n_taps, total);
+    // NaN/Inf check on the scaled taps in the real type (fftw_convolver.c:540-556); zero-extension to whole
+    // blocks as load_coeff does (bfconf.c:1982-2019)
+    std::vector<unsigned char> padded(total * e->rs, 0);
+    if (e->rs == 4) {
+        const float *src = (const float *)taps;
+        const float s = (float)scale;
+        for (size_t i = 0; i < n; i++) {
+            if (!std::isfinite((double)(src[i] * s))) {
+                return fail(BFCUDA_ENONFINITE, "NaN or Inf value among coefficients.");
+            }
+        }
+    } else {
+        const double *src = (const double *)taps;
+        for (size_t i = 0; i < n; i++) {
+            if (!std::isfinite(src[i] * scale)) {
+                return fail(BFCUDA_ENONFINITE, "NaN or Inf value among coefficients.");
+            }
+        }
+    }
+    memcpy(padded.data(), taps, n * e->rs);
+    void *d_taps = nullptr;
+    CU(cudaMalloc(&d_taps, padded.size()));
+    cudaError_t err = cudaMemcpyAsync(d_taps, padded.data(), padded.size(), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) {
+        err = launch_coeff_fft(e->plan, d_taps, nb, scale, e->d_H, e->coeff_hbase[coeff], e->stream);
+    }
+    if (err == cudaSuccess) {
+        err = cudaStreamSynchronize(e->stream);
+    }
+    cudaFree(d_taps);
+    if (err != cudaSuccess) {
+        return fail(BFCUDA_ECUDA, "coefficient preprocessing failed: %s", cudaGetErrorString(err));
+    }
+    return 0;
+}
+
+int bfcuda_coeff_runtime_block(bfcuda_engine *e, int coeff, int block, const void *taps_L)
+{
+    int rc = check_coeff(e, coeff, block);
+    if (rc != 0) return rc;
+    CU(cudaSetDevice(e->device));
+    // convolver_runtime_coeffs2cbuf (fftw_convolver.c:575-596): no scale, no NaN check.  Stream ordered,
+    // so a running engine picks the new block up at a block boundary.
+    CU(cudaMemcpyAsync(e->d_scratch, taps_L, rs_bytes(e, e->L), cudaMemcpyHostToDevice, e->stream));
+    CU(launch_coeff_fft(e->plan, e->d_scratch, 1, 1.0, e->d_H, e->coeff_hbase[coeff] + block, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int bfcuda_coeff_set_block(bfcuda_engine *e, int coeff, int block, const void *cbuf)
+{
+    int rc = check_coeff(e, coeff, block);
+    if (rc != 0) return rc;
+    CU(cudaSetDevice(e->device));
+    char *dst = (char *)e->d_H + rs_bytes(e, (size_t)(e->coeff_hbase[coeff] + block) * e->N);
+    CU(cudaMemcpyAsync(e->d_scratch, cbuf, rs_bytes(e, e->N), cudaMemcpyHostToDevice, e->stream));
+    CU(launch_permute(e->plan, e->d_scratch, dst, 1, BLOCKED_TO_PLANAR, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int bfcuda_coeff_get_block(bfcuda_engine *e, int coeff, int block, void *cbuf)
+{
+    int rc = check_coeff(e, coeff, block);
+    if (rc != 0) return rc;
+    CU(cudaSetDevice(e->device));
+    const char *src = (const char *)e->d_H + rs_bytes(e, (size_t)(e->coeff_hbase[coeff] + block) * e->N);
+    CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
+    CU(cudaMemcpyAsync(cbuf, e->d_scratch, rs_bytes(e, e->N), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ---- control -----------------------------------------------------------------------------------------
+
+int bfcuda_set_control(bfcuda_engine *e, int filter, const struct bfcuda_filter_control *c)
+{
+    if (e == nullptr || c == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    if (filter < 0 || filter >= e->n_filters) return fail(BFCUDA_EINVAL, "filter index out of range");
+    if (c->coeff >= e->n_coeffs) return fail(BFCUDA_EINVAL, "coefficient index %d out of range", c->coeff);
+    FilterState &fs = e->filters[filter];
+    fs.coeff = c->coeff < 0 ? -1 : c->coeff;
+    fs.delayblocks = c->delayblocks;
+    for (int io = 0; io < 2; io++) {
+        if (c->scale[io] != nullptr) {
+            fs.scale[io].assign(c->scale[io], c->scale[io] + fs.ch[io].size());
+        }
+    }
+    e->dirty = true;    // takes effect at the next block, like the snapshot at bfrun.c:1462-1478
+    return 0;
+}
+
+// ---- the block step ------------------------------------------------------------------------------------
+
+static int flush_timing_ring(bfcuda_engine *e)
+{
+    if (e->ring_fill == 0) {
+        return 0;
+    }
+    CU(cudaEventSynchronize(e->ring[e->ring_fill - 1][3]));
+    for (int i = 0; i < e->ring_fill; i++) {
+        for (int s = 0; s < BFCUDA_N_STAGES; s++) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e->ring[i][s], e->ring[i][s + 1]));
+            e->stage_ms[s] += ms;
+        }
+    }
+    e->stage_blocks += e->ring_fill;
+    e->ring_fill = 0;
+    return 0;
+}
+
+// enqueue the kernels of one block on the engine stream; input already in d_raw[IN]
+static int enqueue_block(bfcuda_engine *e)
+{
+    if (e->dirty || e->xfade_active) {
+        build_tables(e);
+        int rc = upload_tables(e);
+        if (rc != 0) return rc;
+    }
+    const bool timing = (e->flags & BFCUDA_FLAG_STAGE_TIMING) != 0;
+    cudaEvent_t *ev = nullptr;
+    if (timing) {
+        if (e->ring_fill == TIMING_RING) {
+            int rc = flush_timing_ring(e);
+            if (rc != 0) return rc;
+        }
+        ev = e->ring[e->ring_fill];
+        CU(cudaEventRecord(ev[0], e->stream));
+    }
+
+    ForwardArgs fa;
+    fa.raw_in = e->d_raw[0];
+    fa.fmt = e->d_fmt[0];
+    fa.prev = e->d_prev;
+    fa.fdl = e->d_fdl;
+    fa.xin = e->d_xin;
+    fa.need_xin = e->d_need_xin;
+    fa.dest_first = e->d_dest_first;
+    fa.dests = e->d_dests;
+    fa.n_in = e->n_ch[0];
+    fa.P = e->P;
+    fa.t = e->t;
+    CU(launch_forward(e->plan, fa, e->stream));
+    e->launches += e->n_ch[0] > 0;
+    if (!e->h_mix_streams.empty()) {
+        StreamMixArgs sa;
+        sa.xin = e->d_xin;
+        sa.fdl = e->d_fdl;
+        sa.streams = e->d_mix_streams;
+        sa.terms = e->d_mix_terms;
+        sa.n_streams = (int)e->h_mix_streams.size();
+        sa.P = e->P;
+        sa.t = e->t;
+        CU(launch_stream_mix(e->plan, sa, e->stream));
+        e->launches++;
+    }
+    if (timing) CU(cudaEventRecord(ev[1], e->stream));
+
+    MacArgs ma;
+    ma.fdl = e->d_fdl;
+    ma.H = e->d_H;
+    ma.Y = e->d_Y;
+    ma.jobs = e->d_jobs;
+    ma.n_jobs = (int)e->h_jobs.size();
+    ma.n_slots = 2 * std::max(1, e->n_filters);
+    ma.P = e->P;
+    ma.split = e->split;
+    ma.t = e->t;
+    ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
+    CU(launch_mac(e->plan, ma, e->stream));
+    e->launches += ma.n_jobs > 0;
+    if (timing) CU(cudaEventRecord(ev[2], e->stream));
+
+    InverseArgs ia;
+    ia.Y = e->d_Y;
+    ia.chans = e->d_chans;
+    ia.terms = e->d_out_terms;
+    ia.out_time = e->d_out_time;
+    ia.raw_out = e->d_raw[1];
+    ia.fmt = e->d_fmt[1];
+    ia.overflow = e->d_overflow;
+    ia.status = e->d_status;
+    ia.n_out = e->n_ch[1];
+    ia.n_slots = ma.n_slots;
+    ia.split = e->split;
+    ia.safety_limit = e->safety_limit;
+    CU(launch_inverse(e->plan, ia, e->stream));
+    e->launches += e->n_ch[1] > 0;
+    if (!e->shared_out.empty()) {
+        // outputs fed from several ranks: sum the L valid time-domain samples over NVLink, then quantise
+        // (after the inverse FFT, before real2raw)
+        if (e->comm != nullptr) {
+            const int dtype = e->rs == 4 ? 7 /* ncclFloat32 */ : 8 /* ncclFloat64 */;
+            g_nccl.GroupStart();
+            for (int o : e->shared_out) {
+                char *row = (char *)e->d_out_time + rs_bytes(e, (size_t)o * e->L);
+                int r = g_nccl.AllReduce(row, row, (size_t)e->L, dtype, 0 /* ncclSum */, e->comm, e->stream);
+                if (r != 0) {
+                    g_nccl.GroupEnd();
+                    return fail(BFCUDA_ECOMM, "ncclAllReduce failed: %s",
+                                g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+                }
+            }
+            g_nccl.GroupEnd();
+        }
+        CU(launch_quantise_shared(e->plan, ia, e->stream));
+        e->launches++;
+    }
+    if (timing) {
+        CU(cudaEventRecord(ev[3], e->stream));
+        e->ring_fill++;
+    }
+
+    // bfrun.c:1838, 2034
+    for (FilterState &fs : e->filters) {
+        fs.prevcoeff = fs.coeff;
+    }
+    e->t++;
+    return 0;
+}
+
+static int check_status(bfcuda_engine *e)
+{
+    const unsigned int st = *e->h_status;
+    if (st & 1u) {
+        return fail(BFCUDA_ENONFINITE, "NaN or Inf values in the output! Bad output.");
+    }
+    if (st & 2u) {
+        return fail(BFCUDA_ESAFETY, "Safety limit exceeded on output.");
+    }
+    return 0;
+}
+
+int bfcuda_process_block_async(bfcuda_engine *e, const void *raw_in, void *raw_out)
+{
+    if (e == nullptr || raw_in == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(e->d_raw[0], raw_in, (size_t)e->n_bytes[0], cudaMemcpyHostToDevice, e->stream));
+    int rc = enqueue_block(e);
+    if (rc != 0) return rc;
+    CU(cudaMemcpyAsync(raw_out, e->d_raw[1], (size_t)e->n_bytes[1], cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
+    return 0;
+}
+
+int bfcuda_synchronize(bfcuda_engine *e)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return check_status(e);
+}
+
+int bfcuda_process_block(bfcuda_engine *e, const void *raw_in, void *raw_out)
+{
+    int rc = bfcuda_process_block_async(e, raw_in, raw_out);
+    if (rc != 0) return rc;
+    return bfcuda_synchronize(e);
+}
+
+int bfcuda_process_block_device(bfcuda_engine *e)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    return enqueue_block(e);
+}
+
+int bfcuda_device_io(bfcuda_engine *e, int io, void **device_ptr, size_t *n_bytes)
+{
+    if (e == nullptr || (io != 0 && io != 1)) return fail(BFCUDA_EINVAL, "bad argument");
+    if (device_ptr) *device_ptr = e->d_raw[io];
+    if (n_bytes) *n_bytes = (size_t)e->n_bytes[io];
+    return 0;
+}
+
+int bfcuda_upload_input(bfcuda_engine *e, const void *raw_in)
+{
+    if (e == nullptr || raw_in == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(e->d_raw[0], raw_in, (size_t)e->n_bytes[0], cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int bfcuda_download_output(bfcuda_engine *e, void *raw_out)
+{
+    if (e == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(raw_out, e->d_raw[1], (size_t)e->n_bytes[1], cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return check_status(e);
+}
+
+void *bfcuda_host_alloc(size_t n_bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, n_bytes ? n_bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        fail(BFCUDA_ENOMEM, "cudaMallocHost(%zu) failed", n_bytes);
+        return nullptr;
+    }
+    memset(p, 0, n_bytes);
+    return p;
+}
+
+void bfcuda_host_free(void *p)
+{
+    if (p != nullptr) {
+        cudaFreeHost(p);
+    }
+}
+
+// ---- measurement ---------------------------------------------------------------------------------------
+
+int bfcuda_timer_start(bfcuda_engine *e)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaEventRecord(e->timer[0], e->stream));
+    return 0;
+}
+
+int bfcuda_timer_stop(bfcuda_engine *e, double *elapsed_ms)
+{
+    if (e == nullptr || elapsed_ms == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaEventRecord(e->timer[1], e->stream));
+    CU(cudaEventSynchronize(e->timer[1]));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->timer[0], e->timer[1]));
+    *elapsed_ms = (double)ms;
+    return 0;
+}
+
+int bfcuda_stage_times(bfcuda_engine *e, double mean_ms[BFCUDA_N_STAGES], long *n_blocks, long *n_kernel_launches)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    int rc = flush_timing_ring(e);
+    if (rc != 0) return rc;
+    for (int s = 0; s < BFCUDA_N_STAGES; s++) {
+        if (mean_ms) mean_ms[s] = e->stage_blocks > 0 ? e->stage_ms[s] / (double)e->stage_blocks : 0.0;
+        e->stage_ms[s] = 0.0;
+    }
+    if (n_blocks) *n_blocks = e->stage_blocks;
+    if (n_kernel_launches) *n_kernel_launches = e->launches;
+    e->stage_blocks = 0;
+    e->launches = 0;
+    return 0;
+}
+
+int bfcuda_get_info(bfcuda_engine *e, struct bfcuda_info *info)
+{
+    if (e == nullptr || info == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    if (e->dirty) {
+        build_tables(e);
+        e->dirty = true;
+    }
+    memset(info, 0, sizeof(*info));
+    info->n_fft = e->N;
+    info->mac_split = e->split;
+    info->n_streams = e->n_filters;
+    info->kernels_per_block = 3 + (e->h_mix_streams.empty() ? 0 : 1) + (e->shared_out.empty() ? 0 : 1);
+    info->uses_graph = 0;
+    info->sm_count = e->sm_count;
+    info->mac_bytes_per_block = e->mac_bytes;
+    info->device_bytes = e->device_bytes;
+    snprintf(info->device_name, sizeof(info->device_name), "%s", e->device_name);
+    return 0;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------------
+
+int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst)
+{
+    if (e == nullptr || dst == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    const size_t nb = rs_bytes(e, e->N);
+    switch (what) {
+    case BFCUDA_DBG_INPUT_SPECTRUM: {
+        if (!(e->flags & 4u)) return fail(BFCUDA_EINVAL, "input spectra are only kept with flag 4 (debug)");
+        if (index < 0 || index >= e->n_ch[0]) return fail(BFCUDA_EINVAL, "input channel out of range");
+        const char *src = (const char *)e->d_xin + nb * index;
+        CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_HC, e->stream));
+        CU(cudaMemcpyAsync(dst, e->d_scratch, nb, cudaMemcpyDeviceToHost, e->stream));
+        break;
+    }
+    case BFCUDA_DBG_DELAYLINE: {
+        if (index < 0 || index >= e->n_filters || slot < 0 || slot >= e->P) {
+            return fail(BFCUDA_EINVAL, "filter or slot out of range");
+        }
+        const char *src = (const char *)e->d_fdl + nb * ((size_t)index * e->P + slot);
+        CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
+        CU(cudaMemcpyAsync(dst, e->d_scratch, nb, cudaMemcpyDeviceToHost, e->stream));
+        break;
+    }
+    case BFCUDA_DBG_FILTER_OUTPUT: {
+        if (index < 0 || index >= 2 * e->n_filters) return fail(BFCUDA_EINVAL, "filter out of range");
+        const size_t n_slots = 2 * (size_t)std::max(1, e->n_filters);
+        std::vector<unsigned char> part(nb);
+        for (int z = 0; z < e->split; z++) {
+            const char *src = (const char *)e->d_Y + nb * ((size_t)z * n_slots + index);
+            CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
+            CU(cudaMemcpyAsync(z == 0 ? dst : (void *)part.data(), e->d_scratch, nb, cudaMemcpyDeviceToHost,
+                               e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            if (z > 0) {
+                // same order as the inverse kernel's partial sum
+                if (e->rs == 4) {
+                    float *a = (float *)dst;
+                    const float *b = (const float *)part.data();
+                    for (int i = 0; i < e->N; i++) a[i] = a[i] + b[i];
+                } else {
+                    double *a = (double *)dst;
+                    const double *b = (const double *)part.data();
+                    for (int i = 0; i < e->N; i++) a[i] = a[i] + b[i];
+                }
+            }
+        }
+        break;
+    }
+    case BFCUDA_DBG_OUTPUT_TIME: {
+        if (index < 0 || index >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
+        const char *src = (const char *)e->d_out_time + rs_bytes(e, (size_t)index * e->L);
+        CU(cudaMemcpyAsync(dst, src, rs_bytes(e, e->L), cudaMemcpyDeviceToHost, e->stream));
+        break;
+    }
+    default:
+        return fail(BFCUDA_EINVAL, "unknown debug item %d", what);
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------------
+
+int bfcuda_comm_unique_id(void *id_128_bytes)
+{
+    if (id_128_bytes == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    int rc = nccl_load();
+    if (rc != 0) return rc;
+    nccl_uid_t id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(BFCUDA_ECOMM, "ncclGetUniqueId failed (%d)", r);
+    memcpy(id_128_bytes, &id, sizeof(id));
+    return 0;
+}
+
+int bfcuda_comm_init(bfcuda_engine *e, int rank, int n_ranks, const void *id_128_bytes)
+{
+    if (e == nullptr || id_128_bytes == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    int rc = nccl_load();
+    if (rc != 0) return rc;
+    CU(cudaSetDevice(e->device));
+    nccl_uid_t id;
+    memcpy(&id, id_128_bytes, sizeof(id));
+    int r = g_nccl.CommInitRank(&e->comm, n_ranks, id, rank);
+    if (r != 0) {
+        e->comm = nullptr;
+        return fail(BFCUDA_ECOMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    e->n_ranks = n_ranks;
+    return 0;
+}
+
+int bfcuda_comm_shared_outputs(bfcuda_engine *e, int n_shared, const int *out_channels)
+{
+    if (e == nullptr || (n_shared > 0 && out_channels == nullptr)) return fail(BFCUDA_EINVAL, "null argument");
+    for (int i = 0; i < n_shared; i++) {
+        if (out_channels[i] < 0 || out_channels[i] >= e->n_ch[1]) {
+            return fail(BFCUDA_EINVAL, "shared output channel out of range");
+        }
+    }
+    e->shared_out.assign(out_channels, out_channels + n_shared);
+    e->dirty = true;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,912 @@
+// bf_kernels.cu -- hand-written sm_100a kernels of the partitioned-convolution engine.
+//
+//   k_forward      raw2real + frame assembly + N-point real FFT + input scale, written straight into
+//                  the frequency-domain delay line (K1+K2+K3 of SURVEY.md 2.2; bfrun.c:1494-1560, 1671)
+//   k_stream_mix   delay-line slots that mix several inputs (mixnscale INPUT, n_bufs > 1)
+//   k_mac          the delay-line complex multiply-accumulate over partitions (K4/K5; bfrun.c:1737-1754)
+//   k_inverse      output mix + inverse real FFT + overlap-save discard + crossfade + quantise/pack
+//                  (K6..K9; bfrun.c:1847-1936, fftw_convolver.c:330-368, real2raw.h)
+//   k_coeff_fft    coefficient preprocessing (K10; fftw_convolver.c:526-573)
+//   k_cv_*         the per-call convolver.h surface on the reference's own layouts
+//
+// Roofline notes (DESIGN.md has the full table): k_mac is a pure HBM stream, 16 B of operands per
+// complex bin-partition and 8 "flop"; the FFT kernels move ~1 % of its bytes.  Tensor cores are not
+// used: there is no contraction here, only element-wise complex products.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <vector>
+
+#include "bf_kernels.h"
+#include "bf_fft.cuh"
+#include "bf_sample.cuh"
+
+namespace bf {
+
+// ======================================================================================================
+// FFT plan (twiddle table)
+// ======================================================================================================
+
+bool fft_size_supported(int N, int realsize)
+{
+    if (N < 8 || (N & (N - 1)) != 0) {
+        return false;
+    }
+    // one block holds the packed M = N/2 complex points in shared memory (227 KB max per block)
+    return realsize == 4 ? N <= 32768 : N <= 16384;
+}
+
+cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize)
+{
+    plan->N = N;
+    plan->realsize = realsize;
+    plan->tw = nullptr;
+    const int half = N / 2;
+    cudaError_t err = cudaMalloc(&plan->tw, (size_t)N * realsize);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    std::vector<double> td((size_t)N);
+    for (int j = 0; j < half; j++) {
+        // roots in long double, rounded once to the real type
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
+        td[2 * (size_t)j] = (double)cosl(a);
+        td[2 * (size_t)j + 1] = (double)sinl(a);
+    }
+    if (N >= 8) {
+        td[2 * (size_t)(N / 4)] = 0.0;          // W^{N/4} = -i exactly
+        td[2 * (size_t)(N / 4) + 1] = -1.0;
+    }
+    if (realsize == 4) {
+        std::vector<float> tf((size_t)N);
+        for (size_t i = 0; i < (size_t)N; i++) {
+            tf[i] = (float)td[i];
+        }
+        err = cudaMemcpy(plan->tw, tf.data(), (size_t)N * 4, cudaMemcpyHostToDevice);
+    } else {
+        err = cudaMemcpy(plan->tw, td.data(), (size_t)N * 8, cudaMemcpyHostToDevice);
+    }
+    return err;
+}
+
+void fft_plan_destroy(FftPlan *plan)
+{
+    if (plan->tw != nullptr) {
+        cudaFree(plan->tw);
+        plan->tw = nullptr;
+    }
+}
+
+// ======================================================================================================
+// device building blocks
+// ======================================================================================================
+
+template <typename T>
+__device__ __forceinline__ T *smem_re()
+{
+    extern __shared__ __align__(16) unsigned char bf_smem_raw[];
+    return reinterpret_cast<T *>(bf_smem_raw);
+}
+
+// forward real transform of the frame already packed in (sre, sim); calls emit(k, re, im) for every
+// bin k in [0, M); the Nyquist value is passed as the imaginary part of bin 0 (planar convention).
+template <typename T, int E, typename Emit>
+__device__ __forceinline__ void forward_and_emit(T *sre, T *sim, const T *__restrict__ tw, int M, int tid, int nt,
+                                                 Emit emit)
+{
+    fft_complex_inplace<T, E, false>(sre, sim, tw, M, tid, nt, BlockSync());
+    for (int k = tid; k <= M / 2; k += nt) {
+        if (k == 0) {
+            const T zr = sre[0], zi = sim[0];
+            emit(0, zr + zi, zr - zi);
+        } else {
+            T wr, wi, xkr, xki, xmr, xmi;
+            fft_twiddle<T>(tw, M, k, false, wr, wi);
+            fft_split_pair<T>(sre[fft_pad(k)], sim[fft_pad(k)], sre[fft_pad(M - k)], sim[fft_pad(M - k)], wr, wi,
+                              xkr, xki, xmr, xmi);
+            emit(k, xkr, xki);
+            if (k != M - k) {
+                emit(M - k, xmr, xmi);
+            }
+        }
+    }
+}
+
+// inverse real transform: load(i) returns planar element i of the spectrum; on return the time
+// samples sit in shared memory as y[2j] = sre[pad(j)], y[2j+1] = sim[pad(j)], and a sync was issued.
+template <typename T, int E, typename Load>
+__device__ __forceinline__ void load_and_inverse(T *sre, T *sim, const T *__restrict__ tw, int M, int tid, int nt,
+                                                 Load load)
+{
+    for (int k = tid; k <= M / 2; k += nt) {
+        if (k == 0) {
+            const T x0 = load(0), xm = load(M);
+            sre[0] = x0 + xm;
+            sim[0] = x0 - xm;
+        } else {
+            T wr, wi, zkr, zki, zmr, zmi;
+            const T xkr = load(k), xki = load(M + k);
+            const T xmr = load(M - k), xmi = load(2 * M - k);
+            fft_twiddle<T>(tw, M, k, false, wr, wi);
+            fft_merge_pair<T>(xkr, xki, xmr, xmi, wr, wi, zkr, zki, zmr, zmi);
+            sre[fft_pad(k)] = zkr;
+            sim[fft_pad(k)] = zki;
+            if (k != M - k) {
+                sre[fft_pad(M - k)] = zmr;
+                sim[fft_pad(M - k)] = zmi;
+            }
+        }
+    }
+    __syncthreads();
+    fft_complex_inplace<T, E, true>(sre, sim, tw, M, tid, nt, BlockSync());
+}
+
+// the reference's blocked complex product for one bin: (re, im) = b (*) c with separate roundings
+// (fftw_convfuns.h:548-556 / convolver_xmm.c:25-30)
+template <typename T>
+__device__ __forceinline__ void cprod(T br, T bi, T cr, T ci, T &re, T &im)
+{
+    re = sub_rn(mul_rn(br, cr), mul_rn(bi, ci));
+    im = add_rn(mul_rn(br, ci), mul_rn(bi, cr));
+}
+
+// block-wide reduction of the quantiser statistics into overflow[o] / status
+__device__ __forceinline__ void reduce_stats(QuantStats st, Overflow *of, unsigned int *status, void *smem, int tid,
+                                             int nt)
+{
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        st.n_overflows += __shfl_down_sync(full, st.n_overflows, d);
+        st.intlargest = max(st.intlargest, __shfl_down_sync(full, st.intlargest, d));
+        st.largest = fmax(st.largest, __shfl_down_sync(full, st.largest, d));
+        st.status |= __shfl_down_sync(full, st.status, d);
+    }
+    QuantStats *w = reinterpret_cast<QuantStats *>(smem);
+    __syncthreads();        // shared memory is about to be reused
+    if ((tid & 31) == 0) {
+        w[tid >> 5] = st;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = (nt + 31) >> 5;
+        for (int i = 1; i < nw; i++) {
+            st.n_overflows += w[i].n_overflows;
+            st.intlargest = max(st.intlargest, w[i].intlargest);
+            st.largest = fmax(st.largest, w[i].largest);
+            st.status |= w[i].status;
+        }
+        of->n_overflows += st.n_overflows;
+        if (st.intlargest > of->intlargest) {
+            of->intlargest = st.intlargest;
+        }
+        if (st.largest > of->largest) {
+            of->largest = st.largest;
+        }
+        if (st.status != 0) {
+            atomicOr(status, st.status);
+        }
+    }
+}
+
+// ======================================================================================================
+// k_forward
+// ======================================================================================================
+
+template <typename T, int E>
+__global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__restrict__ tw, int L)
+{
+    const int M = L, N = 2 * L;
+    const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    T *sre = smem_re<T>();
+    T *sim = sre + (M + (M >> 5) + 1);
+    const SampleFormat f = a.fmt[c];
+    T *prev = reinterpret_cast<T *>(a.prev) + (size_t)c * L;
+    const uint8_t *raw = a.raw_in + f.byte_offset;
+    const size_t stride = (size_t)f.sample_spacing * f.bytes;
+
+    // frame = [previous block | this block] (fftw_convolver.c:180-193), packed z_j = x_2j + i x_2j+1
+    for (int n = tid; n < L; n += nt) {
+        const T cur = raw_to_real<T>(raw + (size_t)n * stride, f.bytes, f.isfloat, f.swap);
+        const T old = prev[n];
+        prev[n] = cur;
+        const int j0 = fft_pad(n >> 1), j1 = fft_pad((L + n) >> 1);
+        if (n & 1) {
+            sim[j0] = old;
+            sim[j1] = cur;
+        } else {
+            sre[j0] = old;
+            sre[j1] = cur;
+        }
+    }
+    __syncthreads();
+
+    const int d0 = a.dest_first[c], d1 = a.dest_first[c + 1];
+    T *xin = (a.xin != nullptr && a.need_xin[c]) ? reinterpret_cast<T *>(a.xin) + (size_t)c * N : nullptr;
+    T *fdl = reinterpret_cast<T *>(a.fdl);
+    const FwdDest *dests = a.dests;
+    const int P = a.P;
+    const unsigned int t = a.t;
+    forward_and_emit<T, E>(sre, sim, tw, M, tid, nt, [&](int k, T re, T im) {
+        if (xin != nullptr) {
+            xin[k] = re;
+            xin[M + k] = im;
+        }
+        for (int d = d0; d < d1; d++) {
+            const FwdDest ds = dests[d];
+            const unsigned int slot = (t + (unsigned int)ds.delay) % (unsigned int)P;
+            T *dst = fdl + ((size_t)ds.stream * P + slot) * N;
+            const T s = (T)ds.scale;
+            dst[k] = mul_rn(re, s);
+            dst[M + k] = mul_rn(im, s);
+        }
+    });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_stream_mix(StreamMixArgs a, int N)
+{
+    const MixStream ms = a.streams[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) {
+        return;
+    }
+    const T *xin = reinterpret_cast<const T *>(a.xin);
+    const unsigned int slot = (a.t + (unsigned int)ms.delay) % (unsigned int)a.P;
+    T acc = (T)0;
+    for (int j = 0; j < ms.n_inputs; j++) {
+        const MixTerm tm = a.terms[ms.first + j];
+        const T v = mul_rn(xin[(size_t)tm.index * N + i], (T)tm.scale);
+        acc = j == 0 ? v : add_rn(acc, v);
+    }
+    reinterpret_cast<T *>(a.fdl)[((size_t)ms.stream * a.P + slot) * N + i] = acc;
+}
+
+// ======================================================================================================
+// k_mac -- variant 0: direct streaming loads
+// ======================================================================================================
+
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { typedef float4 type; };
+template <> struct Vec16<double> { typedef double2 type; };
+
+// 16-byte streaming load: read-only path, do not allocate in L1 (every operand byte is used once)
+template <typename V>
+__device__ __forceinline__ V ldg_stream(const V *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return *reinterpret_cast<V *>(&r);
+}
+
+template <typename T, int W>
+struct __align__(16) Lanes {
+    T v[W];
+};
+template <typename T, int W, typename V>
+__device__ __forceinline__ Lanes<T, W> as_lanes(const V &x)
+{
+    return *reinterpret_cast<const Lanes<T, W> *>(&x);
+}
+
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
+{
+    constexpr int W = 16 / (int)sizeof(T);
+    typedef typename Vec16<T>::type V;
+    const int M = N >> 1;
+    const int vecs = M / W;     // 16-byte vectors per half spectrum
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long)a.n_jobs * vecs) {
+        return;
+    }
+    const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
+    const MacJob jb = a.jobs[job];
+    const int z = blockIdx.y;
+    const int P = a.P;
+    T *out = reinterpret_cast<T *>(a.Y) + ((size_t)z * a.n_slots + jb.out) * N + (size_t)v * W;
+    const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * P * N + (size_t)v * W;
+    const int slot0 = (int)(a.t % (unsigned int)P);
+
+    Lanes<T, W> are, aim;
+#pragma unroll
+    for (int l = 0; l < W; l++) {
+        are.v[l] = (T)0;
+        aim.v[l] = (T)0;
+    }
+
+    if (jb.hbase < 0) {
+        // coeff = -1: unit pulse in the shifted-coefficient convention = (+1/N, -1/N, ...) per bin
+        if (z == 0) {
+            const T fr = (T)(1.0 / (T)N);
+            const Lanes<T, W> xr = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(X + (size_t)slot0 * N)));
+            const Lanes<T, W> xi = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(X + (size_t)slot0 * N + M)));
+#pragma unroll
+            for (int l = 0; l < W; l++) {
+                const T s = (l & 1) ? -fr : fr;
+                are.v[l] = mul_rn(xr.v[l], s);
+                aim.v[l] = mul_rn(xi.v[l], s);
+            }
+        }
+    } else {
+        const int chunk = (jb.n_parts + a.split - 1) / a.split;
+        int i = z * chunk;
+        const int i1 = min(jb.n_parts, i + chunk);
+        const T *H = reinterpret_cast<const T *>(a.H) + (size_t)jb.hbase * N + (size_t)v * W;
+        T dc = (T)0, ny = (T)0;
+        if (i < i1) {
+            // convolver_convolve: plain product for the first partition of the range
+            int slot = slot0 - i;
+            slot += (slot < 0) ? P : 0;
+            const T *xp = X + (size_t)slot * N;
+            const T *hp = H + (size_t)i * N;
+            const Lanes<T, W> br = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(xp)));
+            const Lanes<T, W> bi = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(xp + M)));
+            const Lanes<T, W> cr = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(hp)));
+            const Lanes<T, W> ci = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(hp + M)));
+#pragma unroll
+            for (int l = 0; l < W; l++) {
+                cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], are.v[l], aim.v[l]);
+            }
+            dc = mul_rn(br.v[0], cr.v[0]);
+            ny = mul_rn(bi.v[0], ci.v[0]);
+            i++;
+        }
+        // convolver_convolve_add: partitions ascending, accumulated in the real type -- the
+        // reference's summation order; UNROLL partitions of loads are in flight per thread
+        for (; i < i1; i += UNROLL) {
+            V xr[UNROLL], xi[UNROLL], hr[UNROLL], hi[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (i + u < i1) {
+                    int slot = slot0 - (i + u);
+                    slot += (slot < 0) ? P : 0;
+                    const T *xp = X + (size_t)slot * N;
+                    const T *hp = H + (size_t)(i + u) * N;
+                    xr[u] = ldg_stream(reinterpret_cast<const V *>(xp));
+                    xi[u] = ldg_stream(reinterpret_cast<const V *>(xp + M));
+                    hr[u] = ldg_stream(reinterpret_cast<const V *>(hp));
+                    hi[u] = ldg_stream(reinterpret_cast<const V *>(hp + M));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (i + u < i1) {
+                    const Lanes<T, W> br = as_lanes<T, W>(xr[u]), bi = as_lanes<T, W>(xi[u]);
+                    const Lanes<T, W> cr = as_lanes<T, W>(hr[u]), ci = as_lanes<T, W>(hi[u]);
+#pragma unroll
+                    for (int l = 0; l < W; l++) {
+                        T re, im;
+                        cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], re, im);
+                        are.v[l] = add_rn(are.v[l], re);
+                        aim.v[l] = add_rn(aim.v[l], im);
+                    }
+                    dc = add_rn(dc, mul_rn(br.v[0], cr.v[0]));
+                    ny = add_rn(ny, mul_rn(bi.v[0], ci.v[0]));
+                }
+            }
+        }
+        if (v == 0) {
+            // slots [0] and [4] of the blocked layout: DC and Nyquist are real products
+            are.v[0] = dc;
+            aim.v[0] = ny;
+        }
+    }
+    *reinterpret_cast<V *>(out) = *reinterpret_cast<V *>(&are);
+    *reinterpret_cast<V *>(out + M) = *reinterpret_cast<V *>(&aim);
+}
+
+// ======================================================================================================
+// k_inverse
+// ======================================================================================================
+
+template <typename T>
+__device__ __forceinline__ T xfade(T old, T nw, int n, int L);
+template <>
+__device__ __forceinline__ float xfade<float>(float old, float nw, int n, int L)
+{
+    // fftw_convolver.c:349-355, literally: f and f*n in float, the old term in double
+    const float f = (float)(1.0 / (double)(float)(L - 1));
+    const float fn = __fmul_rn(f, (float)n);
+    const double a = __dmul_rn((double)old, __dsub_rn(1.0, (double)fn));
+    const float b = __fmul_rn(__fmul_rn(nw, f), (float)n);
+    return (float)__dadd_rn(a, (double)b);
+}
+template <>
+__device__ __forceinline__ double xfade<double>(double old, double nw, int n, int L)
+{
+    // the float branch's formula in double (the reference's own double branch is broken)
+    const double d = 1.0 / (double)(L - 1);
+    const double a = __dmul_rn(old, __dsub_rn(1.0, __dmul_rn(d, (double)n)));
+    const double b = __dmul_rn(__dmul_rn(nw, d), (double)n);
+    return __dadd_rn(a, b);
+}
+
+template <typename T>
+__device__ __forceinline__ T mix_terms(const T *__restrict__ Y, const MixTerm *__restrict__ terms, int first, int n,
+                                       int n_slots, int split, int N, int i)
+{
+    T acc = (T)0;
+    for (int j = 0; j < n; j++) {
+        const MixTerm tm = terms[first + j];
+        T y = Y[(size_t)tm.index * N + i];
+        for (int z = 1; z < split; z++) {
+            y = add_rn(y, Y[((size_t)z * n_slots + tm.index) * N + i]);
+        }
+        const T v = mul_rn(y, (T)tm.scale);
+        acc = j == 0 ? v : add_rn(acc, v);
+    }
+    return acc;
+}
+
+template <typename T, int E>
+__global__ void __launch_bounds__(1024, 1) k_inverse(InverseArgs a, const T *__restrict__ tw, int L)
+{
+    const int M = L, N = 2 * L;
+    const int o = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    T *sre = smem_re<T>();
+    T *sim = sre + (M + (M >> 5) + 1);
+    const OutChan ch = a.chans[o];
+    const T *Y = reinterpret_cast<const T *>(a.Y);
+    const int npass = ch.xf_first >= 0 ? 2 : 1;
+    T keep[E];
+
+    for (int pass = 0; pass < npass; pass++) {
+        const int first = (npass == 2 && pass == 0) ? ch.xf_first : ch.first;
+        load_and_inverse<T, E>(sre, sim, tw, M, tid, nt, [&](int i) {
+            return mix_terms<T>(Y, a.terms, first, ch.n, a.n_slots, a.split, N, i);
+        });
+        if (pass + 1 < npass) {
+            // stash the "old" signal's valid half in registers, then reuse shared memory
+#pragma unroll
+            for (int b = 0; b < E / 2; b++) {
+                const int j = tid + b * nt;
+                if (j < M / 2) {
+                    keep[2 * b] = sre[fft_pad(j)];
+                    keep[2 * b + 1] = sim[fft_pad(j)];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // overlap-save: the first L samples are the valid output (fftw_convolver.c:498-501)
+    const SampleFormat f = a.fmt[o];
+    T *tdst = reinterpret_cast<T *>(a.out_time) + (size_t)o * L;
+    uint8_t *raw = a.raw_out + f.byte_offset;
+    const size_t stride = (size_t)f.sample_spacing * f.bytes;
+    const double of_max = a.overflow[o].max;
+    QuantStats st;
+    quant_stats_init(st);
+#pragma unroll
+    for (int b = 0; b < E / 2; b++) {
+        const int j = tid + b * nt;
+        if (j < M / 2) {
+            T y0 = sre[fft_pad(j)], y1 = sim[fft_pad(j)];
+            if (npass == 2) {
+                y0 = xfade<T>(keep[2 * b], y0, 2 * j, L);
+                y1 = xfade<T>(keep[2 * b + 1], y1, 2 * j + 1, L);
+            }
+            tdst[2 * j] = y0;
+            tdst[2 * j + 1] = y1;
+            if (!ch.shared) {
+                real_to_raw<T>(y0, raw + (size_t)(2 * j) * stride, f.bytes, f.sbytes, f.isfloat, f.swap,
+                               a.safety_limit, of_max, st);
+                real_to_raw<T>(y1, raw + (size_t)(2 * j + 1) * stride, f.bytes, f.sbytes, f.isfloat, f.swap,
+                               a.safety_limit, of_max, st);
+            }
+        }
+    }
+    if (!ch.shared) {
+        reduce_stats(st, &a.overflow[o], a.status, sre, tid, nt);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_quantise_shared(InverseArgs a, int L)
+{
+    const int o = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    __shared__ QuantStats wstats[32];
+    if (!a.chans[o].shared) {
+        return;
+    }
+    const SampleFormat f = a.fmt[o];
+    const T *src = reinterpret_cast<const T *>(a.out_time) + (size_t)o * L;
+    uint8_t *raw = a.raw_out + f.byte_offset;
+    const size_t stride = (size_t)f.sample_spacing * f.bytes;
+    const double of_max = a.overflow[o].max;
+    QuantStats st;
+    quant_stats_init(st);
+    for (int n = tid; n < L; n += nt) {
+        real_to_raw<T>(src[n], raw + (size_t)n * stride, f.bytes, f.sbytes, f.isfloat, f.swap, a.safety_limit,
+                       of_max, st);
+    }
+    reduce_stats(st, &a.overflow[o], a.status, wstats, tid, nt);
+}
+
+// ======================================================================================================
+// coefficient preprocessing and plain transforms
+// ======================================================================================================
+
+template <typename T, int E>
+__global__ void __launch_bounds__(1024, 1) k_coeff_fft(const T *__restrict__ taps, T scale, T *__restrict__ H,
+                                                       int hbase, const T *__restrict__ tw, int L)
+{
+    const int M = L, N = 2 * L;
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    T *sre = smem_re<T>();
+    T *sim = sre + (M + (M >> 5) + 1);
+    // [0_L | scale * h] : the circular shift by L makes the FIRST half of the inverse transform valid
+    for (int n = tid; n < L; n += nt) {
+        const T cur = mul_rn(taps[(size_t)b * L + n], scale);
+        const int j0 = fft_pad(n >> 1), j1 = fft_pad((L + n) >> 1);
+        if (n & 1) {
+            sim[j0] = (T)0;
+            sim[j1] = cur;
+        } else {
+            sre[j0] = (T)0;
+            sre[j1] = cur;
+        }
+    }
+    __syncthreads();
+    T *dst = H + (size_t)(hbase + b) * N;
+    const T inv_n = (T)(1.0 / (double)N);
+    forward_and_emit<T, E>(sre, sim, tw, M, tid, nt, [&](int k, T re, T im) {
+        dst[k] = mul_rn(re, inv_n);
+        dst[M + k] = mul_rn(im, inv_n);
+    });
+}
+
+template <typename T, int E>
+__global__ void __launch_bounds__(1024, 1) k_r2hc(const T *in, T *out, const T *__restrict__ tw, int L)
+{
+    const int M = L, N = 2 * L;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    T *sre = smem_re<T>();
+    T *sim = sre + (M + (M >> 5) + 1);
+    const T *src = in + (size_t)blockIdx.x * N;
+    T *dst = out + (size_t)blockIdx.x * N;
+    for (int j = tid; j < M; j += nt) {
+        sre[fft_pad(j)] = src[2 * j];
+        sim[fft_pad(j)] = src[2 * j + 1];
+    }
+    __syncthreads();
+    forward_and_emit<T, E>(sre, sim, tw, M, tid, nt, [&](int k, T re, T im) {
+        dst[k] = re;                    // hc[k] = Re X_k
+        if (k == 0) {
+            dst[M] = im;                // Nyquist
+        } else {
+            dst[N - k] = im;            // hc[N-k] = Im X_k
+        }
+    });
+}
+
+template <typename T, int E>
+__global__ void __launch_bounds__(1024, 1) k_hc2r(const T *in, T *out, const T *__restrict__ tw, int L)
+{
+    const int M = L, N = 2 * L;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    T *sre = smem_re<T>();
+    T *sim = sre + (M + (M >> 5) + 1);
+    const T *src = in + (size_t)blockIdx.x * N;
+    T *dst = out + (size_t)blockIdx.x * N;
+    load_and_inverse<T, E>(sre, sim, tw, M, tid, nt, [&](int i) { return src[planar_to_hc(i, M)]; });
+    for (int j = tid; j < M; j += nt) {
+        dst[2 * j] = sre[fft_pad(j)];
+        dst[2 * j + 1] = sim[fft_pad(j)];
+    }
+}
+
+// ======================================================================================================
+// layout permutation and per-call kernels on the reference layouts
+// ======================================================================================================
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_permute(const T *__restrict__ src, T *__restrict__ dst, int N, int mode)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;    // planar index
+    if (i >= N) {
+        return;
+    }
+    const int M = N >> 1;
+    const size_t base = (size_t)blockIdx.y * N;
+    switch (mode) {
+    case BLOCKED_TO_PLANAR: dst[base + i] = src[base + planar_to_blocked(i, M)]; break;
+    case PLANAR_TO_BLOCKED: dst[base + planar_to_blocked(i, M)] = src[base + i]; break;
+    case HC_TO_PLANAR: dst[base + i] = src[base + planar_to_hc(i, M)]; break;
+    default: dst[base + planar_to_hc(i, M)] = src[base + i]; break;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cv_mixnscale(const void *const *in_ptrs, const double *scales, int n_bufs,
+                                                      T *out, int N, int mode)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;    // planar index
+    if (i >= N) {
+        return;
+    }
+    const int M = N >> 1;
+    const int hc = planar_to_hc(i, M), bl = planar_to_blocked(i, M);
+    const int si = mode == 1 ? hc : bl, di = mode == 1 ? bl : hc;
+    T acc = (T)0;
+    for (int j = 0; j < n_bufs; j++) {
+        const T v = mul_rn(reinterpret_cast<const T *>(in_ptrs[j])[si], (T)scales[j]);
+        acc = j == 0 ? v : add_rn(acc, v);
+    }
+    out[di] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cv_convolve(const T *b, const T *c, T *d, int N, int op)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;    // 8-real chunk
+    if (q >= N / 8) {
+        return;
+    }
+    T br[4], bi[4], cr[4], ci[4], dr[4], di[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        br[j] = b[8 * q + j];
+        bi[j] = b[8 * q + 4 + j];
+        cr[j] = c[8 * q + j];
+        ci[j] = c[8 * q + 4 + j];
+        dr[j] = op ? d[8 * q + j] : (T)0;
+        di[j] = op ? d[8 * q + 4 + j] : (T)0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        T re, im;
+        cprod<T>(br[j], bi[j], cr[j], ci[j], re, im);
+        if (q == 0 && j == 0) {
+            re = mul_rn(br[0], cr[0]);      // DC
+            im = mul_rn(bi[0], ci[0]);      // Nyquist
+        }
+        d[8 * q + j] = op ? add_rn(dr[j], re) : re;
+        d[8 * q + 4 + j] = op ? add_rn(di[j], im) : im;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cv_dirac(const T *b, T *d, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) {
+        return;
+    }
+    const T fr = (T)(1.0 / (T)N);
+    d[i] = mul_rn(b[i], (i & 1) ? -fr : fr);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cv_xfade_blend(const T *old_time, T *new_time, int L)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < L) {
+        new_time[n] = xfade<T>(old_time[n], new_time[n], n, L);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cv_raw2real(const uint8_t *raw, SampleFormat f, T *dst, int L)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < L) {
+        dst[n] = raw_to_real<T>(raw + f.byte_offset + (size_t)n * f.sample_spacing * f.bytes, f.bytes, f.isfloat,
+                                f.swap);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cv_real2raw(const T *src, uint8_t *raw, SampleFormat f, Overflow *of,
+                                                     unsigned int *status, double safety_limit, int L)
+{
+    __shared__ QuantStats wstats[32];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double of_max = of->max;
+    QuantStats st;
+    quant_stats_init(st);
+    for (int n = tid; n < L; n += nt) {
+        real_to_raw<T>(src[n], raw + f.byte_offset + (size_t)n * f.sample_spacing * f.bytes, f.bytes, f.sbytes,
+                       f.isfloat, f.swap, safety_limit, of_max, st);
+    }
+    reduce_stats(st, of, status, wstats, tid, nt);
+}
+
+// ======================================================================================================
+// launchers
+// ======================================================================================================
+
+static size_t fft_smem_bytes(int M, int realsize)
+{
+    return (size_t)fft_smem_reals(M) * realsize;
+}
+
+template <typename K>
+static cudaError_t allow_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) {
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    }
+    return cudaSuccess;
+}
+
+// dispatch on (realsize, points per thread): float uses 16 points per thread above M = 8192
+#define BF_FFT_DISPATCH(plan, KERNEL, grid, stream, ...)                                                   \
+    do {                                                                                                   \
+        const int M_ = (plan).N / 2;                                                                       \
+        const size_t smem_ = fft_smem_bytes(M_, (plan).realsize);                                          \
+        cudaError_t e_;                                                                                    \
+        if ((plan).realsize == 4) {                                                                        \
+            typedef float T;                                                                               \
+            if (M_ > 8192) {                                                                               \
+                if ((e_ = allow_smem(KERNEL<float, 16>, smem_)) != cudaSuccess) return e_;                 \
+                KERNEL<float, 16><<<grid, M_ / 16, smem_, stream>>>(__VA_ARGS__);                          \
+            } else {                                                                                       \
+                if ((e_ = allow_smem(KERNEL<float, 8>, smem_)) != cudaSuccess) return e_;                  \
+                KERNEL<float, 8><<<grid, fft_threads(M_), smem_, stream>>>(__VA_ARGS__);                   \
+            }                                                                                              \
+        } else {                                                                                           \
+            typedef double T;                                                                              \
+            if ((e_ = allow_smem(KERNEL<double, 8>, smem_)) != cudaSuccess) return e_;                     \
+            KERNEL<double, 8><<<grid, fft_threads(M_), smem_, stream>>>(__VA_ARGS__);                      \
+        }                                                                                                  \
+        return cudaGetLastError();                                                                         \
+    } while (0)
+
+cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
+{
+    if (a.n_in == 0) return cudaSuccess;
+    BF_FFT_DISPATCH(plan, k_forward, a.n_in, s, a, (const T *)plan.tw, plan.N / 2);
+}
+
+cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaStream_t s)
+{
+    if (a.n_streams == 0) return cudaSuccess;
+    dim3 grid((plan.N + 255) / 256, a.n_streams);
+    if (plan.realsize == 4) {
+        k_stream_mix<float><<<grid, 256, 0, s>>>(a, plan.N);
+    } else {
+        k_stream_mix<double><<<grid, 256, 0, s>>>(a, plan.N);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mac_tma(const FftPlan &plan, const MacArgs &a, cudaStream_t s);   // bf_mac_tma.cu
+
+cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
+{
+    if (a.n_jobs == 0) return cudaSuccess;
+    if (a.variant == 1) {
+        return launch_mac_tma(plan, a, s);
+    }
+    const int W = 16 / plan.realsize;
+    const long threads = (long)a.n_jobs * (plan.N / 2 / W);
+    dim3 grid((unsigned int)((threads + 255) / 256), a.split);
+    if (plan.realsize == 4) {
+        k_mac<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
+    } else {
+        k_mac<double, 4><<<grid, 256, 0, s>>>(a, plan.N);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
+{
+    if (a.n_out == 0) return cudaSuccess;
+    BF_FFT_DISPATCH(plan, k_inverse, a.n_out, s, a, (const T *)plan.tw, plan.N / 2);
+}
+
+cudaError_t launch_quantise_shared(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
+{
+    if (a.n_out == 0) return cudaSuccess;
+    if (plan.realsize == 4) {
+        k_quantise_shared<float><<<a.n_out, 256, 0, s>>>(a, plan.N / 2);
+    } else {
+        k_quantise_shared<double><<<a.n_out, 256, 0, s>>>(a, plan.N / 2);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_coeff_fft(const FftPlan &plan, const void *taps, int n_blocks, double scale, void *H, int hbase,
+                             cudaStream_t s)
+{
+    if (n_blocks == 0) return cudaSuccess;
+    BF_FFT_DISPATCH(plan, k_coeff_fft, n_blocks, s, (const T *)taps, (T)scale, (T *)H, hbase, (const T *)plan.tw,
+                    plan.N / 2);
+}
+
+cudaError_t launch_r2hc(const FftPlan &plan, const void *in, void *out, int batch, cudaStream_t s)
+{
+    BF_FFT_DISPATCH(plan, k_r2hc, batch, s, (const T *)in, (T *)out, (const T *)plan.tw, plan.N / 2);
+}
+
+cudaError_t launch_hc2r(const FftPlan &plan, const void *in, void *out, int batch, cudaStream_t s)
+{
+    BF_FFT_DISPATCH(plan, k_hc2r, batch, s, (const T *)in, (T *)out, (const T *)plan.tw, plan.N / 2);
+}
+
+cudaError_t launch_permute(const FftPlan &plan, const void *src, void *dst, int n_spectra, int mode, cudaStream_t s)
+{
+    if (n_spectra == 0) return cudaSuccess;
+    dim3 grid((plan.N + 255) / 256, n_spectra);
+    if (plan.realsize == 4) {
+        k_permute<float><<<grid, 256, 0, s>>>((const float *)src, (float *)dst, plan.N, mode);
+    } else {
+        k_permute<double><<<grid, 256, 0, s>>>((const double *)src, (double *)dst, plan.N, mode);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cv_mixnscale(const FftPlan &plan, const void *const *in_ptrs, const double *scales, int n_bufs,
+                                void *out, int mode, cudaStream_t s)
+{
+    const int grid = (plan.N + 255) / 256;
+    if (plan.realsize == 4) {
+        k_cv_mixnscale<float><<<grid, 256, 0, s>>>(in_ptrs, scales, n_bufs, (float *)out, plan.N, mode);
+    } else {
+        k_cv_mixnscale<double><<<grid, 256, 0, s>>>(in_ptrs, scales, n_bufs, (double *)out, plan.N, mode);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cv_convolve(const FftPlan &plan, const void *b, const void *c, void *d, int op, cudaStream_t s)
+{
+    const int grid = (plan.N / 8 + 255) / 256;
+    if (plan.realsize == 4) {
+        k_cv_convolve<float><<<grid, 256, 0, s>>>((const float *)b, (const float *)c, (float *)d, plan.N, op);
+    } else {
+        k_cv_convolve<double><<<grid, 256, 0, s>>>((const double *)b, (const double *)c, (double *)d, plan.N, op);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cv_dirac(const FftPlan &plan, const void *b, void *d, cudaStream_t s)
+{
+    const int grid = (plan.N + 255) / 256;
+    if (plan.realsize == 4) {
+        k_cv_dirac<float><<<grid, 256, 0, s>>>((const float *)b, (float *)d, plan.N);
+    } else {
+        k_cv_dirac<double><<<grid, 256, 0, s>>>((const double *)b, (double *)d, plan.N);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cv_xfade_blend(const FftPlan &plan, const void *old_time, void *new_time, cudaStream_t s)
+{
+    const int L = plan.N / 2;
+    const int grid = (L + 255) / 256;
+    if (plan.realsize == 4) {
+        k_cv_xfade_blend<float><<<grid, 256, 0, s>>>((const float *)old_time, (float *)new_time, L);
+    } else {
+        k_cv_xfade_blend<double><<<grid, 256, 0, s>>>((const double *)old_time, (double *)new_time, L);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cv_raw2real(const FftPlan &plan, const uint8_t *raw, SampleFormat fmt, void *dst, cudaStream_t s)
+{
+    const int L = plan.N / 2;
+    const int grid = (L + 255) / 256;
+    if (plan.realsize == 4) {
+        k_cv_raw2real<float><<<grid, 256, 0, s>>>(raw, fmt, (float *)dst, L);
+    } else {
+        k_cv_raw2real<double><<<grid, 256, 0, s>>>(raw, fmt, (double *)dst, L);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cv_real2raw(const FftPlan &plan, const void *src, uint8_t *raw, SampleFormat fmt,
+                               Overflow *overflow, unsigned int *status, double safety_limit, cudaStream_t s)
+{
+    const int L = plan.N / 2;
+    if (plan.realsize == 4) {
+        k_cv_real2raw<float><<<1, 256, 0, s>>>((const float *)src, raw, fmt, overflow, status, safety_limit, L);
+    } else {
+        k_cv_real2raw<double><<<1, 256, 0, s>>>((const double *)src, raw, fmt, overflow, status, safety_limit, L);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace bf

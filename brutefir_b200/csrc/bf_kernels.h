@@ -1,0 +1,153 @@
+// bf_kernels.h -- host-callable launchers of the sm_100a kernels (bf_kernels.cu).
+//
+// Plain C++ declarations; every pointer is a DEVICE pointer unless named host_*.  `realsize` selects
+// the float (4) or double (8) instantiation, mirroring the reference's realsize switch
+// (fftw_convolver.c:42, 796-808).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "bf_common.cuh"
+
+namespace bf {
+
+// ---- descriptors living in device memory ----------------------------------------------------------
+
+// One destination of an input channel's spectrum: delay-line stream `stream`, multiplied by `scale`
+// (= (real_t)(fctrl.scale[IN] * sf.scale), bfrun.c:1664-1665 + fftw_convfuns.h:18-20), written to ring
+// slot (t + delay) % P (bfrun.c:1600).
+struct FwdDest {
+    int stream;
+    int delay;
+    double scale;   // already rounded to the real type
+};
+
+// A delay-line stream that mixes several inputs (mixnscale INPUT with n_bufs > 1)
+struct MixStream {
+    int stream;
+    int delay;
+    int n_inputs;
+    int first;      // index into the (channel, scale) term arrays
+};
+struct MixTerm {
+    int index;      // input channel (forward mix) or y-slot (output mix)
+    double scale;   // already rounded to the real type
+};
+
+// One multiply-accumulate job: out[slot] = sum_{i < n_parts} FDL[stream][(t - i) % P] (*) H[hbase + i]
+// (bfrun.c:1737-1754), or the dirac short cut (bfrun.c:1809, fftw_convfuns.h:606-619) when hbase < 0.
+struct MacJob {
+    int stream;
+    int hbase;      // first coefficient block (units of N reals), -1 = dirac
+    int n_parts;
+    int out;        // y-slot
+};
+
+// One output channel of the inverse stage: terms [first, first + n) of the "new" mix and, when a
+// feeding filter is crossfading this block, terms [xf_first, xf_first + n) of the "old" mix.
+struct OutChan {
+    int first;
+    int n;
+    int xf_first;   // -1 = no crossfade this block
+    int shared;     // 1 = summed across ranks before quantisation: stop after the time-domain store
+};
+
+struct FftPlan {
+    int N;          // real length = 2 L
+    int realsize;
+    void *tw;       // device: N/2 complex roots e^{-2 pi i j / N}
+};
+
+cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize);
+void fft_plan_destroy(FftPlan *plan);
+bool fft_size_supported(int N, int realsize);
+
+// ---- engine kernels --------------------------------------------------------------------------------
+
+struct ForwardArgs {
+    const uint8_t *raw_in;
+    const SampleFormat *fmt;    // [n_in]
+    void *prev;                 // [n_in][L] reals: previous block of every input
+    void *fdl;                  // [U][P][N] planar spectra
+    void *xin;                  // [n_in][N] unscaled planar spectra, or NULL
+    const uint8_t *need_xin;    // [n_in]
+    const int *dest_first;      // [n_in + 1]
+    const FwdDest *dests;
+    int n_in;
+    int P;
+    unsigned int t;
+};
+cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s);
+
+struct StreamMixArgs {
+    const void *xin;
+    void *fdl;
+    const MixStream *streams;
+    const MixTerm *terms;
+    int n_streams;
+    int P;
+    unsigned int t;
+};
+cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaStream_t s);
+
+struct MacArgs {
+    const void *fdl;
+    const void *H;
+    void *Y;                    // [split][n_slots][N]
+    const MacJob *jobs;
+    int n_jobs;
+    int n_slots;
+    int P;
+    int split;
+    unsigned int t;
+    int variant;                // 0 = direct streaming loads, 1 = bulk-copy (TMA) staged
+};
+cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
+
+struct InverseArgs {
+    const void *Y;
+    const OutChan *chans;       // [n_out]
+    const MixTerm *terms;
+    void *out_time;             // [n_out][L] reals (time domain, LSB units)
+    uint8_t *raw_out;
+    const SampleFormat *fmt;    // [n_out]
+    Overflow *overflow;         // [n_out]
+    unsigned int *status;       // BF_STATUS_* bits
+    int n_out;
+    int n_slots;
+    int split;
+    double safety_limit;
+};
+cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
+
+// quantise + pack out_time rows of the channels with chans[o].shared (after the cross-rank sum)
+cudaError_t launch_quantise_shared(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
+
+// coefficient preprocessing (convolver_coeffs2cbuf, fftw_convolver.c:526-573): taps[b][L] -> H block
+// hbase + b; blocks are scaled by `scale`, placed in the upper half of a zero frame, transformed and
+// multiplied by 1/N.
+cudaError_t launch_coeff_fft(const FftPlan &plan, const void *taps, int n_blocks, double scale, void *H,
+                             int hbase, cudaStream_t s);
+
+// ---- layout permutation and the per-call (convolver.h) kernels ----------------------------------------
+enum PermuteMode { BLOCKED_TO_PLANAR = 0, PLANAR_TO_BLOCKED = 1, HC_TO_PLANAR = 2, PLANAR_TO_HC = 3 };
+cudaError_t launch_permute(const FftPlan &plan, const void *src, void *dst, int n_spectra, int mode,
+                           cudaStream_t s);
+
+cudaError_t launch_r2hc(const FftPlan &plan, const void *in, void *out, int batch, cudaStream_t s);
+cudaError_t launch_hc2r(const FftPlan &plan, const void *in, void *out, int batch, cudaStream_t s);
+// mixnscale on the reference layouts: mode 1 = INPUT (hc -> blocked), 3 = OUTPUT (blocked -> hc)
+cudaError_t launch_cv_mixnscale(const FftPlan &plan, const void *const *in_ptrs, const double *scales,
+                                int n_bufs, void *out, int mode, cudaStream_t s);
+// blocked-layout complex multiply: op 0 = convolve (d = b*c), 1 = convolve_add (d += b*c)
+cudaError_t launch_cv_convolve(const FftPlan &plan, const void *b, const void *c, void *d, int op,
+                               cudaStream_t s);
+cudaError_t launch_cv_dirac(const FftPlan &plan, const void *b, void *d, cudaStream_t s);
+// crossfade ramp over the first L samples (fftw_convolver.c:349-355): nw = old*(1-f n) + nw*f n
+cudaError_t launch_cv_xfade_blend(const FftPlan &plan, const void *old_time, void *new_time, cudaStream_t s);
+cudaError_t launch_cv_raw2real(const FftPlan &plan, const uint8_t *raw, SampleFormat fmt, void *dst,
+                               cudaStream_t s);
+cudaError_t launch_cv_real2raw(const FftPlan &plan, const void *src, uint8_t *raw, SampleFormat fmt,
+                               Overflow *overflow, unsigned int *status, double safety_limit, cudaStream_t s);
+
+}  // namespace bf
