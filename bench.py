@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's headline configuration.
+
+Workload (configs[2], "c3"): 64 inputs -> 64 outputs, 64 filters of 1 048 576 taps, uniformly partitioned
+8192 x 128, 48 kHz, float_bits 32, S24_4LE interleaved I/O, dither off, synthetic white noise and random
+unit-energy filters.  A "step" is one audio block (8192 samples on every channel = 170.67 ms of audio)
+through the whole hot path: raw2real -> FFT -> delay-line MAC over all partitions -> IFFT -> real2raw.
+
+  value   realtime multiple with the raw input block already resident in HBM (device-timed, CUDA events on
+          the engine's stream), whole job over all ranks
+  e2e     the same through the C ABI with HOST buffers: pinned host -> device copy of every input block and
+          device -> host copy of every output block inside the timed region (pipelined streaming), plus the
+          fully synchronous per-block latency
+  roofline  the MAC kernel's algorithmic bytes / its measured duration against the measured HBM peak
+  cpu_baseline  the reference's own convolver (oracle/_ref) on the host cores, bounded sample
+
+N > 1 (torchrun): the 64 filters are sharded by filter over the ranks exactly as the reference deals
+filter groups over CPUs (brutefir_b200/sharding.py); diagonal graph => no data-path collective; strong
+scaling (the job is fixed, each rank holds 64/N filters); time = max over ranks.
+
+`--impl reference` times the reference's CPU implementation of the same step on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "realtime_multiple"
+UNIT = "x realtime (64ch x 1M-tap @48kHz); Gtap-MAC/s and per-block latency alongside"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_graph(name):
+    from brutefir_b200 import configs
+    return {"c2": configs.config_c2, "c3": configs.config_c3, "c4": configs.config_c4}[name]()
+
+
+def workload_config(name, graph, n_gpus):
+    return {"workload": f"{name}: {len(graph.filters)} filters x {graph.taps_per_filter()} taps, "
+                        f"{graph.filter_length} x {graph.n_blocks} partitions, {graph.sampling_rate} Hz, "
+                        f"float_bits {graph.realsize * 8}, {graph.in_formats[0].sf.name} I/O, dither off",
+            "n_filters": len(graph.filters), "filter_length": graph.filter_length, "n_blocks": graph.n_blocks,
+            "sampling_rate": graph.sampling_rate, "parallelism": f"filters sharded over {n_gpus} GPU(s), no collective",
+            "l2": "per-block working set (coefficients + delay lines) exceeds L2 many times over; nothing is re-read "
+                  "from L2 between steps"}
+
+
+def fast_filters(graph, seed):
+    """Random unit-energy decaying filters; float32 generation keeps the set-up short."""
+    rng = np.random.default_rng(seed)
+    taps = graph.taps_per_filter()
+    env = np.exp(-np.arange(taps, dtype=np.float32) / (taps / 4.0))
+    out = []
+    for _ in range(len(graph.coeff_n_blocks)):
+        h = rng.standard_normal(taps, dtype=np.float32) * env
+        h /= np.sqrt(np.sum(h.astype(np.float64) ** 2))
+        out.append(h.astype(np.float32 if graph.realsize == 4 else np.float64))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.proc = None
+        self.lines = []
+        self.device_index = device_index
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, smax, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0.5 * smax] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(graph, taps, sig_block, n_warm, n_steps, budget_s=None):
+    """Time the reference's own convolver (oracle/_ref, else the oracle port) on all host cores."""
+    from oracle import pyoracle as po
+    kind, lib_kind = ("reference", "ref") if po.available("ref") else ("port", "oracle")
+    if not po.available(lib_kind):
+        po.build()
+    cores = len(os.sched_getaffinity(0))
+    d = po.BlockDriver(lib_kind, graph, n_threads=cores)
+    for c, h in enumerate(taps):
+        d.coeff_from_taps(c, h)
+    d.run_timed(sig_block, max(1, n_warm))
+    if budget_s is not None:
+        probe = d.run_timed(sig_block, 3) / 3
+        n_steps = int(max(5, min(400, budget_s / max(probe, 1e-6))))
+    secs = d.run_timed(sig_block, n_steps)
+    d.close()
+    return secs / n_steps, n_steps, cores, kind
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from brutefir_b200 import configs
+
+    graph = workload_graph(args.workload)
+    cfg = workload_config(args.workload, graph, world)
+    block_s = graph.block_seconds()
+    gtap_unit = graph.gtap_mac_per_realtime()
+    cid = int(args.workload[1])
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        taps = fast_filters(graph, 2000 + cid)
+        sig = configs.synthetic_signal(graph, cid, 1)[0]
+        per_block, n, cores, kind = cpu_reference_run(graph, taps, sig, args.warmup, args.steps)
+        rt = block_s / per_block
+        line = {"impl": "reference", "metric": METRIC, "value": rt, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+                "warmup": args.warmup, "ms_per_step": per_block * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32" if graph.realsize == 4 else "f64", "data": "synthetic",
+                "config": cfg, "gtap_mac_per_s": rt * gtap_unit,
+                "cpu_baseline": {"value": rt, "unit": UNIT, "cores": cores, "kind": kind,
+                                 "sample": f"{n} blocks of the full workload on {cores} host threads"},
+                "e2e": {"value": rt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from brutefir_b200 import _abi
+    from brutefir_b200.engine import Engine, PinnedBuffer
+    from brutefir_b200.sharding import shard_graph
+
+    distributed = world > 1
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if not distributed:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    shard = shard_graph(graph, world)[rank]
+    sub = shard.graph
+    taps = fast_filters(graph, 2000 + cid)
+    eng = Engine(sub, device=local_rank, flags=_abi.FLAG_STAGE_TIMING)
+    for c in sorted({f.coeff for f in sub.filters if f.coeff >= 0}):
+        eng.coeff_from_taps(c, taps[c])
+    sig = configs.synthetic_signal(graph, cid, 4)
+    pin_in = [PinnedBuffer(sub.in_bytes) for _ in range(4)]
+    pin_out = [PinnedBuffer(sub.out_bytes) for _ in range(4)]
+    for i in range(4):
+        pin_in[i].array[:] = sig[i]
+    info = eng.info()
+
+    # fill the delay line once so that every partition multiplies real data
+    eng.upload_input(pin_in[0].array)
+    for _ in range(graph.n_blocks):
+        eng.process_block_device()
+    eng.synchronize()
+
+    # ---- device-resident timing: `value` ---------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        eng.process_block_device()
+    eng.synchronize()
+    eng.stage_times()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.process_block_device()
+    ms = eng.timer_stop()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    stage_ms, stage_blocks, launches = eng.stage_times()
+    ms_step = max_over_ranks(ms / args.steps)
+    rt = block_s / (ms_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------
+    for i in range(max(3, args.warmup)):
+        eng.process_block_async(pin_in[i % 4].array, pin_out[i % 4].array)
+    eng.synchronize()
+    barrier()
+    eng.timer_start()
+    for i in range(args.steps):
+        eng.process_block_async(pin_in[i % 4].array, pin_out[i % 4].array)
+    e2e_ms = eng.timer_stop()
+    eng.synchronize()
+    barrier()
+    e2e_step = max_over_ranks(e2e_ms / args.steps)
+    lat = []
+    for i in range(min(50, args.steps)):
+        t0 = time.perf_counter()
+        eng.process_block(pin_in[i % 4].array, pin_out[i % 4].array)
+        lat.append(time.perf_counter() - t0)
+    latency_ms = max_over_ranks(float(np.median(lat)) * 1e3)
+    eng.stage_times()
+
+    # ---- roofline of the dominant kernel (MAC) --------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    mac_ms = stage_ms[1]
+    achieved = info.mac_bytes_per_block / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "mac_dram_bytes.json")) as f:
+            traffic = json.load(f).get(f"{args.workload}_n{world}")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_mac", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
+                "algorithmic_bytes_per_launch": info.mac_bytes_per_block, "kernel_ms": mac_ms,
+                "stage_ms": {"forward": stage_ms[0], "mac": stage_ms[1], "inverse": stage_ms[2]}}
+
+    line = {"metric": METRIC, "value": rt, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if graph.realsize == 4 else "f64", "data": "synthetic", "config": cfg,
+            "gtap_mac_per_s": rt * gtap_unit, "latency_ms_per_block": latency_ms,
+            "e2e": {"value": block_s / (e2e_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_step,
+                    "h2d_bytes_per_step": sub.in_bytes, "d2h_bytes_per_step": sub.out_bytes,
+                    "mode": "pipelined streaming through bfcuda_process_block_async, pinned host buffers",
+                    "sync_latency_ms_per_block": latency_ms},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+            "engine": {"mac_split": info.mac_split, "kernels_per_block": info.kernels_per_block,
+                       "device": info.device_name.decode(), "device_bytes": info.device_bytes,
+                       "filters_on_rank0": len(sub.filters)}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            per_block, n, cores, kind = cpu_reference_run(graph, taps, sig[0], 2, 0, budget_s=15.0)
+            crt = block_s / per_block
+            line["cpu_baseline"] = {"value": crt, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": per_block * 1e3,
+                                    "sample": f"{n} blocks of the full workload, {cores} host threads, filters dealt "
+                                              "over threads like load_balance_filters"}
+        except Exception as exc:     # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"error": repr(exc)}
+    eng.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -141,7 +141,8 @@ def convolver_coeffs2cbuf(coeffs, scale: float, optional_dest: np.ndarray):
 
 
 def convolver_runtime_coeffs2cbuf(src, dest):
-    _lib().convolver_runtime_coeffs2cbuf(_p(np.ascontiguousarray(src, _dtype())), _p(dest))
+    src = np.ascontiguousarray(src, _dtype())   # keep alive across the call
+    _lib().convolver_runtime_coeffs2cbuf(_p(src), _p(dest))
 
 
 def convolver_verify_cbuf(cbufs) -> bool:

@@ -1,0 +1,109 @@
+"""Filter sharding over GPUs: the reference's "one filter process per CPU" rule applied to devices.
+
+``load_balance_filters`` (/root/reference/bfconf.c:2227-2318) groups filters that are connected
+(``to_filters``/``from_filters``) or that mix into the same output -- "mixing to an output channel or a
+filter input must be done within the same process" (bfconf.c:2893-2931) -- and deals the groups round
+robin over the CPUs.  Here a "process" is one rank = one GPU with its own engine: it holds the
+coefficient spectra and delay lines of its filters only (HBM is sized per shard), reads just the input
+channels those filters use and writes just the output channels they feed.  Diagonal workloads need no
+exchange at all.  When the caller insists on splitting the filters of one output over ranks
+(``split_outputs=True``, BASELINE config 5), that output is marked shared and its L time-domain samples
+are summed over NVLink by the engine (ncclAllReduce) before quantisation.
+"""
+from __future__ import annotations
+
+import copy
+import dataclasses
+from typing import Dict, List
+
+from .graph import Filter, FilterGraph
+
+
+def filter_groups(graph: FilterGraph) -> List[List[int]]:
+    """Connected components under "shares an output" / "is chained to" (bfconf.c:2234-2298)."""
+    n = len(graph.filters)
+    group = [-1] * n
+    groups: List[List[int]] = []
+    for start in range(n):
+        if group[start] != -1:
+            continue
+        gid = len(groups)
+        group[start] = gid
+        changed = True
+        while changed:
+            changed = False
+            outs = {o for i in range(n) if group[i] == gid for o in graph.filters[i].outputs}
+            for i in range(n):
+                fi = graph.filters[i]
+                if group[i] == gid:
+                    for k in fi.from_filters:
+                        if group[k] != gid:
+                            group[k] = gid
+                            changed = True
+                    continue
+                linked = any(o in outs for o in fi.outputs) or any(group[k] == gid for k in fi.from_filters)
+                if linked:
+                    group[i] = gid
+                    changed = True
+        groups.append([i for i in range(n) if group[i] == gid])
+    return groups
+
+
+def assign_filters(graph: FilterGraph, n_ranks: int, split_outputs: bool = False) -> List[int]:
+    """rank of every filter.  Default: whole groups round robin (bfconf.c:2300-2316).  With
+    ``split_outputs`` filters are dealt round robin individually, ignoring the same-output rule."""
+    owner = [0] * len(graph.filters)
+    if split_outputs:
+        for f in range(len(graph.filters)):
+            owner[f] = f % n_ranks
+        return owner
+    for g, members in enumerate(filter_groups(graph)):
+        for f in members:
+            owner[f] = g % n_ranks
+    return owner
+
+
+@dataclasses.dataclass
+class Shard:
+    rank: int
+    graph: FilterGraph              # this rank's sub-graph (channel numbering is rank-local)
+    filters: List[int]              # global filter indices, in local order
+    inputs: List[int]               # global input channels, in local order
+    outputs: List[int]              # global output channels, in local order
+    coeffs: List[int]               # global coefficient sets, in local order
+    shared_outputs: List[int]       # LOCAL output indices that other ranks also feed
+
+
+def shard_graph(graph: FilterGraph, n_ranks: int, split_outputs: bool = False) -> List[Shard]:
+    """One sub-graph per rank.  The buffer formats keep their byte offsets and spacings, i.e. every rank
+    addresses its channels inside the ORIGINAL raw block layout (the dai buffers, dai.c:537-576): the host
+    hands each rank the same block layout and no repacking is needed."""
+    owner = assign_filters(graph, n_ranks, split_outputs)
+    feeders: Dict[int, set] = {}
+    for f, flt in enumerate(graph.filters):
+        for o in flt.outputs:
+            feeders.setdefault(o, set()).add(owner[f])
+    shards = []
+    for r in range(n_ranks):
+        mine = [f for f in range(len(graph.filters)) if owner[f] == r]
+        ins = sorted({c for f in mine for c in graph.filters[f].inputs})
+        outs = sorted({c for f in mine for c in graph.filters[f].outputs})
+        # every coefficient set stays addressable by its global index at run time (cfc), so keep them all
+        coeffs = list(range(len(graph.coeff_n_blocks)))
+        imap = {c: i for i, c in enumerate(ins)}
+        omap = {c: i for i, c in enumerate(outs)}
+        fmap = {f: i for i, f in enumerate(mine)}
+        local = []
+        for f in mine:
+            flt = copy.deepcopy(graph.filters[f])
+            flt.inputs = [imap[c] for c in flt.inputs]
+            flt.outputs = [omap[c] for c in flt.outputs]
+            flt.from_filters = [fmap[k] for k in flt.from_filters]
+            local.append(flt)
+        sub = FilterGraph(graph.filter_length, graph.n_blocks, graph.realsize,
+                          [graph.in_formats[c] for c in ins], [graph.out_formats[c] for c in outs],
+                          graph.in_bytes, graph.out_bytes, local, list(graph.coeff_n_blocks),
+                          safety_limit=graph.safety_limit, sampling_rate=graph.sampling_rate)
+        shared = [omap[o] for o in outs if len(feeders[o]) > 1]
+        shards.append(Shard(r, sub, mine, ins, outs, coeffs, shared))
+    return shards

@@ -82,9 +82,21 @@ class _Lib:
         fn("cv_runtime_coeffs2cbuf", None, V, V)
 
 
+MAX_LENGTH = 16384
+
+
 def lib(kind: str = "oracle") -> _Lib:
     if kind not in _libs:
-        _libs[kind] = _Lib(kind)
+        l = _Lib(kind)
+        if kind == "ref":
+            # The reference's convolver_runtime_coeffs2cbuf keeps a `static` scratch buffer sized by the
+            # FIRST configuration it runs under (fftw_convolver.c:579-584).  This process re-initialises
+            # the convolver with many sizes, so size that scratch for the largest one up front.
+            l.cv_init(MAX_LENGTH, 8)
+            src = np.zeros(MAX_LENGTH, np.float64)
+            dst = np.zeros(2 * MAX_LENGTH, np.float64)
+            l.cv_runtime_coeffs2cbuf(C.c_void_p(src.ctypes.data), C.c_void_p(dst.ctypes.data))
+        _libs[kind] = l
     return _libs[kind]
 
 
@@ -128,12 +140,14 @@ class Convolver:
 
     def time2freq(self, x):
         out = self.new()
-        self.l.cv_time2freq(_ptr(np.ascontiguousarray(x, self.dtype).copy()), _ptr(out))
+        src = np.ascontiguousarray(x, self.dtype).copy()    # keep alive across the call
+        self.l.cv_time2freq(_ptr(src), _ptr(out))
         return out
 
     def freq2time(self, x):
         out = self.new()
-        self.l.cv_freq2time(_ptr(np.ascontiguousarray(x, self.dtype).copy()), _ptr(out))
+        src = np.ascontiguousarray(x, self.dtype).copy()
+        self.l.cv_freq2time(_ptr(src), _ptr(out))
         return out
 
     def mixnscale(self, bufs, scales, mode):
@@ -180,7 +194,8 @@ class Convolver:
 
     def runtime_coeffs2cbuf(self, taps_L):
         out = self.new()
-        self.l.cv_runtime_coeffs2cbuf(_ptr(np.ascontiguousarray(taps_L, self.dtype)), _ptr(out))
+        src = np.ascontiguousarray(taps_L, self.dtype)
+        self.l.cv_runtime_coeffs2cbuf(_ptr(src), _ptr(out))
         return out
 
 
@@ -216,7 +231,8 @@ class BlockDriver:
             raise RuntimeError(f"coeff_from_taps: {rc}")
 
     def coeff_set_block(self, coeff, block, cbuf):
-        assert self.l.coeff_set_block(self.h, coeff, block, _ptr(np.ascontiguousarray(cbuf, self.dtype))) == 0
+        src = np.ascontiguousarray(cbuf, self.dtype)
+        assert self.l.coeff_set_block(self.h, coeff, block, _ptr(src)) == 0
 
     def coeff_get_block(self, coeff, block):
         out = np.zeros(self.graph.n_fft, self.dtype)

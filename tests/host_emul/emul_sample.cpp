@@ -1,0 +1,104 @@
+// CPU emulation of the device sample conversion (brutefir_b200/csrc/bf_sample.cuh) against the oracle
+// restatement (oracle/bf_oracle.c): raw->real for every format, and the quantiser / packer / overflow
+// accounting on adversarial values, must agree bit for bit.  Built and run by tests/test_host_emulation.py.
+#define BF_HOST_EMULATION 1
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "../../brutefir_b200/csrc/bf_sample.cuh"
+extern "C" {
+#include "../../oracle/bf_oracle.h"
+}
+
+using namespace bf;
+
+struct Fmt { const char *name; int isfloat, swap, bytes, sbytes; };
+static const Fmt FORMATS[] = {
+    {"S8", 0, 1, 1, 1}, {"S16_LE", 0, 0, 2, 2}, {"S16_BE", 0, 1, 2, 2}, {"S24_LE", 0, 0, 3, 3}, {"S24_BE", 0, 1, 3, 3},
+    {"S24_4LE", 0, 0, 4, 3}, {"S24_4BE", 0, 1, 4, 3}, {"S32_LE", 0, 0, 4, 4}, {"S32_BE", 0, 1, 4, 4},
+    {"FLOAT_LE", 1, 0, 4, 4}, {"FLOAT_BE", 1, 1, 4, 4}, {"FLOAT64_LE", 1, 0, 8, 8}, {"FLOAT64_BE", 1, 1, 8, 8},
+};
+
+template <typename T>
+static int run(int L)
+{
+    int bad = 0;
+    const int rs = (int)sizeof(T);
+    orc_init(NULL, L, rs);
+    for (const Fmt &f : FORMATS) {
+        const int spacing = 3, offset = f.bytes;   // channel 1 of 3, interleaved
+        std::vector<uint8_t> raw((size_t)L * spacing * f.bytes + 64);
+        for (auto &b : raw) b = (uint8_t)(rand() & 0xff);
+        if (f.isfloat) {    // keep float inputs finite
+            for (int n = 0; n < L; n++) {
+                double v = ((double)rand() / RAND_MAX - 0.5) * 4.0;
+                uint8_t t[8];
+                if (f.bytes == 4) { float x = (float)v; memcpy(t, &x, 4); } else { memcpy(t, &v, 8); }
+                for (int i = 0; i < f.bytes; i++) raw[offset + (size_t)n * spacing * f.bytes + i] = f.swap ? t[f.bytes - 1 - i] : t[i];
+            }
+        }
+        orc_buffer_format bf;
+        memset(&bf, 0, sizeof(bf));
+        bf.sf.isfloat = f.isfloat; bf.sf.swap = f.swap; bf.sf.bytes = f.bytes; bf.sf.sbytes = f.sbytes;
+        bf.sample_spacing = spacing; bf.byte_offset = offset;
+        std::vector<T> cbuf(2 * L), next(2 * L);
+        orc_raw2cbuf(raw.data(), cbuf.data(), next.data(), &bf, NULL, NULL);
+        for (int n = 0; n < L; n++) {
+            T v = raw_to_real<T>(raw.data() + offset + (size_t)n * spacing * f.bytes, f.bytes, f.isfloat, f.swap);
+            if (memcmp(&v, &next[n], sizeof(T)) != 0) { bad++; break; }
+        }
+        // output side
+        const double of_max = f.isfloat ? 1.0 : (double)(((uint64_t)1 << ((f.sbytes << 3) - 1)) - 1);
+        std::vector<T> y(2 * L, (T)0);
+        for (int n = 0; n < L; n++) {
+            double u = (double)rand() / RAND_MAX - 0.5;
+            switch (n % 8) {
+            case 0:                                                           // around and beyond full scale
+                y[n] = (T)(u * 2.2 * of_max);
+                if (f.sbytes == 4 && (double)y[n] < -of_max * 0.999 && (double)y[n] > -of_max - 2.0) y[n] = (T)0;
+                break;
+            case 1: y[n] = (T)(floor(u * 100.0) + 0.5); break;               // exact halves
+            case 2: y[n] = (T)floor(u * 1000.0); break;                      // exact integers (negative quirk)
+            case 3: y[n] = (T)(of_max + (u > 0 ? 0.4 : 0.6)); break;         // clip edge, positive
+            case 4:                                                           // clip edge, negative
+                // 32-bit: a value quantising to exactly INT32_MIN makes the reference negate INT32_MIN
+                // (dither_funs.h:93-95, undefined behaviour), so stay one LSB inside there
+                y[n] = f.sbytes == 4 ? (T)(-of_max * 0.999) : (T)(-of_max - 1.0 - (u > 0 ? 0.4 : 0.6));
+                break;
+            case 5: y[n] = (T)(u * 1e-3); break;
+            case 6: y[n] = (T)(u * of_max); break;
+            default: y[n] = (T)(-0.5 - 1e-7 * n); break;
+            }
+        }
+        orc_overflow of_o = {2, 5, 0.25, of_max};
+        std::vector<uint8_t> out_o((size_t)L * spacing * f.bytes + 64, 0x55), out_e(out_o);
+        orc_cbuf2raw(y.data(), out_o.data(), &bf, 0, NULL, &of_o);
+        QuantStats st;
+        quant_stats_init(st);
+        for (int n = 0; n < L; n++) {
+            real_to_raw<T>(y[n], out_e.data() + offset + (size_t)n * spacing * f.bytes, f.bytes, f.sbytes, f.isfloat,
+                           f.swap, 0.0, of_max, st);
+        }
+        // merge like reduce_stats does
+        unsigned n_over = 2 + st.n_overflows;
+        int32_t intl = st.intlargest > 5 ? st.intlargest : 5;
+        double larg = st.largest > 0.25 ? st.largest : 0.25;
+        const bool same = out_o == out_e && n_over == of_o.n_overflows && intl == of_o.intlargest && larg == of_o.largest;
+        if (!same) {
+            printf("MISMATCH %s rs=%d: overflows %u/%u intlargest %d/%d largest %.17g/%.17g bytes %s\n", f.name, rs, n_over,
+                   of_o.n_overflows, intl, of_o.intlargest, larg, of_o.largest, out_o == out_e ? "same" : "DIFFER");
+            bad++;
+        }
+    }
+    return bad;
+}
+
+int main()
+{
+    srand(12345);
+    int bad = run<float>(256) + run<double>(256);
+    printf("%s\n", bad ? "FAIL" : "emul_sample ok");
+    return bad;
+}

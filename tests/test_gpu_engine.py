@@ -1,0 +1,228 @@
+"""GPU parity of the block-level engine (include/bfcuda.h) against the CPU oracle's replay of
+filter_process() on the same seeded inputs.
+
+Criteria (BASELINE.json north_star, dither off):
+  * integer output: within 1 LSB of the reference at float_bits 32 (|diff| <= 1), identical at float_bits 64;
+  * float32 output: max abs error <= 1e-6 of full scale; float64: <= 1e-12;
+  * the multiply-accumulate stage alone: BIT-EXACT against the reference's convolve / convolve_add applied to
+    the very same delay-line and coefficient buffers (split 1 keeps the reference's summation order)."""
+import os
+
+import numpy as np
+import pytest
+
+from brutefir_b200 import _abi, configs
+from brutefir_b200.engine import Engine
+from brutefir_b200.formats import interleaved_layout, pack_block, planar_layout
+from brutefir_b200.graph import Filter, FilterGraph
+from oracle import pyoracle as po
+from helpers import unpack_run
+from test_golden import golden_graph_a, golden_graph_b, run_golden_b
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_both(graph, taps, sig, mac_split=0, scale=1.0, flags=0):
+    with Engine(graph, mac_split=mac_split, flags=flags) as e:
+        d = po.BlockDriver("oracle", graph)
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h, scale)
+            d.coeff_from_taps(c, h, scale)
+        got, ref = e.run(sig), d.run(sig)
+        of = [(e.overflow(o), d.overflow(o)) for o in range(len(graph.out_formats))]
+        d.close()
+    return got, ref, of
+
+
+def assert_parity(graph, got, ref):
+    L = graph.filter_length
+    g, r = unpack_run(got, graph.out_formats, L), unpack_run(ref, graph.out_formats, L)
+    for c, bf in enumerate(graph.out_formats):
+        diff = np.abs(g[c] - r[c]).max()
+        if bf.sf.isfloat:
+            tol = 1e-6 if graph.realsize == 4 or bf.sf.bytes == 4 else 1e-12
+            assert diff <= tol, (c, diff)
+        elif graph.realsize == 8:
+            assert diff == 0, (c, diff)
+        else:
+            assert diff <= 1, (c, diff)        # 1 LSB
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("L,P", [(4, 3), (64, 16), (1024, 8), (8192, 4)])
+@pytest.mark.parametrize("fmt", ["S24_4LE", "FLOAT_LE"])
+def test_diagonal_graph(gpu_lib, oracle_libs, L, P, fmt, rs):
+    g = configs.diagonal_graph(3, L, P, rs, fmt)
+    taps = configs.synthetic_filters(g, 11)
+    sig = configs.synthetic_signal(g, 11, P + 8)
+    got, ref, of = run_both(g, taps, sig, mac_split=1)
+    assert_parity(g, got, ref)
+    for a, b in of:
+        assert a.n_overflows == b.n_overflows and a.max == b.max
+
+
+@pytest.mark.parametrize("fmt_in,fmt_out", [("S16_LE", "S32_LE"), ("S24_LE", "S16_BE"), ("S32_BE", "S24_BE"),
+                                            ("FLOAT64_LE", "FLOAT64_BE"), ("S8", "S8"), ("FLOAT_BE", "S24_4BE")])
+def test_sample_formats_end_to_end(gpu_lib, oracle_libs, fmt_in, fmt_out):
+    L, P = 128, 4
+    inb, nin = interleaved_layout(2, fmt_in, L)
+    outb, nout = planar_layout(2, fmt_out, L)
+    g = FilterGraph(L, P, 8, inb, outb, nin, nout, [Filter([0], [0], coeff=0), Filter([1], [1], coeff=1)], [P, 2])
+    taps = configs.synthetic_filters(g, 12)
+    sig = configs.synthetic_signal(g, 12, 10)
+    got, ref, _ = run_both(g, taps, sig)
+    assert_parity(g, got, ref)
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_mixing_delays_scales_and_dirac(gpu_lib, oracle_libs, rs):
+    """Several inputs per filter (mixnscale INPUT, n_bufs > 1), several filters per output, one filter to two
+    outputs, block delays, attenuations, a coeff:-1 filter, a short coefficient set, an unused output."""
+    L, P = 256, 6
+    inb, nin = interleaved_layout(3, "S24_4LE", L)
+    outb, nout = interleaved_layout(4, "S24_LE", L)
+    filters = [Filter([0], [0], coeff=0), Filter([1, 2], [1], in_scales=[0.7, -0.2], coeff=1, delayblocks=2),
+               Filter([2], [1, 2], out_scales=[0.5, 2.0], coeff=-1), Filter([0, 1, 2], [2], in_scales=[0.3, 0.3, 0.3], coeff=2),
+               Filter([1], [0], out_scales=[-0.25], coeff=0, delayblocks=7)]
+    g = FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [P, 3, 1])
+    taps = configs.synthetic_filters(g, 13)
+    sig = configs.synthetic_signal(g, 13, 16)
+    got, ref, _ = run_both(g, taps, sig, mac_split=1, scale=0.9)
+    assert_parity(g, got, ref)
+    # the unused output stays silent (bfrun.c never mixes into it)
+    assert np.all(unpack_run(got, g.out_formats, L)[3] == 0)
+
+
+@pytest.mark.parametrize("split", [2, 5])
+def test_split_partition_sum_stays_within_tolerance(gpu_lib, oracle_libs, split):
+    g = configs.diagonal_graph(2, 64, 40, 4, "S24_4LE")
+    taps = configs.synthetic_filters(g, 14)
+    sig = configs.synthetic_signal(g, 14, 50)
+    got, ref, _ = run_both(g, taps, sig, mac_split=split)
+    assert_parity(g, got, ref)
+
+
+def test_runtime_control_and_crossfade(gpu_lib, oracle_libs):
+    """cfc / cfia / cfoa / cfd at block boundaries (bfrun.c:1462-1478) including crossfaded coefficient
+    switches to another set, to 'no coefficients' and back (bfrun.c:1726-1837), float_bits 32."""
+    L, P = 128, 8
+    inb, nin = interleaved_layout(2, "S24_4LE", L)
+    outb, nout = interleaved_layout(2, "S24_4LE", L)
+    filters = [Filter([0], [0], coeff=0, crossfade=True), Filter([1], [0], coeff=1, crossfade=True),
+               Filter([1], [1], coeff=2, crossfade=False), Filter([0], [1], coeff=-1, crossfade=True)]
+    g = FilterGraph(L, P, 4, inb, outb, nin, nout, filters, [P, P, 4])
+    taps = configs.synthetic_filters(g, 15)
+    sig = configs.synthetic_signal(g, 15, 30)
+    script = {4: [(0, dict(coeff=1))], 9: [(0, dict(coeff=-1)), (2, dict(coeff=0))],
+              12: [(3, dict(coeff=2)), (1, dict(coeff=1, in_scales=[0.5], out_scales=[1.5]))],
+              13: [(3, dict(coeff=0, delayblocks=3))], 20: [(0, dict(coeff=0)), (1, dict(coeff=0, delayblocks=1))]}
+    with Engine(g, mac_split=1) as e:
+        d = po.BlockDriver("oracle", g)
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+            d.coeff_from_taps(c, h)
+        got, ref = [], []
+        for b in range(30):
+            for filt, kw in script.get(b, []):
+                e.set_control(filt, **kw)
+                d.set_control(filt, **kw)
+            got.append(e.process_block(sig[b]))
+            ref.append(d.process_block(sig[b]))
+        d.close()
+    assert_parity(g, np.stack(got), np.stack(ref))
+
+
+def test_golden_block_sequences(gpu_lib):
+    """The committed vectors the reference itself produced (tests/golden/make_golden.py), no oracle involved."""
+    blk = np.load(os.path.join(HERE, "golden", "blocks.npz"))
+    ga = golden_graph_a()
+    with Engine(ga) as e:
+        e.coeff_from_taps(0, blk["a_taps0"])
+        e.coeff_from_taps(1, blk["a_taps1"])
+        assert_parity(ga, e.run(blk["a_sig"]), blk["a_out"])
+    gb = golden_graph_b()
+    with Engine(gb) as e:
+        e.coeff_from_taps(0, blk["b_taps0"])
+        e.coeff_from_taps(1, blk["b_taps1"])
+        assert_parity(gb, run_golden_b(e, blk["b_sig"]), blk["b_out"])
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+@pytest.mark.parametrize("rs", [4, 8])
+def test_mac_stage_bit_exact(gpu_lib, oracle_libs, rs, variant, monkeypatch):
+    """Read the delay line and the coefficient blocks back from the device in the reference's blocked layout,
+    run the reference's own convolve / convolve_add order on exactly those buffers (bfrun.c:1737-1754), and
+    require the engine's filter outputs to match bit for bit -- for both data paths of the MAC kernel."""
+    monkeypatch.setenv("BFCUDA_MAC_VARIANT", variant)
+    L, P, nb = 1024, 12, 17
+    g = configs.diagonal_graph(2, L, P, rs, "S24_4LE")
+    g.filters[1].coeff = 0
+    g.filters.append(Filter([0], [1], coeff=-1))
+    g.coeff_n_blocks = [P, 5]
+    taps = configs.synthetic_filters(g, 16)
+    sig = configs.synthetic_signal(g, 16, nb)
+    o = po.Convolver("oracle", L, rs)
+    with Engine(g, mac_split=1) as e:
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+        for b in range(nb):
+            e.process_block(sig[b])
+        t = nb - 1
+        H = [[e.coeff_get_block(c, i) for i in range(g.coeff_n_blocks[c])] for c in range(2)]
+        for f in range(3):
+            coeff = g.filters[f].coeff
+            got = e.debug_read(_abi.DBG_FILTER_OUTPUT, f)
+            slot = lambda i: e.debug_read(_abi.DBG_DELAYLINE, f, (t - i) % P)
+            if coeff < 0:
+                want = o.dirac_convolve(slot(0))
+            else:
+                want = o.convolve(slot(0), H[coeff][0])
+                for i in range(1, g.coeff_n_blocks[coeff]):
+                    o.convolve_add(slot(i), H[coeff][i], want)
+            assert np.array_equal(got, want), (f, np.abs(got - want).max())
+
+
+def test_coefficient_layouts_round_trip(gpu_lib, oracle_libs):
+    """bfaccess->coeffs_data / the "processed" coefficient format stay in the reference's blocked layout."""
+    L, P = 512, 3
+    g = configs.diagonal_graph(1, L, P, 8, "S24_4LE")
+    o = po.Convolver("oracle", L, 8)
+    taps = configs.synthetic_filters(g, 17)[0]
+    with Engine(g) as e:
+        e.coeff_from_taps(0, taps, 0.5)
+        for i in range(P):
+            want = o.coeffs2cbuf(taps[i * L:(i + 1) * L], 0.5)
+            got = e.coeff_get_block(0, i)
+            assert np.abs(got - want).max() <= 1e-15
+            e.coeff_set_block(0, i, want)
+            assert np.array_equal(e.coeff_get_block(0, i), want)         # processed blocks survive verbatim
+        e.coeff_runtime_block(0, 1, taps[:L])
+        assert np.abs(e.coeff_get_block(0, 1) - o.runtime_coeffs2cbuf(taps[:L])).max() <= 1e-15
+        with pytest.raises(_abi.BfcudaError) as err:
+            bad = taps.copy()
+            bad[3] = np.inf
+            e.coeff_from_taps(0, bad)
+        assert err.value.code == -5
+
+
+def test_errors_and_limits(gpu_lib):
+    g = configs.config_c1_chained()
+    with pytest.raises(_abi.BfcudaError) as err:
+        Engine(g)
+    assert err.value.code == -7 and "filter-to-filter" in str(err.value)      # BFCUDA_ENOTSUP, a "next" row
+    g = configs.diagonal_graph(1, 64, 2, 4, "S16_LE")
+    with Engine(g) as e:
+        e.coeff_from_taps(0, np.full(128, 1e3, np.float32))
+        x = np.full((1, 64), 30000.0)
+        raw = pack_block(x, g.in_formats, g.in_bytes)
+        out = e.process_block(raw)
+        of = e.overflow(0)
+        assert of.n_overflows == 64 and of.max == 32767.0 and of.largest > 32767.0
+        assert np.all(unpack_run(out[None], g.out_formats, 64)[0] == 32767)
+        e.reset_overflow()
+        assert e.overflow(0).n_overflows == 0
+        e.coeff_from_taps(0, np.full(128, 3e38, np.float32))
+        with pytest.raises(_abi.BfcudaError) as err:
+            e.process_block(raw)
+        assert err.value.code == -5             # NaN/Inf in the output: the reference abort()s

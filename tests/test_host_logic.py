@@ -1,0 +1,87 @@
+"""Host-side logic: sample formats, raw block layouts, graph lowering, sharding (single process and a
+world_size-2 gloo run of the rank-local logic)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from brutefir_b200 import configs
+from brutefir_b200.formats import (interleaved_layout, pack_block, parse_sample_format, planar_layout,
+                                   unpack_block)
+from brutefir_b200.graph import Filter, FilterGraph
+from brutefir_b200.sharding import assign_filters, filter_groups, shard_graph
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("fmt", ["S8", "S16_LE", "S16_BE", "S24_LE", "S24_BE", "S24_4LE", "S24_4BE", "S32_LE",
+                                 "S32_BE", "FLOAT_LE", "FLOAT_BE", "FLOAT64_LE", "FLOAT64_BE", "s24_3le", "S24_NE"])
+def test_sample_format_table_and_round_trip(fmt):
+    sf = parse_sample_format(fmt)
+    assert sf.scale == (1.0 if sf.isfloat else 2.0 ** -(8 * sf.sbytes - 1))     # bfconf.c:473-477
+    assert sf.swap == fmt.upper().endswith("BE") or sf.bytes == 1
+    for layout in (interleaved_layout, planar_layout):
+        bfs, nb = layout(3, sf, 16)
+        assert nb % 32 == 0                                                    # dai.c:571-573
+        rng = np.random.default_rng(1)
+        v = rng.standard_normal((3, 16)) if sf.isfloat else \
+            rng.integers(-(1 << (sf.bits - 1)), 1 << (sf.bits - 1), (3, 16)).astype(np.float64)
+        back = unpack_block(pack_block(v, bfs, nb), bfs, 16)
+        if sf.isfloat and sf.bytes == 4:
+            v = v.astype(np.float32).astype(np.float64)
+        assert np.array_equal(back, v)
+
+
+def test_ambiguous_reference_formats_are_refused():
+    for fmt in ("FLOAT_NE", "FLOAT64_NE", "U8"):
+        with pytest.raises(ValueError):
+            parse_sample_format(fmt)
+
+
+def test_graph_lowering_matches_c_struct():
+    g = configs.config_c5()
+    cfg, keep = g.to_config(device=3, flags=1, mac_split=2)
+    assert (cfg.filter_length, cfg.n_blocks, cfg.realsize, cfg.n_filters, cfg.n_coeffs) == (64, 64, 4, 4, 2)
+    assert cfg.formats[0][1].byte_offset == 3 and cfg.formats[0][1].sample_spacing == 2
+    assert cfg.filters[1].channels[0][0] == 1 and cfg.filters[1].channels[1][0] == 0 and cfg.filters[1].crossfade == 1
+    assert cfg.device == 3 and cfg.flags == 1 and cfg.mac_split == 2
+    with pytest.raises(ValueError):
+        FilterGraph(48, 2, 4, g.in_formats, g.out_formats, g.in_bytes, g.out_bytes, [], []).validate()
+
+
+def test_filter_groups_follow_the_same_output_rule():
+    g = configs.config_c5()     # filters 0,1 -> out 0; filters 2,3 -> out 1
+    assert filter_groups(g) == [[0, 1], [2, 3]]
+    assert assign_filters(g, 2) == [0, 0, 1, 1]
+    assert assign_filters(g, 2, split_outputs=True) == [0, 1, 0, 1]
+    d = configs.diagonal_graph(8, 64, 2)
+    assert len(filter_groups(d)) == 8 and assign_filters(d, 4) == [0, 1, 2, 3, 0, 1, 2, 3]
+    chained = configs.config_c1_chained()
+    assert filter_groups(chained) == [[0, 3, 4], [1, 2, 5]]
+
+
+def test_shards_cover_the_graph_once():
+    g = configs.config_c3(n_ch=16, L=64, P=4)
+    shards = shard_graph(g, 4)
+    assert sorted(f for s in shards for f in s.filters) == list(range(16))
+    for s in shards:
+        assert len(s.filters) == 4 and s.shared_outputs == []
+        for lf, gf in zip(s.graph.filters, s.filters):
+            assert s.inputs[lf.inputs[0]] == g.filters[gf].inputs[0]
+            assert s.graph.in_formats[lf.inputs[0]].byte_offset == g.in_formats[g.filters[gf].inputs[0]].byte_offset
+    split = shard_graph(configs.config_c5(), 2, split_outputs=True)
+    assert [s.shared_outputs for s in split] == [[0, 1], [0, 1]]
+
+
+def test_world_size_2_gloo(tmp_path):
+    """The N > 1 host path on CPU: two ranks over gloo shard a graph, run their shards through the CPU
+    oracle (stand-in for the per-rank engines) and rank 0 reassembles the output of the whole graph."""
+    script = os.path.join(ROOT, "tests", "dist_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script, str(tmp_path)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "DIST_OK" in r.stdout
