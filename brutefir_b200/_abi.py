@@ -12,7 +12,7 @@ import os
 IN, OUT = 0, 1
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libbfcuda.so")
+LIB_PATH = os.environ.get("BFCUDA_LIB", os.path.join(PKG_DIR, "libbfcuda.so"))
 
 
 class SampleFormatC(C.Structure):

@@ -123,9 +123,15 @@ struct bfcuda_engine {
     std::vector<int> coeff_n_blocks, coeff_hbase;
     int total_coeff_blocks;
 
-    cudaStream_t stream;
+    // streams: `stream` runs forward + MAC of every block, `s_inv` the inverse stage (so that the inverse of
+    // block t overlaps the forward of block t+1), `s_in` / `s_out` the host<->device copies of the streaming
+    // interface (double-buffered raw blocks, so copies overlap compute)
+    cudaStream_t stream, s_inv, s_in, s_out;
+    cudaEvent_t ev_h2d[2], ev_fwd[2], ev_d2h[2], ev_mac, ev_inv;
+    unsigned int io_count;      // blocks submitted through the host-buffer interface
     FftPlan plan;
-    uint8_t *d_raw[2];
+    uint8_t *d_raw[2];          // raw blocks of the device-resident interface (and buffer 0 of the streaming one)
+    uint8_t *d_raw2[2];         // second buffers of the streaming interface
     SampleFormat *d_fmt[2];
     void *d_prev, *d_fdl, *d_xin, *d_H, *d_Y, *d_out_time, *d_scratch;
     Overflow *d_overflow;
@@ -157,7 +163,7 @@ struct bfcuda_engine {
     unsigned int t;
     // measurement
     cudaEvent_t timer[2];
-    cudaEvent_t ring[TIMING_RING][4];
+    cudaEvent_t ring[TIMING_RING][6];
     int ring_fill;
     double stage_ms[BFCUDA_N_STAGES];
     long stage_blocks, launches;
@@ -391,13 +397,13 @@ void bfcuda_destroy(bfcuda_engine *e)
         return;
     }
     cudaSetDevice(e->device);
-    if (e->stream) {
-        cudaStreamSynchronize(e->stream);
+    for (cudaStream_t st : { e->stream, e->s_inv, e->s_in, e->s_out }) {
+        if (st) cudaStreamSynchronize(st);
     }
     if (e->comm != nullptr && g_nccl.handle != nullptr) {
         g_nccl.CommDestroy(e->comm);
     }
-    void *ptrs[] = { e->d_raw[0], e->d_raw[1], e->d_fmt[0], e->d_fmt[1], e->d_prev, e->d_fdl, e->d_xin, e->d_H,
+    void *ptrs[] = { e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev, e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms };
     for (void *p : ptrs) {
@@ -411,11 +417,17 @@ void bfcuda_destroy(bfcuda_engine *e)
         if (e->timer[i]) cudaEventDestroy(e->timer[i]);
     }
     for (int i = 0; i < TIMING_RING; i++) {
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 6; j++) {
             if (e->ring[i][j]) cudaEventDestroy(e->ring[i][j]);
         }
     }
-    if (e->stream) cudaStreamDestroy(e->stream);
+    for (cudaEvent_t ev : { e->ev_h2d[0], e->ev_h2d[1], e->ev_fwd[0], e->ev_fwd[1], e->ev_d2h[0], e->ev_d2h[1],
+                            e->ev_mac, e->ev_inv }) {
+        if (ev) cudaEventDestroy(ev);
+    }
+    for (cudaStream_t st : { e->stream, e->s_inv, e->s_in, e->s_out }) {
+        if (st) cudaStreamDestroy(st);
+    }
     delete e;
 }
 
@@ -500,7 +512,10 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->safety_limit = c->safety_limit;
     e->n_filters = c->n_filters;
     e->n_coeffs = c->n_coeffs;
-    e->stream = nullptr;
+    e->stream = e->s_inv = e->s_in = e->s_out = nullptr;
+    e->ev_h2d[0] = e->ev_h2d[1] = e->ev_fwd[0] = e->ev_fwd[1] = e->ev_d2h[0] = e->ev_d2h[1] = nullptr;
+    e->ev_mac = e->ev_inv = nullptr;
+    e->io_count = 0;
     e->comm = nullptr;
     e->n_ranks = 1;
     e->device_bytes = 0;
@@ -511,7 +526,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
     memset(e->timer, 0, sizeof(e->timer));
     memset(e->ring, 0, sizeof(e->ring));
-    void **zero[] = { (void **)&e->d_raw[0], (void **)&e->d_raw[1], (void **)&e->d_fmt[0], (void **)&e->d_fmt[1],
+    void **zero[] = { (void **)&e->d_raw[0], (void **)&e->d_raw[1], (void **)&e->d_raw2[0], (void **)&e->d_raw2[1],
+                      (void **)&e->d_fmt[0], (void **)&e->d_fmt[1],
                       &e->d_prev, &e->d_fdl, &e->d_xin, &e->d_H, &e->d_Y, &e->d_out_time, &e->d_scratch,
                       (void **)&e->d_overflow, (void **)&e->d_status, (void **)&e->d_dests, (void **)&e->d_dest_first,
                       (void **)&e->d_need_xin, (void **)&e->d_mix_streams, (void **)&e->d_mix_terms,
@@ -572,12 +588,19 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     {
         const size_t N = e->N, L = e->L, P = e->P, F = std::max(1, e->n_filters);
         TRYCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        TRYCU(cudaStreamCreateWithFlags(&e->s_inv, cudaStreamNonBlocking));
+        TRYCU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+        TRYCU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+        for (cudaEvent_t *ev : { &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_fwd[0], &e->ev_fwd[1], &e->ev_d2h[0],
+                                 &e->ev_d2h[1], &e->ev_mac, &e->ev_inv }) {
+            TRYCU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        }
         TRYCU(fft_plan_create(&e->plan, e->N, e->rs));
         TRYCU(cudaEventCreate(&e->timer[0]));
         TRYCU(cudaEventCreate(&e->timer[1]));
         if (e->flags & BFCUDA_FLAG_STAGE_TIMING) {
             for (int i = 0; i < TIMING_RING; i++) {
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < 6; j++) {
                     TRYCU(cudaEventCreate(&e->ring[i][j]));
                 }
             }
@@ -586,6 +609,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         *e->h_status = 0;
         TRY(dev_alloc(e, &e->d_raw[0], (size_t)e->n_bytes[0]));
         TRY(dev_alloc(e, &e->d_raw[1], (size_t)e->n_bytes[1]));
+        TRY(dev_alloc(e, &e->d_raw2[0], (size_t)e->n_bytes[0]));
+        TRY(dev_alloc(e, &e->d_raw2[1], (size_t)e->n_bytes[1]));
         TRY(dev_alloc(e, &e->d_fmt[0], sizeof(SampleFormat) * std::max(1, e->n_ch[0])));
         TRY(dev_alloc(e, &e->d_fmt[1], sizeof(SampleFormat) * std::max(1, e->n_ch[1])));
         TRY(dev_alloc(e, &e->d_prev, rs_bytes(e, (size_t)e->n_ch[0] * L)));
@@ -659,7 +684,9 @@ int bfcuda_reset_overflow(bfcuda_engine *e)
             of[n].max = (double)((uint64_t)1 << ((e->fmt[1][n].sf.sbytes << 3) - 1)) - 1;
         }
     }
-    CU(cudaStreamSynchronize(e->stream));
+    for (cudaStream_t st : { e->s_in, e->stream, e->s_inv, e->s_out }) {
+        CU(cudaStreamSynchronize(st));
+    }
     if (!of.empty()) {
         CU(cudaMemcpy(e->d_overflow, of.data(), sizeof(Overflow) * of.size(), cudaMemcpyHostToDevice));
     }
@@ -672,7 +699,9 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
     if (e == nullptr || overflow == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     if (out_channel < 0 || out_channel >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
     CU(cudaSetDevice(e->device));
-    CU(cudaStreamSynchronize(e->stream));
+    for (cudaStream_t st : { e->s_in, e->stream, e->s_inv, e->s_out }) {
+        CU(cudaStreamSynchronize(st));
+    }
     Overflow of;
     CU(cudaMemcpy(&of, e->d_overflow + out_channel, sizeof(of), cudaMemcpyDeviceToHost));
     overflow->n_overflows = of.n_overflows;
@@ -802,11 +831,13 @@ static int flush_timing_ring(bfcuda_engine *e)
     if (e->ring_fill == 0) {
         return 0;
     }
-    CU(cudaEventSynchronize(e->ring[e->ring_fill - 1][3]));
+    CU(cudaEventSynchronize(e->ring[e->ring_fill - 1][5]));
     for (int i = 0; i < e->ring_fill; i++) {
+        // forward: [0,1], MAC: [2,3] on the main stream; inverse: [4,5] on its own stream
+        static const int from[BFCUDA_N_STAGES] = { 0, 2, 4 }, to[BFCUDA_N_STAGES] = { 1, 3, 5 };
         for (int s = 0; s < BFCUDA_N_STAGES; s++) {
             float ms = 0.f;
-            CU(cudaEventElapsedTime(&ms, e->ring[i][s], e->ring[i][s + 1]));
+            CU(cudaEventElapsedTime(&ms, e->ring[i][from[s]], e->ring[i][to[s]]));
             e->stage_ms[s] += ms;
         }
     }
@@ -815,11 +846,19 @@ static int flush_timing_ring(bfcuda_engine *e)
     return 0;
 }
 
-// enqueue the kernels of one block on the engine stream; input already in d_raw[IN]
-static int enqueue_block(bfcuda_engine *e)
+// Enqueue the kernels of one block: forward + MAC on the main stream, inverse on s_inv.
+//   raw_in / raw_out : device raw blocks of this block
+//   in_ready         : event the forward stage must wait for (input copy), or null
+//   out_free         : event the inverse stage must wait for (previous read-out of raw_out), or null
+//   fwd_done         : recorded after the forward stage (raw_in may be overwritten afterwards), or null
+// On return e->ev_inv marks the end of this block's inverse stage.
+static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cudaEvent_t in_ready,
+                         cudaEvent_t out_free, cudaEvent_t fwd_done)
 {
     if (e->dirty || e->xfade_active) {
         build_tables(e);
+        // the previous block's inverse stage (other stream) still reads the output-mix tables
+        CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));
         int rc = upload_tables(e);
         if (rc != 0) return rc;
     }
@@ -831,11 +870,14 @@ static int enqueue_block(bfcuda_engine *e)
             if (rc != 0) return rc;
         }
         ev = e->ring[e->ring_fill];
-        CU(cudaEventRecord(ev[0], e->stream));
     }
+    if (in_ready != nullptr) {
+        CU(cudaStreamWaitEvent(e->stream, in_ready, 0));
+    }
+    if (timing) CU(cudaEventRecord(ev[0], e->stream));
 
     ForwardArgs fa;
-    fa.raw_in = e->d_raw[0];
+    fa.raw_in = raw_in;
     fa.fmt = e->d_fmt[0];
     fa.prev = e->d_prev;
     fa.fdl = e->d_fdl;
@@ -861,6 +903,13 @@ static int enqueue_block(bfcuda_engine *e)
         e->launches++;
     }
     if (timing) CU(cudaEventRecord(ev[1], e->stream));
+    if (fwd_done != nullptr) {
+        CU(cudaEventRecord(fwd_done, e->stream));
+    }
+    // the previous block's inverse stage reads Y: the MAC may not overwrite it earlier.  (The forward stage
+    // above does not touch Y, so it runs concurrently with that inverse stage.)
+    CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));
+    if (timing) CU(cudaEventRecord(ev[2], e->stream));
 
     MacArgs ma;
     ma.fdl = e->d_fdl;
@@ -875,14 +924,20 @@ static int enqueue_block(bfcuda_engine *e)
     ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
     CU(launch_mac(e->plan, ma, e->stream));
     e->launches += ma.n_jobs > 0;
-    if (timing) CU(cudaEventRecord(ev[2], e->stream));
+    if (timing) CU(cudaEventRecord(ev[3], e->stream));
+    CU(cudaEventRecord(e->ev_mac, e->stream));
+    CU(cudaStreamWaitEvent(e->s_inv, e->ev_mac, 0));
+    if (out_free != nullptr) {
+        CU(cudaStreamWaitEvent(e->s_inv, out_free, 0));
+    }
+    if (timing) CU(cudaEventRecord(ev[4], e->s_inv));
 
     InverseArgs ia;
     ia.Y = e->d_Y;
     ia.chans = e->d_chans;
     ia.terms = e->d_out_terms;
     ia.out_time = e->d_out_time;
-    ia.raw_out = e->d_raw[1];
+    ia.raw_out = raw_out;
     ia.fmt = e->d_fmt[1];
     ia.overflow = e->d_overflow;
     ia.status = e->d_status;
@@ -890,7 +945,7 @@ static int enqueue_block(bfcuda_engine *e)
     ia.n_slots = ma.n_slots;
     ia.split = e->split;
     ia.safety_limit = e->safety_limit;
-    CU(launch_inverse(e->plan, ia, e->stream));
+    CU(launch_inverse(e->plan, ia, e->s_inv));
     e->launches += e->n_ch[1] > 0;
     if (!e->shared_out.empty()) {
         // outputs fed from several ranks: sum the L valid time-domain samples over NVLink, then quantise
@@ -900,7 +955,7 @@ static int enqueue_block(bfcuda_engine *e)
             g_nccl.GroupStart();
             for (int o : e->shared_out) {
                 char *row = (char *)e->d_out_time + rs_bytes(e, (size_t)o * e->L);
-                int r = g_nccl.AllReduce(row, row, (size_t)e->L, dtype, 0 /* ncclSum */, e->comm, e->stream);
+                int r = g_nccl.AllReduce(row, row, (size_t)e->L, dtype, 0 /* ncclSum */, e->comm, e->s_inv);
                 if (r != 0) {
                     g_nccl.GroupEnd();
                     return fail(BFCUDA_ECOMM, "ncclAllReduce failed: %s",
@@ -909,13 +964,14 @@ static int enqueue_block(bfcuda_engine *e)
             }
             g_nccl.GroupEnd();
         }
-        CU(launch_quantise_shared(e->plan, ia, e->stream));
+        CU(launch_quantise_shared(e->plan, ia, e->s_inv));
         e->launches++;
     }
     if (timing) {
-        CU(cudaEventRecord(ev[3], e->stream));
+        CU(cudaEventRecord(ev[5], e->s_inv));
         e->ring_fill++;
     }
+    CU(cudaEventRecord(e->ev_inv, e->s_inv));
 
     // bfrun.c:1838, 2034
     for (FilterState &fs : e->filters) {
@@ -937,15 +993,36 @@ static int check_status(bfcuda_engine *e)
     return 0;
 }
 
+static int sync_all(bfcuda_engine *e)
+{
+    CU(cudaStreamSynchronize(e->s_in));
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->s_inv));
+    CU(cudaStreamSynchronize(e->s_out));
+    return 0;
+}
+
 int bfcuda_process_block_async(bfcuda_engine *e, const void *raw_in, void *raw_out)
 {
     if (e == nullptr || raw_in == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemcpyAsync(e->d_raw[0], raw_in, (size_t)e->n_bytes[0], cudaMemcpyHostToDevice, e->stream));
-    int rc = enqueue_block(e);
+    // double-buffered raw blocks: copy-in of block t+1 and copy-out of block t-1 overlap the kernels of block t
+    const int b = (int)(e->io_count & 1u);
+    uint8_t *d_in = b ? e->d_raw2[0] : e->d_raw[0];
+    uint8_t *d_out = b ? e->d_raw2[1] : e->d_raw[1];
+    const bool reuse = e->io_count >= 2;
+    if (reuse) {
+        CU(cudaStreamWaitEvent(e->s_in, e->ev_fwd[b], 0));      // forward of block t-2 has consumed d_in
+    }
+    CU(cudaMemcpyAsync(d_in, raw_in, (size_t)e->n_bytes[0], cudaMemcpyHostToDevice, e->s_in));
+    CU(cudaEventRecord(e->ev_h2d[b], e->s_in));
+    int rc = enqueue_block(e, d_in, d_out, e->ev_h2d[b], reuse ? e->ev_d2h[b] : nullptr, e->ev_fwd[b]);
     if (rc != 0) return rc;
-    CU(cudaMemcpyAsync(raw_out, e->d_raw[1], (size_t)e->n_bytes[1], cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamWaitEvent(e->s_out, e->ev_inv, 0));
+    CU(cudaMemcpyAsync(raw_out, d_out, (size_t)e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_out));
+    CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->s_out));
+    CU(cudaEventRecord(e->ev_d2h[b], e->s_out));
+    e->io_count++;
     return 0;
 }
 
@@ -953,7 +1030,8 @@ int bfcuda_synchronize(bfcuda_engine *e)
 {
     if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
     CU(cudaSetDevice(e->device));
-    CU(cudaStreamSynchronize(e->stream));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
     return check_status(e);
 }
 
@@ -968,7 +1046,7 @@ int bfcuda_process_block_device(bfcuda_engine *e)
 {
     if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
     CU(cudaSetDevice(e->device));
-    return enqueue_block(e);
+    return enqueue_block(e, e->d_raw[0], e->d_raw[1], nullptr, nullptr, nullptr);
 }
 
 int bfcuda_device_io(bfcuda_engine *e, int io, void **device_ptr, size_t *n_bytes)
@@ -983,6 +1061,8 @@ int bfcuda_upload_input(bfcuda_engine *e, const void *raw_in)
 {
     if (e == nullptr || raw_in == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
     CU(cudaMemcpyAsync(e->d_raw[0], raw_in, (size_t)e->n_bytes[0], cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return 0;
@@ -992,6 +1072,8 @@ int bfcuda_download_output(bfcuda_engine *e, void *raw_out)
 {
     if (e == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
     CU(cudaMemcpyAsync(raw_out, e->d_raw[1], (size_t)e->n_bytes[1], cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -1023,7 +1105,8 @@ int bfcuda_timer_start(bfcuda_engine *e)
 {
     if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
     CU(cudaSetDevice(e->device));
-    CU(cudaStreamSynchronize(e->stream));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
     CU(cudaEventRecord(e->timer[0], e->stream));
     return 0;
 }
@@ -1032,6 +1115,11 @@ int bfcuda_timer_stop(bfcuda_engine *e, double *elapsed_ms)
 {
     if (e == nullptr || elapsed_ms == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
+    // the stop event must come after everything enqueued on any of the engine's streams
+    CU(cudaEventRecord(e->ev_mac, e->s_inv));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_mac, 0));
+    CU(cudaEventRecord(e->ev_mac, e->s_out));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_mac, 0));
     CU(cudaEventRecord(e->timer[1], e->stream));
     CU(cudaEventSynchronize(e->timer[1]));
     float ms = 0.f;
@@ -1083,6 +1171,9 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
 {
     if (e == nullptr || dst == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
+    for (cudaStream_t st : { e->s_in, e->stream, e->s_inv, e->s_out }) {
+        CU(cudaStreamSynchronize(st));
+    }
     const size_t nb = rs_bytes(e, e->N);
     switch (what) {
     case BFCUDA_DBG_INPUT_SPECTRUM: {

