@@ -1,0 +1,233 @@
+/*
+ * bfcuda_run.c -- a C host for the GPU convolution engine: the part of BruteFIR's filter process that stays
+ * on the CPU, written against the C ABI of include/bfcuda.h only.
+ *
+ * It does what filter_process() + bfio_file do for the benchmark configurations of the reference
+ * (/root/reference/bfrun.c:1420-2083, bfio_file.c:418-451, 569-586): read raw interleaved PCM blocks of
+ * filter_length frames from a file (or stdin), run them through the engine, write raw PCM blocks to a file
+ * (or stdout), zero-filling the last partial block the way dai_input does at end of input
+ * (dai.c:1312-1332), and print the reference's per-stage benchmark table (bfrun.c:2035-2078) and realtime
+ * index (bfrun.c:649-677).  The graph is "n channels, filter i: input i -> output i", optionally a full
+ * n x n matrix (-m), which covers bench2/3/5-style and massive_config-style set-ups; bfconf's parser is not
+ * duplicated here (INTEGRATION.md shows where the same three calls go in an unmodified bfrun.c).
+ *
+ *   cc -O2 -Iinclude host/bfcuda_run.c -o host/bfcuda_run -Lbrutefir_b200 -lbfcuda -Wl,-rpath,'$ORIGIN/../brutefir_b200' -lm
+ *
+ *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] in.raw out.raw
+ *     taps.f32: raw little-endian float32 (float64 with -r 64) taps, one filter after the other, L*P each
+ *               ("dirac" = unit pulses, the reference's "dirac pulse" coefficient, bfconf.c:1905-1913)
+ */
+#include <errno.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <time.h>
+
+#include "bfcuda.h"
+
+struct fmt_entry {
+    const char *name;
+    int isfloat, bytes, sbytes, big_endian, id;
+};
+/* bfconf.c:377-472 (parse_sample_format); ids bfmod.h:33-48 */
+static const struct fmt_entry FORMATS[] = {
+    { "S8", 0, 1, 1, 0, 1 },          { "S16_LE", 0, 2, 2, 0, 2 },     { "S16_BE", 0, 2, 2, 1, 3 },
+    { "S24_LE", 0, 3, 3, 0, 6 },      { "S24_3LE", 0, 3, 3, 0, 6 },    { "S24_BE", 0, 3, 3, 1, 7 },
+    { "S24_3BE", 0, 3, 3, 1, 7 },     { "S24_4LE", 0, 4, 3, 0, 8 },    { "S24_4BE", 0, 4, 3, 1, 9 },
+    { "S32_LE", 0, 4, 4, 0, 10 },     { "S32_BE", 0, 4, 4, 1, 11 },    { "FLOAT_LE", 1, 4, 4, 0, 12 },
+    { "FLOAT_BE", 1, 4, 4, 1, 13 },   { "FLOAT64_LE", 1, 8, 8, 0, 14 }, { "FLOAT64_BE", 1, 8, 8, 1, 15 },
+};
+
+static int
+parse_format(const char *s, struct bfcuda_sample_format *sf)
+{
+    size_t i;
+    for (i = 0; i < sizeof(FORMATS) / sizeof(FORMATS[0]); i++) {
+        if (strcasecmp(s, FORMATS[i].name) == 0) {
+            sf->isfloat = FORMATS[i].isfloat;
+            sf->bytes = FORMATS[i].bytes;
+            sf->sbytes = FORMATS[i].sbytes;
+            sf->swap = FORMATS[i].big_endian;   /* little-endian host */
+            sf->format = FORMATS[i].id;
+            sf->scale = sf->isfloat ? 1.0 : 1.0 / (double)((uint64_t)1 << ((sf->sbytes << 3) - 1));
+            return 0;
+        }
+    }
+    return -1;
+}
+
+/* calc_buffer_format for one interleaved device, dai.c:537-576 */
+static int
+interleaved(struct bfcuda_buffer_format *bf, int n, const struct bfcuda_sample_format *sf, int fragsize)
+{
+    int c, n_bytes = n * sf->bytes * fragsize;
+    for (c = 0; c < n; c++) {
+        bf[c].sf = *sf;
+        bf[c].sample_spacing = n;
+        bf[c].byte_offset = c * sf->bytes;
+    }
+    if (n_bytes % 32 != 0) {
+        n_bytes += 32 - n_bytes % 32;
+    }
+    return n_bytes;
+}
+
+static double
+now(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+#define DIE(...) do { fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); exit(1); } while (0)
+#define CHECK(call) do { int rc__ = (call); if (rc__ != 0) DIE("%s failed (%d): %s", #call, rc__, bfcuda_strerror()); } while (0)
+
+int
+main(int argc, char *argv[])
+{
+    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, device = 0, a;
+    const char *fin = "S24_4LE", *fout = "S24_4LE", *coeff_path = "dirac", *in_path = NULL, *out_path = NULL;
+    struct bfcuda_sample_format sf_in, sf_out;
+    struct bfcuda_buffer_format *bf_in, *bf_out;
+    struct bfcuda_filter *filters;
+    struct bfcuda_config cfg;
+    struct bfcuda_info info;
+    bfcuda_engine *eng = NULL;
+    int n_filters, *chan, *coeff_blocks, f, c, rs;
+    double *ones, t0, t1, stage[BFCUDA_N_STAGES];
+    long blocks = 0, stage_blocks = 0, launches = 0;
+    void *raw_in, *raw_out;
+    FILE *in, *out;
+
+    for (a = 1; a < argc; a++) {
+        if (!strcmp(argv[a], "-n") && a + 1 < argc) n = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "-L") && a + 1 < argc) L = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "-P") && a + 1 < argc) P = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "-r") && a + 1 < argc) realbits = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "-s") && a + 1 < argc) rate = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "-d") && a + 1 < argc) device = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "-i") && a + 1 < argc) fin = argv[++a];
+        else if (!strcmp(argv[a], "-o") && a + 1 < argc) fout = argv[++a];
+        else if (!strcmp(argv[a], "-c") && a + 1 < argc) coeff_path = argv[++a];
+        else if (!strcmp(argv[a], "-m")) matrix = 1;
+        else if (!strcmp(argv[a], "-b")) bench = 1;
+        else if (in_path == NULL) in_path = argv[a];
+        else if (out_path == NULL) out_path = argv[a];
+        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [in [out]]", argv[0]);
+    }
+    if (parse_format(fin, &sf_in) != 0 || parse_format(fout, &sf_out) != 0) DIE("Unknown sample format.");
+    rs = realbits / 8;
+    n_filters = matrix ? n * n : n;
+    bf_in = calloc(n, sizeof(*bf_in));
+    bf_out = calloc(n, sizeof(*bf_out));
+    filters = calloc(n_filters, sizeof(*filters));
+    chan = calloc(2 * n_filters, sizeof(int));
+    coeff_blocks = calloc(n_filters, sizeof(int));
+    ones = calloc(1, sizeof(double));
+    ones[0] = matrix ? 1.0 / n : 1.0;
+
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.filter_length = L;
+    cfg.n_blocks = P;
+    cfg.realsize = rs;
+    cfg.n_channels[BFCUDA_IN] = cfg.n_channels[BFCUDA_OUT] = n;
+    cfg.n_bytes[BFCUDA_IN] = interleaved(bf_in, n, &sf_in, L);
+    cfg.n_bytes[BFCUDA_OUT] = interleaved(bf_out, n, &sf_out, L);
+    cfg.formats[BFCUDA_IN] = bf_in;
+    cfg.formats[BFCUDA_OUT] = bf_out;
+    for (f = 0; f < n_filters; f++) {
+        chan[2 * f] = matrix ? f % n : f;       /* from_inputs */
+        chan[2 * f + 1] = matrix ? f / n : f;   /* to_outputs */
+        filters[f].n_channels[BFCUDA_IN] = filters[f].n_channels[BFCUDA_OUT] = 1;
+        filters[f].channels[BFCUDA_IN] = &chan[2 * f];
+        filters[f].channels[BFCUDA_OUT] = &chan[2 * f + 1];
+        filters[f].scale[BFCUDA_IN] = filters[f].scale[BFCUDA_OUT] = ones;
+        filters[f].coeff = f;
+        coeff_blocks[f] = P;
+    }
+    cfg.n_filters = n_filters;
+    cfg.filters = filters;
+    cfg.n_coeffs = n_filters;
+    cfg.coeff_n_blocks = coeff_blocks;
+    cfg.device = device;
+    cfg.flags = bench ? BFCUDA_FLAG_STAGE_TIMING : 0;
+    CHECK(bfcuda_create(&cfg, &eng));
+    CHECK(bfcuda_get_info(eng, &info));
+
+    /* coefficients: load_coeff (bfconf.c:1867-2030) for the raw and "dirac pulse" cases */
+    {
+        size_t taps = (size_t)L * P;
+        void *h = calloc(taps, rs);
+        FILE *cf = NULL;
+        if (strcmp(coeff_path, "dirac") != 0 && (cf = fopen(coeff_path, "rb")) == NULL) {
+            DIE("Could not open \"%s\" for reading.", coeff_path);
+        }
+        for (f = 0; f < n_filters; f++) {
+            if (cf != NULL) {
+                memset(h, 0, taps * rs);
+                if (fread(h, rs, taps, cf) == 0) DIE("\"%s\" holds fewer than %d filters.", coeff_path, n_filters);
+            } else if (rs == 4) {
+                ((float *)h)[0] = 1.0f;
+            } else {
+                ((double *)h)[0] = 1.0;
+            }
+            CHECK(bfcuda_coeff_from_taps(eng, f, h, (int)taps, 1.0));
+        }
+        if (cf != NULL) fclose(cf);
+        free(h);
+    }
+
+    in = in_path == NULL || !strcmp(in_path, "-") ? stdin : fopen(in_path, "rb");
+    out = out_path == NULL || !strcmp(out_path, "-") ? stdout : fopen(out_path, "wb");
+    if (in == NULL || out == NULL) DIE("Could not open input or output: %s", strerror(errno));
+    raw_in = bfcuda_host_alloc((size_t)cfg.n_bytes[BFCUDA_IN]);
+    raw_out = bfcuda_host_alloc((size_t)cfg.n_bytes[BFCUDA_OUT]);
+    if (raw_in == NULL || raw_out == NULL) DIE("%s", bfcuda_strerror());
+
+    fprintf(stderr, "bfcuda_run: %d filters x %d taps (%d x %d) on %s, MAC %.1f MB/block\n", n_filters, L * P, L, P,
+            info.device_name, (double)info.mac_bytes_per_block / 1e6);
+    t0 = now();
+    for (;;) {
+        size_t got = fread(raw_in, 1, (size_t)cfg.n_bytes[BFCUDA_IN], in);
+        if (got == 0) {
+            break;
+        }
+        if (got < (size_t)cfg.n_bytes[BFCUDA_IN]) {
+            memset((char *)raw_in + got, 0, (size_t)cfg.n_bytes[BFCUDA_IN] - got);     /* dai.c:1312-1332 */
+        }
+        CHECK(bfcuda_process_block(eng, raw_in, raw_out));
+        if (fwrite(raw_out, 1, (size_t)cfg.n_bytes[BFCUDA_OUT], out) != (size_t)cfg.n_bytes[BFCUDA_OUT]) {
+            DIE("write failed: %s", strerror(errno));
+        }
+        blocks++;
+    }
+    t1 = now();
+    if (out != stdout) fclose(out);
+
+    for (c = 0; c < n; c++) {
+        struct bfcuda_overflow of;
+        CHECK(bfcuda_get_overflow(eng, c, &of));
+        if (of.n_overflows > 0) {
+            fprintf(stderr, "output %d: %u overflows, peak %.2f dB\n", c, of.n_overflows,
+                    20.0 * log10(of.largest / of.max));     /* bfrun.c:555-618 */
+        }
+    }
+    if (blocks > 0) {
+        const double per_block = (t1 - t0) / (double)blocks, block_s = (double)L / (double)rate;
+        fprintf(stderr, "%ld blocks, %.3f ms/block wall (file I/O included), rti %.4f, realtime multiple %.1f\n", blocks,
+                per_block * 1e3, per_block / block_s, block_s / per_block);
+        if (bench) {
+            CHECK(bfcuda_stage_times(eng, stage, &stage_blocks, &launches));
+            fprintf(stderr, "  device ms per period | raw2real+time2freq+mixscale1 | convolve | mixscale2+freq2time+real2raw\n"
+                            "                       | %28.3f | %8.3f | %28.3f   (%ld kernel launches)\n",
+                    stage[0], stage[1], stage[2], launches);
+        }
+    }
+    bfcuda_host_free(raw_in);
+    bfcuda_host_free(raw_out);
+    bfcuda_destroy(eng);
+    return 0;
+}

@@ -1,0 +1,48 @@
+"""The C host program (host/bfcuda_run.c) -- raw PCM file in, raw PCM file out through the C ABI from plain C,
+like the reference's filter process + bfio_file -- against the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from brutefir_b200 import configs
+from oracle import pyoracle as po
+from helpers import unpack_run
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_host_streams_files_like_bfio_file(gpu_lib, oracle_libs, tmp_path):
+    exe = os.path.join(ROOT, "host", "bfcuda_run")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L, P, n = 512, 6, 3
+    g = configs.diagonal_graph(n, L, P, 4, "S24_4LE")
+    taps = configs.synthetic_filters(g, 21)
+    sig = configs.synthetic_signal(g, 21, 9, sigma=0.02)
+    raw = sig.reshape(-1)[: sig.size - 1000]                  # last block is partial: must be zero-filled
+    (tmp_path / "in.raw").write_bytes(raw.tobytes())
+    (tmp_path / "taps.f32").write_bytes(np.concatenate(taps).astype("<f4").tobytes())
+    r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-i", "S24_4LE", "-o", "S24_4LE", "-b",
+                        "-c", str(tmp_path / "taps.f32"), str(tmp_path / "in.raw"), str(tmp_path / "out.raw")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "realtime multiple" in r.stderr and "convolve" in r.stderr
+    out = np.frombuffer((tmp_path / "out.raw").read_bytes(), np.uint8).reshape(9, g.out_bytes)
+    padded = sig.copy().reshape(-1)
+    padded[sig.size - 1000:] = 0
+    d = po.BlockDriver("oracle", g)
+    for c, h in enumerate(taps):
+        d.coeff_from_taps(c, h)
+    ref = d.run(padded.reshape(9, g.in_bytes))
+    d.close()
+    assert np.abs(unpack_run(out, g.out_formats, L) - unpack_run(ref, g.out_formats, L)).max() <= 1
+
+    # "dirac pulse" coefficients: the output file equals the input file (bfconf.c:1905-1913)
+    r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-r", "64", str(tmp_path / "in.raw"),
+                        str(tmp_path / "out2.raw")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out2 = np.frombuffer((tmp_path / "out2.raw").read_bytes(), np.uint8)
+    assert np.array_equal(out2, padded)
