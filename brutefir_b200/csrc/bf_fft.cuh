@@ -11,8 +11,8 @@
 // outputs.  Shared memory is split re[] / im[] and padded one word per 32 so that the strided
 // writes of the first passes spread over the banks.
 //
-// Twiddles come from a table W[j] = e^{-2 pi i j/N}, j in [0, N/2), computed on the host in double
-// and rounded once; the upper half circle is the negated lower half.
+// Twiddles come from a table W[j] = e^{-2 pi i j/N}, j in [0, N/2), computed on the host in long
+// double and rounded once; the upper half circle is the negated lower half.
 //
 // All functions are written per thread ("tid of nt") with the block-wide synchronisation left to the
 // caller, so the same code runs under the CPU emulation harness (tests/host_emul).
@@ -139,12 +139,14 @@ BF_HD void fft_pass_read(const T *sre, const T *sim, const T *__restrict__ tw, i
                 i[q] = sim[a];
             }
             if (Ns > 1) {
-                // Twiddles w^q = e^{-+2 pi i q k / (Ns R)}, q = 1..R-1.  Only w^1, w^2 and w^4 are fetched
-                // from the table (their indices never reach the upper half circle); the odd ones are
-                // products of two table entries -- one extra rounding, no dependent-load chain.
+                // Twiddles w^q = e^{-+2 pi i q k / (Ns R)}, q = 1..R-1.  -DBF_TWIDDLE_DERIVED fetches only w^1, w^2,
+                // w^4 and forms the others as products of two table entries: ~7 us faster per FFT stage at the
+                // headline shape, but the extra rounding measurably widens the distance to the reference
+                // (tools/diag_accuracy.py), so it is off.
                 T wr[R], wi[R];
                 const int i1 = k * tstep;
-#ifdef BF_TWIDDLE_DIRECT
+#ifndef BF_TWIDDLE_DERIVED
+                // every power straight from the table: one rounding each (the accurate default)
 #pragma unroll
                 for (int q = 1; q < R; q++) {
                     fft_twiddle<T>(tw, M, q * i1, INV, wr[q], wi[q]);

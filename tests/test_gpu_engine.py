@@ -109,13 +109,14 @@ def test_sample_formats_end_to_end(gpu_lib, oracle_libs, fmt_in, fmt_out):
 def test_mixing_delays_scales_and_dirac(gpu_lib, oracle_libs, rs):
     """Several inputs per filter (mixnscale INPUT, n_bufs > 1), several filters per output, one filter to two
     outputs, block delays, attenuations, a coeff:-1 filter, a short coefficient set, an unused output.
-    (The dirac filter's attenuation is 0.53, not 0.5: integer input x 0.5 lands exactly on the quantiser's
-    .5 ties, where 1e-16 of FFT noise decides the rounding and "identical at float_bits 64" cannot hold.)"""
+    (The dirac filter's attenuation is 1/3: integer input x 0.5 (or x 0.53 = 53/100) lands exactly on the
+    quantiser's .5 ties, where 1e-16 of FFT noise decides the rounding and "identical at float_bits 64" cannot hold;
+    x/3 never does.)"""
     L, P = 256, 6
     inb, nin = interleaved_layout(3, "S24_4LE", L)
     outb, nout = interleaved_layout(4, "S24_LE", L)
     filters = [Filter([0], [0], coeff=0), Filter([1, 2], [1], in_scales=[0.7, -0.2], coeff=1, delayblocks=2),
-               Filter([2], [1, 2], out_scales=[0.53, 2.0], coeff=-1), Filter([0, 1, 2], [2], in_scales=[0.3, 0.3, 0.3], coeff=2),
+               Filter([2], [1, 2], out_scales=[1.0 / 3.0, 2.0], coeff=-1), Filter([0, 1, 2], [2], in_scales=[0.3, 0.3, 0.3], coeff=2),
                Filter([1], [0], out_scales=[-0.25], coeff=0, delayblocks=7)]
     g = FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [P, 3, 1])
     taps = configs.synthetic_filters(g, 13)
