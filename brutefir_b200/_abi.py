@@ -57,14 +57,16 @@ class ConfigC(C.Structure):
                 ("safety_limit", C.c_double),
                 ("device", C.c_int),
                 ("flags", C.c_uint),
-                ("mac_split", C.c_int)]
+                ("mac_split", C.c_int),
+                ("max_batch", C.c_int)]
 
 
 class InfoC(C.Structure):
     _fields_ = [("n_fft", C.c_int), ("mac_split", C.c_int), ("n_streams", C.c_int),
                 ("kernels_per_block", C.c_int), ("uses_graph", C.c_int), ("sm_count", C.c_int),
                 ("mac_bytes_per_block", C.c_size_t), ("device_bytes", C.c_size_t),
-                ("device_name", C.c_char * 64)]
+                ("device_name", C.c_char * 64),
+                ("max_batch", C.c_int), ("mac_bytes_per_batch", C.c_size_t)]
 
 
 FLAG_STAGE_TIMING = 1
@@ -78,7 +80,9 @@ ENGINE_SYMBOLS = [
     "bfcuda_coeff_from_taps", "bfcuda_coeff_set_block", "bfcuda_coeff_get_block",
     "bfcuda_coeff_runtime_block", "bfcuda_set_control", "bfcuda_get_overflow", "bfcuda_reset_overflow",
     "bfcuda_process_block", "bfcuda_process_block_async", "bfcuda_synchronize",
+    "bfcuda_process_blocks", "bfcuda_process_blocks_async", "bfcuda_process_blocks_device",
     "bfcuda_process_block_device", "bfcuda_device_io", "bfcuda_upload_input", "bfcuda_download_output",
+    "bfcuda_upload_inputs", "bfcuda_download_outputs",
     "bfcuda_host_alloc", "bfcuda_host_free", "bfcuda_timer_start", "bfcuda_timer_stop",
     "bfcuda_stage_times", "bfcuda_get_info", "bfcuda_debug_read", "bfcuda_comm_unique_id",
     "bfcuda_comm_init", "bfcuda_comm_shared_outputs",
@@ -130,6 +134,11 @@ def load_library() -> C.CDLL:
     lib.bfcuda_process_block_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bfcuda_synchronize.argtypes = [C.c_void_p]
     lib.bfcuda_process_block_device.argtypes = [C.c_void_p]
+    lib.bfcuda_process_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.bfcuda_process_blocks_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.bfcuda_process_blocks_device.argtypes = [C.c_void_p, C.c_int]
+    lib.bfcuda_upload_inputs.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.bfcuda_download_outputs.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.bfcuda_device_io.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.bfcuda_upload_input.argtypes = [C.c_void_p, C.c_void_p]
     lib.bfcuda_download_output.argtypes = [C.c_void_p, C.c_void_p]

@@ -110,6 +110,10 @@ struct FilterState {
 
 struct bfcuda_engine {
     int L, P, N, rs;
+    int max_batch, fdl_ring;    // blocks per launch at most; delay-line slots per stream = P + max_batch - 1
+    int slot_t;                 // ring slot of the next block (0 <= slot_t < ring)
+    int prev_par;               // which of the two `prev` buffers holds the last input block
+    int last_batch;             // blocks in the most recent launch (layout of Y for debug_read)
     int n_ch[2], n_bytes[2];
     int n_filters, n_coeffs;
     int device;
@@ -133,7 +137,7 @@ struct bfcuda_engine {
     uint8_t *d_raw[2];          // raw blocks of the device-resident interface (and buffer 0 of the streaming one)
     uint8_t *d_raw2[2];         // second buffers of the streaming interface
     SampleFormat *d_fmt[2];
-    void *d_prev, *d_fdl, *d_xin, *d_H, *d_Y, *d_out_time, *d_scratch;
+    void *d_prev[2], *d_fdl, *d_xin, *d_H, *d_Y, *d_out_time, *d_scratch;
     Overflow *d_overflow;
     unsigned int *d_status;
     unsigned int *h_status;     // pinned
@@ -158,13 +162,15 @@ struct bfcuda_engine {
     OutChan *d_chans;
     MixTerm *d_out_terms;
     bool dirty, xfade_active;
-    size_t mac_bytes;
+    size_t mac_bytes;           // algorithmic MAC bytes of one block launched alone
+    size_t mac_bytes_batch;     // compulsory MAC bytes of one full batch of max_batch blocks
 
     unsigned int t;
     // measurement
     cudaEvent_t timer[2];
     cudaEvent_t ring[TIMING_RING][6];
     int ring_fill;
+    int ring_blocks[TIMING_RING];
     double stage_ms[BFCUDA_N_STAGES];
     long stage_blocks, launches;
     // multi-GPU
@@ -331,6 +337,10 @@ static void build_tables(bfcuda_engine *e)
     }
     // algorithmic MAC traffic, SURVEY.md 8(d): rs * N * (coefficient blocks + delay-line blocks + outputs)
     e->mac_bytes = (size_t)e->rs * e->N * (blocks_h + blocks_x + e->h_jobs.size());
+    // a batch of B blocks reads every coefficient block once, a window of n_parts + B - 1 delay-line blocks per
+    // job, and writes B outputs per job
+    const size_t Bm = (size_t)e->max_batch;
+    e->mac_bytes_batch = (size_t)e->rs * e->N * (blocks_h + blocks_x + e->h_jobs.size() * (Bm - 1) + e->h_jobs.size() * Bm);
     e->dirty = false;
 }
 
@@ -403,7 +413,7 @@ void bfcuda_destroy(bfcuda_engine *e)
     if (e->comm != nullptr && g_nccl.handle != nullptr) {
         g_nccl.CommDestroy(e->comm);
     }
-    void *ptrs[] = { e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev, e->d_fdl, e->d_xin, e->d_H,
+    void *ptrs[] = { e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms };
     for (void *p : ptrs) {
@@ -446,6 +456,9 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     }
     if (c->n_blocks < 1) {
         return fail(BFCUDA_EINVAL, "Invalid number of blocks %d.", c->n_blocks);
+    }
+    if (c->max_batch > (c->realsize == 4 ? 8 : 4)) {
+        return fail(BFCUDA_EINVAL, "max_batch %d exceeds %d", c->max_batch, c->realsize == 4 ? 8 : 4);
     }
     if (c->n_channels[0] < 0 || c->n_channels[0] > BFCUDA_MAXCHANNELS || c->n_channels[1] < 0 ||
         c->n_channels[1] > BFCUDA_MAXCHANNELS || c->n_filters < 0 || c->n_filters > BFCUDA_MAXFILTERS) {
@@ -507,6 +520,11 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->P = c->n_blocks;
     e->N = 2 * e->L;
     e->rs = c->realsize;
+    e->max_batch = c->max_batch < 1 ? 1 : c->max_batch;
+    e->fdl_ring = e->P + e->max_batch - 1;
+    e->slot_t = 0;
+    e->prev_par = 0;
+    e->last_batch = 1;
     e->device = c->device;
     e->flags = c->flags;
     e->safety_limit = c->safety_limit;
@@ -528,7 +546,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     memset(e->ring, 0, sizeof(e->ring));
     void **zero[] = { (void **)&e->d_raw[0], (void **)&e->d_raw[1], (void **)&e->d_raw2[0], (void **)&e->d_raw2[1],
                       (void **)&e->d_fmt[0], (void **)&e->d_fmt[1],
-                      &e->d_prev, &e->d_fdl, &e->d_xin, &e->d_H, &e->d_Y, &e->d_out_time, &e->d_scratch,
+                      &e->d_prev[0], &e->d_prev[1], &e->d_fdl, &e->d_xin, &e->d_H, &e->d_Y, &e->d_out_time, &e->d_scratch,
                       (void **)&e->d_overflow, (void **)&e->d_status, (void **)&e->d_dests, (void **)&e->d_dest_first,
                       (void **)&e->d_need_xin, (void **)&e->d_mix_streams, (void **)&e->d_mix_terms,
                       (void **)&e->d_jobs, (void **)&e->d_chans, (void **)&e->d_out_terms };
@@ -586,7 +604,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         }                                                                                          \
     } while (0)
     {
-        const size_t N = e->N, L = e->L, P = e->P, F = std::max(1, e->n_filters);
+        const size_t N = e->N, L = e->L, F = std::max(1, e->n_filters);
         TRYCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
         TRYCU(cudaStreamCreateWithFlags(&e->s_inv, cudaStreamNonBlocking));
         TRYCU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
@@ -607,18 +625,20 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         }
         TRYCU(cudaMallocHost((void **)&e->h_status, sizeof(unsigned int)));
         *e->h_status = 0;
-        TRY(dev_alloc(e, &e->d_raw[0], (size_t)e->n_bytes[0]));
-        TRY(dev_alloc(e, &e->d_raw[1], (size_t)e->n_bytes[1]));
-        TRY(dev_alloc(e, &e->d_raw2[0], (size_t)e->n_bytes[0]));
-        TRY(dev_alloc(e, &e->d_raw2[1], (size_t)e->n_bytes[1]));
+        const size_t B = (size_t)e->max_batch;
+        TRY(dev_alloc(e, &e->d_raw[0], B * e->n_bytes[0]));
+        TRY(dev_alloc(e, &e->d_raw[1], B * e->n_bytes[1]));
+        TRY(dev_alloc(e, &e->d_raw2[0], B * e->n_bytes[0]));
+        TRY(dev_alloc(e, &e->d_raw2[1], B * e->n_bytes[1]));
         TRY(dev_alloc(e, &e->d_fmt[0], sizeof(SampleFormat) * std::max(1, e->n_ch[0])));
         TRY(dev_alloc(e, &e->d_fmt[1], sizeof(SampleFormat) * std::max(1, e->n_ch[1])));
-        TRY(dev_alloc(e, &e->d_prev, rs_bytes(e, (size_t)e->n_ch[0] * L)));
-        TRY(dev_alloc(e, &e->d_fdl, rs_bytes(e, F * P * N)));
-        TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, (size_t)std::max(1, e->n_ch[0]) * N)));
+        TRY(dev_alloc(e, &e->d_prev[0], rs_bytes(e, (size_t)e->n_ch[0] * L)));
+        TRY(dev_alloc(e, &e->d_prev[1], rs_bytes(e, (size_t)e->n_ch[0] * L)));
+        TRY(dev_alloc(e, &e->d_fdl, rs_bytes(e, F * (size_t)e->fdl_ring * N)));
+        TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * N)));
         TRY(dev_alloc(e, &e->d_H, rs_bytes(e, (size_t)std::max(1, e->total_coeff_blocks) * N)));
-        TRY(dev_alloc(e, &e->d_Y, rs_bytes(e, (size_t)e->split * 2 * F * N)));
-        TRY(dev_alloc(e, &e->d_out_time, rs_bytes(e, (size_t)std::max(1, e->n_ch[1]) * L)));
+        TRY(dev_alloc(e, &e->d_Y, rs_bytes(e, (size_t)e->split * B * 2 * F * N)));
+        TRY(dev_alloc(e, &e->d_out_time, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[1]) * L)));
         TRY(dev_alloc(e, &e->d_scratch, rs_bytes(e, 4 * N)));
         TRY(dev_alloc(e, &e->d_overflow, sizeof(Overflow) * std::max(1, e->n_ch[1])));
         TRY(dev_alloc(e, &e->d_status, sizeof(unsigned int)));
@@ -841,27 +861,23 @@ static int flush_timing_ring(bfcuda_engine *e)
             e->stage_ms[s] += ms;
         }
     }
-    e->stage_blocks += e->ring_fill;
+    for (int i = 0; i < e->ring_fill; i++) {
+        e->stage_blocks += e->ring_blocks[i];
+    }
     e->ring_fill = 0;
     return 0;
 }
 
-// Enqueue the kernels of one block: forward + MAC on the main stream, inverse on s_inv.
-//   raw_in / raw_out : device raw blocks of this block
+// Enqueue the kernels of `nb` consecutive blocks as ONE launch per stage (nb <= max_batch; callers make sure
+// no control change or crossfade falls inside): forward + MAC on the main stream, inverse on s_inv.
+//   raw_in / raw_out : device raw blocks, block b at + b * n_bytes
 //   in_ready         : event the forward stage must wait for (input copy), or null
 //   out_free         : event the inverse stage must wait for (previous read-out of raw_out), or null
 //   fwd_done         : recorded after the forward stage (raw_in may be overwritten afterwards), or null
-// On return e->ev_inv marks the end of this block's inverse stage.
-static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cudaEvent_t in_ready,
+// On return e->ev_inv marks the end of the inverse stage.
+static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw_out, cudaEvent_t in_ready,
                          cudaEvent_t out_free, cudaEvent_t fwd_done)
 {
-    if (e->dirty || e->xfade_active) {
-        build_tables(e);
-        // the previous block's inverse stage (other stream) still reads the output-mix tables
-        CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));
-        int rc = upload_tables(e);
-        if (rc != 0) return rc;
-    }
     const bool timing = (e->flags & BFCUDA_FLAG_STAGE_TIMING) != 0;
     cudaEvent_t *ev = nullptr;
     if (timing) {
@@ -870,6 +886,7 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
             if (rc != 0) return rc;
         }
         ev = e->ring[e->ring_fill];
+        e->ring_blocks[e->ring_fill] = nb;
     }
     if (in_ready != nullptr) {
         CU(cudaStreamWaitEvent(e->stream, in_ready, 0));
@@ -879,16 +896,20 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
     ForwardArgs fa;
     fa.raw_in = raw_in;
     fa.fmt = e->d_fmt[0];
-    fa.prev = e->d_prev;
+    fa.prev_in = e->d_prev[e->prev_par];
+    fa.prev_out = e->d_prev[e->prev_par ^ 1];
     fa.fdl = e->d_fdl;
     fa.xin = e->d_xin;
     fa.need_xin = e->d_need_xin;
     fa.dest_first = e->d_dest_first;
     fa.dests = e->d_dests;
     fa.n_in = e->n_ch[0];
-    fa.P = e->P;
-    fa.t = e->t;
+    fa.ring = e->fdl_ring;
+    fa.t = e->slot_t;
+    fa.batch = nb;
+    fa.in_stride = (size_t)e->n_bytes[0];
     CU(launch_forward(e->plan, fa, e->stream));
+    e->prev_par ^= 1;
     e->launches += e->n_ch[0] > 0;
     if (!e->h_mix_streams.empty()) {
         StreamMixArgs sa;
@@ -897,8 +918,10 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
         sa.streams = e->d_mix_streams;
         sa.terms = e->d_mix_terms;
         sa.n_streams = (int)e->h_mix_streams.size();
-        sa.P = e->P;
-        sa.t = e->t;
+        sa.n_in = e->n_ch[0];
+        sa.ring = e->fdl_ring;
+        sa.t = e->slot_t;
+        sa.batch = nb;
         CU(launch_stream_mix(e->plan, sa, e->stream));
         e->launches++;
     }
@@ -906,7 +929,7 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
     if (fwd_done != nullptr) {
         CU(cudaEventRecord(fwd_done, e->stream));
     }
-    // the previous block's inverse stage reads Y: the MAC may not overwrite it earlier.  (The forward stage
+    // the previous launch's inverse stage reads Y: the MAC may not overwrite it earlier.  (The forward stage
     // above does not touch Y, so it runs concurrently with that inverse stage.)
     CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));
     if (timing) CU(cudaEventRecord(ev[2], e->stream));
@@ -918,9 +941,10 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
     ma.jobs = e->d_jobs;
     ma.n_jobs = (int)e->h_jobs.size();
     ma.n_slots = 2 * std::max(1, e->n_filters);
-    ma.P = e->P;
+    ma.ring = e->fdl_ring;
     ma.split = e->split;
-    ma.t = e->t;
+    ma.t = e->slot_t;
+    ma.batch = nb;
     ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
     CU(launch_mac(e->plan, ma, e->stream));
     e->launches += ma.n_jobs > 0;
@@ -944,6 +968,8 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
     ia.n_out = e->n_ch[1];
     ia.n_slots = ma.n_slots;
     ia.split = e->split;
+    ia.batch = nb;
+    ia.out_stride = (size_t)e->n_bytes[1];
     ia.safety_limit = e->safety_limit;
     CU(launch_inverse(e->plan, ia, e->s_inv));
     e->launches += e->n_ch[1] > 0;
@@ -953,13 +979,15 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
         if (e->comm != nullptr) {
             const int dtype = e->rs == 4 ? 7 /* ncclFloat32 */ : 8 /* ncclFloat64 */;
             g_nccl.GroupStart();
-            for (int o : e->shared_out) {
-                char *row = (char *)e->d_out_time + rs_bytes(e, (size_t)o * e->L);
-                int r = g_nccl.AllReduce(row, row, (size_t)e->L, dtype, 0 /* ncclSum */, e->comm, e->s_inv);
-                if (r != 0) {
-                    g_nccl.GroupEnd();
-                    return fail(BFCUDA_ECOMM, "ncclAllReduce failed: %s",
-                                g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+            for (int b = 0; b < nb; b++) {
+                for (int o : e->shared_out) {
+                    char *row = (char *)e->d_out_time + rs_bytes(e, ((size_t)b * e->n_ch[1] + o) * e->L);
+                    int r = g_nccl.AllReduce(row, row, (size_t)e->L, dtype, 0 /* ncclSum */, e->comm, e->s_inv);
+                    if (r != 0) {
+                        g_nccl.GroupEnd();
+                        return fail(BFCUDA_ECOMM, "ncclAllReduce failed: %s",
+                                    g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+                    }
                 }
             }
             g_nccl.GroupEnd();
@@ -977,7 +1005,38 @@ static int enqueue_block(bfcuda_engine *e, uint8_t *raw_in, uint8_t *raw_out, cu
     for (FilterState &fs : e->filters) {
         fs.prevcoeff = fs.coeff;
     }
-    e->t++;
+    e->t += (unsigned int)nb;
+    e->slot_t = (e->slot_t + nb) % e->fdl_ring;
+    e->last_batch = nb;
+    return 0;
+}
+
+// Process n blocks that already sit in device memory: split them into launches of at most max_batch blocks;
+// a pending control change or a crossfade block is processed on its own (its tables differ from its
+// neighbours', bfrun.c:1462-1478, 1726-1777).
+static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw_out, cudaEvent_t in_ready,
+                          cudaEvent_t out_free, cudaEvent_t fwd_done)
+{
+    int done = 0;
+    while (done < n) {
+        int nb = std::min(n - done, e->max_batch);
+        if (e->dirty || e->xfade_active) {
+            build_tables(e);
+            // the previous launch's inverse stage (other stream) still reads the output-mix tables
+            CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));
+            int rc = upload_tables(e);
+            if (rc != 0) return rc;
+            if (e->xfade_active) {
+                nb = 1;
+            }
+        }
+        const bool lastpart = done + nb == n;
+        int rc = enqueue_batch(e, nb, raw_in + (size_t)done * e->n_bytes[0], raw_out + (size_t)done * e->n_bytes[1],
+                               done == 0 ? in_ready : nullptr, done == 0 ? out_free : nullptr,
+                               lastpart ? fwd_done : nullptr);
+        if (rc != 0) return rc;
+        done += nb;
+    }
     return 0;
 }
 
@@ -1002,28 +1061,36 @@ static int sync_all(bfcuda_engine *e)
     return 0;
 }
 
-int bfcuda_process_block_async(bfcuda_engine *e, const void *raw_in, void *raw_out)
+int bfcuda_process_blocks_async(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out)
 {
     if (e == nullptr || raw_in == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    if (n_blocks < 1 || n_blocks > e->max_batch) {
+        return fail(BFCUDA_EINVAL, "n_blocks %d outside 1..max_batch (%d)", n_blocks, e->max_batch);
+    }
     CU(cudaSetDevice(e->device));
-    // double-buffered raw blocks: copy-in of block t+1 and copy-out of block t-1 overlap the kernels of block t
+    // double-buffered raw blocks: copy-in of call k+1 and copy-out of call k-1 overlap the kernels of call k
     const int b = (int)(e->io_count & 1u);
     uint8_t *d_in = b ? e->d_raw2[0] : e->d_raw[0];
     uint8_t *d_out = b ? e->d_raw2[1] : e->d_raw[1];
     const bool reuse = e->io_count >= 2;
     if (reuse) {
-        CU(cudaStreamWaitEvent(e->s_in, e->ev_fwd[b], 0));      // forward of block t-2 has consumed d_in
+        CU(cudaStreamWaitEvent(e->s_in, e->ev_fwd[b], 0));      // forward of call k-2 has consumed d_in
     }
-    CU(cudaMemcpyAsync(d_in, raw_in, (size_t)e->n_bytes[0], cudaMemcpyHostToDevice, e->s_in));
+    CU(cudaMemcpyAsync(d_in, raw_in, (size_t)n_blocks * e->n_bytes[0], cudaMemcpyHostToDevice, e->s_in));
     CU(cudaEventRecord(e->ev_h2d[b], e->s_in));
-    int rc = enqueue_block(e, d_in, d_out, e->ev_h2d[b], reuse ? e->ev_d2h[b] : nullptr, e->ev_fwd[b]);
+    int rc = enqueue_blocks(e, n_blocks, d_in, d_out, e->ev_h2d[b], reuse ? e->ev_d2h[b] : nullptr, e->ev_fwd[b]);
     if (rc != 0) return rc;
     CU(cudaStreamWaitEvent(e->s_out, e->ev_inv, 0));
-    CU(cudaMemcpyAsync(raw_out, d_out, (size_t)e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_out));
+    CU(cudaMemcpyAsync(raw_out, d_out, (size_t)n_blocks * e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_out));
     CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->s_out));
     CU(cudaEventRecord(e->ev_d2h[b], e->s_out));
     e->io_count++;
     return 0;
+}
+
+int bfcuda_process_block_async(bfcuda_engine *e, const void *raw_in, void *raw_out)
+{
+    return bfcuda_process_blocks_async(e, 1, raw_in, raw_out);
 }
 
 int bfcuda_synchronize(bfcuda_engine *e)
@@ -1042,39 +1109,66 @@ int bfcuda_process_block(bfcuda_engine *e, const void *raw_in, void *raw_out)
     return bfcuda_synchronize(e);
 }
 
-int bfcuda_process_block_device(bfcuda_engine *e)
+int bfcuda_process_blocks(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out)
+{
+    int rc = bfcuda_process_blocks_async(e, n_blocks, raw_in, raw_out);
+    if (rc != 0) return rc;
+    return bfcuda_synchronize(e);
+}
+
+int bfcuda_process_blocks_device(bfcuda_engine *e, int n_blocks)
 {
     if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    if (n_blocks < 1 || n_blocks > e->max_batch) {
+        return fail(BFCUDA_EINVAL, "n_blocks %d outside 1..max_batch (%d)", n_blocks, e->max_batch);
+    }
     CU(cudaSetDevice(e->device));
-    return enqueue_block(e, e->d_raw[0], e->d_raw[1], nullptr, nullptr, nullptr);
+    return enqueue_blocks(e, n_blocks, e->d_raw[0], e->d_raw[1], nullptr, nullptr, nullptr);
+}
+
+int bfcuda_process_block_device(bfcuda_engine *e)
+{
+    return bfcuda_process_blocks_device(e, 1);
 }
 
 int bfcuda_device_io(bfcuda_engine *e, int io, void **device_ptr, size_t *n_bytes)
 {
     if (e == nullptr || (io != 0 && io != 1)) return fail(BFCUDA_EINVAL, "bad argument");
     if (device_ptr) *device_ptr = e->d_raw[io];
-    if (n_bytes) *n_bytes = (size_t)e->n_bytes[io];
+    if (n_bytes) *n_bytes = (size_t)e->n_bytes[io] * e->max_batch;
+    return 0;
+}
+
+int bfcuda_upload_inputs(bfcuda_engine *e, int n_blocks, const void *raw_in)
+{
+    if (e == nullptr || raw_in == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    if (n_blocks < 1 || n_blocks > e->max_batch) return fail(BFCUDA_EINVAL, "n_blocks outside 1..max_batch");
+    CU(cudaSetDevice(e->device));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
+    CU(cudaMemcpyAsync(e->d_raw[0], raw_in, (size_t)n_blocks * e->n_bytes[0], cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
 int bfcuda_upload_input(bfcuda_engine *e, const void *raw_in)
 {
-    if (e == nullptr || raw_in == nullptr) return fail(BFCUDA_EINVAL, "null argument");
-    CU(cudaSetDevice(e->device));
-    int rc = sync_all(e);
-    if (rc != 0) return rc;
-    CU(cudaMemcpyAsync(e->d_raw[0], raw_in, (size_t)e->n_bytes[0], cudaMemcpyHostToDevice, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    return 0;
+    return bfcuda_upload_inputs(e, 1, raw_in);
 }
 
 int bfcuda_download_output(bfcuda_engine *e, void *raw_out)
 {
+    return bfcuda_download_outputs(e, 1, raw_out);
+}
+
+int bfcuda_download_outputs(bfcuda_engine *e, int n_blocks, void *raw_out)
+{
     if (e == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
+    if (n_blocks < 1 || n_blocks > e->max_batch) return fail(BFCUDA_EINVAL, "n_blocks outside 1..max_batch");
     CU(cudaSetDevice(e->device));
     int rc = sync_all(e);
     if (rc != 0) return rc;
-    CU(cudaMemcpyAsync(raw_out, e->d_raw[1], (size_t)e->n_bytes[1], cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(raw_out, e->d_raw[1], (size_t)n_blocks * e->n_bytes[1], cudaMemcpyDeviceToHost, e->stream));
     CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return check_status(e);
@@ -1158,6 +1252,8 @@ int bfcuda_get_info(bfcuda_engine *e, struct bfcuda_info *info)
     info->n_streams = e->n_filters;
     info->kernels_per_block = 3 + (e->h_mix_streams.empty() ? 0 : 1) + (e->shared_out.empty() ? 0 : 1);
     info->uses_graph = 0;
+    info->max_batch = e->max_batch;
+    info->mac_bytes_per_batch = e->mac_bytes_batch;
     info->sm_count = e->sm_count;
     info->mac_bytes_per_block = e->mac_bytes;
     info->device_bytes = e->device_bytes;
@@ -1188,7 +1284,10 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
         if (index < 0 || index >= e->n_filters || slot < 0 || slot >= e->P) {
             return fail(BFCUDA_EINVAL, "filter or slot out of range");
         }
-        const char *src = (const char *)e->d_fdl + nb * ((size_t)index * e->P + slot);
+        if (e->max_batch != 1) {
+            return fail(BFCUDA_EINVAL, "delay-line slots follow the reference's numbering only with max_batch 1");
+        }
+        const char *src = (const char *)e->d_fdl + nb * ((size_t)index * e->fdl_ring + slot);
         CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
         CU(cudaMemcpyAsync(dst, e->d_scratch, nb, cudaMemcpyDeviceToHost, e->stream));
         break;
@@ -1198,7 +1297,9 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
         const size_t n_slots = 2 * (size_t)std::max(1, e->n_filters);
         std::vector<unsigned char> part(nb);
         for (int z = 0; z < e->split; z++) {
-            const char *src = (const char *)e->d_Y + nb * ((size_t)z * n_slots + index);
+            // the last block of the most recent launch
+            const char *src = (const char *)e->d_Y +
+                              nb * (((size_t)z * e->last_batch + (e->last_batch - 1)) * n_slots + index);
             CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
             CU(cudaMemcpyAsync(z == 0 ? dst : (void *)part.data(), e->d_scratch, nb, cudaMemcpyDeviceToHost,
                                e->stream));
@@ -1220,7 +1321,8 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
     }
     case BFCUDA_DBG_OUTPUT_TIME: {
         if (index < 0 || index >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
-        const char *src = (const char *)e->d_out_time + rs_bytes(e, (size_t)index * e->L);
+        const char *src = (const char *)e->d_out_time +
+                          rs_bytes(e, ((size_t)(e->last_batch - 1) * e->n_ch[1] + index) * e->L);
         CU(cudaMemcpyAsync(dst, src, rs_bytes(e, e->L), cudaMemcpyDeviceToHost, e->stream));
         break;
     }

@@ -185,13 +185,15 @@ __device__ __forceinline__ void reduce_stats(QuantStats st, Overflow *of, unsign
             st.largest = fmax(st.largest, w[i].largest);
             st.status |= w[i].status;
         }
-        of->n_overflows += st.n_overflows;
-        if (st.intlargest > of->intlargest) {
-            of->intlargest = st.intlargest;
+        // atomics: the blocks of one batch update the same output's counters concurrently (sum / max
+        // commute, so the result equals the reference's sequential running count / maximum)
+        if (st.n_overflows != 0) {
+            atomicAdd(&of->n_overflows, st.n_overflows);
         }
-        if (st.largest > of->largest) {
-            of->largest = st.largest;
-        }
+        atomicMax(&of->intlargest, st.intlargest);
+        // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long *>(&of->largest),
+                  (unsigned long long)__double_as_longlong(st.largest));
         if (st.status != 0) {
             atomicOr(status, st.status);
         }
@@ -206,13 +208,15 @@ template <typename T, int E>
 __global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__restrict__ tw, int L)
 {
     const int M = L, N = 2 * L;
-    const int c = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int c = blockIdx.x, blk = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     T *sre = smem_re<T>();
     T *sim = sre + (M + (M >> 5) + 1);
     const SampleFormat f = a.fmt[c];
-    T *prev = reinterpret_cast<T *>(a.prev) + (size_t)c * L;
-    const uint8_t *raw = a.raw_in + f.byte_offset;
+    const T *prev_in = reinterpret_cast<const T *>(a.prev_in) + (size_t)c * L;
+    T *prev_out = reinterpret_cast<T *>(a.prev_out) + (size_t)c * L;
+    const uint8_t *raw = a.raw_in + (size_t)blk * a.in_stride + f.byte_offset;
     const size_t stride = (size_t)f.sample_spacing * f.bytes;
+    const bool last = blk == a.batch - 1;
 
     // frame = [previous block | this block] (fftw_convolver.c:180-193), packed z_j = x_2j + i x_2j+1.
     // All loads of this thread's samples are issued before the first use: the interleaved layouts put every
@@ -225,7 +229,11 @@ __global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__r
             const int n = tid + b * nt;
             if (n < L) {
                 bits[b] = load_raw_le(raw + (size_t)n * stride, f.bytes);
-                old[b] = prev[n];
+                // first half of the frame: the previous block -- kept in real form across calls for the first
+                // block of a batch, re-read from the raw batch otherwise
+                old[b] = blk == 0 ? prev_in[n]
+                                  : decode_sample<T>(load_raw_le(raw - a.in_stride + (size_t)n * stride, f.bytes),
+                                                     f.bytes, f.isfloat, f.swap);
             }
         }
 #pragma unroll
@@ -233,7 +241,9 @@ __global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__r
             const int n = tid + b * nt;
             if (n < L) {
                 const T cur = decode_sample<T>(bits[b], f.bytes, f.isfloat, f.swap);
-                prev[n] = cur;
+                if (last) {
+                    prev_out[n] = cur;
+                }
                 const int j0 = fft_pad(n >> 1), j1 = fft_pad((L + n) >> 1);
                 if (n & 1) {
                     sim[j0] = old[b];
@@ -248,11 +258,12 @@ __global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__r
     __syncthreads();
 
     const int d0 = a.dest_first[c], d1 = a.dest_first[c + 1];
-    T *xin = (a.xin != nullptr && a.need_xin[c]) ? reinterpret_cast<T *>(a.xin) + (size_t)c * N : nullptr;
+    T *xin = (a.xin != nullptr && a.need_xin[c])
+                 ? reinterpret_cast<T *>(a.xin) + ((size_t)blk * a.n_in + c) * N : nullptr;
     T *fdl = reinterpret_cast<T *>(a.fdl);
     const FwdDest *dests = a.dests;
-    const int P = a.P;
-    const unsigned int t = a.t;
+    const int ring = a.ring;
+    const int t = a.t + blk;
     forward_and_emit<T, E>(sre, sim, tw, M, tid, nt, [&](int k, T re, T im) {
         if (xin != nullptr) {
             xin[k] = re;
@@ -260,8 +271,8 @@ __global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__r
         }
         for (int d = d0; d < d1; d++) {
             const FwdDest ds = dests[d];
-            const unsigned int slot = (t + (unsigned int)ds.delay) % (unsigned int)P;
-            T *dst = fdl + ((size_t)ds.stream * P + slot) * N;
+            const int slot = (t + ds.delay) % ring;
+            T *dst = fdl + ((size_t)ds.stream * ring + slot) * N;
             const T s = (T)ds.scale;
             dst[k] = mul_rn(re, s);
             dst[M + k] = mul_rn(im, s);
@@ -273,19 +284,20 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_stream_mix(StreamMixArgs a, int N)
 {
     const MixStream ms = a.streams[blockIdx.y];
+    const int blk = blockIdx.z;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) {
         return;
     }
-    const T *xin = reinterpret_cast<const T *>(a.xin);
-    const unsigned int slot = (a.t + (unsigned int)ms.delay) % (unsigned int)a.P;
+    const T *xin = reinterpret_cast<const T *>(a.xin) + (size_t)blk * a.n_in * N;
+    const int slot = (a.t + blk + ms.delay) % a.ring;
     T acc = (T)0;
     for (int j = 0; j < ms.n_inputs; j++) {
         const MixTerm tm = a.terms[ms.first + j];
         const T v = mul_rn(xin[(size_t)tm.index * N + i], (T)tm.scale);
         acc = j == 0 ? v : add_rn(acc, v);
     }
-    reinterpret_cast<T *>(a.fdl)[((size_t)ms.stream * a.P + slot) * N + i] = acc;
+    reinterpret_cast<T *>(a.fdl)[((size_t)ms.stream * a.ring + slot) * N + i] = acc;
 }
 
 // ======================================================================================================
@@ -331,10 +343,10 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
     const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
     const MacJob jb = a.jobs[job];
     const int z = blockIdx.y;
-    const int P = a.P;
+    const int P = a.ring;       // ring slots per stream
     T *out = reinterpret_cast<T *>(a.Y) + ((size_t)z * a.n_slots + jb.out) * N + (size_t)v * W;
     const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * P * N + (size_t)v * W;
-    const int slot0 = (int)(a.t % (unsigned int)P);
+    const int slot0 = a.t;
 
     Lanes<T, W> are, aim;
 #pragma unroll
@@ -425,6 +437,171 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
 }
 
 // ======================================================================================================
+// k_mac_batch -- B consecutive audio blocks per launch, coefficient and delay-line spectra reused in
+// registers across the batch
+//
+// Output block t+b needs  sum_i FDL[t+b-i] (*) H[i].  Walking the partitions i upwards with B accumulators, step
+// i uses ONE coefficient vector H[i] for all B blocks and the window FDL[t-i .. t-i+B-1], which differs from the
+// previous step's window by one new slot.  So a step costs two 16-byte vector pairs of traffic for B complex
+// vector MACs instead of 2 B: the HBM traffic of a batch is rs*N*(P + (P+B-1) + B) per filter instead of
+// B*rs*N*(2P+1), while every output block still accumulates its partitions in ascending order with the
+// reference's roundings -- results are bit-identical to B single-block launches.
+// The window lives in registers and is rotated by unrolling the partition loop B times; loads run D = 2 steps
+// ahead of their use.
+// ======================================================================================================
+
+template <typename T, int B>
+__global__ void __launch_bounds__(256) k_mac_batch(MacArgs a, int N)
+{
+    constexpr int W = 16 / (int)sizeof(T);
+    constexpr int D = 2;
+    typedef typename Vec16<T>::type V;
+    typedef Lanes<T, W> L;
+    const int M = N >> 1;
+    const int vecs = M / W;
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long)a.n_jobs * vecs) {
+        return;
+    }
+    const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
+    const MacJob jb = a.jobs[job];
+    const int z = blockIdx.y;
+    const int R = a.ring;
+    const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * R * N + (size_t)v * W;
+    auto xslot = [&](int s) -> const T * {      // s in (-R, 2R)
+        s += (s < 0) ? R : 0;
+        s -= (s >= R) ? R : 0;
+        return X + (size_t)s * N;
+    };
+
+    L are[B], aim[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+#pragma unroll
+        for (int l = 0; l < W; l++) {
+            are[b].v[l] = (T)0;
+            aim[b].v[l] = (T)0;
+        }
+    }
+
+    if (jb.hbase < 0) {
+        if (z == 0) {
+            const T fr = (T)(1.0 / (T)N);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                if (b < a.batch) {
+                    const T *xp = xslot(a.t + b);
+                    const L xr = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(xp)));
+                    const L xi = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(xp + M)));
+#pragma unroll
+                    for (int l = 0; l < W; l++) {
+                        const T s = (l & 1) ? -fr : fr;
+                        are[b].v[l] = mul_rn(xr.v[l], s);
+                        aim[b].v[l] = mul_rn(xi.v[l], s);
+                    }
+                }
+            }
+        }
+    } else {
+        const int chunk = (jb.n_parts + a.split - 1) / a.split;
+        const int i0 = z * chunk;
+        const int i1 = min(jb.n_parts, i0 + chunk);
+        const T *H = reinterpret_cast<const T *>(a.H) + (size_t)jb.hbase * N + (size_t)v * W;
+        T dc[B], ny[B];
+        V wr[B], wi[B];         // window: logical block b of step i sits in physical slot (b - (i - i0)) mod B
+        V ph_r[D], ph_i[D], px_r[D], px_i[D];
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            dc[b] = (T)0;
+            ny[b] = (T)0;
+        }
+        if (i0 < i1) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const T *xp = xslot(a.t + b - i0);
+                wr[b] = ldg_stream(reinterpret_cast<const V *>(xp));
+                wi[b] = ldg_stream(reinterpret_cast<const V *>(xp + M));
+            }
+#pragma unroll
+            for (int d = 0; d < D; d++) {
+                if (i0 + d < i1) {
+                    const T *hp = H + (size_t)(i0 + d) * N;
+                    ph_r[d] = ldg_stream(reinterpret_cast<const V *>(hp));
+                    ph_i[d] = ldg_stream(reinterpret_cast<const V *>(hp + M));
+                    if (d > 0) {
+                        const T *xp = xslot(a.t - (i0 + d));
+                        px_r[d] = ldg_stream(reinterpret_cast<const V *>(xp));
+                        px_i[d] = ldg_stream(reinterpret_cast<const V *>(xp + M));
+                    }
+                }
+            }
+        }
+        for (int base = i0; base < i1; base += B) {
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const int i = base + u;
+                if (i < i1) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int d = u % D;
+                    const L cr = as_lanes<T, W>(ph_r[d]), ci = as_lanes<T, W>(ph_i[d]);
+                    if (i > i0) {
+                        // the block that left the window makes room for the new oldest-partition slot
+                        wr[(B - u) % B] = px_r[d];
+                        wi[(B - u) % B] = px_i[d];
+                    }
+                    if (i + D < i1) {
+                        const T *hp = H + (size_t)(i + D) * N;
+                        const T *xp = xslot(a.t - (i + D));
+                        ph_r[d] = ldg_stream(reinterpret_cast<const V *>(hp));
+                        ph_i[d] = ldg_stream(reinterpret_cast<const V *>(hp + M));
+                        px_r[d] = ldg_stream(reinterpret_cast<const V *>(xp));
+                        px_i[d] = ldg_stream(reinterpret_cast<const V *>(xp + M));
+                    }
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        const L br = as_lanes<T, W>(wr[(b - u + B) % B]), bi = as_lanes<T, W>(wi[(b - u + B) % B]);
+                        if (i == i0) {
+#pragma unroll
+                            for (int l = 0; l < W; l++) {
+                                cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], are[b].v[l], aim[b].v[l]);
+                            }
+                            dc[b] = mul_rn(br.v[0], cr.v[0]);
+                            ny[b] = mul_rn(bi.v[0], ci.v[0]);
+                        } else {
+#pragma unroll
+                            for (int l = 0; l < W; l++) {
+                                T re, im;
+                                cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], re, im);
+                                are[b].v[l] = add_rn(are[b].v[l], re);
+                                aim[b].v[l] = add_rn(aim[b].v[l], im);
+                            }
+                            dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
+                            ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
+                        }
+                    }
+                }
+            }
+        }
+        if (v == 0) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                are[b].v[0] = dc[b];
+                aim[b].v[0] = ny[b];
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+        if (b < a.batch) {
+            T *out = reinterpret_cast<T *>(a.Y) + (((size_t)z * a.batch + b) * a.n_slots + jb.out) * N + (size_t)v * W;
+            *reinterpret_cast<V *>(out) = *reinterpret_cast<V *>(&are[b]);
+            *reinterpret_cast<V *>(out + M) = *reinterpret_cast<V *>(&aim[b]);
+        }
+    }
+}
+
+// ======================================================================================================
 // k_inverse
 // ======================================================================================================
 
@@ -481,18 +658,19 @@ template <typename T, int E>
 __global__ void __launch_bounds__(1024, 1) k_inverse(InverseArgs a, const T *__restrict__ tw, int L)
 {
     const int M = L, N = 2 * L;
-    const int o = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int o = blockIdx.x, blk = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     T *sre = smem_re<T>();
     T *sim = sre + (M + (M >> 5) + 1);
     const OutChan ch = a.chans[o];
-    const T *Y = reinterpret_cast<const T *>(a.Y);
+    const T *Y = reinterpret_cast<const T *>(a.Y) + (size_t)blk * a.n_slots * N;
+    const int zstride = a.batch * a.n_slots;    // Y slots between two partial sums of the split
     const int npass = ch.xf_first >= 0 ? 2 : 1;
     T keep[E];
 
     for (int pass = 0; pass < npass; pass++) {
         const int first = (npass == 2 && pass == 0) ? ch.xf_first : ch.first;
         load_and_inverse<T, E>(sre, sim, tw, M, tid, nt, [&](int i) {
-            return mix_terms<T>(Y, a.terms, first, ch.n, a.n_slots, a.split, N, i);
+            return mix_terms<T>(Y, a.terms, first, ch.n, zstride, a.split, N, i);
         });
         if (pass + 1 < npass) {
             // stash the "old" signal's valid half in registers, then reuse shared memory
@@ -510,8 +688,8 @@ __global__ void __launch_bounds__(1024, 1) k_inverse(InverseArgs a, const T *__r
 
     // overlap-save: the first L samples are the valid output (fftw_convolver.c:498-501)
     const SampleFormat f = a.fmt[o];
-    T *tdst = reinterpret_cast<T *>(a.out_time) + (size_t)o * L;
-    uint8_t *raw = a.raw_out + f.byte_offset;
+    T *tdst = reinterpret_cast<T *>(a.out_time) + ((size_t)blk * a.n_out + o) * L;
+    uint8_t *raw = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset;
     const size_t stride = (size_t)f.sample_spacing * f.bytes;
     const double of_max = a.overflow[o].max;
     QuantStats st;
@@ -551,14 +729,14 @@ __global__ void __launch_bounds__(1024, 1) k_inverse(InverseArgs a, const T *__r
 template <typename T>
 __global__ void __launch_bounds__(256) k_quantise_shared(InverseArgs a, int L)
 {
-    const int o = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int o = blockIdx.x, blk = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     __shared__ QuantStats wstats[32];
     if (!a.chans[o].shared) {
         return;
     }
     const SampleFormat f = a.fmt[o];
-    const T *src = reinterpret_cast<const T *>(a.out_time) + (size_t)o * L;
-    uint8_t *raw = a.raw_out + f.byte_offset;
+    const T *src = reinterpret_cast<const T *>(a.out_time) + ((size_t)blk * a.n_out + o) * L;
+    uint8_t *raw = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset;
     const size_t stride = (size_t)f.sample_spacing * f.bytes;
     const double of_max = a.overflow[o].max;
     QuantStats st;
@@ -803,13 +981,13 @@ static cudaError_t allow_smem(K kernel, size_t bytes)
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
-    BF_FFT_DISPATCH(plan, k_forward, a.n_in, s, a, (const T *)plan.tw, plan.N / 2);
+    BF_FFT_DISPATCH(plan, k_forward, dim3(a.n_in, a.batch), s, a, (const T *)plan.tw, plan.N / 2);
 }
 
 cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaStream_t s)
 {
     if (a.n_streams == 0) return cudaSuccess;
-    dim3 grid((plan.N + 255) / 256, a.n_streams);
+    dim3 grid((plan.N + 255) / 256, a.n_streams, a.batch);
     if (plan.realsize == 4) {
         k_stream_mix<float><<<grid, 256, 0, s>>>(a, plan.N);
     } else {
@@ -823,12 +1001,27 @@ cudaError_t launch_mac_tma(const FftPlan &plan, const MacArgs &a, cudaStream_t s
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
     if (a.n_jobs == 0) return cudaSuccess;
-    if (a.variant == 1) {
+    if (a.variant == 1 && a.batch == 1) {
         return launch_mac_tma(plan, a, s);
     }
     const int W = 16 / plan.realsize;
     const long threads = (long)a.n_jobs * (plan.N / 2 / W);
     dim3 grid((unsigned int)((threads + 255) / 256), a.split);
+    if (a.batch > 1) {
+        // a batch smaller than the template's B leaves the surplus accumulators unused (their window slots
+        // are still read, always inside the ring)
+        if (plan.realsize == 4) {
+            if (a.batch <= 2) k_mac_batch<float, 2><<<grid, 256, 0, s>>>(a, plan.N);
+            else if (a.batch <= 4) k_mac_batch<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
+            else if (a.batch <= 8) k_mac_batch<float, 8><<<grid, 256, 0, s>>>(a, plan.N);
+            else return cudaErrorInvalidValue;
+        } else {
+            if (a.batch <= 2) k_mac_batch<double, 2><<<grid, 256, 0, s>>>(a, plan.N);
+            else if (a.batch <= 4) k_mac_batch<double, 4><<<grid, 256, 0, s>>>(a, plan.N);
+            else return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     if (plan.realsize == 4) {
         k_mac<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
     } else {
@@ -840,16 +1033,16 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
-    BF_FFT_DISPATCH(plan, k_inverse, a.n_out, s, a, (const T *)plan.tw, plan.N / 2);
+    BF_FFT_DISPATCH(plan, k_inverse, dim3(a.n_out, a.batch), s, a, (const T *)plan.tw, plan.N / 2);
 }
 
 cudaError_t launch_quantise_shared(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
     if (plan.realsize == 4) {
-        k_quantise_shared<float><<<a.n_out, 256, 0, s>>>(a, plan.N / 2);
+        k_quantise_shared<float><<<dim3(a.n_out, a.batch), 256, 0, s>>>(a, plan.N / 2);
     } else {
-        k_quantise_shared<double><<<a.n_out, 256, 0, s>>>(a, plan.N / 2);
+        k_quantise_shared<double><<<dim3(a.n_out, a.batch), 256, 0, s>>>(a, plan.N / 2);
     }
     return cudaGetLastError();
 }

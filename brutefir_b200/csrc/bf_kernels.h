@@ -64,58 +64,70 @@ bool fft_size_supported(int N, int realsize);
 
 // ---- engine kernels --------------------------------------------------------------------------------
 
+// Batching: one launch may process `batch` consecutive audio blocks (grid y = block within the batch).
+// The delay-line ring then has `ring` = P + max_batch - 1 slots per stream, so that the spectra of the
+// later blocks of a batch do not overwrite slots the earlier blocks still read; `t` is the ring slot of
+// the batch's first block (0 <= t < ring).  batch = 1, ring = P is the reference's block-by-block schedule.
 struct ForwardArgs {
-    const uint8_t *raw_in;
+    const uint8_t *raw_in;      // block b at raw_in + b * in_stride
     const SampleFormat *fmt;    // [n_in]
-    void *prev;                 // [n_in][L] reals: previous block of every input
-    void *fdl;                  // [U][P][N] planar spectra
-    void *xin;                  // [n_in][N] unscaled planar spectra, or NULL
+    const void *prev_in;        // [n_in][L] reals: the block before the batch's first one
+    void *prev_out;             // [n_in][L] reals: receives the batch's last block (never aliases prev_in when batch > 1)
+    void *fdl;                  // [U][ring][N] planar spectra
+    void *xin;                  // [batch][n_in][N] unscaled planar spectra, or NULL
     const uint8_t *need_xin;    // [n_in]
     const int *dest_first;      // [n_in + 1]
     const FwdDest *dests;
     int n_in;
-    int P;
-    unsigned int t;
+    int ring;
+    int t;
+    int batch;
+    size_t in_stride;
 };
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s);
 
 struct StreamMixArgs {
-    const void *xin;
+    const void *xin;            // [batch][n_in][N]
     void *fdl;
     const MixStream *streams;
     const MixTerm *terms;
     int n_streams;
-    int P;
-    unsigned int t;
+    int n_in;
+    int ring;
+    int t;
+    int batch;
 };
 cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaStream_t s);
 
 struct MacArgs {
     const void *fdl;
     const void *H;
-    void *Y;                    // [split][n_slots][N]
+    void *Y;                    // [split][batch][n_slots][N]
     const MacJob *jobs;
     int n_jobs;
     int n_slots;
-    int P;
+    int ring;
     int split;
-    unsigned int t;
-    int variant;                // 0 = direct streaming loads, 1 = bulk-copy (TMA) staged
+    int t;
+    int batch;
+    int variant;                // 0 = direct streaming loads, 1 = bulk-copy (TMA) staged (batch 1 only)
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 
 struct InverseArgs {
-    const void *Y;
+    const void *Y;              // [split][batch][n_slots][N]
     const OutChan *chans;       // [n_out]
     const MixTerm *terms;
-    void *out_time;             // [n_out][L] reals (time domain, LSB units)
-    uint8_t *raw_out;
+    void *out_time;             // [batch][n_out][L] reals (time domain, LSB units)
+    uint8_t *raw_out;           // block b at raw_out + b * out_stride
     const SampleFormat *fmt;    // [n_out]
     Overflow *overflow;         // [n_out]
     unsigned int *status;       // BF_STATUS_* bits
     int n_out;
     int n_slots;
     int split;
+    int batch;
+    size_t out_stride;
     double safety_limit;
 };
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);

@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(PB / 16 + 32) k_mac_tma(MacArgs a, int N, int 
     uint64_t *empty = full + STAGES;
     const int tid = threadIdx.x;
     const int M = N >> 1;
-    const int P = a.P;
-    const int slot0 = (int)(a.t % (unsigned int)P);
+    const int P = a.ring;
+    const int slot0 = a.t;
     const T *Xall = reinterpret_cast<const T *>(a.fdl);
     const T *Hall = reinterpret_cast<const T *>(a.H);
 

@@ -43,11 +43,12 @@ class PinnedBuffer:
 
 
 class Engine:
-    def __init__(self, graph: FilterGraph, device: int = 0, flags: int = 0, mac_split: int = 0):
+    def __init__(self, graph: FilterGraph, device: int = 0, flags: int = 0, mac_split: int = 0, max_batch: int = 1):
         self.lib = _abi.load_library()
         self.graph = graph
+        self.max_batch = max_batch
         self.dtype = np.float32 if graph.realsize == 4 else np.float64
-        cfg, keep = graph.to_config(device=device, flags=flags, mac_split=mac_split)
+        cfg, keep = graph.to_config(device=device, flags=flags, mac_split=mac_split, max_batch=max_batch)
         h = C.c_void_p()
         check(self.lib.bfcuda_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -125,13 +126,19 @@ class Engine:
     def synchronize(self):
         check(self.lib.bfcuda_synchronize(self.h))
 
+    def process_blocks_async(self, raw_in: np.ndarray, raw_out: np.ndarray, n_blocks: int):
+        check(self.lib.bfcuda_process_blocks_async(self.h, n_blocks, raw_in.ctypes.data, raw_out.ctypes.data))
+
     def run(self, raw_in_blocks: np.ndarray) -> np.ndarray:
-        """uint8[n_blocks, in_bytes] -> uint8[n_blocks, out_bytes], pipelined."""
+        """uint8[n_blocks, in_bytes] -> uint8[n_blocks, out_bytes], pipelined, max_batch blocks per call."""
         n = raw_in_blocks.shape[0]
         out = np.zeros((n, self.graph.out_bytes), np.uint8)
         raw_in_blocks = np.ascontiguousarray(raw_in_blocks)
-        for b in range(n):
-            self.process_block_async(raw_in_blocks[b], out[b])
+        b = 0
+        while b < n:
+            nb = min(self.max_batch, n - b)
+            self.process_blocks_async(raw_in_blocks[b:b + nb], out[b:b + nb], nb)
+            b += nb
         self.synchronize()
         return out
 
@@ -140,6 +147,12 @@ class Engine:
 
     def process_block_device(self):
         check(self.lib.bfcuda_process_block_device(self.h))
+
+    def upload_inputs(self, raw_in_blocks: np.ndarray):
+        check(self.lib.bfcuda_upload_inputs(self.h, raw_in_blocks.shape[0], raw_in_blocks.ctypes.data))
+
+    def process_blocks_device(self, n_blocks: int):
+        check(self.lib.bfcuda_process_blocks_device(self.h, n_blocks))
 
     def download_output(self) -> np.ndarray:
         out = np.zeros(self.graph.out_bytes, np.uint8)

@@ -71,7 +71,7 @@ class FilterGraph:
             if f.coeff >= len(self.coeff_n_blocks):
                 raise ValueError("coefficient index out of range")
 
-    def to_config(self, device: int = 0, flags: int = 0, mac_split: int = 0):
+    def to_config(self, device: int = 0, flags: int = 0, mac_split: int = 0, max_batch: int = 1):
         """Build ``struct bfcuda_config``.  Returns (config, keepalive): ``keepalive`` owns the arrays
         the config points into and must outlive the bfcuda_create call."""
         self.validate()
@@ -134,6 +134,7 @@ class FilterGraph:
         cfg.device = device
         cfg.flags = flags
         cfg.mac_split = mac_split
+        cfg.max_batch = max_batch
         return cfg, keep
 
     # ---- derived figures used by bench.py -------------------------------------

@@ -113,6 +113,10 @@ struct bfcuda_config {
     unsigned int flags;         /* BFCUDA_FLAG_* */
     int mac_split;              /* 0 = automatic; 1 = never split the partition sum (reference summation order);
                                    S > 1 = split it S ways */
+    int max_batch;              /* 0/1 = block by block (the reference's schedule).  B > 1 (<= 8 at realsize 4, <= 4 at
+                                   realsize 8) lets bfcuda_process_blocks* take up to B consecutive blocks per call:
+                                   offline / file-to-file throughput mode.  Results are bit-identical to B single
+                                   calls; the I/O delay grows by the batch (not for real-time use). */
 };
 
 #define BFCUDA_FLAG_STAGE_TIMING 1u     /* record CUDA events around each stage of every block */
@@ -158,12 +162,24 @@ int bfcuda_process_block(bfcuda_engine *engine, const void *raw_in, void *raw_ou
 int bfcuda_process_block_async(bfcuda_engine *engine, const void *raw_in, void *raw_out);
 int bfcuda_synchronize(bfcuda_engine *engine);
 
+/* Batched form (config.max_batch > 1): n_blocks (1..max_batch) consecutive blocks, stored back to back
+ * (n_bytes[IN] / n_bytes[OUT] apart), in one call.  Each stage runs once for the whole batch and the
+ * multiply-accumulate reuses every coefficient and delay-line spectrum across the batch in registers, so
+ * its HBM traffic per block drops ~n_blocks-fold; every output block is still computed with the reference's
+ * operation order (bit-identical to n_blocks single-block calls).  A pending bfcuda_set_control() or a
+ * crossfade block is split off and processed on its own. */
+int bfcuda_process_blocks(bfcuda_engine *engine, int n_blocks, const void *raw_in, void *raw_out);
+int bfcuda_process_blocks_async(bfcuda_engine *engine, int n_blocks, const void *raw_in, void *raw_out);
+
 /* Device-resident form: input already in the engine's device staging buffer (see bfcuda_device_io),
  * output left in the device output buffer; no host<->device copy.  Enqueue only. */
 int bfcuda_process_block_device(bfcuda_engine *engine);
+int bfcuda_process_blocks_device(bfcuda_engine *engine, int n_blocks);
 int bfcuda_device_io(bfcuda_engine *engine, int io, void **device_ptr, size_t *n_bytes);
 int bfcuda_upload_input(bfcuda_engine *engine, const void *raw_in);
+int bfcuda_upload_inputs(bfcuda_engine *engine, int n_blocks, const void *raw_in);
 int bfcuda_download_output(bfcuda_engine *engine, void *raw_out);
+int bfcuda_download_outputs(bfcuda_engine *engine, int n_blocks, void *raw_out);
 
 void *bfcuda_host_alloc(size_t n_bytes);    /* page-locked host memory */
 void bfcuda_host_free(void *p);
@@ -193,6 +209,8 @@ struct bfcuda_info {
     size_t mac_bytes_per_block; /* algorithmic: rs * N * (P*F + P*U + F), current coefficient lengths */
     size_t device_bytes;        /* device memory held by the engine */
     char device_name[64];
+    int max_batch;
+    size_t mac_bytes_per_batch; /* compulsory bytes of one full batch: rs * N * (P*F + (P+B-1)*U + B*F) */
 };
 int bfcuda_get_info(bfcuda_engine *engine, struct bfcuda_info *info);
 
