@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/bfcuda.h"
@@ -153,6 +154,8 @@ struct bfcuda_engine {
     std::vector<OutChan> h_chans;
     std::vector<MixTerm> h_out_terms;
     std::vector<int> shared_out;
+    std::vector<std::pair<int, int>> delay_fixups;     // (filter, old delay) of delay changes not yet applied to the ring
+    void *d_fix;                // staging for the ring fix-up, P spectra, allocated on first use
     FwdDest *d_dests;
     int *d_dest_first;
     uint8_t *d_need_xin;
@@ -421,6 +424,7 @@ void bfcuda_destroy(bfcuda_engine *e)
             cudaFree(p);
         }
     }
+    if (e->d_fix) cudaFree(e->d_fix);
     if (e->h_status) cudaFreeHost(e->h_status);
     fft_plan_destroy(&e->plan);
     for (int i = 0; i < 2; i++) {
@@ -534,6 +538,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->ev_h2d[0] = e->ev_h2d[1] = e->ev_fwd[0] = e->ev_fwd[1] = e->ev_d2h[0] = e->ev_d2h[1] = nullptr;
     e->ev_mac = e->ev_inv = nullptr;
     e->io_count = 0;
+    e->d_fix = nullptr;
     e->comm = nullptr;
     e->n_ranks = 1;
     e->device_bytes = 0;
@@ -834,6 +839,9 @@ int bfcuda_set_control(bfcuda_engine *e, int filter, const struct bfcuda_filter_
     if (c->coeff >= e->n_coeffs) return fail(BFCUDA_EINVAL, "coefficient index %d out of range", c->coeff);
     FilterState &fs = e->filters[filter];
     fs.coeff = c->coeff < 0 ? -1 : c->coeff;
+    if (e->fdl_ring != e->P && clamp_delay(e, c->delayblocks) != clamp_delay(e, fs.delayblocks)) {
+        e->delay_fixups.push_back(std::make_pair(filter, clamp_delay(e, fs.delayblocks)));
+    }
     fs.delayblocks = c->delayblocks;
     for (int io = 0; io < 2; io++) {
         if (c->scale[io] != nullptr) {
@@ -1011,6 +1019,40 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     return 0;
 }
 
+// A run-time change of a filter's block delay (cfd, bfrun.c:1579-1600) makes the reference read delay-line
+// slots that were written under the old delay: its ring has exactly P slots, so the spectra written "ahead"
+// (slot (w + d_old) % P for the last d_old - 1 blocks w) alias the oldest partitions.  With a longer ring
+// (batched mode) those slots are distinct, so the aliasing is reproduced once, at the block boundary where the
+// change takes effect, by copying ring[v] -> ring[v - P] for the d_old - 1 virtual slots v ahead of "now".
+// After that every read sees what the reference's P-slot ring would hold.
+static int apply_delay_fixups(bfcuda_engine *e)
+{
+    if (e->delay_fixups.empty()) {
+        return 0;
+    }
+    const size_t nb = rs_bytes(e, e->N);
+    const int R = e->fdl_ring, P = e->P;
+    if (e->d_fix == nullptr) {
+        CU(cudaMalloc(&e->d_fix, nb * (size_t)P));
+    }
+    for (const std::pair<int, int> &fx : e->delay_fixups) {
+        const int f = fx.first, d_old = fx.second;
+        char *ring = (char *)e->d_fdl + nb * (size_t)f * R;
+        for (int j = 1; j < d_old; j++) {       // stage first: sources and destinations may overlap
+            const int src = (e->slot_t + j) % R;
+            CU(cudaMemcpyAsync((char *)e->d_fix + nb * (size_t)j, ring + nb * (size_t)src, nb, cudaMemcpyDeviceToDevice,
+                               e->stream));
+        }
+        for (int j = 1; j < d_old; j++) {
+            const int dst = ((e->slot_t + j - P) % R + R) % R;
+            CU(cudaMemcpyAsync(ring + nb * (size_t)dst, (char *)e->d_fix + nb * (size_t)j, nb, cudaMemcpyDeviceToDevice,
+                               e->stream));
+        }
+    }
+    e->delay_fixups.clear();
+    return 0;
+}
+
 // Process n blocks that already sit in device memory: split them into launches of at most max_batch blocks;
 // a pending control change or a crossfade block is processed on its own (its tables differ from its
 // neighbours', bfrun.c:1462-1478, 1726-1777).
@@ -1021,6 +1063,8 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
     while (done < n) {
         int nb = std::min(n - done, e->max_batch);
         if (e->dirty || e->xfade_active) {
+            int frc = apply_delay_fixups(e);
+            if (frc != 0) return frc;
             build_tables(e);
             // the previous launch's inverse stage (other stream) still reads the output-mix tables
             CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));

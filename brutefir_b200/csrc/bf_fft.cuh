@@ -42,7 +42,10 @@ BF_HD void fft_twiddle(const T *__restrict__ tw, int halfN, int idx, bool invers
         idx -= halfN;
         neg = true;
     }
-    T c = tw[2 * idx], s = tw[2 * idx + 1];
+    // one vector load for the (cos, -sin) pair
+    struct alignas(2 * sizeof(T)) Pair { T c, s; };
+    const Pair pr = reinterpret_cast<const Pair *>(tw)[idx];
+    T c = pr.c, s = pr.s;
     if (neg) {
         c = -c;
         s = -s;

@@ -14,6 +14,7 @@
 // used: there is no contraction here, only element-wise complex products.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "bf_kernels.h"
@@ -94,7 +95,7 @@ __device__ __forceinline__ void forward_and_emit(T *sre, T *sim, const T *__rest
                                                  Emit emit)
 {
     fft_complex_inplace<T, E, false>(sre, sim, tw, M, tid, nt, BlockSync());
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b <= E / 2; b++) {
         const int k = tid + b * nt;
         if (k > M / 2) {
@@ -122,7 +123,7 @@ template <typename T, int E, typename Load>
 __device__ __forceinline__ void load_and_inverse(T *sre, T *sim, const T *__restrict__ tw, int M, int tid, int nt,
                                                  Load load)
 {
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b <= E / 2; b++) {
         const int k = tid + b * nt;
         if (k > M / 2) {
@@ -308,19 +309,32 @@ template <typename T> struct Vec16;
 template <> struct Vec16<float> { typedef float4 type; };
 template <> struct Vec16<double> { typedef double2 type; };
 
-// 16-byte streaming load: read-only path, do not allocate in L1 (every operand byte is used once)
+// W reals of type T as one vector register group
+template <typename T, int W> struct VecN;
+template <> struct VecN<float, 4> { typedef float4 type; };
+template <> struct VecN<float, 2> { typedef float2 type; };
+template <> struct VecN<double, 2> { typedef double2 type; };
+template <> struct VecN<double, 1> { typedef double type; };
+
+// streaming loads: read-only path, do not allocate in L1 (every operand byte is used once)
 template <typename V>
 __device__ __forceinline__ V ldg_stream(const V *p)
 {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return *reinterpret_cast<V *>(&r);
+    if (sizeof(V) == 16) {
+        uint4 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                     : "l"(p));
+        return *reinterpret_cast<V *>(&r);
+    } else {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return *reinterpret_cast<V *>(&r);
+    }
 }
 
 template <typename T, int W>
-struct __align__(16) Lanes {
+struct __align__(sizeof(T) * W) Lanes {
     T v[W];
 };
 template <typename T, int W, typename V>
@@ -450,12 +464,14 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
 // ahead of their use.
 // ======================================================================================================
 
-template <typename T, int B>
-__global__ void __launch_bounds__(256) k_mac_batch(MacArgs a, int N)
+struct TagTrue { static constexpr bool value = true; };
+struct TagFalse { static constexpr bool value = false; };
+
+template <typename T, int W, int B, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_mac_batch(MacArgs a, int N)
 {
-    constexpr int W = 16 / (int)sizeof(T);
     constexpr int D = 2;
-    typedef typename Vec16<T>::type V;
+    typedef typename VecN<T, W>::type V;
     typedef Lanes<T, W> L;
     const int M = N >> 1;
     const int vecs = M / W;
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(256) k_mac_batch(MacArgs a, int N)
                     const L xi = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(xp + M)));
 #pragma unroll
                     for (int l = 0; l < W; l++) {
-                        const T s = (l & 1) ? -fr : fr;
+                        const T s = ((v * W + l) & 1) ? -fr : fr;     // sign by bin parity (W may be odd)
                         are[b].v[l] = mul_rn(xr.v[l], s);
                         aim[b].v[l] = mul_rn(xi.v[l], s);
                     }
@@ -536,39 +552,61 @@ __global__ void __launch_bounds__(256) k_mac_batch(MacArgs a, int N)
                 }
             }
         }
-        for (int base = i0; base < i1; base += B) {
+        // DC and Nyquist ride in lane 0 of the job's first vector and are REAL products (fftw_convfuns.h:546-547):
+        // only the warp that holds that vector carries the two extra accumulators through the loop.
+        const bool has0 = __any_sync(0xffffffffu, v == 0);
+        auto body = [&](auto dcny_tag) {
+            constexpr bool DCNY = decltype(dcny_tag)::value;
+            const T *hnext = H + (size_t)(i0 + D) * N;      // coefficient block of step i + D
+            int xs = a.t - (i0 + D);                        // ring slot of the new delay-line block of step i + D
+            xs += (xs < 0) ? R : 0;
+            xs += (xs < 0) ? R : 0;
+            auto prefetch = [&](int d, int i) {
+                if (i + D < i1) {
+                    const T *xp = X + (size_t)xs * N;
+                    ph_r[d] = ldg_stream(reinterpret_cast<const V *>(hnext));
+                    ph_i[d] = ldg_stream(reinterpret_cast<const V *>(hnext + M));
+                    px_r[d] = ldg_stream(reinterpret_cast<const V *>(xp));
+                    px_i[d] = ldg_stream(reinterpret_cast<const V *>(xp + M));
+                }
+                hnext += N;
+                xs = xs == 0 ? R - 1 : xs - 1;
+            };
+            if (i0 < i1) {
+                // first partition of the range: convolver_convolve, a plain product (peeled so that the main
+                // loop carries no assign/accumulate branch -- its unrolled body must stay in the instruction cache)
+                const L cr = as_lanes<T, W>(ph_r[0]), ci = as_lanes<T, W>(ph_i[0]);
+                prefetch(0, i0);
 #pragma unroll
-            for (int u = 0; u < B; u++) {
-                const int i = base + u;
-                if (i < i1) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
-                    const int d = u % D;
-                    const L cr = as_lanes<T, W>(ph_r[d]), ci = as_lanes<T, W>(ph_i[d]);
-                    if (i > i0) {
+                for (int b = 0; b < B; b++) {
+                    const L br = as_lanes<T, W>(wr[b]), bi = as_lanes<T, W>(wi[b]);
+#pragma unroll
+                    for (int l = 0; l < W; l++) {
+                        cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], are[b].v[l], aim[b].v[l]);
+                    }
+                    if (DCNY) {
+                        dc[b] = mul_rn(br.v[0], cr.v[0]);
+                        ny[b] = mul_rn(bi.v[0], ci.v[0]);
+                    }
+                }
+            }
+            // remaining partitions: convolver_convolve_add.  Step i = base + k has window rotation
+            // u = (i - i0) % B and prefetch slot d = (i - i0) % D; base - i0 = 1 (mod B): compile-time constants.
+            for (int base = i0 + 1; base < i1; base += B) {
+#pragma unroll
+                for (int k = 0; k < B; k++) {
+                    const int i = base + k;
+                    if (i < i1) {
+                        const int u = (k + 1) % B;
+                        const int d = (k + 1) % D;
+                        const L cr = as_lanes<T, W>(ph_r[d]), ci = as_lanes<T, W>(ph_i[d]);
                         // the block that left the window makes room for the new oldest-partition slot
                         wr[(B - u) % B] = px_r[d];
                         wi[(B - u) % B] = px_i[d];
-                    }
-                    if (i + D < i1) {
-                        const T *hp = H + (size_t)(i + D) * N;
-                        const T *xp = xslot(a.t - (i + D));
-                        ph_r[d] = ldg_stream(reinterpret_cast<const V *>(hp));
-                        ph_i[d] = ldg_stream(reinterpret_cast<const V *>(hp + M));
-                        px_r[d] = ldg_stream(reinterpret_cast<const V *>(xp));
-                        px_i[d] = ldg_stream(reinterpret_cast<const V *>(xp + M));
-                    }
+                        prefetch(d, i);
 #pragma unroll
-                    for (int b = 0; b < B; b++) {
-                        const L br = as_lanes<T, W>(wr[(b - u + B) % B]), bi = as_lanes<T, W>(wi[(b - u + B) % B]);
-                        if (i == i0) {
-#pragma unroll
-                            for (int l = 0; l < W; l++) {
-                                cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], are[b].v[l], aim[b].v[l]);
-                            }
-                            dc[b] = mul_rn(br.v[0], cr.v[0]);
-                            ny[b] = mul_rn(bi.v[0], ci.v[0]);
-                        } else {
+                        for (int b = 0; b < B; b++) {
+                            const L br = as_lanes<T, W>(wr[(b - u + B) % B]), bi = as_lanes<T, W>(wi[(b - u + B) % B]);
 #pragma unroll
                             for (int l = 0; l < W; l++) {
                                 T re, im;
@@ -576,12 +614,19 @@ __global__ void __launch_bounds__(256) k_mac_batch(MacArgs a, int N)
                                 are[b].v[l] = add_rn(are[b].v[l], re);
                                 aim[b].v[l] = add_rn(aim[b].v[l], im);
                             }
-                            dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
-                            ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
+                            if (DCNY) {
+                                dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
+                                ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
+                            }
                         }
                     }
                 }
             }
+        };
+        if (has0) {
+            body(TagTrue());
+        } else {
+            body(TagFalse());
         }
         if (v == 0) {
 #pragma unroll
@@ -955,6 +1000,16 @@ static cudaError_t allow_smem(K kernel, size_t bytes)
     return cudaSuccess;
 }
 
+static bool fft_force16()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BFCUDA_FFT_E16");
+        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 // dispatch on (realsize, points per thread): float uses 16 points per thread above M = 8192
 #define BF_FFT_DISPATCH(plan, KERNEL, grid, stream, ...)                                                   \
     do {                                                                                                   \
@@ -963,7 +1018,7 @@ static cudaError_t allow_smem(K kernel, size_t bytes)
         cudaError_t e_;                                                                                    \
         if ((plan).realsize == 4) {                                                                        \
             typedef float T;                                                                               \
-            if (M_ > 8192) {                                                                               \
+            if (M_ > 8192 || (fft_force16() && M_ >= 512)) {                                               \
                 if ((e_ = allow_smem(KERNEL<float, 16>, smem_)) != cudaSuccess) return e_;                 \
                 KERNEL<float, 16><<<grid, M_ / 16, smem_, stream>>>(__VA_ARGS__);                          \
             } else {                                                                                       \
@@ -1008,16 +1063,20 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
     const long threads = (long)a.n_jobs * (plan.N / 2 / W);
     dim3 grid((unsigned int)((threads + 255) / 256), a.split);
     if (a.batch > 1) {
-        // a batch smaller than the template's B leaves the surplus accumulators unused (their window slots
-        // are still read, always inside the ring)
+        // Instantiations: (lanes per thread W, batch B, resident blocks per SM).  Larger batches use narrower
+        // vectors so that B accumulators + the B-slot window stay within 128 registers (2 blocks of 256
+        // threads per SM) and the unrolled loop stays inside the instruction cache.  A batch smaller than B
+        // leaves the surplus accumulators unused (their window slots are still read, always inside the ring).
+        const int M = plan.N / 2;
+        auto blocks = [&](int w) { return dim3((unsigned int)(((long)a.n_jobs * (M / w) + 255) / 256), a.split); };
         if (plan.realsize == 4) {
-            if (a.batch <= 2) k_mac_batch<float, 2><<<grid, 256, 0, s>>>(a, plan.N);
-            else if (a.batch <= 4) k_mac_batch<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
-            else if (a.batch <= 8) k_mac_batch<float, 8><<<grid, 256, 0, s>>>(a, plan.N);
+            if (a.batch <= 2) k_mac_batch<float, 4, 2, 2><<<blocks(4), 256, 0, s>>>(a, plan.N);
+            else if (a.batch <= 4) k_mac_batch<float, 4, 4, 2><<<blocks(4), 256, 0, s>>>(a, plan.N);
+            else if (a.batch <= 8) k_mac_batch<float, 2, 8, 2><<<blocks(2), 256, 0, s>>>(a, plan.N);
             else return cudaErrorInvalidValue;
         } else {
-            if (a.batch <= 2) k_mac_batch<double, 2><<<grid, 256, 0, s>>>(a, plan.N);
-            else if (a.batch <= 4) k_mac_batch<double, 4><<<grid, 256, 0, s>>>(a, plan.N);
+            if (a.batch <= 2) k_mac_batch<double, 2, 2, 2><<<blocks(2), 256, 0, s>>>(a, plan.N);
+            else if (a.batch <= 4) k_mac_batch<double, 1, 4, 2><<<blocks(1), 256, 0, s>>>(a, plan.N);
             else return cudaErrorInvalidValue;
         }
         return cudaGetLastError();

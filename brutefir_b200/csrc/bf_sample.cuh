@@ -19,7 +19,7 @@ namespace bf {
 // A sample of `bytes` bytes is moved as ONE access of its natural width when its address allows it
 // (the common interleaved / planar layouts of 2-, 4- and 8-byte formats do), otherwise byte by byte.
 // No arrays: everything stays in registers.
-BF_HD uint64_t load_raw_le(const uint8_t *p, int bytes)
+BF_HD_NOINLINE uint64_t load_raw_le(const uint8_t *p, int bytes)
 {
     const uintptr_t a = (uintptr_t)p;
     if (bytes == 4 && (a & 3) == 0) {
@@ -41,7 +41,7 @@ BF_HD uint64_t load_raw_le(const uint8_t *p, int bytes)
     return v;
 }
 
-BF_HD void store_raw_le(uint8_t *p, uint64_t v, int bytes)
+BF_HD_NOINLINE void store_raw_le(uint8_t *p, uint64_t v, int bytes)
 {
     const uintptr_t a = (uintptr_t)p;
     if (bytes == 4 && (a & 3) == 0) {
@@ -79,7 +79,7 @@ BF_HD uint64_t swap_bytes(uint64_t v, int bytes)
 
 // sample bits (as fetched by load_raw_le) -> real, unscaled
 template <typename T>
-BF_HD T decode_sample(uint64_t bits, int bytes, int isfloat, int swap)
+BF_HD_NOINLINE T decode_sample(uint64_t bits, int bytes, int isfloat, int swap)
 {
     if (swap && bytes > 1) {
         bits = swap_bytes(bits, bytes);
@@ -207,7 +207,7 @@ BF_HD void float_overflow_update(T v, T rmin, T rmax, QuantStats &s)
 // One output sample: test, quantise or copy, account; returns the sample's bytes as a little-endian word
 // (already byte-swapped for the _BE formats), ready for store_raw_le.
 template <typename T>
-BF_HD uint64_t encode_sample(T v, int bytes, int sbytes, int isfloat, int swap, double safety_limit, double of_max,
+BF_HD_NOINLINE uint64_t encode_sample(T v, int bytes, int sbytes, int isfloat, int swap, double safety_limit, double of_max,
                              QuantStats &s)
 {
     uint64_t bits;
