@@ -25,7 +25,7 @@
 #define BF_D __device__ __forceinline__
 // out-of-line on the device: the sample conversion routines are format-generic and large; inlining them at
 // every use made the fused FFT kernels 5-13 k instructions and instruction-fetch bound (ncu: 34 % no_inst)
-#define BF_HD_NOINLINE __host__ __device__ __noinline__
+#define BF_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define BF_HD inline
 #define BF_D inline

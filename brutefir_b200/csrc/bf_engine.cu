@@ -116,6 +116,7 @@ struct bfcuda_engine {
     int prev_par;               // which of the two `prev` buffers holds the last input block
     int last_batch;             // blocks in the most recent launch (layout of Y for debug_read)
     int n_ch[2], n_bytes[2];
+    int fast_fmt[2];            // uniform aligned 4-byte sample layout of all inputs / outputs (ForwardArgs::fast_fmt)
     int n_filters, n_coeffs;
     int device;
     unsigned int flags;
@@ -570,6 +571,16 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         e->n_ch[io] = c->n_channels[io];
         e->n_bytes[io] = c->n_bytes[io];
         e->fmt[io].assign(c->formats[io], c->formats[io] + c->n_channels[io]);
+        // the layouts every shipped config uses get compile-time paths in the FFT stages: all channels aligned
+        // 4-byte little-endian integers (S32_LE, S24_4LE) or all FLOAT_LE
+        int fast = e->n_ch[io] > 0 && e->n_bytes[io] % 4 == 0 ? (e->fmt[io][0].sf.isfloat ? 2 : 1) : 0;
+        for (const bfcuda_buffer_format &b : e->fmt[io]) {
+            if (b.sf.bytes != 4 || b.sf.swap || (b.byte_offset & 3) != 0 || (b.sf.isfloat ? 2 : 1) != fast ||
+                (!b.sf.isfloat && b.sf.sbytes != 3 && b.sf.sbytes != 4)) {
+                fast = 0;
+            }
+        }
+        e->fast_fmt[io] = fast;
     }
     e->filters.resize(e->n_filters);
     for (int f = 0; f < e->n_filters; f++) {
@@ -916,6 +927,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     fa.t = e->slot_t;
     fa.batch = nb;
     fa.in_stride = (size_t)e->n_bytes[0];
+    fa.fast_fmt = e->fast_fmt[0];
     CU(launch_forward(e->plan, fa, e->stream));
     e->prev_par ^= 1;
     e->launches += e->n_ch[0] > 0;
@@ -979,6 +991,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ia.batch = nb;
     ia.out_stride = (size_t)e->n_bytes[1];
     ia.safety_limit = e->safety_limit;
+    ia.fast_fmt = e->fast_fmt[1];
     CU(launch_inverse(e->plan, ia, e->s_inv));
     e->launches += e->n_ch[1] > 0;
     if (!e->shared_out.empty()) {

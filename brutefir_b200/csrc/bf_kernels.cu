@@ -20,6 +20,7 @@
 #include "bf_kernels.h"
 #include "bf_fft.cuh"
 #include "bf_sample.cuh"
+#include "bf_dev_utils.cuh"
 
 namespace bf {
 
@@ -41,6 +42,7 @@ cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize)
     plan->N = N;
     plan->realsize = realsize;
     plan->tw = nullptr;
+    plan->tw2 = nullptr;
     const int half = N / 2;
     cudaError_t err = cudaMalloc(&plan->tw, (size_t)N * realsize);
     if (err != cudaSuccess) {
@@ -66,7 +68,10 @@ cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize)
     } else {
         err = cudaMemcpy(plan->tw, td.data(), (size_t)N * 8, cudaMemcpyHostToDevice);
     }
-    return err;
+    if (err != cudaSuccess) {
+        return err;
+    }
+    return fft2_plan_create(plan);
 }
 
 void fft_plan_destroy(FftPlan *plan)
@@ -75,18 +80,15 @@ void fft_plan_destroy(FftPlan *plan)
         cudaFree(plan->tw);
         plan->tw = nullptr;
     }
+    if (plan->tw2 != nullptr) {
+        cudaFree(plan->tw2);
+        plan->tw2 = nullptr;
+    }
 }
 
 // ======================================================================================================
 // device building blocks
 // ======================================================================================================
-
-template <typename T>
-__device__ __forceinline__ T *smem_re()
-{
-    extern __shared__ __align__(16) unsigned char bf_smem_raw[];
-    return reinterpret_cast<T *>(bf_smem_raw);
-}
 
 // forward real transform of the frame already packed in (sre, sim); calls emit(k, re, im) for every
 // bin k in [0, M); the Nyquist value is passed as the imaginary part of bin 0 (planar convention).
@@ -149,56 +151,6 @@ __device__ __forceinline__ void load_and_inverse(T *sre, T *sim, const T *__rest
     }
     __syncthreads();
     fft_complex_inplace<T, E, true>(sre, sim, tw, M, tid, nt, BlockSync());
-}
-
-// the reference's blocked complex product for one bin: (re, im) = b (*) c with separate roundings
-// (fftw_convfuns.h:548-556 / convolver_xmm.c:25-30)
-template <typename T>
-__device__ __forceinline__ void cprod(T br, T bi, T cr, T ci, T &re, T &im)
-{
-    re = sub_rn(mul_rn(br, cr), mul_rn(bi, ci));
-    im = add_rn(mul_rn(br, ci), mul_rn(bi, cr));
-}
-
-// block-wide reduction of the quantiser statistics into overflow[o] / status
-__device__ __forceinline__ void reduce_stats(QuantStats st, Overflow *of, unsigned int *status, void *smem, int tid,
-                                             int nt)
-{
-    const unsigned full = 0xffffffffu;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        st.n_overflows += __shfl_down_sync(full, st.n_overflows, d);
-        st.intlargest = max(st.intlargest, __shfl_down_sync(full, st.intlargest, d));
-        st.largest = fmax(st.largest, __shfl_down_sync(full, st.largest, d));
-        st.status |= __shfl_down_sync(full, st.status, d);
-    }
-    QuantStats *w = reinterpret_cast<QuantStats *>(smem);
-    __syncthreads();        // shared memory is about to be reused
-    if ((tid & 31) == 0) {
-        w[tid >> 5] = st;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const int nw = (nt + 31) >> 5;
-        for (int i = 1; i < nw; i++) {
-            st.n_overflows += w[i].n_overflows;
-            st.intlargest = max(st.intlargest, w[i].intlargest);
-            st.largest = fmax(st.largest, w[i].largest);
-            st.status |= w[i].status;
-        }
-        // atomics: the blocks of one batch update the same output's counters concurrently (sum / max
-        // commute, so the result equals the reference's sequential running count / maximum)
-        if (st.n_overflows != 0) {
-            atomicAdd(&of->n_overflows, st.n_overflows);
-        }
-        atomicMax(&of->intlargest, st.intlargest);
-        // non-negative doubles order like their bit patterns
-        atomicMax(reinterpret_cast<unsigned long long *>(&of->largest),
-                  (unsigned long long)__double_as_longlong(st.largest));
-        if (st.status != 0) {
-            atomicOr(status, st.status);
-        }
-    }
 }
 
 // ======================================================================================================
@@ -650,55 +602,6 @@ __global__ void __launch_bounds__(256, MINB) k_mac_batch(MacArgs a, int N)
 // k_inverse
 // ======================================================================================================
 
-template <typename T> struct Vec2;
-template <> struct Vec2<float> {
-    typedef float2 type;
-    static __device__ __forceinline__ float2 make(float a, float b) { return make_float2(a, b); }
-};
-template <> struct Vec2<double> {
-    typedef double2 type;
-    static __device__ __forceinline__ double2 make(double a, double b) { return make_double2(a, b); }
-};
-
-template <typename T>
-__device__ __forceinline__ T xfade(T old, T nw, int n, int L);
-template <>
-__device__ __forceinline__ float xfade<float>(float old, float nw, int n, int L)
-{
-    // fftw_convolver.c:349-355, literally: f and f*n in float, the old term in double
-    const float f = (float)(1.0 / (double)(float)(L - 1));
-    const float fn = __fmul_rn(f, (float)n);
-    const double a = __dmul_rn((double)old, __dsub_rn(1.0, (double)fn));
-    const float b = __fmul_rn(__fmul_rn(nw, f), (float)n);
-    return (float)__dadd_rn(a, (double)b);
-}
-template <>
-__device__ __forceinline__ double xfade<double>(double old, double nw, int n, int L)
-{
-    // the float branch's formula in double (the reference's own double branch is broken)
-    const double d = 1.0 / (double)(L - 1);
-    const double a = __dmul_rn(old, __dsub_rn(1.0, __dmul_rn(d, (double)n)));
-    const double b = __dmul_rn(__dmul_rn(nw, d), (double)n);
-    return __dadd_rn(a, b);
-}
-
-template <typename T>
-__device__ __forceinline__ T mix_terms(const T *__restrict__ Y, const MixTerm *__restrict__ terms, int first, int n,
-                                       int n_slots, int split, int N, int i)
-{
-    T acc = (T)0;
-    for (int j = 0; j < n; j++) {
-        const MixTerm tm = terms[first + j];
-        T y = Y[(size_t)tm.index * N + i];
-        for (int z = 1; z < split; z++) {
-            y = add_rn(y, Y[((size_t)z * n_slots + tm.index) * N + i]);
-        }
-        const T v = mul_rn(y, (T)tm.scale);
-        acc = j == 0 ? v : add_rn(acc, v);
-    }
-    return acc;
-}
-
 template <typename T, int E>
 __global__ void __launch_bounds__(1024, 1) k_inverse(InverseArgs a, const T *__restrict__ tw, int L)
 {
@@ -1036,6 +939,7 @@ static bool fft_force16()
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
+    if (plan.tw2 != nullptr) return launch_forward2(plan, a, s);
     BF_FFT_DISPATCH(plan, k_forward, dim3(a.n_in, a.batch), s, a, (const T *)plan.tw, plan.N / 2);
 }
 
@@ -1052,6 +956,17 @@ cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaS
 }
 
 cudaError_t launch_mac_tma(const FftPlan &plan, const MacArgs &a, cudaStream_t s);   // bf_mac_tma.cu
+cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_t s); // bf_mac_batch.cu
+
+static bool mac_batch_v1()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BFCUDA_MAC_BATCH_V1");
+        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    }
+    return v == 1;
+}
 
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
@@ -1062,6 +977,9 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
     const int W = 16 / plan.realsize;
     const long threads = (long)a.n_jobs * (plan.N / 2 / W);
     dim3 grid((unsigned int)((threads + 255) / 256), a.split);
+    if (a.batch > 1 && !mac_batch_v1()) {
+        return launch_mac_batch2(plan, a, s);
+    }
     if (a.batch > 1) {
         // Instantiations: (lanes per thread W, batch B, resident blocks per SM).  Larger batches use narrower
         // vectors so that B accumulators + the B-slot window stay within 128 registers (2 blocks of 256
@@ -1092,6 +1010,7 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
+    if (plan.tw2 != nullptr) return launch_inverse2(plan, a, s);
     BF_FFT_DISPATCH(plan, k_inverse, dim3(a.n_out, a.batch), s, a, (const T *)plan.tw, plan.N / 2);
 }
 

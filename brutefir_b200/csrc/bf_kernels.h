@@ -56,9 +56,15 @@ struct FftPlan {
     int N;          // real length = 2 L
     int realsize;
     void *tw;       // device: N/2 complex roots e^{-2 pi i j / N}
+    void *tw2;      // device: per-pass tables of the size-specialised transform (bf_fft2.cuh), or NULL
 };
 
 cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize);
+// bf_fft2_kernels.cu: the size-specialised forward / inverse stages (float, 1024 <= L <= 16384)
+bool fft2_supported(int N, int realsize);
+cudaError_t fft2_plan_create(FftPlan *plan);
+cudaError_t launch_forward2(const FftPlan &plan, const struct ForwardArgs &a, cudaStream_t s);
+cudaError_t launch_inverse2(const FftPlan &plan, const struct InverseArgs &a, cudaStream_t s);
 void fft_plan_destroy(FftPlan *plan);
 bool fft_size_supported(int N, int realsize);
 
@@ -83,6 +89,7 @@ struct ForwardArgs {
     int t;
     int batch;
     size_t in_stride;
+    int fast_fmt;               // 1: every input is an aligned 4-byte LE integer, 2: FLOAT_LE, 0: per-sample generic decode
 };
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s);
 
@@ -129,6 +136,7 @@ struct InverseArgs {
     int batch;
     size_t out_stride;
     double safety_limit;
+    int fast_fmt;               // as ForwardArgs::fast_fmt, for the outputs
 };
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
 

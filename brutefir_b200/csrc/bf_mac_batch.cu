@@ -1,0 +1,295 @@
+// bf_mac_batch.cu -- the delay-line multiply-accumulate for B consecutive audio blocks per launch.
+//
+// Output block t+b needs  sum_i FDL[t+b-i] (*) H[i]  (/root/reference/bfrun.c:1737-1754 for every block of the
+// batch).  Walking the partitions i upwards with B accumulators, step i uses ONE coefficient vector H[i] for all B
+// blocks and the window FDL[t-i .. t-i+B-1], which differs from the previous step's window by one new slot.  So a
+// step moves two operand vectors (H[i] and the new delay-line slot, real and imaginary part each) for B complex
+// vector MACs instead of 2 B: the HBM traffic of a batch is rs*N*(P + (P+B-1) + B) per filter instead of
+// B*rs*N*(2P+1), while every output block still accumulates its partitions in ascending order with the reference's
+// separately rounded products and sums (convolver_xmm.c:25-30) -- bit-identical to B single-block launches.
+//
+// At B = 8 the kernel is no longer HBM-bound (0.5 -> ~3.8 flop/byte): what limits it is FP32 issue and, before
+// this version, exposed load latency (ncu: 62 % of the stall samples waiting on the two-steps-ahead register
+// prefetch).  Here every thread streams its operands through a private ring of S stages in shared memory with
+// cp.async (LDGSTS): S-1 steps of loads in flight per thread without holding registers, no block-wide barrier
+// (a thread only reads what it copied itself; cp.async.wait_group orders it).  The window lives in registers and is
+// rotated by unrolling the partition loop.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bf_kernels.h"
+#include "bf_sample.cuh"
+#include "bf_dev_utils.cuh"
+
+namespace bf {
+
+template <typename T, int W> struct VecB;
+template <> struct VecB<float, 4> { typedef float4 type; };
+template <> struct VecB<float, 2> { typedef float2 type; };
+template <> struct VecB<double, 2> { typedef double2 type; };
+template <> struct VecB<double, 1> { typedef double type; };
+
+template <typename T, int W>
+struct __align__(sizeof(T) * W) LanesB {
+    T v[W];
+};
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src)
+{
+    if (BYTES == 16) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N_PENDING>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N_PENDING) : "memory");
+}
+
+template <typename V>
+__device__ __forceinline__ V ldg_once(const V *p)
+{
+    return __ldg(p);
+}
+
+struct DcTrue { static constexpr bool value = true; };
+struct DcFalse { static constexpr bool value = false; };
+
+template <typename T, int W, int B, int S, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_mac_batch2(MacArgs a, int N)
+{
+    static_assert(S % B == 0, "the unrolled body must cover whole window rotations");
+    constexpr int VB = W * (int)sizeof(T);
+    typedef typename VecB<T, W>::type V;
+    typedef LanesB<T, W> L;
+    extern __shared__ __align__(16) unsigned char mac_ring[];
+    V *ring = reinterpret_cast<V *>(mac_ring) + threadIdx.x;       // [S][4][256] vectors, this thread's column
+    auto stage_ptr = [&](int stage, int op) -> V * { return ring + (stage * 4 + op) * 256; };
+
+    const int M = N >> 1;
+    const int vecs = M / W;
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long)a.n_jobs * vecs) {
+        return;
+    }
+    const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
+    const MacJob jb = a.jobs[job];
+    const int z = blockIdx.y;
+    const int R = a.ring;
+    const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * R * N + (size_t)v * W;
+    auto xslot = [&](int s) -> const T * {      // s in (-R, 2R)
+        s += (s < 0) ? R : 0;
+        s -= (s >= R) ? R : 0;
+        return X + (size_t)s * N;
+    };
+
+    L are[B], aim[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+#pragma unroll
+        for (int l = 0; l < W; l++) {
+            are[b].v[l] = (T)0;
+            aim[b].v[l] = (T)0;
+        }
+    }
+
+    if (jb.hbase < 0) {
+        // coeff = -1: unit pulse in the shifted-coefficient convention = (+1/N, -1/N, ...) per bin
+        // (fftw_convfuns.h:606-619)
+        if (z == 0) {
+            const T fr = (T)(1.0 / (T)N);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                if (b < a.batch) {
+                    const T *xp = xslot(a.t + b);
+                    const V xr = ldg_once(reinterpret_cast<const V *>(xp));
+                    const V xi = ldg_once(reinterpret_cast<const V *>(xp + M));
+                    const L lr = *reinterpret_cast<const L *>(&xr), li = *reinterpret_cast<const L *>(&xi);
+#pragma unroll
+                    for (int l = 0; l < W; l++) {
+                        const T s = ((v * W + l) & 1) ? -fr : fr;     // sign by bin parity
+                        are[b].v[l] = mul_rn(lr.v[l], s);
+                        aim[b].v[l] = mul_rn(li.v[l], s);
+                    }
+                }
+            }
+        }
+    } else {
+        const int chunk = (jb.n_parts + a.split - 1) / a.split;
+        const int i0 = z * chunk;
+        const int i1 = min(jb.n_parts, i0 + chunk);
+        const int n = i1 - i0;                  // steps of this thread
+        const T *H = reinterpret_cast<const T *>(a.H) + ((size_t)jb.hbase + i0) * N + (size_t)v * W;
+        T dc[B], ny[B];
+        V wr[B], wi[B];         // window: logical block b of step j sits in physical slot (b - j) mod B
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            dc[b] = (T)0;
+            ny[b] = (T)0;
+        }
+        if (n > 0) {
+            // producer state: the next step to request
+            const T *hnext = H;
+            int xs = a.t - i0;                  // ring slot of step j's new delay-line block, j = 0 (not loaded: in the window)
+            xs += (xs < 0) ? R : 0;
+            int jn = 0;
+            auto issue = [&](int stage) {       // request step jn into `stage`; always closes a group
+                if (jn < n) {
+                    cp_async<VB>(stage_ptr(stage, 0), hnext);
+                    cp_async<VB>(stage_ptr(stage, 1), hnext + M);
+                    if (jn > 0) {
+                        const T *xp = X + (size_t)xs * N;
+                        cp_async<VB>(stage_ptr(stage, 2), xp);
+                        cp_async<VB>(stage_ptr(stage, 3), xp + M);
+                    }
+                }
+                cp_async_commit();
+                hnext += N;
+                xs = xs == 0 ? R - 1 : xs - 1;
+                jn++;
+            };
+#pragma unroll
+            for (int st = 0; st < S - 1; st++) {
+                issue(st);
+            }
+            // the initial window (blocks t .. t+B-1 against partition i0) straight into registers
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const T *xp = xslot(a.t + b - i0);
+                wr[b] = ldg_once(reinterpret_cast<const V *>(xp));
+                wi[b] = ldg_once(reinterpret_cast<const V *>(xp + M));
+            }
+            // DC and Nyquist ride in lane 0 of the job's first vector and are REAL products (fftw_convfuns.h:546-547):
+            // only the warp that holds that vector carries the two extra accumulators through the loop.
+            const bool has0 = __any_sync(__activemask(), v == 0);
+            auto body = [&](auto dcny_tag) {
+                constexpr bool DCNY = decltype(dcny_tag)::value;
+                {
+                    // step 0: convolver_convolve, a plain product (peeled so that the main loop carries no
+                    // assign/accumulate branch)
+                    cp_async_wait<S - 2>();
+                    const V hr = *stage_ptr(0, 0), hi = *stage_ptr(0, 1);
+                    issue(S - 1);
+                    const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        const L br = *reinterpret_cast<const L *>(&wr[b]), bi = *reinterpret_cast<const L *>(&wi[b]);
+#pragma unroll
+                        for (int l = 0; l < W; l++) {
+                            cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], are[b].v[l], aim[b].v[l]);
+                        }
+                        if (DCNY) {
+                            dc[b] = mul_rn(br.v[0], cr.v[0]);
+                            ny[b] = mul_rn(bi.v[0], ci.v[0]);
+                        }
+                    }
+                }
+                // remaining steps: convolver_convolve_add.  Step j = base + k has ring stage j % S = (k + 1) % S and
+                // window rotation u = j % B = (k + 1) % B: compile-time constants because base = 1 (mod S).
+                for (int base = 1; base < n; base += S) {
+#pragma unroll
+                    for (int k = 0; k < S; k++) {
+                        const int j = base + k;
+                        if (j < n) {
+                            const int stage = (k + 1) % S;
+                            const int u = (k + 1) % B;
+                            cp_async_wait<S - 2>();
+                            const V hr = *stage_ptr(stage, 0), hi = *stage_ptr(stage, 1);
+                            // the block that left the window makes room for the new oldest-partition slot
+                            wr[(B - u) % B] = *stage_ptr(stage, 2);
+                            wi[(B - u) % B] = *stage_ptr(stage, 3);
+                            issue(k % S);       // stage (j + S - 1) % S = the one consumed by the previous step
+                            const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
+#pragma unroll
+                            for (int b = 0; b < B; b++) {
+                                const L br = *reinterpret_cast<const L *>(&wr[(b - u + B) % B]);
+                                const L bi = *reinterpret_cast<const L *>(&wi[(b - u + B) % B]);
+#pragma unroll
+                                for (int l = 0; l < W; l++) {
+                                    T re, im;
+                                    cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], re, im);
+                                    are[b].v[l] = add_rn(are[b].v[l], re);
+                                    aim[b].v[l] = add_rn(aim[b].v[l], im);
+                                }
+                                if (DCNY) {
+                                    dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
+                                    ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
+                                }
+                            }
+                        }
+                    }
+                }
+            };
+            if (has0) {
+                body(DcTrue());
+            } else {
+                body(DcFalse());
+            }
+            cp_async_wait<0>();
+        }
+        if (v == 0) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                are[b].v[0] = dc[b];
+                aim[b].v[0] = ny[b];
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+        if (b < a.batch) {
+            T *out = reinterpret_cast<T *>(a.Y) + (((size_t)z * a.batch + b) * a.n_slots + jb.out) * N + (size_t)v * W;
+            *reinterpret_cast<V *>(out) = *reinterpret_cast<V *>(&are[b]);
+            *reinterpret_cast<V *>(out + M) = *reinterpret_cast<V *>(&aim[b]);
+        }
+    }
+}
+
+template <typename T, int W, int B, int S>
+static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
+{
+    constexpr size_t smem = (size_t)S * 4 * 256 * W * sizeof(T);
+    static bool configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        if (dev >= 0 && dev < 64) {
+            configured[dev] = true;
+        }
+    }
+    const long threads = (long)a.n_jobs * (N / 2 / W);
+    dim3 grid((unsigned int)((threads + 255) / 256), a.split);
+    k_mac_batch2<T, W, B, S, 2><<<grid, 256, smem, s>>>(a, N);
+    return cudaGetLastError();
+}
+
+// Instantiations: (lanes per thread W, batch B, ring stages S).  Larger batches use narrower vectors so that
+// B accumulators + the B-slot window stay within 128 registers (2 blocks of 256 threads per SM).  A batch smaller
+// than B leaves the surplus accumulators unused (their window slots are still read, always inside the ring).
+cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
+{
+    if (plan.realsize == 4) {
+        if (a.batch <= 2) return launch_one<float, 4, 2, 4>(a, plan.N, s);
+        if (a.batch <= 4) return launch_one<float, 4, 4, 4>(a, plan.N, s);
+        if (a.batch <= 8) return launch_one<float, 2, 8, 8>(a, plan.N, s);
+        return cudaErrorInvalidValue;
+    }
+    if (a.batch <= 2) return launch_one<double, 2, 2, 4>(a, plan.N, s);
+    if (a.batch <= 4) return launch_one<double, 1, 4, 8>(a, plan.N, s);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace bf

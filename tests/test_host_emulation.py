@@ -25,6 +25,14 @@ def test_device_fft_on_host(tmp_path):
     assert "FAIL" not in r.stdout and r.stdout.count("ok") >= 25
 
 
+def test_device_fft2_on_host(tmp_path):
+    """The size-specialised FFT core (bf_fft2.cuh): all five sizes, forward / inverse / registers-only last pass,
+    and the bank-conflict check of every shared-memory access pattern."""
+    r = build_and_run(tmp_path, "emul_fft2.cpp", [])
+    assert r.returncode == 0, r.stdout
+    assert "FAIL" not in r.stdout and r.stdout.count("ok") == 14
+
+
 def test_device_sample_conversion_on_host(tmp_path, oracle_libs):
     objs = tmp_path / "orc.o"
     shim = tmp_path / "shim.o"
