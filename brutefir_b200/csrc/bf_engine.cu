@@ -140,6 +140,9 @@ struct bfcuda_engine {
     uint8_t *d_raw2[2];         // second buffers of the streaming interface
     SampleFormat *d_fmt[2];
     void *d_prev[2], *d_fdl, *d_xin, *d_H, *d_Y, *d_out_time, *d_scratch;
+    void *d_xt[2];              // size-specialised path: unpacked input blocks [max_batch][n_in][L], two generations
+    int xt_par, xt_last_nb;     // generation holding the most recent launch's blocks, and how many it holds
+    bool single_dest, simple_mix;   // ForwardArgs::single_dest / InverseArgs::simple_mix of the current tables
     Overflow *d_overflow;
     unsigned int *d_status;
     unsigned int *h_status;     // pinned
@@ -345,6 +348,14 @@ static void build_tables(bfcuda_engine *e)
     // job, and writes B outputs per job
     const size_t Bm = (size_t)e->max_batch;
     e->mac_bytes_batch = (size_t)e->rs * e->N * (blocks_h + blocks_x + e->h_jobs.size() * (Bm - 1) + e->h_jobs.size() * Bm);
+    e->single_dest = !(e->flags & 4u) && e->h_mix_streams.empty();
+    for (int c = 0; c < e->n_ch[0]; c++) {
+        e->single_dest = e->single_dest && per_ch[c].size() == 1;
+    }
+    e->simple_mix = e->split == 1 && !e->xfade_active;
+    for (int o = 0; o < e->n_ch[1]; o++) {
+        e->simple_mix = e->simple_mix && e->h_chans[o].n == 1;
+    }
     e->dirty = false;
 }
 
@@ -417,7 +428,7 @@ void bfcuda_destroy(bfcuda_engine *e)
     if (e->comm != nullptr && g_nccl.handle != nullptr) {
         g_nccl.CommDestroy(e->comm);
     }
-    void *ptrs[] = { e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
+    void *ptrs[] = { e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms };
     for (void *p : ptrs) {
@@ -528,6 +539,10 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->max_batch = c->max_batch < 1 ? 1 : c->max_batch;
     e->fdl_ring = e->P + e->max_batch - 1;
     e->slot_t = 0;
+    e->d_xt[0] = e->d_xt[1] = nullptr;
+    e->xt_par = 0;
+    e->xt_last_nb = 1;
+    e->single_dest = e->simple_mix = false;
     e->prev_par = 0;
     e->last_batch = 1;
     e->device = c->device;
@@ -650,6 +665,10 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         TRY(dev_alloc(e, &e->d_fmt[1], sizeof(SampleFormat) * std::max(1, e->n_ch[1])));
         TRY(dev_alloc(e, &e->d_prev[0], rs_bytes(e, (size_t)e->n_ch[0] * L)));
         TRY(dev_alloc(e, &e->d_prev[1], rs_bytes(e, (size_t)e->n_ch[0] * L)));
+        if (e->plan.tw2 != nullptr) {
+            TRY(dev_alloc(e, &e->d_xt[0], rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * L)));
+            TRY(dev_alloc(e, &e->d_xt[1], rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * L)));
+        }
         TRY(dev_alloc(e, &e->d_fdl, rs_bytes(e, F * (size_t)e->fdl_ring * N)));
         TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * N)));
         TRY(dev_alloc(e, &e->d_H, rs_bytes(e, (size_t)std::max(1, e->total_coeff_blocks) * N)));
@@ -928,6 +947,27 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     fa.batch = nb;
     fa.in_stride = (size_t)e->n_bytes[0];
     fa.fast_fmt = e->fast_fmt[0];
+    fa.xt_cur = fa.xt_prev = nullptr;
+    fa.single_dest = e->single_dest ? 1 : 0;
+    if (e->plan.tw2 != nullptr) {
+        // size-specialised path: unpack the raw blocks into planar reals first (raw2real), transforms read those
+        e->xt_par ^= 1;
+        UnpackArgs ua;
+        ua.raw_in = raw_in;
+        ua.fmt = e->d_fmt[0];
+        ua.xt = e->d_xt[e->xt_par];
+        ua.n_in = e->n_ch[0];
+        ua.batch = nb;
+        ua.L = e->L;
+        ua.in_stride = (size_t)e->n_bytes[0];
+        ua.fast_fmt = e->fast_fmt[0];
+        CU(launch_unpack(e->plan, ua, e->stream));
+        e->launches += e->n_ch[0] > 0;
+        fa.xt_cur = e->d_xt[e->xt_par];
+        fa.xt_prev = (const char *)e->d_xt[e->xt_par ^ 1] +
+                     rs_bytes(e, (size_t)(e->xt_last_nb - 1) * e->n_ch[0] * e->L);
+        e->xt_last_nb = nb;
+    }
     CU(launch_forward(e->plan, fa, e->stream));
     e->prev_par ^= 1;
     e->launches += e->n_ch[0] > 0;
@@ -992,12 +1032,14 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ia.out_stride = (size_t)e->n_bytes[1];
     ia.safety_limit = e->safety_limit;
     ia.fast_fmt = e->fast_fmt[1];
+    ia.simple_mix = e->simple_mix ? 1 : 0;
     CU(launch_inverse(e->plan, ia, e->s_inv));
     e->launches += e->n_ch[1] > 0;
-    if (!e->shared_out.empty()) {
+    const bool pack_all = e->plan.tw2 != nullptr;   // size-specialised path: real2raw is a kernel of its own
+    if (!e->shared_out.empty() || pack_all) {
         // outputs fed from several ranks: sum the L valid time-domain samples over NVLink, then quantise
         // (after the inverse FFT, before real2raw)
-        if (e->comm != nullptr) {
+        if (e->comm != nullptr && !e->shared_out.empty()) {
             const int dtype = e->rs == 4 ? 7 /* ncclFloat32 */ : 8 /* ncclFloat64 */;
             g_nccl.GroupStart();
             for (int b = 0; b < nb; b++) {
@@ -1013,7 +1055,11 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
             }
             g_nccl.GroupEnd();
         }
-        CU(launch_quantise_shared(e->plan, ia, e->s_inv));
+        if (pack_all) {
+            CU(launch_pack(e->plan, ia, e->s_inv));
+        } else {
+            CU(launch_quantise_shared(e->plan, ia, e->s_inv));
+        }
         e->launches++;
     }
     if (timing) {
@@ -1307,7 +1353,8 @@ int bfcuda_get_info(bfcuda_engine *e, struct bfcuda_info *info)
     info->n_fft = e->N;
     info->mac_split = e->split;
     info->n_streams = e->n_filters;
-    info->kernels_per_block = 3 + (e->h_mix_streams.empty() ? 0 : 1) + (e->shared_out.empty() ? 0 : 1);
+    info->kernels_per_block = 3 + (e->h_mix_streams.empty() ? 0 : 1) +
+                              (e->plan.tw2 != nullptr ? 2 : (e->shared_out.empty() ? 0 : 1));
     info->uses_graph = 0;
     info->max_batch = e->max_batch;
     info->mac_bytes_per_batch = e->mac_bytes_batch;

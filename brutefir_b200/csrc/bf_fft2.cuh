@@ -397,4 +397,60 @@ BF_D void fft2_merge_load(cpx<T> *s, const cpx<T> *tw, int tid, Load load)
     }
 }
 
+// The same in two halves, so that the loads of the NEXT transform can be in flight while the current one finishes:
+// fetch the 32 spectrum values this thread merges (x[4b .. 4b+3] = S[k], S[M+k], S[M-k], S[2M-k], k = tid + b NT;
+// thread 0's first group is S[0], S[M], S[M/2], S[M + M/2]) ...
+template <typename T, int LOG2M, typename Load>
+BF_D void fft2_merge_fetch(int tid, T *x, Load load)
+{
+    typedef Fft2<LOG2M> F;
+    constexpr int M = F::M;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const int k = tid + b * F::NT;
+        if (b == 0 && tid == 0) {
+            x[0] = load(0);
+            x[1] = load(M);
+            x[2] = load(M / 2);
+            x[3] = load(M + M / 2);
+        } else {
+            x[4 * b] = load(k);
+            x[4 * b + 1] = load(M + k);
+            x[4 * b + 2] = load(M - k);
+            x[4 * b + 3] = load(2 * M - k);
+        }
+    }
+}
+
+// ... and merge them into shared memory.
+template <typename T, int LOG2M>
+BF_D void fft2_merge_store(cpx<T> *s, const cpx<T> *tw, int tid, const T *x)
+{
+    typedef Fft2<LOG2M> F;
+    constexpr int M = F::M;
+    const cpx<T> *ts = tw + F::TW_SPLIT;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const int k = tid + b * F::NT;
+        if (b == 0 && tid == 0) {
+            cpx<T> z;
+            z.x = x[0] + x[1];
+            z.y = x[0] - x[1];
+            s[0] = z;
+            const cpx<T> w = ts[M / 2];
+            T zkr, zki, zmr, zmi;
+            fft_merge_pair<T>(x[2], x[3], x[2], x[3], w.x, w.y, zkr, zki, zmr, zmi);
+            z.x = zkr;
+            z.y = zki;
+            s[M / 2] = z;
+        } else {
+            const cpx<T> w = ts[k];
+            cpx<T> zk, zm;
+            fft_merge_pair<T>(x[4 * b], x[4 * b + 1], x[4 * b + 2], x[4 * b + 3], w.x, w.y, zk.x, zk.y, zm.x, zm.y);
+            s[k] = zk;
+            s[M - k] = zm;
+        }
+    }
+}
+
 }  // namespace bf

@@ -1,9 +1,11 @@
 // bf_fft2_kernels.cu -- the forward and inverse stages on the size-specialised FFT core (bf_fft2.cuh).
 //
-//   k_forward2   raw2real + frame assembly + R2HC + input scale into the delay line
-//                (K1..K3; /root/reference/bfrun.c:1494-1560, 1671; fftw_convolver.c:170-214; raw2real.h)
-//   k_inverse2   output mix + HC2R + overlap-save discard + crossfade + real2raw
-//                (K6..K9; bfrun.c:1847-1936; fftw_convolver.c:330-368, 391-409, 482-518; real2raw.h)
+//   k_unpack     raw2real: raw PCM block -> planar reals (K1; /root/reference/raw2real.h, fftw_convolver.c:170-194)
+//   k_forward2   frame assembly + R2HC + input scale into the delay line
+//                (K2, K3; bfrun.c:1494-1560, 1671; fftw_convolver.c:180-214)
+//   k_inverse2   output mix + HC2R + overlap-save discard + crossfade
+//                (K6..K8; bfrun.c:1847-1936; fftw_convolver.c:330-368, 391-409)
+//   k_pack       real2raw: planar reals -> raw PCM block, overflow accounting (K9; real2raw.h, fftw_convolver.c:482-518)
 //
 // Same results contract as k_forward / k_inverse in bf_kernels.cu (which stay as the path for float_bits 64 and
 // for partitions shorter than 1024 samples); what changes is the cost:
@@ -12,9 +14,9 @@
 //   * forward: the first radix-16 pass reads its samples straight from the raw block / the previous-block buffer;
 //   * inverse: the last pass leaves its results in registers -- only the L valid samples of the overlap-save
 //     frame are produced -- and the crossfade / quantise / pack epilogue consumes them there;
-//   * sample formats: the two layouts every shipped config uses (aligned 4-byte little-endian integers --
-//     S32_LE and S24_4LE -- and FLOAT_LE) are compile-time fast paths; everything else takes the generic
-//     per-sample routines of bf_sample.cuh.
+//   * sample conversion lives in two transposing kernels (k_unpack before the forward stage, k_pack after the
+//     inverse one), so the transforms read and write planar reals with fully coalesced accesses; the next
+//     transform's operands are fetched while the current one's results are stored.
 // Roofline: per transform N*4 bytes of spectrum + L*bytes of samples; ~2.5 N log2 N flop.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -27,8 +29,6 @@
 #include "bf_dev_utils.cuh"
 
 namespace bf {
-
-enum { FMT_GENERIC = 0, FMT_INT32LE = 1, FMT_FLOAT32LE = 2 };
 
 struct BlockSync2 {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -78,93 +78,207 @@ __device__ __forceinline__ void wait_twiddles(unsigned char *smem)
     }
 }
 
-// two consecutive samples n, n + 1 of one channel of a raw block -> complex (raw2real.h:7-160; integers unscaled)
-template <int FMT>
-__device__ __forceinline__ cpx<float> load_pair(const uint8_t *chan_base, size_t stride, int n, const SampleFormat &f)
+// ======================================================================================================
+// k_unpack / k_pack -- raw PCM <-> planar reals, transposed through shared memory
+//
+// The dai block layouts interleave the channels (dai.c:537-576: byte_offset = channel * bytes, sample_spacing =
+// channels), so the samples of ONE channel are a 4-byte access every 256 bytes at the headline shape: a transform
+// reading them directly touches 8192 sectors for 32 KB of payload and the LSU serialises every warp access into 32
+// requests (ncu: the forward stage spent ~half its time there).  These two kernels do the layout change at full
+// coalescing instead: a warp moves a 32 channel x 32 sample tile, lanes along the channels on the raw side and
+// along time on the planar side.  They also carry the whole sample conversion (raw2real.h / real2raw.h), so the
+// transforms themselves are format-free.
+// ======================================================================================================
+
+template <typename T> struct TileWarps { static constexpr int value = sizeof(T) == 4 ? 8 : 4; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_unpack(UnpackArgs a)
 {
-    cpx<float> z;
-    const uint8_t *p = chan_base + (size_t)n * stride;
-    if (FMT == FMT_INT32LE) {
-        z.x = (float)*reinterpret_cast<const int32_t *>(p);
-        z.y = (float)*reinterpret_cast<const int32_t *>(p + stride);
-    } else if (FMT == FMT_FLOAT32LE) {
-        z.x = *reinterpret_cast<const float *>(p);
-        z.y = *reinterpret_cast<const float *>(p + stride);
-    } else {
-        z.x = decode_sample<float>(load_raw_le(p, f.bytes), f.bytes, f.isfloat, f.swap);
-        z.y = decode_sample<float>(load_raw_le(p + stride, f.bytes), f.bytes, f.isfloat, f.swap);
+    constexpr int WPB = TileWarps<T>::value;
+    __shared__ T tile[WPB][32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n0 = (blockIdx.x * WPB + w) * 32, c0 = blockIdx.y * 32, blk = blockIdx.z;
+    if (n0 >= a.L) {
+        return;
     }
-    return z;
+    const uint8_t *raw = a.raw_in + (size_t)blk * a.in_stride;
+    {
+        const int c = c0 + lane;
+        if (c < a.n_in) {
+            const SampleFormat f = a.fmt[c];
+            const size_t stride = (size_t)f.sample_spacing * f.bytes;
+            const uint8_t *p = raw + f.byte_offset + (size_t)n0 * stride;
+            if (a.fast_fmt == 1) {
+#pragma unroll 8
+                for (int r = 0; r < 32; r++) {
+                    tile[w][r][lane] = (T)*reinterpret_cast<const int32_t *>(p + r * stride);
+                }
+            } else if (a.fast_fmt == 2) {
+#pragma unroll 8
+                for (int r = 0; r < 32; r++) {
+                    tile[w][r][lane] = (T)*reinterpret_cast<const float *>(p + r * stride);
+                }
+            } else {
+                for (int r = 0; r < 32; r++) {
+                    tile[w][r][lane] = decode_sample<T>(load_raw_le(p + r * stride, f.bytes), f.bytes, f.isfloat, f.swap);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    T *xt = reinterpret_cast<T *>(a.xt) + ((size_t)blk * a.n_in + c0) * a.L + n0 + lane;
+    const int nc = min(32, a.n_in - c0);
+    for (int r = 0; r < nc; r++) {
+        xt[(size_t)r * a.L] = tile[w][lane][r];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack(InverseArgs a, int L)
+{
+    constexpr int WPB = TileWarps<T>::value;
+    __shared__ T tile[WPB][32][33];
+    __shared__ QuantStats wstats[WPB][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n0 = (blockIdx.x * WPB + w) * 32, c0 = blockIdx.y * 32, blk = blockIdx.z;
+    const int nc = min(32, a.n_out - c0);
+    QuantStats st;
+    quant_stats_init(st);
+    if (n0 < L) {
+        const T *src = reinterpret_cast<const T *>(a.out_time) + ((size_t)blk * a.n_out + c0) * L + n0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            if (r < nc) {
+                tile[w][r][lane] = src[(size_t)r * L];
+            }
+        }
+        __syncwarp();
+        const int c = c0 + lane;
+        if (c < a.n_out) {
+            const SampleFormat f = a.fmt[c];
+            const size_t stride = (size_t)f.sample_spacing * f.bytes;
+            uint8_t *p = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset + (size_t)n0 * stride;
+            const double of_max = a.overflow[c].max;
+            if (a.fast_fmt == 1) {
+                const int bits_n = f.sbytes << 3;
+                const int32_t imin = (int32_t)(-((uint64_t)1 << (bits_n - 1)));
+                const int32_t imax = (int32_t)(((uint64_t)1 << (bits_n - 1)) - 1);
+                const double rmin = (double)(T)imin, rmax = (double)(T)imax;
+#pragma unroll 4
+                for (int r = 0; r < 32; r++) {
+                    const T y = tile[w][lane][r];
+                    sample_test<T>(y, a.safety_limit, of_max, st);
+                    *reinterpret_cast<int32_t *>(p + r * stride) = real_to_int<T>(y, rmin, rmax, imin, imax, st);
+                }
+            } else if (a.fast_fmt == 2) {
+#pragma unroll 4
+                for (int r = 0; r < 32; r++) {
+                    const T y = tile[w][lane][r];
+                    sample_test<T>(y, a.safety_limit, of_max, st);
+                    float_overflow_update<T>(y, (T)-of_max, (T)of_max, st);
+                    *reinterpret_cast<float *>(p + r * stride) = (float)y;
+                }
+            } else {
+                for (int r = 0; r < 32; r++) {
+                    const T y = tile[w][lane][r];
+                    store_raw_le(p + r * stride,
+                                 encode_sample<T>(y, f.bytes, f.sbytes, f.isfloat, f.swap, a.safety_limit, of_max, st),
+                                 f.bytes);
+                }
+            }
+        }
+    }
+    // the eight warps of a block hold the same 32 channels: combine, then one set of atomics per channel -- and
+    // only where the block actually raises a maximum / counted something (sum and max commute, so the totals equal
+    // the reference's sequential running count and maxima, real2raw.h:44-59, dither_funs.h:70-114)
+    wstats[w][lane] = st;
+    __syncthreads();
+    if (w == 0 && c0 + lane < a.n_out) {
+#pragma unroll
+        for (int i = 1; i < WPB; i++) {
+            const QuantStats o = wstats[i][lane];
+            st.n_overflows += o.n_overflows;
+            st.intlargest = max(st.intlargest, o.intlargest);
+            st.largest = fmax(st.largest, o.largest);
+            st.status |= o.status;
+        }
+        Overflow *of = &a.overflow[c0 + lane];
+        if (st.n_overflows != 0) {
+            atomicAdd(&of->n_overflows, st.n_overflows);
+        }
+        if (st.intlargest > of->intlargest) {
+            atomicMax(&of->intlargest, st.intlargest);
+        }
+        if (st.largest > of->largest) {
+            // non-negative doubles order like their bit patterns
+            atomicMax(reinterpret_cast<unsigned long long *>(&of->largest),
+                      (unsigned long long)__double_as_longlong(st.largest));
+        }
+        if (st.status != 0) {
+            atomicOr(a.status, st.status);
+        }
+    }
 }
 
 // ======================================================================================================
 // k_forward2
 // ======================================================================================================
 
-template <int LOG2M, int FMT, bool TWS>
+// frame = [previous block | this block] (fftw_convolver.c:180-193) packed as z_i = x_2i + i x_2i+1; a thread's
+// first-pass butterfly takes z[tid + q NT]: q < 8 lies in the previous block, q >= 8 in this one.
+template <int LOG2M>
+__device__ __forceinline__ void load_frame(const ForwardArgs &a, int item, int tid, cpx<float> *v)
+{
+    typedef Fft2<LOG2M> F;
+    constexpr int L = F::M, NT = F::NT;
+    const int c = item % a.n_in, blk = item / a.n_in;
+    const float *cur = reinterpret_cast<const float *>(a.xt_cur) + ((size_t)blk * a.n_in + c) * L;
+    const float *old = blk == 0 ? reinterpret_cast<const float *>(a.xt_prev) + (size_t)c * L
+                                : cur - (size_t)a.n_in * L;
+    const cpx<float> *po = reinterpret_cast<const cpx<float> *>(old), *pc = reinterpret_cast<const cpx<float> *>(cur);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        v[q] = po[tid + q * NT];
+        v[8 + q] = pc[tid + q * NT];
+    }
+}
+
+template <int LOG2M, bool SINGLE, bool TWS>
 __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_forward2(ForwardArgs a, const cpx<float> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
-    constexpr int M = F::M, L = F::M, N = 2 * F::M, NT = F::NT;
+    constexpr int M = F::M, N = 2 * F::M;
+    constexpr bool PREFETCH = F::NT < 1024;     // 1024 threads leave 64 registers: no room to hold the next frame
     extern __shared__ __align__(128) unsigned char smem2[];
     cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2);
     const int tid = threadIdx.x;
     const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, tid);
     const int total = a.n_in * a.batch;
-    bool first = true;
+    float *fdl = reinterpret_cast<float *>(a.fdl);
+    const int ring = a.ring;
 
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    cpx<float> v[16];
+    int item = blockIdx.x;
+    if (item < total) {
+        load_frame<LOG2M>(a, item, tid, v);
+    }
+    wait_twiddles<LOG2M, TWS>(smem2);
+    for (; item < total; item += gridDim.x) {
         const int c = item % a.n_in, blk = item / a.n_in;
-        const SampleFormat f = a.fmt[c];
-        const size_t stride = (size_t)f.sample_spacing * f.bytes;
-        const uint8_t *raw = a.raw_in + (size_t)blk * a.in_stride + f.byte_offset;
-        const bool last = blk == a.batch - 1;
-
-        // frame = [previous block | this block] (fftw_convolver.c:180-193) packed as z_i = x_2i + i x_2i+1; this
-        // thread's first-pass butterfly takes z[tid + q NT]: q < 8 lies in the previous block, q >= 8 in this one.
-        cpx<float> v[16];
-        if (blk == 0) {
-            const cpx<float> *pv = reinterpret_cast<const cpx<float> *>(reinterpret_cast<const float *>(a.prev_in) +
-                                                                         (size_t)c * L);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                v[q] = pv[tid + q * NT];
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                v[q] = load_pair<FMT>(raw - a.in_stride, stride, 2 * (tid + q * NT), f);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            v[8 + q] = load_pair<FMT>(raw, stride, 2 * (tid + q * NT), f);
-        }
-        if (last) {
-            cpx<float> *po = reinterpret_cast<cpx<float> *>(reinterpret_cast<float *>(a.prev_out) + (size_t)c * L);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                po[tid + q * NT] = v[8 + q];
-            }
-        }
-        if (first) {
-            wait_twiddles<LOG2M, TWS>(smem2);
-            first = false;
-        } else {
-            __syncthreads();        // the previous transform's split phase has finished reading shared memory
+        if (!PREFETCH && item != (int)blockIdx.x) {
+            load_frame<LOG2M>(a, item, tid, v);
         }
         fft2_complex<float, LOG2M, false, false>(s, tw, tid, v, BlockSync2());
-
+        // the next transform's samples travel while this one's spectrum is split and stored
+        if (PREFETCH && item + (int)gridDim.x < total) {
+            load_frame<LOG2M>(a, item + gridDim.x, tid, v);
+        }
         const int d0 = a.dest_first[c], d1 = a.dest_first[c + 1];
-        float *xin = (a.xin != nullptr && a.need_xin[c])
-                         ? reinterpret_cast<float *>(a.xin) + ((size_t)blk * a.n_in + c) * N : nullptr;
-        float *fdl = reinterpret_cast<float *>(a.fdl);
-        const FwdDest *dests = a.dests;
-        const int ring = a.ring;
         const int t = a.t + blk;
-        if (d1 - d0 == 1 && xin == nullptr) {
-            // the usual case, one filter per input: one destination, hoisted out of the bin loop
-            const FwdDest ds = dests[d0];
+        if (SINGLE) {
+            // one filter per input: one destination, hoisted out of the bin loop
+            const FwdDest ds = a.dests[d0];
             float *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
             const float sc = (float)ds.scale;
             fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
@@ -172,6 +286,9 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_forward2(ForwardArgs a, 
                 dst[M + k] = mul_rn(im, sc);
             });
         } else {
+            float *xin = (a.xin != nullptr && a.need_xin[c])
+                             ? reinterpret_cast<float *>(a.xin) + ((size_t)blk * a.n_in + c) * N : nullptr;
+            const FwdDest *dests = a.dests;
             fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
                 if (xin != nullptr) {
                     xin[k] = re;
@@ -186,6 +303,7 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_forward2(ForwardArgs a, 
                 }
             });
         }
+        __syncthreads();        // the split phase has finished reading shared memory
     }
 }
 
@@ -193,66 +311,69 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_forward2(ForwardArgs a, 
 // k_inverse2
 // ======================================================================================================
 
-// one output sample: test, quantise or copy, account, store (real2raw.h:61-251, dither_funs.h:70-114)
-template <int FMT>
-__device__ __forceinline__ void store_sample(float y, uint8_t *p, const SampleFormat &f, double safety_limit,
-                                             double of_max, double rmin, double rmax, int32_t imin, int32_t imax,
-                                             QuantStats &st)
-{
-    if (FMT == FMT_INT32LE) {
-        sample_test<float>(y, safety_limit, of_max, st);
-        *reinterpret_cast<int32_t *>(p) = real_to_int<float>(y, rmin, rmax, imin, imax, st);
-    } else if (FMT == FMT_FLOAT32LE) {
-        sample_test<float>(y, safety_limit, of_max, st);
-        float_overflow_update<float>(y, (float)-of_max, (float)of_max, st);
-        *reinterpret_cast<float *>(p) = y;
-    } else {
-        store_raw_le(p, encode_sample<float>(y, f.bytes, f.sbytes, f.isfloat, f.swap, safety_limit, of_max, st), f.bytes);
-    }
-}
-
-template <int LOG2M, int FMT, bool TWS>
+// SIMPLE: every output is fed by exactly one filter, the partition sum is not split and no crossfade is pending
+// (the usual block): one scaled spectrum per transform, and the next transform's spectrum is fetched while this
+// one's samples are stored.
+template <int LOG2M, bool SIMPLE, bool TWS>
 __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, const cpx<float> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, L = F::M, N = 2 * F::M, NT = F::NT;
     constexpr int RL = F::radix(F::NP - 1);         // radix of the last pass
     constexpr int BPT = 16 / RL, HALF = RL / 2;      // butterflies per thread, valid outputs per butterfly
+    constexpr bool PREFETCH = F::NT < 1024;
     extern __shared__ __align__(128) unsigned char smem2[];
     cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2);
-    void *stats_scratch = smem2 + Smem2<LOG2M, TWS>::stats_off;
     const int tid = threadIdx.x;
     const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, tid);
     const int total = a.n_out * a.batch;
     const int zstride = a.batch * a.n_slots;        // Y slots between two partial sums of the split
-    bool first = true;
+    cpx<float> v[16];
 
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const int o = item % a.n_out, blk = item / a.n_out;
-        const OutChan ch = a.chans[o];
-        const float *Y = reinterpret_cast<const float *>(a.Y) + (size_t)blk * a.n_slots * N;
-        const int npass = ch.xf_first >= 0 ? 2 : 1;
-        cpx<float> v[16], keep[BPT * HALF];
+    // overlap-save: only the first L samples are output (fftw_convolver.c:498-501); they are elements
+    // i = (tid + b NT) + q M/RL, q < RL/2, of the complex result, sample 2i in .x and 2i + 1 in .y
+    auto store_time = [&](int o, int blk, const cpx<float> *keep) {
+        float *tdst = reinterpret_cast<float *>(a.out_time) + ((size_t)blk * a.n_out + o) * L;
+#pragma unroll
+        for (int b = 0; b < BPT; b++) {
+#pragma unroll
+            for (int q = 0; q < HALF; q++) {
+                const int i = (tid + b * NT) + q * (M / RL);
+                cpx<float> y = v[b * RL + q];
+                if (keep != nullptr) {
+                    y.x = xfade<float>(keep[b * HALF + q].x, y.x, 2 * i, L);
+                    y.y = xfade<float>(keep[b * HALF + q].y, y.y, 2 * i + 1, L);
+                }
+                *reinterpret_cast<cpx<float> *>(tdst + 2 * i) = y;
+            }
+        }
+    };
 
-        for (int pass = 0; pass < npass; pass++) {
-            const int term0 = (npass == 2 && pass == 0) ? ch.xf_first : ch.first;
-            if (first) {
-                wait_twiddles<LOG2M, TWS>(smem2);
-                first = false;
-            } else {
-                __syncthreads();    // the previous transform's last pass has finished reading shared memory
+    if (SIMPLE) {
+        float x[32];
+        float sc = 0.f;
+        auto fetch = [&](int item) {
+            const int o = item % a.n_out, blk = item / a.n_out;
+            const MixTerm tm = a.terms[a.chans[o].first];
+            const float *y = reinterpret_cast<const float *>(a.Y) + ((size_t)blk * a.n_slots + tm.index) * N;
+            sc = (float)tm.scale;
+            fft2_merge_fetch<float, LOG2M>(tid, x, [&](int i) { return __ldg(y + i); });
+        };
+        int item = blockIdx.x;
+        if (item < total) {
+            fetch(item);
+        }
+        wait_twiddles<LOG2M, TWS>(smem2);
+        for (; item < total; item += gridDim.x) {
+            const int o = item % a.n_out, blk = item / a.n_out;
+            if (!PREFETCH && item != (int)blockIdx.x) {
+                fetch(item);
             }
-            if (ch.n == 1 && a.split == 1) {
-                // the usual case, one filter per output: one scaled spectrum, hoisted out of the bin loop
-                const MixTerm tm = a.terms[term0];
-                const float *y = Y + (size_t)tm.index * N;
-                const float sc = (float)tm.scale;
-                fft2_merge_load<float, LOG2M>(s, tw, tid, [&](int i) { return mul_rn(__ldg(y + i), sc); });
-            } else {
-                fft2_merge_load<float, LOG2M>(s, tw, tid, [&](int i) {
-                    return mix_terms<float>(Y, a.terms, term0, ch.n, zstride, a.split, N, i);
-                });
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                x[i] = mul_rn(x[i], sc);        // mixnscale(OUTPUT) with one term (fftw_convfuns.h:268-494)
             }
+            fft2_merge_store<float, LOG2M>(s, tw, tid, x);
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < 16; q++) {
@@ -260,50 +381,44 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, 
             }
             __syncthreads();        // everybody holds its inputs: pass 0 may overwrite
             fft2_complex<float, LOG2M, true, true>(s, tw, tid, v, BlockSync2());
-            if (pass + 1 < npass) {
+            if (PREFETCH && item + (int)gridDim.x < total) {
+                fetch(item + gridDim.x);
+            }
+            store_time(o, blk, nullptr);
+            __syncthreads();        // the last pass has finished reading shared memory
+        }
+    } else {
+        cpx<float> keep[BPT * HALF];
+        wait_twiddles<LOG2M, TWS>(smem2);
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int o = item % a.n_out, blk = item / a.n_out;
+            const OutChan ch = a.chans[o];
+            const float *Y = reinterpret_cast<const float *>(a.Y) + (size_t)blk * a.n_slots * N;
+            const int npass = ch.xf_first >= 0 ? 2 : 1;
+            for (int pass = 0; pass < npass; pass++) {
+                const int term0 = (npass == 2 && pass == 0) ? ch.xf_first : ch.first;
+                fft2_merge_load<float, LOG2M>(s, tw, tid, [&](int i) {
+                    return mix_terms<float>(Y, a.terms, term0, ch.n, zstride, a.split, N, i);
+                });
+                __syncthreads();
 #pragma unroll
-                for (int b = 0; b < BPT; b++) {
+                for (int q = 0; q < 16; q++) {
+                    v[q] = s[tid + q * NT];
+                }
+                __syncthreads();    // everybody holds its inputs: pass 0 may overwrite
+                fft2_complex<float, LOG2M, true, true>(s, tw, tid, v, BlockSync2());
+                if (pass + 1 < npass) {
 #pragma unroll
-                    for (int q = 0; q < HALF; q++) {
-                        keep[b * HALF + q] = v[b * RL + q];
+                    for (int b = 0; b < BPT; b++) {
+#pragma unroll
+                        for (int q = 0; q < HALF; q++) {
+                            keep[b * HALF + q] = v[b * RL + q];
+                        }
                     }
                 }
+                __syncthreads();    // the last pass has finished reading shared memory
             }
-        }
-
-        // overlap-save: only the first L samples are output (fftw_convolver.c:498-501); they are elements
-        // i = (tid + b NT) + q M/RL, q < RL/2, of the complex result, sample 2i in .x and 2i + 1 in .y
-        const SampleFormat f = a.fmt[o];
-        float *tdst = reinterpret_cast<float *>(a.out_time) + ((size_t)blk * a.n_out + o) * L;
-        uint8_t *raw = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset;
-        const size_t stride = (size_t)f.sample_spacing * f.bytes;
-        const double of_max = a.overflow[o].max;
-        const int bits_n = f.sbytes << 3;
-        const int32_t imin = (int32_t)(-((uint64_t)1 << (bits_n - 1)));
-        const int32_t imax = (int32_t)(((uint64_t)1 << (bits_n - 1)) - 1);
-        const double rmin = (double)(float)imin, rmax = (double)(float)imax;
-        QuantStats st;
-        quant_stats_init(st);
-#pragma unroll
-        for (int b = 0; b < BPT; b++) {
-#pragma unroll
-            for (int q = 0; q < HALF; q++) {
-                const int i = (tid + b * NT) + q * (M / RL);
-                cpx<float> y = v[b * RL + q];
-                if (npass == 2) {
-                    y.x = xfade<float>(keep[b * HALF + q].x, y.x, 2 * i, L);
-                    y.y = xfade<float>(keep[b * HALF + q].y, y.y, 2 * i + 1, L);
-                }
-                *reinterpret_cast<cpx<float> *>(tdst + 2 * i) = y;
-                if (!ch.shared) {
-                    uint8_t *p = raw + (size_t)(2 * i) * stride;
-                    store_sample<FMT>(y.x, p, f, a.safety_limit, of_max, rmin, rmax, imin, imax, st);
-                    store_sample<FMT>(y.y, p + stride, f, a.safety_limit, of_max, rmin, rmax, imin, imax, st);
-                }
-            }
-        }
-        if (!ch.shared) {
-            reduce_stats(st, &a.overflow[o], a.status, stats_scratch, tid, NT);
+            store_time(o, blk, npass == 2 ? keep : nullptr);
         }
     }
 }
@@ -390,80 +505,97 @@ static cudaError_t persistent_grid(K kernel, int threads, size_t smem, int total
     return cudaSuccess;
 }
 
-template <int LOG2M, int FMT, bool TWS>
+template <int LOG2M, bool SINGLE, bool TWS>
 static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
-    static int grid_cache[64][2];       // [device][0 = resident blocks]
+    static int resident[64];
     const size_t smem = Smem2<LOG2M, TWS>::total;
     int dev = 0;
     cudaGetDevice(&dev);
-    const int total = a.n_in * a.batch;
-    int grid = 0;
-    if (dev >= 0 && dev < 64 && grid_cache[dev][0] > 0) {
-        grid = total < grid_cache[dev][0] ? total : grid_cache[dev][0];
-    } else {
-        cudaError_t err = persistent_grid(k_forward2<LOG2M, FMT, TWS>, F::NT, smem, 1 << 30, &grid);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (resident[dev] == 0) {
+        cudaError_t err = persistent_grid(k_forward2<LOG2M, SINGLE, TWS>, F::NT, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
-        if (dev >= 0 && dev < 64) grid_cache[dev][0] = grid;
-        grid = total < grid ? total : grid;
     }
-    k_forward2<LOG2M, FMT, TWS><<<grid, F::NT, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    const int total = a.n_in * a.batch;
+    const int grid = total < resident[dev] ? total : resident[dev];
+    k_forward2<LOG2M, SINGLE, TWS><<<grid, F::NT, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
     return cudaGetLastError();
 }
 
-template <int LOG2M, int FMT, bool TWS>
+template <int LOG2M, bool SIMPLE, bool TWS>
 static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
-    static int grid_cache[64][2];
+    static int resident[64];
     const size_t smem = Smem2<LOG2M, TWS>::total;
     int dev = 0;
     cudaGetDevice(&dev);
-    const int total = a.n_out * a.batch;
-    int grid = 0;
-    if (dev >= 0 && dev < 64 && grid_cache[dev][0] > 0) {
-        grid = total < grid_cache[dev][0] ? total : grid_cache[dev][0];
-    } else {
-        cudaError_t err = persistent_grid(k_inverse2<LOG2M, FMT, TWS>, F::NT, smem, 1 << 30, &grid);
+    dev = (dev >= 0 && dev < 64) ? dev : 0;
+    if (resident[dev] == 0) {
+        cudaError_t err = persistent_grid(k_inverse2<LOG2M, SIMPLE, TWS>, F::NT, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
-        if (dev >= 0 && dev < 64) grid_cache[dev][0] = grid;
-        grid = total < grid ? total : grid;
     }
-    k_inverse2<LOG2M, FMT, TWS><<<grid, F::NT, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    const int total = a.n_out * a.batch;
+    const int grid = total < resident[dev] ? total : resident[dev];
+    k_inverse2<LOG2M, SIMPLE, TWS><<<grid, F::NT, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
     return cudaGetLastError();
 }
 
-#define BF_FFT2_SIZES(FN, FMT, ...)                                                    \
+#define BF_FFT2_SIZES(FN, FLAG, ...)                                                   \
     switch (plan.N) {                                                                  \
-    case 2048: return FN<10, FMT, true>(__VA_ARGS__);                                  \
-    case 4096: return FN<11, FMT, true>(__VA_ARGS__);                                  \
-    case 8192: return FN<12, FMT, true>(__VA_ARGS__);                                  \
-    case 16384: return FN<13, FMT, true>(__VA_ARGS__);                                 \
-    case 32768: return FN<14, FMT, false>(__VA_ARGS__);                                \
+    case 2048: return FN<10, FLAG, true>(__VA_ARGS__);                                 \
+    case 4096: return FN<11, FLAG, true>(__VA_ARGS__);                                 \
+    case 8192: return FN<12, FLAG, true>(__VA_ARGS__);                                 \
+    case 16384: return FN<13, FLAG, true>(__VA_ARGS__);                                \
+    case 32768: return FN<14, FLAG, false>(__VA_ARGS__);                               \
     default: return cudaErrorInvalidValue;                                             \
     }
+
+cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t s)
+{
+    if (a.n_in == 0) return cudaSuccess;
+    const int wpb = plan.realsize == 4 ? TileWarps<float>::value : TileWarps<double>::value;
+    dim3 grid((a.L + 32 * wpb - 1) / (32 * wpb), (a.n_in + 31) / 32, a.batch);
+    if (plan.realsize == 4) {
+        k_unpack<float><<<grid, 32 * wpb, 0, s>>>(a);
+    } else {
+        k_unpack<double><<<grid, 32 * wpb, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
+{
+    if (a.n_out == 0) return cudaSuccess;
+    const int L = plan.N / 2;
+    const int wpb = plan.realsize == 4 ? TileWarps<float>::value : TileWarps<double>::value;
+    dim3 grid((L + 32 * wpb - 1) / (32 * wpb), (a.n_out + 31) / 32, a.batch);
+    if (plan.realsize == 4) {
+        k_pack<float><<<grid, 32 * wpb, 0, s>>>(a, L);
+    } else {
+        k_pack<double><<<grid, 32 * wpb, 0, s>>>(a, L);
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launch_forward2(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
-    if (a.fast_fmt == FMT_INT32LE) {
-        BF_FFT2_SIZES(launch_forward2_t, FMT_INT32LE, plan, a, s)
-    } else if (a.fast_fmt == FMT_FLOAT32LE) {
-        BF_FFT2_SIZES(launch_forward2_t, FMT_FLOAT32LE, plan, a, s)
+    if (a.single_dest) {
+        BF_FFT2_SIZES(launch_forward2_t, true, plan, a, s)
     }
-    BF_FFT2_SIZES(launch_forward2_t, FMT_GENERIC, plan, a, s)
+    BF_FFT2_SIZES(launch_forward2_t, false, plan, a, s)
 }
 
 cudaError_t launch_inverse2(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
-    if (a.fast_fmt == FMT_INT32LE) {
-        BF_FFT2_SIZES(launch_inverse2_t, FMT_INT32LE, plan, a, s)
-    } else if (a.fast_fmt == FMT_FLOAT32LE) {
-        BF_FFT2_SIZES(launch_inverse2_t, FMT_FLOAT32LE, plan, a, s)
+    if (a.simple_mix) {
+        BF_FFT2_SIZES(launch_inverse2_t, true, plan, a, s)
     }
-    BF_FFT2_SIZES(launch_inverse2_t, FMT_GENERIC, plan, a, s)
+    BF_FFT2_SIZES(launch_inverse2_t, false, plan, a, s)
 }
 
 }  // namespace bf

@@ -90,7 +90,23 @@ struct ForwardArgs {
     int batch;
     size_t in_stride;
     int fast_fmt;               // 1: every input is an aligned 4-byte LE integer, 2: FLOAT_LE, 0: per-sample generic decode
+    // size-specialised path (bf_fft2_kernels.cu): the samples arrive unpacked
+    const void *xt_cur;         // [batch][n_in][L] reals, this launch's blocks
+    const void *xt_prev;        // [n_in][L] reals, the block before the first one
+    int single_dest;            // every input feeds exactly one delay-line stream and no input spectrum is kept
 };
+
+struct UnpackArgs {
+    const uint8_t *raw_in;      // block b at raw_in + b * in_stride
+    const SampleFormat *fmt;    // [n_in]
+    void *xt;                   // [batch][n_in][L] reals
+    int n_in;
+    int batch;
+    int L;
+    size_t in_stride;
+    int fast_fmt;
+};
+cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t s);
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s);
 
 struct StreamMixArgs {
@@ -137,7 +153,10 @@ struct InverseArgs {
     size_t out_stride;
     double safety_limit;
     int fast_fmt;               // as ForwardArgs::fast_fmt, for the outputs
+    int simple_mix;             // every output is one filter's output, unsplit partition sum, no crossfade pending
 };
+// size-specialised path: the inverse stage stops at out_time; this quantises / packs ALL channels from it
+cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
 
 // quantise + pack out_time rows of the channels with chans[o].shared (after the cross-rank sum)
