@@ -111,7 +111,7 @@ struct FilterState {
 
 struct bfcuda_engine {
     int L, P, N, rs;
-    int max_batch, fdl_ring;    // blocks per launch at most; delay-line slots per stream = P + max_batch - 1
+    int max_batch, fdl_ring;    // blocks per launch at most; delay-line slots per stream (see bfcuda_create)
     int slot_t;                 // ring slot of the next block (0 <= slot_t < ring)
     int prev_par;               // which of the two `prev` buffers holds the last input block
     int last_batch;             // blocks in the most recent launch (layout of Y for debug_read)
@@ -129,11 +129,16 @@ struct bfcuda_engine {
     std::vector<int> coeff_n_blocks, coeff_hbase;
     int total_coeff_blocks;
 
-    // streams: `stream` runs forward + MAC of every block, `s_inv` the inverse stage (so that the inverse of
-    // block t overlaps the forward of block t+1), `s_in` / `s_out` the host<->device copies of the streaming
-    // interface (double-buffered raw blocks, so copies overlap compute)
-    cudaStream_t stream, s_inv, s_in, s_out;
+    // Three stage streams, software-pipelined over consecutive launches: `stream` runs unpack + forward (and every
+    // table / coefficient update), `s_mac` the multiply-accumulate, `s_inv` inverse + pack.  Launch n+1's forward
+    // stage and launch n-1's inverse stage run beside launch n's MAC (filter outputs Y are double buffered, the
+    // delay-line ring has a launch of slack); the MAC is the HBM-bound stage, the other two fill its gaps and tail.
+    // `s_in` / `s_out` carry the host<->device copies of the streaming interface (double-buffered raw blocks).
+    cudaStream_t stream, s_mac, s_inv, s_in, s_out;
     cudaEvent_t ev_h2d[2], ev_fwd[2], ev_d2h[2], ev_mac, ev_inv;
+    cudaEvent_t ev_fwd_done[2], ev_mac_done[2], ev_inv_done[2], ev_join;  // per launch parity
+    unsigned int launch_no;     // launches enqueued so far
+    size_t y_stride;            // bytes between the two generations of Y
     unsigned int io_count;      // blocks submitted through the host-buffer interface
     FftPlan plan;
     uint8_t *d_raw[2];          // raw blocks of the device-resident interface (and buffer 0 of the streaming one)
@@ -159,7 +164,6 @@ struct bfcuda_engine {
     std::vector<MixTerm> h_out_terms;
     std::vector<int> shared_out;
     std::vector<std::pair<int, int>> delay_fixups;     // (filter, old delay) of delay changes not yet applied to the ring
-    void *d_fix;                // staging for the ring fix-up, P spectra, allocated on first use
     FwdDest *d_dests;
     int *d_dest_first;
     uint8_t *d_need_xin;
@@ -422,7 +426,7 @@ void bfcuda_destroy(bfcuda_engine *e)
         return;
     }
     cudaSetDevice(e->device);
-    for (cudaStream_t st : { e->stream, e->s_inv, e->s_in, e->s_out }) {
+    for (cudaStream_t st : { e->stream, e->s_mac, e->s_inv, e->s_in, e->s_out }) {
         if (st) cudaStreamSynchronize(st);
     }
     if (e->comm != nullptr && g_nccl.handle != nullptr) {
@@ -436,7 +440,6 @@ void bfcuda_destroy(bfcuda_engine *e)
             cudaFree(p);
         }
     }
-    if (e->d_fix) cudaFree(e->d_fix);
     if (e->h_status) cudaFreeHost(e->h_status);
     fft_plan_destroy(&e->plan);
     for (int i = 0; i < 2; i++) {
@@ -448,10 +451,11 @@ void bfcuda_destroy(bfcuda_engine *e)
         }
     }
     for (cudaEvent_t ev : { e->ev_h2d[0], e->ev_h2d[1], e->ev_fwd[0], e->ev_fwd[1], e->ev_d2h[0], e->ev_d2h[1],
-                            e->ev_mac, e->ev_inv }) {
+                            e->ev_mac, e->ev_inv, e->ev_fwd_done[0], e->ev_fwd_done[1], e->ev_mac_done[0],
+                            e->ev_mac_done[1], e->ev_inv_done[0], e->ev_inv_done[1], e->ev_join }) {
         if (ev) cudaEventDestroy(ev);
     }
-    for (cudaStream_t st : { e->stream, e->s_inv, e->s_in, e->s_out }) {
+    for (cudaStream_t st : { e->stream, e->s_mac, e->s_inv, e->s_in, e->s_out }) {
         if (st) cudaStreamDestroy(st);
     }
     delete e;
@@ -537,7 +541,11 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->N = 2 * e->L;
     e->rs = c->realsize;
     e->max_batch = c->max_batch < 1 ? 1 : c->max_batch;
-    e->fdl_ring = e->P + e->max_batch - 1;
+    // Ring slots per delay line.  The reference's ring has exactly P (bfrun.c:1045, 1600).  Here: + 2 B - 1 so that
+    // launch n+1's forward stage can run beside launch n's MAC, + P - 1 so that a block written "ahead" under the
+    // largest block delay (P - 1) never lands on a slot a running MAC still reads and the one-time aliasing fix-up
+    // of a delay change (apply_delay_fixups) always has distinct source and destination slots.
+    e->fdl_ring = 2 * e->P + 2 * e->max_batch;
     e->slot_t = 0;
     e->d_xt[0] = e->d_xt[1] = nullptr;
     e->xt_par = 0;
@@ -550,11 +558,16 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->safety_limit = c->safety_limit;
     e->n_filters = c->n_filters;
     e->n_coeffs = c->n_coeffs;
-    e->stream = e->s_inv = e->s_in = e->s_out = nullptr;
+    e->stream = e->s_mac = e->s_inv = e->s_in = e->s_out = nullptr;
+    for (int i = 0; i < 2; i++) {
+        e->ev_fwd_done[i] = e->ev_mac_done[i] = e->ev_inv_done[i] = nullptr;
+    }
+    e->ev_join = nullptr;
+    e->launch_no = 0;
+    e->y_stride = 0;
     e->ev_h2d[0] = e->ev_h2d[1] = e->ev_fwd[0] = e->ev_fwd[1] = e->ev_d2h[0] = e->ev_d2h[1] = nullptr;
     e->ev_mac = e->ev_inv = nullptr;
     e->io_count = 0;
-    e->d_fix = nullptr;
     e->comm = nullptr;
     e->n_ranks = 1;
     e->device_bytes = 0;
@@ -636,12 +649,21 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     } while (0)
     {
         const size_t N = e->N, L = e->L, F = std::max(1, e->n_filters);
-        TRYCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-        TRYCU(cudaStreamCreateWithFlags(&e->s_inv, cudaStreamNonBlocking));
+        {
+            // the latency-bound FFT stages get the higher priority: their blocks take the SMs the MAC's retiring
+            // blocks free, instead of queueing behind its whole grid
+            int lo = 0, hi = 0;
+            TRYCU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            TRYCU(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
+            TRYCU(cudaStreamCreateWithPriority(&e->s_mac, cudaStreamNonBlocking, lo));
+            TRYCU(cudaStreamCreateWithPriority(&e->s_inv, cudaStreamNonBlocking, hi));
+        }
         TRYCU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
         TRYCU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
         for (cudaEvent_t *ev : { &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_fwd[0], &e->ev_fwd[1], &e->ev_d2h[0],
-                                 &e->ev_d2h[1], &e->ev_mac, &e->ev_inv }) {
+                                 &e->ev_d2h[1], &e->ev_mac, &e->ev_inv, &e->ev_fwd_done[0], &e->ev_fwd_done[1],
+                                 &e->ev_mac_done[0], &e->ev_mac_done[1], &e->ev_inv_done[0], &e->ev_inv_done[1],
+                                 &e->ev_join }) {
             TRYCU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         }
         TRYCU(fft_plan_create(&e->plan, e->N, e->rs));
@@ -672,7 +694,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         TRY(dev_alloc(e, &e->d_fdl, rs_bytes(e, F * (size_t)e->fdl_ring * N)));
         TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * N)));
         TRY(dev_alloc(e, &e->d_H, rs_bytes(e, (size_t)std::max(1, e->total_coeff_blocks) * N)));
-        TRY(dev_alloc(e, &e->d_Y, rs_bytes(e, (size_t)e->split * B * 2 * F * N)));
+        e->y_stride = rs_bytes(e, (size_t)e->split * B * 2 * F * N);
+        TRY(dev_alloc(e, &e->d_Y, 2 * e->y_stride));
         TRY(dev_alloc(e, &e->d_out_time, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[1]) * L)));
         TRY(dev_alloc(e, &e->d_scratch, rs_bytes(e, 4 * N)));
         TRY(dev_alloc(e, &e->d_overflow, sizeof(Overflow) * std::max(1, e->n_ch[1])));
@@ -739,7 +762,7 @@ int bfcuda_reset_overflow(bfcuda_engine *e)
             of[n].max = (double)((uint64_t)1 << ((e->fmt[1][n].sf.sbytes << 3) - 1)) - 1;
         }
     }
-    for (cudaStream_t st : { e->s_in, e->stream, e->s_inv, e->s_out }) {
+    for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
         CU(cudaStreamSynchronize(st));
     }
     if (!of.empty()) {
@@ -754,7 +777,7 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
     if (e == nullptr || overflow == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     if (out_channel < 0 || out_channel >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
     CU(cudaSetDevice(e->device));
-    for (cudaStream_t st : { e->s_in, e->stream, e->s_inv, e->s_out }) {
+    for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
         CU(cudaStreamSynchronize(st));
     }
     Overflow of;
@@ -869,8 +892,15 @@ int bfcuda_set_control(bfcuda_engine *e, int filter, const struct bfcuda_filter_
     if (c->coeff >= e->n_coeffs) return fail(BFCUDA_EINVAL, "coefficient index %d out of range", c->coeff);
     FilterState &fs = e->filters[filter];
     fs.coeff = c->coeff < 0 ? -1 : c->coeff;
-    if (e->fdl_ring != e->P && clamp_delay(e, c->delayblocks) != clamp_delay(e, fs.delayblocks)) {
-        e->delay_fixups.push_back(std::make_pair(filter, clamp_delay(e, fs.delayblocks)));
+    if (clamp_delay(e, c->delayblocks) != clamp_delay(e, fs.delayblocks)) {
+        // remember the delay the ring was last written under (first change since the last block wins)
+        bool known = false;
+        for (const std::pair<int, int> &fx : e->delay_fixups) {
+            known = known || fx.first == filter;
+        }
+        if (!known) {
+            e->delay_fixups.push_back(std::make_pair(filter, clamp_delay(e, fs.delayblocks)));
+        }
     }
     fs.delayblocks = c->delayblocks;
     for (int io = 0; io < 2; io++) {
@@ -907,7 +937,11 @@ static int flush_timing_ring(bfcuda_engine *e)
 }
 
 // Enqueue the kernels of `nb` consecutive blocks as ONE launch per stage (nb <= max_batch; callers make sure
-// no control change or crossfade falls inside): forward + MAC on the main stream, inverse on s_inv.
+// no control change or crossfade falls inside): unpack + forward on the main stream, MAC on s_mac, inverse + pack on
+// s_inv, ordered by per-parity events (launch n: p = n & 1):
+//   forward(n)  after MAC(n-2)      -- the ring slots it overwrites were last read there (ring = P + 2B - 1)
+//   MAC(n)      after forward(n) and inverse(n-2)   -- Y[p] is free again
+//   inverse(n)  after MAC(n)
 //   raw_in / raw_out : device raw blocks, block b at + b * n_bytes
 //   in_ready         : event the forward stage must wait for (input copy), or null
 //   out_free         : event the inverse stage must wait for (previous read-out of raw_out), or null
@@ -926,8 +960,13 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         ev = e->ring[e->ring_fill];
         e->ring_blocks[e->ring_fill] = nb;
     }
+    const int par = (int)(e->launch_no & 1u);
+    const bool have_prev2 = e->launch_no >= 2;
     if (in_ready != nullptr) {
         CU(cudaStreamWaitEvent(e->stream, in_ready, 0));
+    }
+    if (have_prev2) {
+        CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[par], 0));
     }
     if (timing) CU(cudaEventRecord(ev[0], e->stream));
 
@@ -989,15 +1028,17 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     if (fwd_done != nullptr) {
         CU(cudaEventRecord(fwd_done, e->stream));
     }
-    // the previous launch's inverse stage reads Y: the MAC may not overwrite it earlier.  (The forward stage
-    // above does not touch Y, so it runs concurrently with that inverse stage.)
-    CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));
-    if (timing) CU(cudaEventRecord(ev[2], e->stream));
+    CU(cudaEventRecord(e->ev_fwd_done[par], e->stream));
+    CU(cudaStreamWaitEvent(e->s_mac, e->ev_fwd_done[par], 0));
+    if (have_prev2) {
+        CU(cudaStreamWaitEvent(e->s_mac, e->ev_inv_done[par], 0));     // inverse(n-2) has consumed Y[par]
+    }
+    if (timing) CU(cudaEventRecord(ev[2], e->s_mac));
 
     MacArgs ma;
     ma.fdl = e->d_fdl;
     ma.H = e->d_H;
-    ma.Y = e->d_Y;
+    ma.Y = (char *)e->d_Y + (size_t)par * e->y_stride;
     ma.jobs = e->d_jobs;
     ma.n_jobs = (int)e->h_jobs.size();
     ma.n_slots = 2 * std::max(1, e->n_filters);
@@ -1006,18 +1047,18 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ma.t = e->slot_t;
     ma.batch = nb;
     ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
-    CU(launch_mac(e->plan, ma, e->stream));
+    CU(launch_mac(e->plan, ma, e->s_mac));
     e->launches += ma.n_jobs > 0;
-    if (timing) CU(cudaEventRecord(ev[3], e->stream));
-    CU(cudaEventRecord(e->ev_mac, e->stream));
-    CU(cudaStreamWaitEvent(e->s_inv, e->ev_mac, 0));
+    if (timing) CU(cudaEventRecord(ev[3], e->s_mac));
+    CU(cudaEventRecord(e->ev_mac_done[par], e->s_mac));
+    CU(cudaStreamWaitEvent(e->s_inv, e->ev_mac_done[par], 0));
     if (out_free != nullptr) {
         CU(cudaStreamWaitEvent(e->s_inv, out_free, 0));
     }
     if (timing) CU(cudaEventRecord(ev[4], e->s_inv));
 
     InverseArgs ia;
-    ia.Y = e->d_Y;
+    ia.Y = ma.Y;
     ia.chans = e->d_chans;
     ia.terms = e->d_out_terms;
     ia.out_time = e->d_out_time;
@@ -1066,7 +1107,9 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         CU(cudaEventRecord(ev[5], e->s_inv));
         e->ring_fill++;
     }
+    CU(cudaEventRecord(e->ev_inv_done[par], e->s_inv));
     CU(cudaEventRecord(e->ev_inv, e->s_inv));
+    e->launch_no++;
 
     // bfrun.c:1838, 2034
     for (FilterState &fs : e->filters) {
@@ -1078,12 +1121,16 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     return 0;
 }
 
-// A run-time change of a filter's block delay (cfd, bfrun.c:1579-1600) makes the reference read delay-line
-// slots that were written under the old delay: its ring has exactly P slots, so the spectra written "ahead"
-// (slot (w + d_old) % P for the last d_old - 1 blocks w) alias the oldest partitions.  With a longer ring
-// (batched mode) those slots are distinct, so the aliasing is reproduced once, at the block boundary where the
-// change takes effect, by copying ring[v] -> ring[v - P] for the d_old - 1 virtual slots v ahead of "now".
-// After that every read sees what the reference's P-slot ring would hold.
+// A run-time change of a filter's block delay (cfd, bfrun.c:1579-1600).  The reference's ring has exactly P slots,
+// written at (w + delay) % P and read at (t - i) % P, so a change makes it read slots that alias other blocks.  The
+// engine's ring is longer (virtual slot u lives at u % ring, the reference's at u % P), those slots are distinct
+// here, and the aliasing is reproduced ONCE at the block boundary T where the change takes effect:
+//   * decrease d_old -> d_new: the read range grows downwards to T - P + d_new + 1, where the reference finds the
+//     blocks written "ahead" under the old delay: ring[u] = ring[u + P] for u + P in (T + d_new, T + d_old - 1];
+//   * increase d_old -> d_new: virtual slots T + d_old .. T + d_new - 1 are never written, the reference reads the
+//     blocks of one ring turn earlier there: ring[u] = ring[u - P] for those u.
+// After that every read sees what the reference's P-slot ring would hold.  (ring >= 2 P: sources and destinations
+// never share a physical slot.)
 static int apply_delay_fixups(bfcuda_engine *e)
 {
     if (e->delay_fixups.empty()) {
@@ -1091,21 +1138,22 @@ static int apply_delay_fixups(bfcuda_engine *e)
     }
     const size_t nb = rs_bytes(e, e->N);
     const int R = e->fdl_ring, P = e->P;
-    if (e->d_fix == nullptr) {
-        CU(cudaMalloc(&e->d_fix, nb * (size_t)P));
-    }
+    auto phys = [&](long u) { return (int)(((u % R) + R) % R); };
     for (const std::pair<int, int> &fx : e->delay_fixups) {
         const int f = fx.first, d_old = fx.second;
+        const int d_new = clamp_delay(e, e->filters[f].delayblocks);
         char *ring = (char *)e->d_fdl + nb * (size_t)f * R;
-        for (int j = 1; j < d_old; j++) {       // stage first: sources and destinations may overlap
-            const int src = (e->slot_t + j) % R;
-            CU(cudaMemcpyAsync((char *)e->d_fix + nb * (size_t)j, ring + nb * (size_t)src, nb, cudaMemcpyDeviceToDevice,
-                               e->stream));
-        }
-        for (int j = 1; j < d_old; j++) {
-            const int dst = ((e->slot_t + j - P) % R + R) % R;
-            CU(cudaMemcpyAsync(ring + nb * (size_t)dst, (char *)e->d_fix + nb * (size_t)j, nb, cudaMemcpyDeviceToDevice,
-                               e->stream));
+        const long T = e->slot_t;
+        if (d_new < d_old) {
+            for (int j = d_new + 1; j < d_old; j++) {
+                CU(cudaMemcpyAsync(ring + nb * (size_t)phys(T + j - P), ring + nb * (size_t)phys(T + j), nb,
+                                   cudaMemcpyDeviceToDevice, e->stream));
+            }
+        } else {
+            for (int j = d_old; j < d_new; j++) {
+                CU(cudaMemcpyAsync(ring + nb * (size_t)phys(T + j), ring + nb * (size_t)phys(T + j - P), nb,
+                                   cudaMemcpyDeviceToDevice, e->stream));
+            }
         }
     }
     e->delay_fixups.clear();
@@ -1122,11 +1170,16 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
     while (done < n) {
         int nb = std::min(n - done, e->max_batch);
         if (e->dirty || e->xfade_active) {
+            // the previous launches' MAC and inverse stages (other streams) still read the job / output-mix tables,
+            // and a delay fix-up rewrites ring slots the previous MAC reads
+            if (e->launch_no >= 1) {
+                const int prev = (int)((e->launch_no - 1) & 1u);
+                CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[prev], 0));
+                CU(cudaStreamWaitEvent(e->stream, e->ev_inv_done[prev], 0));
+            }
             int frc = apply_delay_fixups(e);
             if (frc != 0) return frc;
             build_tables(e);
-            // the previous launch's inverse stage (other stream) still reads the output-mix tables
-            CU(cudaStreamWaitEvent(e->stream, e->ev_inv, 0));
             int rc = upload_tables(e);
             if (rc != 0) return rc;
             if (e->xfade_active) {
@@ -1159,6 +1212,7 @@ static int sync_all(bfcuda_engine *e)
 {
     CU(cudaStreamSynchronize(e->s_in));
     CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(e->s_mac));
     CU(cudaStreamSynchronize(e->s_inv));
     CU(cudaStreamSynchronize(e->s_out));
     return 0;
@@ -1313,10 +1367,10 @@ int bfcuda_timer_stop(bfcuda_engine *e, double *elapsed_ms)
     if (e == nullptr || elapsed_ms == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
     // the stop event must come after everything enqueued on any of the engine's streams
-    CU(cudaEventRecord(e->ev_mac, e->s_inv));
-    CU(cudaStreamWaitEvent(e->stream, e->ev_mac, 0));
-    CU(cudaEventRecord(e->ev_mac, e->s_out));
-    CU(cudaStreamWaitEvent(e->stream, e->ev_mac, 0));
+    for (cudaStream_t st : { e->s_mac, e->s_inv, e->s_out }) {
+        CU(cudaEventRecord(e->ev_join, st));
+        CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+    }
     CU(cudaEventRecord(e->timer[1], e->stream));
     CU(cudaEventSynchronize(e->timer[1]));
     float ms = 0.f;
@@ -1371,7 +1425,7 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
 {
     if (e == nullptr || dst == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
-    for (cudaStream_t st : { e->s_in, e->stream, e->s_inv, e->s_out }) {
+    for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
         CU(cudaStreamSynchronize(st));
     }
     const size_t nb = rs_bytes(e, e->N);
@@ -1388,10 +1442,19 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
         if (index < 0 || index >= e->n_filters || slot < 0 || slot >= e->P) {
             return fail(BFCUDA_EINVAL, "filter or slot out of range");
         }
-        if (e->max_batch != 1) {
-            return fail(BFCUDA_EINVAL, "delay-line slots follow the reference's numbering only with max_batch 1");
+        // `slot` is the reference's numbering, cbuf[filter][(t + delay) % P] (bfrun.c:1600): the reference's slot s
+        // holds the block written at the latest time tau <= t_last with (tau + delay) % P == s; the engine's ring is
+        // longer (see bfcuda_create) and keeps that block at (tau + delay) % ring.
+        const int d = clamp_delay(e, e->filters[index].delayblocks);
+        const long t_last = (long)e->t - 1;
+        const long back = (((t_last + d - slot) % e->P) + e->P) % e->P;
+        if (t_last - back < 0) {
+            memset(dst, 0, nb);     // never written: still the zeros it was allocated with
+            break;
         }
-        const char *src = (const char *)e->d_fdl + nb * ((size_t)index * e->fdl_ring + slot);
+        const int R = e->fdl_ring;
+        const int phys = (int)((((long)e->slot_t - 1 - back + d) % R + R) % R);
+        const char *src = (const char *)e->d_fdl + nb * ((size_t)index * R + phys);
         CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
         CU(cudaMemcpyAsync(dst, e->d_scratch, nb, cudaMemcpyDeviceToHost, e->stream));
         break;
@@ -1402,7 +1465,7 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
         std::vector<unsigned char> part(nb);
         for (int z = 0; z < e->split; z++) {
             // the last block of the most recent launch
-            const char *src = (const char *)e->d_Y +
+            const char *src = (const char *)e->d_Y + (size_t)((e->launch_no + 1) & 1u) * e->y_stride +
                               nb * (((size_t)z * e->last_batch + (e->last_batch - 1)) * n_slots + index);
             CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
             CU(cudaMemcpyAsync(z == 0 ? dst : (void *)part.data(), e->d_scratch, nb, cudaMemcpyDeviceToHost,

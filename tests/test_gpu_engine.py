@@ -279,7 +279,10 @@ def test_batched_launches_are_bit_identical_to_block_by_block(gpu_lib, oracle_li
     nb = 37
     sig = configs.synthetic_signal(g, 18, nb, sigma=0.3)        # loud: exercises clipping and overflow counters
     script = {5: [(0, dict(coeff=2))], 6: [(1, dict(coeff=1, delayblocks=0, in_scales=[0.1, 0.3]))],
-              16: [(0, dict(coeff=-1)), (3, dict(coeff=0))], 29: [(0, dict(coeff=1))]}
+              16: [(0, dict(coeff=-1)), (3, dict(coeff=0))],
+              22: [(1, dict(coeff=1, delayblocks=6, in_scales=[0.1, 0.3]))],      # delay increase: stale-slot reads
+              29: [(0, dict(coeff=1))],
+              33: [(1, dict(coeff=1, delayblocks=2, in_scales=[0.1, 0.3]))]}      # decrease: "ahead" blocks alias
 
     def run(max_batch, split):
         with Engine(g, mac_split=split, max_batch=max_batch) as e:
@@ -305,3 +308,16 @@ def test_batched_launches_are_bit_identical_to_block_by_block(gpu_lib, oracle_li
         got_out, got_stats = run(B, split)
         assert np.array_equal(got_out, ref_out), split
         assert got_stats == ref_stats and ref_stats[1][0] > 0
+        if split == 1 and B == 2:
+            # ... and the block-by-block engine itself follows the reference's P-slot ring through every delay
+            # change (the engine's ring is longer; bf_engine.cu apply_delay_fixups)
+            d = po.BlockDriver("oracle", g)
+            for c, h in enumerate(taps):
+                d.coeff_from_taps(c, h, 40.0)
+            want = []
+            for b in range(nb):
+                for filt, kw in script.get(b, []):
+                    d.set_control(filt, **kw)
+                want.append(d.process_block(sig[b]))
+            d.close()
+            assert_parity(g, ref_out, np.stack(want))
