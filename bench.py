@@ -224,7 +224,7 @@ def main():
 
     def measure(B, steps, warmup, sample_clocks):
         """One engine with max_batch = B; a step = B consecutive audio blocks in one call."""
-        eng = Engine(sub, device=local_rank, flags=_abi.FLAG_STAGE_TIMING, max_batch=B)
+        eng = Engine(sub, device=local_rank, flags=0, max_batch=B)
         for c in sorted({f.coeff for f in sub.filters if f.coeff >= 0}):
             eng.coeff_from_taps(c, taps[c])
         nbuf = 3
@@ -256,7 +256,7 @@ def main():
         ms = eng.timer_stop()
         barrier()
         clocks = sampler.stop() if sampler else None
-        stage_ms, stage_blocks, launches = eng.stage_times()      # mean ms per BLOCK of each stage
+        _, _, launches = eng.stage_times()
         ms_step = max_over_ranks(ms / steps)
 
         # ---- end to end through the C ABI with host buffers ------------------------------------------
@@ -281,6 +281,32 @@ def main():
         latency_ms = max_over_ranks(float(np.median(lat)) * 1e3)
         eng.stage_times()
 
+        # ---- per-stage durations for the roofline ------------------------------------------------------
+        # The engine overlaps the stages of consecutive launches, so events around a stage in the runs above would
+        # include the time it shares the SMs with its neighbours (and recording them costs a few percent, which is
+        # why the runs above go without).  Here each stage is timed ALONE: same engine, same data, launches
+        # serialised (BFCUDA_FLAG_SERIAL_STAGES), CUDA events on the stage's own stream.
+        eng.set_stage_timing(True)
+        eng.set_serial_stages(True)
+        for _ in range(3):
+            eng.process_blocks_device(B)
+        eng.synchronize()
+        eng.stage_times()
+        for _ in range(max(20, steps // 4)):
+            eng.process_blocks_device(B)
+        eng.synchronize()
+        stage_ms, stage_blocks, _ = eng.stage_times()      # mean ms per BLOCK of each stage, running alone
+        eng.set_serial_stages(False)
+        for _ in range(3):
+            eng.process_blocks_device(B)
+        eng.synchronize()
+        eng.stage_times()
+        for _ in range(max(20, steps // 4)):
+            eng.process_blocks_device(B)
+        eng.synchronize()
+        piped_ms, _, _ = eng.stage_times()                 # the same with the stages of neighbouring launches overlapping
+        eng.set_stage_timing(False)
+
         # ---- roofline of the MAC kernel --------------------------------------------------------------
         mac_ms_launch = stage_ms[1] * B                               # one launch covers B blocks
         compulsory = info.mac_bytes_per_batch if B > 1 else info.mac_bytes_per_block
@@ -290,7 +316,16 @@ def main():
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get(f"{args.workload}_n{world}_b{B}"),
                 "peak_source": peak_source, "algorithmic_bytes_per_launch": compulsory, "kernel_ms": mac_ms_launch,
                 "blocks_per_launch": B,
-                "stage_ms_per_block": {"forward": stage_ms[0], "mac": stage_ms[1], "inverse": stage_ms[2]}}
+                "timing": "CUDA events around the kernel on its stream, stages serialised (each stage alone)",
+                "stage_ms_per_block": {"forward": stage_ms[0], "mac": stage_ms[1], "inverse": stage_ms[2]},
+                "stage_ms_per_block_pipelined": {"forward": piped_ms[0], "mac": piped_ms[1], "inverse": piped_ms[2]},
+                "fft_stages": {
+                    "note": "forward = unpack + R2HC into the delay line, inverse = mix + HC2R + pack; byte roofline "
+                            "n*(L*bytes + N*rs) per stage and block (SURVEY.md 8(d))",
+                    "forward_gbs": (len(sub.in_formats) * (graph.filter_length * sub.in_formats[0].sf.bytes + graph.n_fft * graph.realsize) /
+                                    (stage_ms[0] * 1e-3) / 1e9) if stage_ms[0] > 0 else None,
+                    "inverse_gbs": (len(sub.out_formats) * (graph.filter_length * sub.out_formats[0].sf.bytes + graph.n_fft * graph.realsize) /
+                                    (stage_ms[2] * 1e-3) / 1e9) if stage_ms[2] > 0 else None}}
         if B > 1:
             roof["note"] = ("one launch covers B blocks and reads every coefficient / delay-line spectrum ONCE for all "
                             "of them (register reuse): algorithmic bytes = rs*N*(P*F + (P+B-1)*U + B*F).  With the "

@@ -71,6 +71,8 @@ class InfoC(C.Structure):
 
 FLAG_STAGE_TIMING = 1
 FLAG_NO_GRAPH = 2
+FLAG_KEEP_INPUT_SPECTRA = 4
+FLAG_SERIAL_STAGES = 8
 
 DBG_INPUT_SPECTRUM, DBG_DELAYLINE, DBG_FILTER_OUTPUT, DBG_OUTPUT_TIME = 1, 2, 3, 4
 
@@ -84,7 +86,7 @@ ENGINE_SYMBOLS = [
     "bfcuda_process_block_device", "bfcuda_device_io", "bfcuda_upload_input", "bfcuda_download_output",
     "bfcuda_upload_inputs", "bfcuda_download_outputs",
     "bfcuda_host_alloc", "bfcuda_host_free", "bfcuda_timer_start", "bfcuda_timer_stop",
-    "bfcuda_stage_times", "bfcuda_get_info", "bfcuda_debug_read", "bfcuda_comm_unique_id",
+    "bfcuda_stage_times", "bfcuda_set_serial_stages", "bfcuda_set_stage_timing", "bfcuda_get_info", "bfcuda_debug_read", "bfcuda_comm_unique_id",
     "bfcuda_comm_init", "bfcuda_comm_shared_outputs",
 ]
 CONVOLVER_SYMBOLS = [
@@ -146,6 +148,8 @@ def load_library() -> C.CDLL:
     lib.bfcuda_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.bfcuda_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long),
                                        C.POINTER(C.c_long)]
+    lib.bfcuda_set_serial_stages.argtypes = [C.c_void_p, C.c_int]
+    lib.bfcuda_set_stage_timing.argtypes = [C.c_void_p, C.c_int]
     lib.bfcuda_get_info.argtypes = [C.c_void_p, C.POINTER(InfoC)]
     lib.bfcuda_debug_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.bfcuda_comm_unique_id.argtypes = [C.c_void_p]

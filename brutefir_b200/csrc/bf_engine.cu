@@ -968,6 +968,10 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     if (have_prev2) {
         CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[par], 0));
     }
+    if ((e->flags & BFCUDA_FLAG_SERIAL_STAGES) && e->launch_no >= 1) {
+        // measurement aid: no overlap between launches, so the stage events bracket each stage running alone
+        CU(cudaStreamWaitEvent(e->stream, e->ev_inv_done[par ^ 1], 0));
+    }
     if (timing) CU(cudaEventRecord(ev[0], e->stream));
 
     ForwardArgs fa;
@@ -1376,6 +1380,40 @@ int bfcuda_timer_stop(bfcuda_engine *e, double *elapsed_ms)
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, e->timer[0], e->timer[1]));
     *elapsed_ms = (double)ms;
+    return 0;
+}
+
+int bfcuda_set_stage_timing(bfcuda_engine *e, int on)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
+    rc = flush_timing_ring(e);
+    if (rc != 0) return rc;
+    if (on) {
+        for (int i = 0; i < TIMING_RING; i++) {
+            for (int j = 0; j < 6; j++) {
+                if (e->ring[i][j] == nullptr) {
+                    CU(cudaEventCreate(&e->ring[i][j]));
+                }
+            }
+        }
+        e->flags |= BFCUDA_FLAG_STAGE_TIMING;
+    } else {
+        e->flags &= ~BFCUDA_FLAG_STAGE_TIMING;
+    }
+    return 0;
+}
+
+int bfcuda_set_serial_stages(bfcuda_engine *e, int on)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    if (on) {
+        e->flags |= BFCUDA_FLAG_SERIAL_STAGES;
+    } else {
+        e->flags &= ~BFCUDA_FLAG_SERIAL_STAGES;
+    }
     return 0;
 }
 

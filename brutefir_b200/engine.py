@@ -174,6 +174,15 @@ class Engine:
         check(self.lib.bfcuda_stage_times(self.h, ms, C.byref(nb), C.byref(nl)))
         return list(ms), nb.value, nl.value
 
+    def set_stage_timing(self, on: bool):
+        """BFCUDA_FLAG_STAGE_TIMING at run time (per-stage CUDA events; costs a few percent of throughput)."""
+        check(self.lib.bfcuda_set_stage_timing(self.h, 1 if on else 0))
+
+    def set_serial_stages(self, on: bool):
+        """BFCUDA_FLAG_SERIAL_STAGES at run time: no overlap between the stages of consecutive launches, so that
+        stage_times() reports each stage running alone (roofline measurements)."""
+        check(self.lib.bfcuda_set_serial_stages(self.h, 1 if on else 0))
+
     def info(self) -> _abi.InfoC:
         i = _abi.InfoC()
         check(self.lib.bfcuda_get_info(self.h, C.byref(i)))

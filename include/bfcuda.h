@@ -120,7 +120,11 @@ struct bfcuda_config {
 };
 
 #define BFCUDA_FLAG_STAGE_TIMING 1u     /* record CUDA events around each stage of every block */
-#define BFCUDA_FLAG_NO_GRAPH 2u         /* launch kernels directly instead of replaying a CUDA graph */
+#define BFCUDA_FLAG_NO_GRAPH 2u         /* (reserved) */
+#define BFCUDA_FLAG_KEEP_INPUT_SPECTRA 4u   /* keep every input's unscaled spectrum for bfcuda_debug_read */
+#define BFCUDA_FLAG_SERIAL_STAGES 8u    /* do not overlap the stages of consecutive launches (the engine normally runs
+                                           launch n+1's forward and launch n-1's inverse stage beside launch n's
+                                           multiply-accumulate): stage timings then are each stage running alone */
 
 typedef struct bfcuda_engine bfcuda_engine;
 
@@ -198,6 +202,11 @@ int bfcuda_timer_stop(bfcuda_engine *engine, double *elapsed_ms);   /* synchroni
  * kernel launches since the last call; resets the accumulators. */
 int bfcuda_stage_times(bfcuda_engine *engine, double mean_ms[BFCUDA_N_STAGES], long *n_blocks,
                        long *n_kernel_launches);
+/* switch BFCUDA_FLAG_STAGE_TIMING at run time (synchronises).  The per-stage events cost a few percent of
+ * throughput (they are recorded on three streams per launch): time the whole job without them. */
+int bfcuda_set_stage_timing(bfcuda_engine *engine, int on);
+/* switch BFCUDA_FLAG_SERIAL_STAGES at run time (takes effect at the next launch) */
+int bfcuda_set_serial_stages(bfcuda_engine *engine, int on);
 /* static facts about the engine for roofline arithmetic */
 struct bfcuda_info {
     int n_fft;                  /* N = 2 L */
