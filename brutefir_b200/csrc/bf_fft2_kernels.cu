@@ -85,20 +85,24 @@ __device__ __forceinline__ void wait_twiddles(unsigned char *smem)
 // channels), so the samples of ONE channel are a 4-byte access every 256 bytes at the headline shape: a transform
 // reading them directly touches 8192 sectors for 32 KB of payload and the LSU serialises every warp access into 32
 // requests (ncu: the forward stage spent ~half its time there).  These two kernels do the layout change at full
-// coalescing instead: a warp moves a 32 channel x 32 sample tile, lanes along the channels on the raw side and
+// coalescing instead: a warp moves a 32 channel x 8 sample tile, lanes along the channels on the raw side and
 // along time on the planar side.  They also carry the whole sample conversion (raw2real.h / real2raw.h), so the
 // transforms themselves are format-free.
 // ======================================================================================================
 
-template <typename T> struct TileWarps { static constexpr int value = sizeof(T) == 4 ? 8 : 4; };
+// A warp moves a tile of 32 channels x RW samples; RW = 8 keeps every planar-side access a full 32-byte sector
+// (8 consecutive floats of one channel) while giving four times more warps than a square tile -- the quantiser is a
+// dependent double-precision chain per sample, so it is parallelism, not bytes, that the small launches lack.
+constexpr int RW = 8;           // samples per tile row group
+constexpr int WPB = 8;          // warps per block
+constexpr int TS = RW + 1;      // padded row stride of the shared tile
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_unpack(UnpackArgs a)
+__global__ void __launch_bounds__(32 * WPB) k_unpack(UnpackArgs a)
 {
-    constexpr int WPB = TileWarps<T>::value;
-    __shared__ T tile[WPB][32][33];
+    __shared__ T tile[WPB][32 * TS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int n0 = (blockIdx.x * WPB + w) * 32, c0 = blockIdx.y * 32, blk = blockIdx.z;
+    const int n0 = (blockIdx.x * WPB + w) * RW, c0 = blockIdx.y * 32, blk = blockIdx.z;
     if (n0 >= a.L) {
         return;
     }
@@ -109,48 +113,56 @@ __global__ void __launch_bounds__(256) k_unpack(UnpackArgs a)
             const SampleFormat f = a.fmt[c];
             const size_t stride = (size_t)f.sample_spacing * f.bytes;
             const uint8_t *p = raw + f.byte_offset + (size_t)n0 * stride;
+            T *row = &tile[w][lane * TS];
             if (a.fast_fmt == 1) {
-#pragma unroll 8
-                for (int r = 0; r < 32; r++) {
-                    tile[w][r][lane] = (T)*reinterpret_cast<const int32_t *>(p + r * stride);
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    row[r] = (T)*reinterpret_cast<const int32_t *>(p + r * stride);
                 }
             } else if (a.fast_fmt == 2) {
-#pragma unroll 8
-                for (int r = 0; r < 32; r++) {
-                    tile[w][r][lane] = (T)*reinterpret_cast<const float *>(p + r * stride);
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    row[r] = (T)*reinterpret_cast<const float *>(p + r * stride);
                 }
             } else {
-                for (int r = 0; r < 32; r++) {
-                    tile[w][r][lane] = decode_sample<T>(load_raw_le(p + r * stride, f.bytes), f.bytes, f.isfloat, f.swap);
+                for (int r = 0; r < RW; r++) {
+                    row[r] = decode_sample<T>(load_raw_le(p + r * stride, f.bytes), f.bytes, f.isfloat, f.swap);
                 }
             }
         }
     }
     __syncwarp();
-    T *xt = reinterpret_cast<T *>(a.xt) + ((size_t)blk * a.n_in + c0) * a.L + n0 + lane;
+    // planar side: lanes j = lane % RW along time, RW-lane groups over 32 / RW channels at a time
+    const int j = lane % RW, r0 = lane / RW;
+    T *xt = reinterpret_cast<T *>(a.xt) + ((size_t)blk * a.n_in + c0) * a.L + n0 + j;
     const int nc = min(32, a.n_in - c0);
-    for (int r = 0; r < nc; r++) {
-        xt[(size_t)r * a.L] = tile[w][lane][r];
+#pragma unroll
+    for (int i = 0; i < RW; i++) {
+        const int r = r0 + (32 / RW) * i;
+        if (r < nc) {
+            xt[(size_t)r * a.L] = tile[w][r * TS + j];
+        }
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_pack(InverseArgs a, int L)
+__global__ void __launch_bounds__(32 * WPB) k_pack(InverseArgs a, int L)
 {
-    constexpr int WPB = TileWarps<T>::value;
-    __shared__ T tile[WPB][32][33];
+    __shared__ T tile[WPB][32 * TS];
     __shared__ QuantStats wstats[WPB][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int n0 = (blockIdx.x * WPB + w) * 32, c0 = blockIdx.y * 32, blk = blockIdx.z;
+    const int n0 = (blockIdx.x * WPB + w) * RW, c0 = blockIdx.y * 32, blk = blockIdx.z;
     const int nc = min(32, a.n_out - c0);
     QuantStats st;
     quant_stats_init(st);
     if (n0 < L) {
-        const T *src = reinterpret_cast<const T *>(a.out_time) + ((size_t)blk * a.n_out + c0) * L + n0 + lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {
+        const int j = lane % RW, r0 = lane / RW;
+        const T *src = reinterpret_cast<const T *>(a.out_time) + ((size_t)blk * a.n_out + c0) * L + n0 + j;
+#pragma unroll
+        for (int i = 0; i < RW; i++) {
+            const int r = r0 + (32 / RW) * i;
             if (r < nc) {
-                tile[w][r][lane] = src[(size_t)r * L];
+                tile[w][r * TS + j] = src[(size_t)r * L];
             }
         }
         __syncwarp();
@@ -160,28 +172,29 @@ __global__ void __launch_bounds__(256) k_pack(InverseArgs a, int L)
             const size_t stride = (size_t)f.sample_spacing * f.bytes;
             uint8_t *p = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset + (size_t)n0 * stride;
             const double of_max = a.overflow[c].max;
+            const T *row = &tile[w][lane * TS];
             if (a.fast_fmt == 1) {
                 const int bits_n = f.sbytes << 3;
                 const int32_t imin = (int32_t)(-((uint64_t)1 << (bits_n - 1)));
                 const int32_t imax = (int32_t)(((uint64_t)1 << (bits_n - 1)) - 1);
                 const double rmin = (double)(T)imin, rmax = (double)(T)imax;
-#pragma unroll 4
-                for (int r = 0; r < 32; r++) {
-                    const T y = tile[w][lane][r];
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    const T y = row[r];
                     sample_test<T>(y, a.safety_limit, of_max, st);
                     *reinterpret_cast<int32_t *>(p + r * stride) = real_to_int<T>(y, rmin, rmax, imin, imax, st);
                 }
             } else if (a.fast_fmt == 2) {
-#pragma unroll 4
-                for (int r = 0; r < 32; r++) {
-                    const T y = tile[w][lane][r];
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    const T y = row[r];
                     sample_test<T>(y, a.safety_limit, of_max, st);
                     float_overflow_update<T>(y, (T)-of_max, (T)of_max, st);
                     *reinterpret_cast<float *>(p + r * stride) = (float)y;
                 }
             } else {
-                for (int r = 0; r < 32; r++) {
-                    const T y = tile[w][lane][r];
+                for (int r = 0; r < RW; r++) {
+                    const T y = row[r];
                     store_raw_le(p + r * stride,
                                  encode_sample<T>(y, f.bytes, f.sbytes, f.isfloat, f.swap, a.safety_limit, of_max, st),
                                  f.bytes);
@@ -556,12 +569,11 @@ static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, 
 cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
-    const int wpb = plan.realsize == 4 ? TileWarps<float>::value : TileWarps<double>::value;
-    dim3 grid((a.L + 32 * wpb - 1) / (32 * wpb), (a.n_in + 31) / 32, a.batch);
+    dim3 grid((a.L + RW * WPB - 1) / (RW * WPB), (a.n_in + 31) / 32, a.batch);
     if (plan.realsize == 4) {
-        k_unpack<float><<<grid, 32 * wpb, 0, s>>>(a);
+        k_unpack<float><<<grid, 32 * WPB, 0, s>>>(a);
     } else {
-        k_unpack<double><<<grid, 32 * wpb, 0, s>>>(a);
+        k_unpack<double><<<grid, 32 * WPB, 0, s>>>(a);
     }
     return cudaGetLastError();
 }
@@ -570,12 +582,11 @@ cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t 
 {
     if (a.n_out == 0) return cudaSuccess;
     const int L = plan.N / 2;
-    const int wpb = plan.realsize == 4 ? TileWarps<float>::value : TileWarps<double>::value;
-    dim3 grid((L + 32 * wpb - 1) / (32 * wpb), (a.n_out + 31) / 32, a.batch);
+    dim3 grid((L + RW * WPB - 1) / (RW * WPB), (a.n_out + 31) / 32, a.batch);
     if (plan.realsize == 4) {
-        k_pack<float><<<grid, 32 * wpb, 0, s>>>(a, L);
+        k_pack<float><<<grid, 32 * WPB, 0, s>>>(a, L);
     } else {
-        k_pack<double><<<grid, 32 * wpb, 0, s>>>(a, L);
+        k_pack<double><<<grid, 32 * WPB, 0, s>>>(a, L);
     }
     return cudaGetLastError();
 }
