@@ -42,7 +42,8 @@ class FilterC(C.Structure):
 
 
 class FilterControlC(C.Structure):
-    _fields_ = [("coeff", C.c_int), ("delayblocks", C.c_int), ("scale", C.POINTER(C.c_double) * 2)]
+    _fields_ = [("coeff", C.c_int), ("delayblocks", C.c_int), ("scale", C.POINTER(C.c_double) * 2),
+                ("fscale", C.POINTER(C.c_double))]
 
 
 class ConfigC(C.Structure):

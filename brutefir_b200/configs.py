@@ -40,7 +40,7 @@ def config_c1_direct(realsize: int = 4) -> FilterGraph:
 
 
 def config_c1_chained(realsize: int = 4) -> FilterGraph:
-    """bench1_config exactly (filters 2..5 feed filters 0, 1 through to_filters); CPU oracle only."""
+    """bench1_config exactly (filters 2..5 feed filters 0, 1 through to_filters)."""
     L, P = 8192, 8
     inb, nin = interleaved_layout(2, "S24_4LE", L)
     outb, nout = interleaved_layout(2, "S24_4LE", L)

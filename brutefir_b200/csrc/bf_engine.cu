@@ -104,6 +104,10 @@ struct FilterState {
     int crossfade;
     std::vector<int> ch[2];
     std::vector<double> scale[2];
+    std::vector<int> fin;           // source filters (from_filters), all with a lower index
+    std::vector<double> fscale;
+    int level;                      // 0 = fed by inputs only; 1 + max level of the sources otherwise
+    int eval;                       // index of its evaluated source mix (row n_in + eval of xin), -1 = none
     int coeff, prevcoeff, delayblocks;
 };
 
@@ -172,6 +176,14 @@ struct bfcuda_engine {
     MacJob *d_jobs;
     OutChan *d_chans;
     MixTerm *d_out_terms;
+    // filter -> filter chaining: per level, the ranges of MAC jobs, mix streams and evaluations
+    int n_eval, n_vin, n_levels;
+    void *d_keep;
+    EvalEntry *d_eval_entries;
+    MixTerm *d_eval_terms;
+    std::vector<EvalEntry> h_eval_entries;
+    std::vector<MixTerm> h_eval_terms;
+    std::vector<int> level_job_first, level_mix_first, level_eval_first;   // [n_levels + 1]
     bool dirty, xfade_active;
     size_t mac_bytes;           // algorithmic MAC bytes of one block launched alone
     size_t mac_bytes_batch;     // compulsory MAC bytes of one full batch of max_batch blocks
@@ -258,11 +270,69 @@ static void build_tables(bfcuda_engine *e)
     e->xfade_active = false;
     size_t blocks_h = 0, blocks_x = 0;
 
-    for (int f = 0; f < F; f++) {
+    e->h_eval_entries.clear();
+    e->h_eval_terms.clear();
+    e->level_job_first.assign(e->n_levels + 1, 0);
+    e->level_mix_first.assign(e->n_levels + 1, 0);
+    e->level_eval_first.assign(e->n_levels + 1, 0);
+    for (int level = 0; level < e->n_levels; level++) {
+      e->level_job_first[level] = (int)e->h_jobs.size();
+      e->level_mix_first[level] = (int)e->h_mix_streams.size();
+      e->level_eval_first[level] = (int)e->h_eval_entries.size();
+      for (int f = 0; f < F; f++) {
         const FilterState &fs = e->filters[f];
+        if (fs.level != level) {
+            continue;
+        }
         const int delay = clamp_delay(e, fs.delayblocks);
         const int nin = (int)fs.ch[0].size();
-        if (nin == 1) {
+        if (fs.eval >= 0) {
+            // bfrun.c:1603-1660: the scaled mix of the source filters' outputs, evaluated in the time domain, joins
+            // the channel inputs as one more spectrum with scale 1.0 ("unecessary scale multiply", bfrun.c:1646-1647)
+            EvalEntry en;
+            en.first = (int)e->h_eval_terms.size();
+            en.n = (int)fs.fin.size();
+            en.xf_first = -1;
+            en.vin = e->n_ch[0] + fs.eval;
+            bool any_xf = false;
+            for (size_t i = 0; i < fs.fin.size(); i++) {
+                MixTerm tm;
+                tm.index = fs.fin[i];
+                tm.scale = round_to_real(e, fs.fscale[i]);
+                e->h_eval_terms.push_back(tm);
+                const FilterState &src = e->filters[fs.fin[i]];
+                any_xf |= src.crossfade && src.prevcoeff != src.coeff;
+            }
+            if (any_xf) {
+                en.xf_first = (int)e->h_eval_terms.size();
+                for (size_t i = 0; i < fs.fin.size(); i++) {
+                    MixTerm tm = e->h_eval_terms[en.first + i];
+                    const FilterState &src = e->filters[fs.fin[i]];
+                    if (src.crossfade && src.prevcoeff != src.coeff) {
+                        tm.index = F + tm.index;
+                    }
+                    e->h_eval_terms.push_back(tm);
+                }
+            }
+            e->h_eval_entries.push_back(en);
+            MixStream ms;
+            ms.stream = f;
+            ms.delay = delay;
+            ms.n_inputs = nin + 1;
+            ms.first = (int)e->h_mix_terms.size();
+            for (int i = 0; i < nin; i++) {
+                MixTerm tm;
+                tm.index = fs.ch[0][i];
+                tm.scale = round_to_real(e, fs.scale[0][i] * e->fmt[0][fs.ch[0][i]].sf.scale);
+                e->h_mix_terms.push_back(tm);
+                e->h_need_xin[fs.ch[0][i]] = 1;
+            }
+            MixTerm te;
+            te.index = en.vin;
+            te.scale = 1.0;
+            e->h_mix_terms.push_back(te);
+            e->h_mix_streams.push_back(ms);
+        } else if (nin == 1) {
             FwdDest d;
             d.stream = f;
             d.delay = delay;
@@ -302,7 +372,11 @@ static void build_tables(bfcuda_engine *e)
             blocks_x += old.n_parts;
             e->xfade_active = true;
         }
+      }
     }
+    e->level_job_first[e->n_levels] = (int)e->h_jobs.size();
+    e->level_mix_first[e->n_levels] = (int)e->h_mix_streams.size();
+    e->level_eval_first[e->n_levels] = (int)e->h_eval_entries.size();
     e->h_dests.clear();
     for (int c = 0; c < e->n_ch[0]; c++) {
         e->h_dest_first[c] = (int)e->h_dests.size();
@@ -382,6 +456,8 @@ static int upload_tables(bfcuda_engine *e)
     CU(upload_vec(e->d_jobs, e->h_jobs, e->stream));
     CU(upload_vec(e->d_chans, e->h_chans, e->stream));
     CU(upload_vec(e->d_out_terms, e->h_out_terms, e->stream));
+    CU(upload_vec(e->d_eval_entries, e->h_eval_entries, e->stream));
+    CU(upload_vec(e->d_eval_terms, e->h_eval_terms, e->stream));
     return 0;
 }
 
@@ -434,7 +510,8 @@ void bfcuda_destroy(bfcuda_engine *e)
     }
     void *ptrs[] = { e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
-                     e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms };
+                     e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
+                     e->d_keep, e->d_eval_entries, e->d_eval_terms };
     for (void *p : ptrs) {
         if (p != nullptr) {
             cudaFree(p);
@@ -503,9 +580,12 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     }
     for (int f = 0; f < c->n_filters; f++) {
         const bfcuda_filter &s = c->filters[f];
-        if (s.n_filters_in != 0) {
-            return fail(BFCUDA_ENOTSUP, "filter %d: filter-to-filter inputs (convolver_convolve_eval) are not on "
-                                        "the accelerated path yet", f);
+        for (int i = 0; i < s.n_filters_in; i++) {
+            // processing order is topological, producers first (bfconf.c:2933-2964)
+            if (s.filters_in == nullptr || s.filters_in[i] < 0 || s.filters_in[i] >= f) {
+                return fail(BFCUDA_EINVAL, "filter %d: source filter index must be in 0..%d (filters in processing "
+                                           "order, producers first)", f, f - 1);
+            }
         }
         if (s.coeff >= c->n_coeffs) {
             return fail(BFCUDA_EINVAL, "filter %d: coefficient index %d out of range", f, s.coeff);
@@ -548,6 +628,11 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->fdl_ring = 2 * e->P + 2 * e->max_batch;
     e->slot_t = 0;
     e->d_xt[0] = e->d_xt[1] = nullptr;
+    e->d_keep = nullptr;
+    e->d_eval_entries = nullptr;
+    e->d_eval_terms = nullptr;
+    e->n_eval = 0;
+    e->n_levels = 1;
     e->xt_par = 0;
     e->xt_last_nb = 1;
     e->single_dest = e->simple_mix = false;
@@ -621,7 +706,23 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         }
         fs.coeff = fs.prevcoeff = s.coeff;      // bfrun.c:1326
         fs.delayblocks = s.delayblocks;
+        fs.level = 0;
+        fs.eval = -1;
+        if (s.n_filters_in > 0) {
+            fs.fin.assign(s.filters_in, s.filters_in + s.n_filters_in);
+            if (s.fscale != nullptr) {
+                fs.fscale.assign(s.fscale, s.fscale + s.n_filters_in);
+            } else {
+                fs.fscale.assign(s.n_filters_in, 1.0);
+            }
+            for (int src : fs.fin) {
+                fs.level = std::max(fs.level, e->filters[src].level + 1);
+            }
+            fs.eval = e->n_eval++;
+            e->n_levels = std::max(e->n_levels, fs.level + 1);
+        }
     }
+    e->n_vin = e->n_ch[0] + e->n_eval;
     e->coeff_n_blocks.assign(c->coeff_n_blocks, c->coeff_n_blocks + c->n_coeffs);
     e->coeff_hbase.resize(e->n_coeffs);
     e->total_coeff_blocks = 0;
@@ -692,7 +793,16 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
             TRY(dev_alloc(e, &e->d_xt[1], rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * L)));
         }
         TRY(dev_alloc(e, &e->d_fdl, rs_bytes(e, F * (size_t)e->fdl_ring * N)));
-        TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * N)));
+        TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, B * (size_t)std::max(1, e->n_vin) * N)));
+        TRY(dev_alloc(e, &e->d_keep, rs_bytes(e, (size_t)std::max(1, e->n_eval) * L)));
+        TRY(dev_alloc(e, &e->d_eval_entries, sizeof(EvalEntry) * std::max(1, e->n_eval)));
+        {
+            size_t terms = 1;
+            for (const FilterState &fs : e->filters) {
+                terms += 2 * fs.fin.size();
+            }
+            TRY(dev_alloc(e, &e->d_eval_terms, sizeof(MixTerm) * terms));
+        }
         TRY(dev_alloc(e, &e->d_H, rs_bytes(e, (size_t)std::max(1, e->total_coeff_blocks) * N)));
         e->y_stride = rs_bytes(e, (size_t)e->split * B * 2 * F * N);
         TRY(dev_alloc(e, &e->d_Y, 2 * e->y_stride));
@@ -707,7 +817,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         {
             size_t terms = 1;
             for (const FilterState &fs : e->filters) {
-                terms += fs.ch[0].size();
+                terms += fs.ch[0].size() + 1;
             }
             TRY(dev_alloc(e, &e->d_mix_terms, sizeof(MixTerm) * terms));
             terms = 1;
@@ -908,6 +1018,9 @@ int bfcuda_set_control(bfcuda_engine *e, int filter, const struct bfcuda_filter_
             fs.scale[io].assign(c->scale[io], c->scale[io] + fs.ch[io].size());
         }
     }
+    if (c->fscale != nullptr) {
+        fs.fscale.assign(c->fscale, c->fscale + fs.fin.size());
+    }
     e->dirty = true;    // takes effect at the next block, like the snapshot at bfrun.c:1462-1478
     return 0;
 }
@@ -968,6 +1081,10 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     if (have_prev2) {
         CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[par], 0));
     }
+    if (e->n_levels > 1 && e->launch_no >= 1) {
+        // chained filters: the previous launch's later levels still read the input spectra this forward stage rewrites
+        CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[par ^ 1], 0));
+    }
     if ((e->flags & BFCUDA_FLAG_SERIAL_STAGES) && e->launch_no >= 1) {
         // measurement aid: no overlap between launches, so the stage events bracket each stage running alone
         CU(cudaStreamWaitEvent(e->stream, e->ev_inv_done[par ^ 1], 0));
@@ -985,6 +1102,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     fa.dest_first = e->d_dest_first;
     fa.dests = e->d_dests;
     fa.n_in = e->n_ch[0];
+    fa.n_vin = e->n_vin;
     fa.ring = e->fdl_ring;
     fa.t = e->slot_t;
     fa.batch = nb;
@@ -1014,17 +1132,19 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     CU(launch_forward(e->plan, fa, e->stream));
     e->prev_par ^= 1;
     e->launches += e->n_ch[0] > 0;
-    if (!e->h_mix_streams.empty()) {
-        StreamMixArgs sa;
-        sa.xin = e->d_xin;
-        sa.fdl = e->d_fdl;
+    StreamMixArgs sa;
+    sa.xin = e->d_xin;
+    sa.fdl = e->d_fdl;
+    sa.terms = e->d_mix_terms;
+    sa.n_in = e->n_vin;
+    sa.ring = e->fdl_ring;
+    sa.t = e->slot_t;
+    sa.batch = nb;
+    if (e->level_mix_first[1] > 0) {
+        // mixes of input channels only (level 0); the mixes that contain an evaluated filter output follow their
+        // source filters' MAC below
         sa.streams = e->d_mix_streams;
-        sa.terms = e->d_mix_terms;
-        sa.n_streams = (int)e->h_mix_streams.size();
-        sa.n_in = e->n_ch[0];
-        sa.ring = e->fdl_ring;
-        sa.t = e->slot_t;
-        sa.batch = nb;
+        sa.n_streams = e->level_mix_first[1];
         CU(launch_stream_mix(e->plan, sa, e->stream));
         e->launches++;
     }
@@ -1044,7 +1164,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ma.H = e->d_H;
     ma.Y = (char *)e->d_Y + (size_t)par * e->y_stride;
     ma.jobs = e->d_jobs;
-    ma.n_jobs = (int)e->h_jobs.size();
+    ma.n_jobs = e->level_job_first[1];
     ma.n_slots = 2 * std::max(1, e->n_filters);
     ma.ring = e->fdl_ring;
     ma.split = e->split;
@@ -1053,6 +1173,30 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
     CU(launch_mac(e->plan, ma, e->s_mac));
     e->launches += ma.n_jobs > 0;
+    for (int level = 1; level < e->n_levels; level++) {
+        // filter -> filter chaining (bfrun.c:1603-1660): evaluate the finished source outputs, mix them with the
+        // channel inputs into the consumers' delay lines, then run the consumers' partitions
+        EvalArgs ea;
+        ea.Y = ma.Y;
+        ea.entries = e->d_eval_entries + e->level_eval_first[level];
+        ea.terms = e->d_eval_terms;
+        ea.keep = e->d_keep;
+        ea.xin = e->d_xin;
+        ea.n_entries = e->level_eval_first[level + 1] - e->level_eval_first[level];
+        ea.n_in = e->n_ch[0];
+        ea.n_vin = e->n_vin;
+        ea.n_slots = ma.n_slots;
+        ea.split = e->split;
+        ea.batch = nb;
+        CU(launch_eval(e->plan, ea, e->s_mac));
+        sa.streams = e->d_mix_streams + e->level_mix_first[level];
+        sa.n_streams = e->level_mix_first[level + 1] - e->level_mix_first[level];
+        CU(launch_stream_mix(e->plan, sa, e->s_mac));
+        ma.jobs = e->d_jobs + e->level_job_first[level];
+        ma.n_jobs = e->level_job_first[level + 1] - e->level_job_first[level];
+        CU(launch_mac(e->plan, ma, e->s_mac));
+        e->launches += 3;
+    }
     if (timing) CU(cudaEventRecord(ev[3], e->s_mac));
     CU(cudaEventRecord(e->ev_mac_done[par], e->s_mac));
     CU(cudaStreamWaitEvent(e->s_inv, e->ev_mac_done[par], 0));
@@ -1445,7 +1589,8 @@ int bfcuda_get_info(bfcuda_engine *e, struct bfcuda_info *info)
     info->n_fft = e->N;
     info->mac_split = e->split;
     info->n_streams = e->n_filters;
-    info->kernels_per_block = 3 + (e->h_mix_streams.empty() ? 0 : 1) +
+    info->kernels_per_block = 3 + (e->level_mix_first.size() > 1 && e->level_mix_first[1] > 0 ? 1 : 0) +
+                              3 * (e->n_levels - 1) +
                               (e->plan.tw2 != nullptr ? 2 : (e->shared_out.empty() ? 0 : 1));
     info->uses_graph = 0;
     info->max_batch = e->max_batch;

@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_forward2(ForwardArgs a, 
             });
         } else {
             float *xin = (a.xin != nullptr && a.need_xin[c])
-                             ? reinterpret_cast<float *>(a.xin) + ((size_t)blk * a.n_in + c) * N : nullptr;
+                             ? reinterpret_cast<float *>(a.xin) + ((size_t)blk * a.n_vin + c) * N : nullptr;
             const FwdDest *dests = a.dests;
             fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
                 if (xin != nullptr) {

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(1024, 1) k_forward(ForwardArgs a, const T *__r
 
     const int d0 = a.dest_first[c], d1 = a.dest_first[c + 1];
     T *xin = (a.xin != nullptr && a.need_xin[c])
-                 ? reinterpret_cast<T *>(a.xin) + ((size_t)blk * a.n_in + c) * N : nullptr;
+                 ? reinterpret_cast<T *>(a.xin) + ((size_t)blk * a.n_vin + c) * N : nullptr;
     T *fdl = reinterpret_cast<T *>(a.fdl);
     const FwdDest *dests = a.dests;
     const int ring = a.ring;
@@ -697,6 +697,84 @@ __global__ void __launch_bounds__(256) k_quantise_shared(InverseArgs a, int L)
 }
 
 // ======================================================================================================
+// k_eval -- filter -> filter chaining
+// ======================================================================================================
+
+template <typename T, int E>
+__global__ void __launch_bounds__(1024, 1) k_eval(EvalArgs a, const T *__restrict__ tw, int L)
+{
+    const int M = L, N = 2 * L;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    T *sre = smem_re<T>();
+    T *sim = sre + (M + (M >> 5) + 1);
+    const EvalEntry en = a.entries[blockIdx.x];
+    T *keep = reinterpret_cast<T *>(a.keep) + (size_t)(en.vin - a.n_in) * L;
+    const int zstride = a.batch * a.n_slots;
+    const int npass = en.xf_first >= 0 ? 2 : 1;
+    T old[E];
+
+    for (int blk = 0; blk < a.batch; blk++) {       // the blocks of a batch depend on each other through `keep`
+        const T *Y = reinterpret_cast<const T *>(a.Y) + (size_t)blk * a.n_slots * N;
+        for (int pass = 0; pass < npass; pass++) {
+            const int first = (npass == 2 && pass == 0) ? en.xf_first : en.first;
+            // mixnscale(OUTPUT) of the source filters' outputs (bfrun.c:1611-1615), then HC2R
+            load_and_inverse<T, E>(sre, sim, tw, M, tid, nt, [&](int i) {
+                return mix_terms<T>(Y, a.terms, first, en.n, zstride, a.split, N, i);
+            });
+            if (pass + 1 < npass) {
+#pragma unroll
+                for (int b = 0; b < E / 2; b++) {
+                    const int j = tid + b * nt;
+                    if (j < M / 2) {
+                        old[2 * b] = sre[fft_pad(j)];
+                        old[2 * b + 1] = sim[fft_pad(j)];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // frame = [previous valid block | this valid block] (fftw_convolver.c:416-432); the valid block is the first
+        // L samples, packed complex elements j < M/2
+        T cur[E], prv[E];
+#pragma unroll
+        for (int b = 0; b < E / 2; b++) {
+            const int j = tid + b * nt;
+            if (j < M / 2) {
+                cur[2 * b] = sre[fft_pad(j)];
+                cur[2 * b + 1] = sim[fft_pad(j)];
+                if (npass == 2) {
+                    // the source crossfaded this block: its output is the blend (fftw_convolver.c:349-355)
+                    cur[2 * b] = xfade<T>(old[2 * b], cur[2 * b], 2 * j, L);
+                    cur[2 * b + 1] = xfade<T>(old[2 * b + 1], cur[2 * b + 1], 2 * j + 1, L);
+                }
+                prv[2 * b] = keep[2 * j];
+                prv[2 * b + 1] = keep[2 * j + 1];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < E / 2; b++) {
+            const int j = tid + b * nt;
+            if (j < M / 2) {
+                sre[fft_pad(j)] = prv[2 * b];
+                sim[fft_pad(j)] = prv[2 * b + 1];
+                sre[fft_pad(j + M / 2)] = cur[2 * b];
+                sim[fft_pad(j + M / 2)] = cur[2 * b + 1];
+                keep[2 * j] = cur[2 * b];
+                keep[2 * j + 1] = cur[2 * b + 1];
+            }
+        }
+        __syncthreads();
+        T *dst = reinterpret_cast<T *>(a.xin) + ((size_t)blk * a.n_vin + en.vin) * N;
+        forward_and_emit<T, E>(sre, sim, tw, M, tid, nt, [&](int k, T re, T im) {
+            dst[k] = re;
+            dst[M + k] = im;
+        });
+        __syncthreads();
+    }
+}
+
+// ======================================================================================================
 // coefficient preprocessing and plain transforms
 // ======================================================================================================
 
@@ -1012,6 +1090,12 @@ cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream
     if (a.n_out == 0) return cudaSuccess;
     if (plan.tw2 != nullptr) return launch_inverse2(plan, a, s);
     BF_FFT_DISPATCH(plan, k_inverse, dim3(a.n_out, a.batch), s, a, (const T *)plan.tw, plan.N / 2);
+}
+
+cudaError_t launch_eval(const FftPlan &plan, const EvalArgs &a, cudaStream_t s)
+{
+    if (a.n_entries == 0) return cudaSuccess;
+    BF_FFT_DISPATCH(plan, k_eval, a.n_entries, s, a, (const T *)plan.tw, plan.N / 2);
 }
 
 cudaError_t launch_quantise_shared(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)

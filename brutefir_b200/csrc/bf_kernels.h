@@ -85,6 +85,7 @@ struct ForwardArgs {
     const int *dest_first;      // [n_in + 1]
     const FwdDest *dests;
     int n_in;
+    int n_vin;                  // rows of one block of xin: the inputs plus the evaluated filter outputs (k_eval)
     int ring;
     int t;
     int batch;
@@ -110,7 +111,7 @@ cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s);
 
 struct StreamMixArgs {
-    const void *xin;            // [batch][n_in][N]
+    const void *xin;            // [batch][n_in][N]; n_in here counts the virtual inputs (ForwardArgs::n_vin)
     void *fdl;
     const MixStream *streams;
     const MixTerm *terms;
@@ -121,6 +122,30 @@ struct StreamMixArgs {
     int batch;
 };
 cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaStream_t s);
+
+// Filter -> filter chaining (to_filters / from_filters): the mixed outputs of the source filters are evaluated in
+// the time domain and become one more input spectrum of the consuming filter -- bfrun.c:1603-1660,
+// convolver_convolve_eval (fftw_convolver.c:411-433): HC2R, frame = [previous valid block | this valid block], R2HC.
+struct EvalEntry {
+    int first;      // terms [first, first + n): (Y slot, fscale) of the source filters
+    int n;
+    int xf_first;   // terms of the "old coefficient" mix while a source filter crossfades this block, else -1
+    int vin;        // row of xin that receives the evaluated spectrum (>= n_in); keep row = vin - n_in
+};
+struct EvalArgs {
+    const void *Y;              // [split][batch][n_slots][N]
+    const EvalEntry *entries;
+    const MixTerm *terms;
+    void *keep;                 // [n_eval][L] reals: previous valid block of every evaluated mix
+    void *xin;                  // [batch][n_vin][N]
+    int n_entries;
+    int n_in;
+    int n_vin;
+    int n_slots;
+    int split;
+    int batch;
+};
+cudaError_t launch_eval(const FftPlan &plan, const EvalArgs &a, cudaStream_t s);
 
 struct MacArgs {
     const void *fdl;

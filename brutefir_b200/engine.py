@@ -93,7 +93,8 @@ class Engine:
 
     # ---- control (bfmod.h:128-133, bfrun.c:1462-1478) ---------------------------------------------
     def set_control(self, filt: int, coeff: int, delayblocks: int = 0,
-                    in_scales: Optional[Sequence[float]] = None, out_scales: Optional[Sequence[float]] = None):
+                    in_scales: Optional[Sequence[float]] = None, out_scales: Optional[Sequence[float]] = None,
+                    fscales: Optional[Sequence[float]] = None):
         c = _abi.FilterControlC()
         c.coeff, c.delayblocks = coeff, delayblocks
         keep = []
@@ -102,6 +103,10 @@ class Engine:
                 arr = (C.c_double * len(s))(*s)
                 keep.append(arr)
                 c.scale[io] = C.cast(arr, C.POINTER(C.c_double))
+        if fscales is not None:
+            farr = (C.c_double * len(fscales))(*fscales)
+            keep.append(farr)
+            c.fscale = C.cast(farr, C.POINTER(C.c_double))
         check(self.lib.bfcuda_set_control(self.h, filt, C.byref(c)))
 
     def overflow(self, out_channel: int) -> _abi.OverflowC:

@@ -82,9 +82,9 @@ struct bfcuda_filter {
     int n_channels[2];          /* [BFCUDA_IN] inputs mixed into this filter, [BFCUDA_OUT] outputs fed */
     const int *channels[2];     /* virtual channel indices */
     const double *scale[2];     /* fctrl.scale[IN|OUT][i], linear multipliers */
-    int n_filters_in;           /* filter->filter chaining (convolver_convolve_eval): must be 0, see BFCUDA_ENOTSUP */
-    const int *filters_in;
-    const double *fscale;
+    int n_filters_in;           /* filter->filter chaining (to_filters / from_filters, bfrun.c:1603-1660) */
+    const int *filters_in;      /* source filters; filters are listed in processing order, producers first */
+    const double *fscale;       /* fctrl.fscale[i], NULL = all 1.0 */
     int coeff;                  /* initial coefficient set, -1 = no coefficients (dirac) */
     int delayblocks;            /* initial delay in blocks */
 };
@@ -95,6 +95,7 @@ struct bfcuda_filter_control {
     int coeff;
     int delayblocks;
     const double *scale[2];
+    const double *fscale;       /* multipliers of the source filters (from_filters), NULL = unchanged */
 };
 
 struct bfcuda_config {

@@ -443,6 +443,11 @@ DRV(set_control)(struct drv *d, int filter, const struct bfcuda_filter_control *
             }
         }
     }
+    if (c->fscale != NULL) {
+        for (i = 0; i < f->n_fin; i++) {
+            f->fscale[i] = c->fscale[i];
+        }
+    }
     return 0;
 }
 

@@ -239,7 +239,7 @@ class BlockDriver:
         assert self.l.coeff_get_block(self.h, coeff, block, _ptr(out)) == 0
         return out
 
-    def set_control(self, filt, coeff, delayblocks=0, in_scales=None, out_scales=None):
+    def set_control(self, filt, coeff, delayblocks=0, in_scales=None, out_scales=None, fscales=None):
         c = _abi.FilterControlC()
         c.coeff, c.delayblocks = coeff, delayblocks
         keep = []
@@ -248,6 +248,10 @@ class BlockDriver:
                 arr = (C.c_double * len(s))(*s)
                 keep.append(arr)
                 c.scale[io] = C.cast(arr, C.POINTER(C.c_double))
+        if fscales is not None:
+            farr = (C.c_double * len(fscales))(*fscales)
+            keep.append(farr)
+            c.fscale = C.cast(farr, C.POINTER(C.c_double))
         assert self.l.set_control(self.h, filt, C.byref(c)) == 0
 
     def process_block(self, raw_in: np.ndarray) -> np.ndarray:

@@ -243,9 +243,14 @@ def test_coefficient_layouts_round_trip(gpu_lib, oracle_libs):
 
 def test_errors_and_limits(gpu_lib):
     g = configs.config_c1_chained()
+    g.filters[0].from_filters, g.filters[0].fscales = [4], [1.0]      # a source with a higher index: not topological
     with pytest.raises(_abi.BfcudaError) as err:
         Engine(g)
-    assert err.value.code == -7 and "filter-to-filter" in str(err.value)      # BFCUDA_ENOTSUP, a "next" row
+    assert err.value.code == -1 and "processing order" in str(err.value)      # bfconf.c:2933-2964
+    g = configs.diagonal_graph(1, 32768, 2, 4, "S16_LE")
+    with pytest.raises(_abi.BfcudaError) as err:
+        Engine(g)
+    assert err.value.code == -7                                         # partition beyond the single-block FFT
     g = configs.diagonal_graph(1, 64, 2, 4, "S16_LE")
     with Engine(g) as e:
         e.coeff_from_taps(0, np.full(128, 1e3, np.float32))
@@ -321,3 +326,70 @@ def test_batched_launches_are_bit_identical_to_block_by_block(gpu_lib, oracle_li
                 want.append(d.process_block(sig[b]))
             d.close()
             assert_parity(g, ref_out, np.stack(want))
+
+
+def chained_graph(L, P, rs, fmt="S24_4LE", crossfade=False):
+    """bench1_config's topology (four input-fed filters feeding two filter-fed ones through to_filters,
+    /root/reference/bench1_config:28-57) made harder: a third level, a consumer that also mixes an input channel,
+    source multipliers, a delayed consumer and crossfading sources."""
+    inb, nin = interleaved_layout(2, fmt, L)
+    outb, nout = interleaved_layout(3, fmt, L)
+    filters = [Filter([0], [], coeff=2, crossfade=crossfade), Filter([0], [], coeff=3), Filter([1], [2], coeff=4),
+               Filter([1], [], coeff=5, crossfade=crossfade),
+               Filter([], [0], coeff=0, from_filters=[0, 3], fscales=[1.0, -0.5]),
+               Filter([1], [1], in_scales=[0.25], coeff=1, from_filters=[1, 2], delayblocks=1),
+               Filter([], [2], out_scales=[0.5], coeff=-1, from_filters=[4, 5], fscales=[0.5, 0.25])]
+    return FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [P, P, 2, P, 1, P])
+
+
+@pytest.mark.parametrize("L,P,rs", [(64, 3, 4), (64, 3, 8), (1024, 4, 4), (2048, 3, 8)])
+def test_filter_chaining_against_oracle(gpu_lib, oracle_libs, L, P, rs):
+    """to_filters / from_filters on the device (bfrun.c:1603-1660, convolver_convolve_eval): the sources' outputs are
+    evaluated in the time domain per block and become an input spectrum of the consumer, level by level."""
+    g = chained_graph(L, P, rs)
+    taps = [t * 0.5 for t in configs.synthetic_filters(g, 21)]
+    sig = configs.synthetic_signal(g, 21, 3 * P + 4, sigma=0.02)
+    got, ref, of = run_both(g, taps, sig, mac_split=1)
+    assert_parity(g, got, ref)
+    assert np.abs(unpack_run(ref, g.out_formats, L)).max() > 1e3
+
+
+def test_filter_chaining_control_crossfade_and_batches(gpu_lib, oracle_libs):
+    """Chained filters through coefficient switches with crossfade on the SOURCE filters (the consumer must see the
+    blended block), source-multiplier changes, and the batched mode (bit-identical to block by block)."""
+    L, P, nb = 256, 5, 26
+    g = chained_graph(L, P, 4, crossfade=True)
+    taps = [t * 0.5 for t in configs.synthetic_filters(g, 22)]
+    sig = configs.synthetic_signal(g, 22, nb, sigma=0.02)
+    script = {4: [(0, dict(coeff=3))], 9: [(3, dict(coeff=-1)), (4, dict(coeff=0, fscales=[0.7, 0.1]))],
+              15: [(0, dict(coeff=2)), (5, dict(coeff=1, delayblocks=0, in_scales=[0.25]))], 21: [(3, dict(coeff=5))]}
+
+    def run_engine(max_batch):
+        with Engine(g, mac_split=1, max_batch=max_batch) as e:
+            for c, h in enumerate(taps):
+                e.coeff_from_taps(c, h)
+            out = np.zeros((nb, g.out_bytes), np.uint8)
+            b = 0
+            while b < nb:
+                for filt, kw in script.get(b, []):
+                    e.set_control(filt, **kw)
+                n = 1
+                while n < max_batch and b + n < nb and (b + n) not in script:
+                    n += 1
+                e.process_blocks_async(sig[b:b + n], out[b:b + n], n)
+                b += n
+            e.synchronize()
+        return out
+
+    d = po.BlockDriver("oracle", g)
+    for c, h in enumerate(taps):
+        d.coeff_from_taps(c, h)
+    want = []
+    for b in range(nb):
+        for filt, kw in script.get(b, []):
+            d.set_control(filt, **kw)
+        want.append(d.process_block(sig[b]))
+    d.close()
+    one = run_engine(1)
+    assert_parity(g, one, np.stack(want))
+    assert np.array_equal(run_engine(4), one)

@@ -97,3 +97,30 @@ def test_c2_stereo_against_oracle(gpu_lib, oracle_libs):
         y, r = unpack_run(e.run(sig), g.out_formats, 4096), unpack_run(d.run(sig), g.out_formats, 4096)
         d.close()
     assert np.abs(y - r).max() <= 1e-6      # float32 output, full scale = 1.0
+
+
+def test_c1_bench1_config_graph_on_the_device(gpu_lib, oracle_libs):
+    """BASELINE configs[0]: bench1_config as shipped (/root/reference/bench1_config) -- 8192 x 8 partitions, 2 in / 2 out
+    S24_4LE, six "dirac pulse" filters, four of them feeding the other two through to_filters.  With unit pulses
+    every path is the identity, so out0 = in0 + in1 and out1 = in0 + in1 EXACTLY (integer samples below 2^22);
+    with random coefficients the device follows the oracle's block sequence."""
+    g = configs.config_c1_chained()
+    L = g.filter_length
+    sig = configs.synthetic_signal(g, 1, 12, sigma=0.05)
+    x = unpack_run(sig, g.in_formats, L)
+    pulse = np.zeros(8 * L, np.float32)
+    pulse[0] = 1.0
+    with Engine(g) as e:
+        for c in range(6):
+            e.coeff_from_taps(c, pulse)
+        y = unpack_run(e.run(sig), g.out_formats, L)
+    assert np.array_equal(y[0], x[0] + x[1]) and np.array_equal(y[1], x[0] + x[1])
+    taps = [t * 0.7 for t in configs.synthetic_filters(g, 11)]
+    with Engine(g) as e:
+        d = po.BlockDriver("oracle", g)
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+            d.coeff_from_taps(c, h)
+        got, ref = unpack_run(e.run(sig), g.out_formats, L), unpack_run(d.run(sig), g.out_formats, L)
+        d.close()
+    assert np.abs(ref).max() > 1e4 and np.abs(got - ref).max() <= 2 and np.mean(np.abs(got - ref) > 1) < 1e-4
