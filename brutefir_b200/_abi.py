@@ -83,7 +83,7 @@ ENGINE_SYMBOLS = [
     "bfcuda_coeff_from_taps", "bfcuda_coeff_set_block", "bfcuda_coeff_get_block",
     "bfcuda_coeff_runtime_block", "bfcuda_set_control", "bfcuda_get_overflow", "bfcuda_reset_overflow",
     "bfcuda_process_block", "bfcuda_process_block_async", "bfcuda_synchronize",
-    "bfcuda_process_blocks", "bfcuda_process_blocks_async", "bfcuda_process_blocks_device",
+    "bfcuda_process_blocks", "bfcuda_process_blocks_async", "bfcuda_wait_previous", "bfcuda_process_blocks_device",
     "bfcuda_process_block_device", "bfcuda_device_io", "bfcuda_upload_input", "bfcuda_download_output",
     "bfcuda_upload_inputs", "bfcuda_download_outputs",
     "bfcuda_host_alloc", "bfcuda_host_free", "bfcuda_timer_start", "bfcuda_timer_stop",
@@ -136,6 +136,7 @@ def load_library() -> C.CDLL:
     lib.bfcuda_process_block.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bfcuda_process_block_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bfcuda_synchronize.argtypes = [C.c_void_p]
+    lib.bfcuda_wait_previous.argtypes = [C.c_void_p, C.c_int]
     lib.bfcuda_process_block_device.argtypes = [C.c_void_p]
     lib.bfcuda_process_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.bfcuda_process_blocks_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]

@@ -1398,6 +1398,18 @@ int bfcuda_process_block_async(bfcuda_engine *e, const void *raw_in, void *raw_o
     return bfcuda_process_blocks_async(e, 1, raw_in, raw_out);
 }
 
+int bfcuda_wait_previous(bfcuda_engine *e, int calls_back)
+{
+    if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    if (calls_back < 0 || calls_back > 1 || (unsigned int)calls_back >= e->io_count) {
+        return fail(BFCUDA_EINVAL, "only the two most recent asynchronous calls can be waited for");
+    }
+    CU(cudaSetDevice(e->device));
+    // the raw blocks are double buffered by call parity; a call's read-out event is re-recorded two calls later
+    CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u - (unsigned int)calls_back) & 1u]));
+    return check_status(e);
+}
+
 int bfcuda_synchronize(bfcuda_engine *e)
 {
     if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");

@@ -13,7 +13,9 @@
  *
  *   cc -O2 -Iinclude host/bfcuda_run.c -o host/bfcuda_run -Lbrutefir_b200 -lbfcuda -Wl,-rpath,'$ORIGIN/../brutefir_b200' -lm
  *
- *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] in.raw out.raw
+ *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] [-B blocks] in.raw out.raw
+ *     -B blocks: hand the engine up to `blocks` (<= 8) audio blocks per call and keep two calls in flight while
+ *               the files are read and written (offline mode; bit-identical output, several times the throughput)
  *     taps.f32: raw little-endian float32 (float64 with -r 64) taps, one filter after the other, L*P each
  *               ("dirac" = unit pulses, the reference's "dirac pulse" coefficient, bfconf.c:1905-1913)
  */
@@ -88,7 +90,7 @@ now(void)
 int
 main(int argc, char *argv[])
 {
-    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, device = 0, a;
+    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, device = 0, batch = 1, a;
     const char *fin = "S24_4LE", *fout = "S24_4LE", *coeff_path = "dirac", *in_path = NULL, *out_path = NULL;
     struct bfcuda_sample_format sf_in, sf_out;
     struct bfcuda_buffer_format *bf_in, *bf_out;
@@ -99,7 +101,9 @@ main(int argc, char *argv[])
     int n_filters, *chan, *coeff_blocks, f, c, rs;
     double *ones, t0, t1, stage[BFCUDA_N_STAGES];
     long blocks = 0, stage_blocks = 0, launches = 0;
-    void *raw_in, *raw_out;
+    void *raw_in[3], *raw_out[3];
+    size_t in_bytes, out_bytes;
+    int nblk[3], k;
     FILE *in, *out;
 
     for (a = 1; a < argc; a++) {
@@ -114,9 +118,10 @@ main(int argc, char *argv[])
         else if (!strcmp(argv[a], "-c") && a + 1 < argc) coeff_path = argv[++a];
         else if (!strcmp(argv[a], "-m")) matrix = 1;
         else if (!strcmp(argv[a], "-b")) bench = 1;
+        else if (!strcmp(argv[a], "-B") && a + 1 < argc) batch = atoi(argv[++a]);
         else if (in_path == NULL) in_path = argv[a];
         else if (out_path == NULL) out_path = argv[a];
-        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [in [out]]", argv[0]);
+        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [-B blocks] [in [out]]", argv[0]);
     }
     if (parse_format(fin, &sf_in) != 0 || parse_format(fout, &sf_out) != 0) DIE("Unknown sample format.");
     rs = realbits / 8;
@@ -154,6 +159,7 @@ main(int argc, char *argv[])
     cfg.coeff_n_blocks = coeff_blocks;
     cfg.device = device;
     cfg.flags = bench ? BFCUDA_FLAG_STAGE_TIMING : 0;
+    cfg.max_batch = batch;
     CHECK(bfcuda_create(&cfg, &eng));
     CHECK(bfcuda_get_info(eng, &info));
 
@@ -183,26 +189,46 @@ main(int argc, char *argv[])
     in = in_path == NULL || !strcmp(in_path, "-") ? stdin : fopen(in_path, "rb");
     out = out_path == NULL || !strcmp(out_path, "-") ? stdout : fopen(out_path, "wb");
     if (in == NULL || out == NULL) DIE("Could not open input or output: %s", strerror(errno));
-    raw_in = bfcuda_host_alloc((size_t)cfg.n_bytes[BFCUDA_IN]);
-    raw_out = bfcuda_host_alloc((size_t)cfg.n_bytes[BFCUDA_OUT]);
-    if (raw_in == NULL || raw_out == NULL) DIE("%s", bfcuda_strerror());
+    in_bytes = (size_t)cfg.n_bytes[BFCUDA_IN];
+    out_bytes = (size_t)cfg.n_bytes[BFCUDA_OUT];
+    for (k = 0; k < 3; k++) {
+        raw_in[k] = bfcuda_host_alloc(in_bytes * (size_t)batch);
+        raw_out[k] = bfcuda_host_alloc(out_bytes * (size_t)batch);
+        if (raw_in[k] == NULL || raw_out[k] == NULL) DIE("%s", bfcuda_strerror());
+    }
 
-    fprintf(stderr, "bfcuda_run: %d filters x %d taps (%d x %d) on %s, MAC %.1f MB/block\n", n_filters, L * P, L, P,
-            info.device_name, (double)info.mac_bytes_per_block / 1e6);
+    fprintf(stderr, "bfcuda_run: %d filters x %d taps (%d x %d) on %s, MAC %.1f MB/block, %d block(s) per call\n", n_filters,
+            L * P, L, P, info.device_name, (double)info.mac_bytes_per_block / 1e6, batch);
     t0 = now();
-    for (;;) {
-        size_t got = fread(raw_in, 1, (size_t)cfg.n_bytes[BFCUDA_IN], in);
+    /* Call k is submitted, then call k-1's output (complete while call k runs) is written: the file I/O of the
+     * reference's input / output processes overlapped with the filter process, with three buffer sets instead of
+     * the dai double buffers. */
+    for (k = 0;; k++) {
+        const int s = k % 3;
+        size_t got = fread(raw_in[s], 1, in_bytes * (size_t)batch, in);
         if (got == 0) {
             break;
         }
-        if (got < (size_t)cfg.n_bytes[BFCUDA_IN]) {
-            memset((char *)raw_in + got, 0, (size_t)cfg.n_bytes[BFCUDA_IN] - got);     /* dai.c:1312-1332 */
+        nblk[s] = (int)((got + in_bytes - 1) / in_bytes);
+        if (got < (size_t)nblk[s] * in_bytes) {
+            memset((char *)raw_in[s] + got, 0, (size_t)nblk[s] * in_bytes - got);       /* dai.c:1312-1332 */
         }
-        CHECK(bfcuda_process_block(eng, raw_in, raw_out));
-        if (fwrite(raw_out, 1, (size_t)cfg.n_bytes[BFCUDA_OUT], out) != (size_t)cfg.n_bytes[BFCUDA_OUT]) {
+        CHECK(bfcuda_process_blocks_async(eng, nblk[s], raw_in[s], raw_out[s]));
+        if (k > 0) {
+            const int p = (k - 1) % 3;
+            CHECK(bfcuda_wait_previous(eng, 1));
+            if (fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
+                DIE("write failed: %s", strerror(errno));
+            }
+        }
+        blocks += nblk[s];
+    }
+    if (k > 0) {
+        const int p = (k - 1) % 3;
+        CHECK(bfcuda_synchronize(eng));
+        if (fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
             DIE("write failed: %s", strerror(errno));
         }
-        blocks++;
     }
     t1 = now();
     if (out != stdout) fclose(out);
@@ -226,8 +252,10 @@ main(int argc, char *argv[])
                     stage[0], stage[1], stage[2], launches);
         }
     }
-    bfcuda_host_free(raw_in);
-    bfcuda_host_free(raw_out);
+    for (k = 0; k < 3; k++) {
+        bfcuda_host_free(raw_in[k]);
+        bfcuda_host_free(raw_out[k]);
+    }
     bfcuda_destroy(eng);
     return 0;
 }

@@ -175,6 +175,11 @@ int bfcuda_synchronize(bfcuda_engine *engine);
  * crossfade block is split off and processed on its own. */
 int bfcuda_process_blocks(bfcuda_engine *engine, int n_blocks, const void *raw_in, void *raw_out);
 int bfcuda_process_blocks_async(bfcuda_engine *engine, int n_blocks, const void *raw_in, void *raw_out);
+/* Wait until the output of a recent asynchronous call is complete in host memory without draining the pipeline:
+ * calls_back = 0 is the most recent bfcuda_process_block[s]_async call, 1 the one before it (the engine keeps two
+ * calls in flight).  A file-to-file host submits call k, then waits for call k-1 and writes its output while call k
+ * runs (host/bfcuda_run.c). */
+int bfcuda_wait_previous(bfcuda_engine *engine, int calls_back);
 
 /* Device-resident form: input already in the engine's device staging buffer (see bfcuda_device_io),
  * output left in the device output buffer; no host<->device copy.  Enqueue only. */
