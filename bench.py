@@ -67,7 +67,8 @@ def workload_config(name, graph, n_gpus):
                         f"{graph.filter_length} x {graph.n_blocks} partitions, {graph.sampling_rate} Hz, "
                         f"float_bits {graph.realsize * 8}, {graph.in_formats[0].sf.name} I/O, dither off",
             "n_filters": len(graph.filters), "filter_length": graph.filter_length, "n_blocks": graph.n_blocks,
-            "sampling_rate": graph.sampling_rate, "parallelism": f"filters sharded over {n_gpus} GPU(s), no collective",
+            "sampling_rate": graph.sampling_rate, "parallelism": f"filters sharded over {n_gpus} GPU(s), no collective; every rank is handed and returns "
+                           "only its own channels' interleaved blocks",
             "l2": "per-block working set (coefficients + delay lines) exceeds L2 many times over; nothing is re-read "
                   "from L2 between steps"}
 
@@ -204,7 +205,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    shard = shard_graph(graph, world)[rank]
+    # each rank owns a contiguous group of filters with their inputs and outputs and moves only ITS channels over
+    # its PCIe link: the host fans the interleaved input out into one block per GPU
+    shard = shard_graph(graph, world, compact=world > 1)[rank]
     sub = shard.graph
     taps = fast_filters(graph, 2000 + cid)
     peaks = {}
@@ -229,6 +232,8 @@ def main():
             eng.coeff_from_taps(c, taps[c])
         nbuf = 3
         sig = configs.synthetic_signal(graph, cid, nbuf * B)
+        if world > 1:
+            sig = shard.slice_input(graph, sig)
         pin_in = [PinnedBuffer(B * sub.in_bytes) for _ in range(nbuf)]
         pin_out = [PinnedBuffer(B * sub.out_bytes) for _ in range(nbuf)]
         for i in range(nbuf):

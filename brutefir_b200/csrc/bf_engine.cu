@@ -430,7 +430,7 @@ static void build_tables(bfcuda_engine *e)
     for (int c = 0; c < e->n_ch[0]; c++) {
         e->single_dest = e->single_dest && per_ch[c].size() == 1;
     }
-    e->simple_mix = e->split == 1 && !e->xfade_active;
+    e->simple_mix = !e->xfade_active;   // (a split partition sum is reduced right after the MAC)
     for (int o = 0; o < e->n_ch[1]; o++) {
         e->simple_mix = e->simple_mix && e->h_chans[o].n == 1;
     }
@@ -468,8 +468,14 @@ static int choose_split(const bfcuda_engine *e, int requested)
     }
     // Automatic: keep the reference's summation order (split 1) whenever the (filter, bin) space alone
     // fills the machine; otherwise split the partition sum so that ~512 threads per SM have work.
-    const long threads = (long)std::max(1, e->n_filters) * (e->N / 2 / (16 / e->rs));
-    const long target = (long)e->sm_count * 512;
+    // (The batched kernel gives a thread fewer bins but B blocks of independent work: one 256-thread block per SM
+    // is enough there.)
+    int lanes = 16 / e->rs;
+    if (e->max_batch > 1) {
+        lanes = e->rs == 4 ? (e->max_batch <= 4 ? 4 : 2) : (e->max_batch <= 2 ? 2 : 1);
+    }
+    const long threads = (long)std::max(1, e->n_filters) * (e->N / 2 / lanes);
+    const long target = (long)e->sm_count * (e->max_batch > 1 ? 256 : 512);
     long s = (target + threads - 1) / threads;
     s = std::min<long>(s, std::max(1, e->P / 8));
     return (int)std::max<long>(1, s);
@@ -1173,6 +1179,10 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
     CU(launch_mac(e->plan, ma, e->s_mac));
     e->launches += ma.n_jobs > 0;
+    if (e->split > 1) {
+        CU(launch_split_reduce(e->plan, ma, e->s_mac));
+        e->launches += ma.n_jobs > 0;
+    }
     for (int level = 1; level < e->n_levels; level++) {
         // filter -> filter chaining (bfrun.c:1603-1660): evaluate the finished source outputs, mix them with the
         // channel inputs into the consumers' delay lines, then run the consumers' partitions
@@ -1186,7 +1196,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         ea.n_in = e->n_ch[0];
         ea.n_vin = e->n_vin;
         ea.n_slots = ma.n_slots;
-        ea.split = e->split;
+        ea.split = 1;           // already reduced
         ea.batch = nb;
         CU(launch_eval(e->plan, ea, e->s_mac));
         sa.streams = e->d_mix_streams + e->level_mix_first[level];
@@ -1196,6 +1206,10 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         ma.n_jobs = e->level_job_first[level + 1] - e->level_job_first[level];
         CU(launch_mac(e->plan, ma, e->s_mac));
         e->launches += 3;
+        if (e->split > 1) {
+            CU(launch_split_reduce(e->plan, ma, e->s_mac));
+            e->launches++;
+        }
     }
     if (timing) CU(cudaEventRecord(ev[3], e->s_mac));
     CU(cudaEventRecord(e->ev_mac_done[par], e->s_mac));
@@ -1216,7 +1230,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ia.status = e->d_status;
     ia.n_out = e->n_ch[1];
     ia.n_slots = ma.n_slots;
-    ia.split = e->split;
+    ia.split = 1;               // already reduced (launch_split_reduce)
     ia.batch = nb;
     ia.out_stride = (size_t)e->n_bytes[1];
     ia.safety_limit = e->safety_limit;
@@ -1658,7 +1672,7 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
         if (index < 0 || index >= 2 * e->n_filters) return fail(BFCUDA_EINVAL, "filter out of range");
         const size_t n_slots = 2 * (size_t)std::max(1, e->n_filters);
         std::vector<unsigned char> part(nb);
-        for (int z = 0; z < e->split; z++) {
+        for (int z = 0; z < 1; z++) {       // partial 0 holds the complete sum (launch_split_reduce)
             // the last block of the most recent launch
             const char *src = (const char *)e->d_Y + (size_t)((e->launch_no + 1) & 1u) * e->y_stride +
                               nb * (((size_t)z * e->last_batch + (e->last_batch - 1)) * n_slots + index);

@@ -403,6 +403,50 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
 }
 
 // ======================================================================================================
+// k_split_reduce -- partial sums of a split partition range -> one spectrum per output, summed in range order
+// ======================================================================================================
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_split_reduce(MacArgs a, int N)
+{
+    constexpr int W = 16 / (int)sizeof(T);
+    typedef typename Vec16<T>::type V;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N / W) {
+        return;
+    }
+    const MacJob jb = a.jobs[blockIdx.y];
+    const int b = blockIdx.z;
+    const size_t zstride = (size_t)a.batch * a.n_slots * N;
+    T *y0 = reinterpret_cast<T *>(a.Y) + ((size_t)b * a.n_slots + jb.out) * N + (size_t)v * W;
+    Lanes<T, W> acc = as_lanes<T, W>(*reinterpret_cast<const V *>(y0));
+    int z = 1;
+    for (; z + 4 <= a.split; z += 4) {      // four partials in flight; added in ascending order
+        V p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            p[u] = ldg_stream(reinterpret_cast<const V *>(y0 + (size_t)(z + u) * zstride));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const Lanes<T, W> q = as_lanes<T, W>(p[u]);
+#pragma unroll
+            for (int l = 0; l < W; l++) {
+                acc.v[l] = add_rn(acc.v[l], q.v[l]);
+            }
+        }
+    }
+    for (; z < a.split; z++) {
+        const Lanes<T, W> q = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(y0 + (size_t)z * zstride)));
+#pragma unroll
+        for (int l = 0; l < W; l++) {
+            acc.v[l] = add_rn(acc.v[l], q.v[l]);
+        }
+    }
+    *reinterpret_cast<V *>(y0) = *reinterpret_cast<V *>(&acc);
+}
+
+// ======================================================================================================
 // k_mac_batch -- B consecutive audio blocks per launch, coefficient and delay-line spectra reused in
 // registers across the batch
 //
@@ -1081,6 +1125,19 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
         k_mac<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
     } else {
         k_mac<double, 4><<<grid, 256, 0, s>>>(a, plan.N);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split_reduce(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
+{
+    if (a.n_jobs == 0 || a.split <= 1) return cudaSuccess;
+    const int W = 16 / plan.realsize;
+    dim3 grid((plan.N / W + 255) / 256, a.n_jobs, a.batch);
+    if (plan.realsize == 4) {
+        k_split_reduce<float><<<grid, 256, 0, s>>>(a, plan.N);
+    } else {
+        k_split_reduce<double><<<grid, 256, 0, s>>>(a, plan.N);
     }
     return cudaGetLastError();
 }

@@ -161,6 +161,9 @@ struct MacArgs {
     int variant;                // 0 = direct streaming loads, 1 = bulk-copy (TMA) staged (batch 1 only)
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
+// With split > 1 the MAC leaves `split` partial sums per output: add them, in order, into partial 0 (the consumers
+// -- inverse stage, chaining evaluation -- then read one complete spectrum per filter).
+cudaError_t launch_split_reduce(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 
 struct InverseArgs {
     const void *Y;              // [split][batch][n_slots][N]

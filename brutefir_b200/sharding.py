@@ -16,6 +16,9 @@ import copy
 import dataclasses
 from typing import Dict, List
 
+import numpy as np
+
+from .formats import interleaved_layout
 from .graph import Filter, FilterGraph
 
 
@@ -63,6 +66,17 @@ def assign_filters(graph: FilterGraph, n_ranks: int, split_outputs: bool = False
     return owner
 
 
+def _compact_layout(bfs, fragsize):
+    """Interleave the given channels (all of one sample format) into a block of their own, like
+    calc_buffer_format does for one device (dai.c:537-576)."""
+    if not bfs:
+        return [], 32
+    name = bfs[0].sf.name
+    if any(bf.sf.name != name for bf in bfs):
+        raise ValueError("compact sharding needs one sample format per direction")
+    return interleaved_layout(len(bfs), name, fragsize)
+
+
 @dataclasses.dataclass
 class Shard:
     rank: int
@@ -73,11 +87,36 @@ class Shard:
     coeffs: List[int]               # global coefficient sets, in local order
     shared_outputs: List[int]       # LOCAL output indices that other ranks also feed
 
+    def slice_input(self, full_graph: FilterGraph, raw_blocks: np.ndarray) -> np.ndarray:
+        """raw_blocks[b, full in_bytes] in the full graph's layout -> this rank's blocks [b, in_bytes]."""
+        out = np.zeros((raw_blocks.shape[0], self.graph.in_bytes), np.uint8)
+        for i, c in enumerate(self.inputs):
+            src = _byte_index(full_graph.in_formats[c], full_graph.filter_length)
+            dst = _byte_index(self.graph.in_formats[i], full_graph.filter_length)
+            out[:, dst] = raw_blocks[:, src]
+        return out
 
-def shard_graph(graph: FilterGraph, n_ranks: int, split_outputs: bool = False) -> List[Shard]:
-    """One sub-graph per rank.  The buffer formats keep their byte offsets and spacings, i.e. every rank
-    addresses its channels inside the ORIGINAL raw block layout (the dai buffers, dai.c:537-576): the host
-    hands each rank the same block layout and no repacking is needed."""
+    def scatter_output(self, full_graph: FilterGraph, local_blocks: np.ndarray, full_blocks: np.ndarray) -> None:
+        """Write this rank's output blocks [b, out_bytes] into full_blocks[b, full out_bytes] (in place)."""
+        for i, c in enumerate(self.outputs):
+            src = _byte_index(self.graph.out_formats[i], full_graph.filter_length)
+            dst = _byte_index(full_graph.out_formats[c], full_graph.filter_length)
+            full_blocks[:, dst] = local_blocks[:, src]
+
+
+def _byte_index(bf, fragsize):
+    """Byte offsets of every sample byte of one channel inside a raw block (dai.c:537-576)."""
+    b = bf.sf.bytes
+    return (bf.byte_offset + np.arange(fragsize)[:, None] * (bf.sample_spacing * b) + np.arange(b)[None, :]).reshape(-1)
+
+
+def shard_graph(graph: FilterGraph, n_ranks: int, split_outputs: bool = False, compact: bool = False) -> List[Shard]:
+    """One sub-graph per rank.  By default the buffer formats keep their byte offsets and spacings, i.e. every
+    rank addresses its channels inside the ORIGINAL raw block layout (the dai buffers, dai.c:537-576): the host
+    hands each rank the same block layout and no repacking is needed -- but then every rank moves the whole
+    block over its PCIe link.  With ``compact`` each rank gets its own interleaved block holding only its
+    channels (the host fans the input slices out and gathers the output slices; in BruteFIR
+    terms: one dai device per GPU): ``Shard.slice_input`` / ``Shard.scatter_output`` do that repacking."""
     owner = assign_filters(graph, n_ranks, split_outputs)
     feeders: Dict[int, set] = {}
     for f, flt in enumerate(graph.filters):
@@ -100,9 +139,13 @@ def shard_graph(graph: FilterGraph, n_ranks: int, split_outputs: bool = False) -
             flt.outputs = [omap[c] for c in flt.outputs]
             flt.from_filters = [fmap[k] for k in flt.from_filters]
             local.append(flt)
-        sub = FilterGraph(graph.filter_length, graph.n_blocks, graph.realsize,
-                          [graph.in_formats[c] for c in ins], [graph.out_formats[c] for c in outs],
-                          graph.in_bytes, graph.out_bytes, local, list(graph.coeff_n_blocks),
+        in_fmts, out_fmts = [graph.in_formats[c] for c in ins], [graph.out_formats[c] for c in outs]
+        in_bytes, out_bytes = graph.in_bytes, graph.out_bytes
+        if compact:
+            in_fmts, in_bytes = _compact_layout(in_fmts, graph.filter_length)
+            out_fmts, out_bytes = _compact_layout(out_fmts, graph.filter_length)
+        sub = FilterGraph(graph.filter_length, graph.n_blocks, graph.realsize, in_fmts, out_fmts,
+                          in_bytes, out_bytes, local, list(graph.coeff_n_blocks),
                           safety_limit=graph.safety_limit, sampling_rate=graph.sampling_rate)
         shared = [omap[o] for o in outs if len(feeders[o]) > 1]
         shards.append(Shard(r, sub, mine, ins, outs, coeffs, shared))

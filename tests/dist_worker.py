@@ -20,11 +20,12 @@ def main():
     g = configs.config_c3(n_ch=6, L=32, P=4)
     taps = configs.synthetic_filters(g, 3)
     sig = configs.synthetic_signal(g, 3, 8)
-    shard = shard_graph(g, world)[rank]
+    shard = shard_graph(g, world, compact=True)[rank]   # each rank moves only its own channels' bytes
     d = po.BlockDriver("oracle", shard.graph)
     for c in shard.coeffs:
         d.coeff_from_taps(c, taps[c])
-    out = d.run(sig)                                    # only this rank's output channels are non-zero
+    out = np.zeros((sig.shape[0], g.out_bytes), np.uint8)
+    shard.scatter_output(g, d.run(shard.slice_input(g, sig)), out)     # only this rank's channels are non-zero
     d.close()
     gathered = [torch.zeros(out.shape, dtype=torch.uint8) for _ in range(world)]
     dist.all_gather(gathered, torch.from_numpy(out))

@@ -12,6 +12,7 @@ from brutefir_b200.formats import (interleaved_layout, pack_block, parse_sample_
                                    unpack_block)
 from brutefir_b200.graph import Filter, FilterGraph
 from brutefir_b200.sharding import assign_filters, filter_groups, shard_graph
+from oracle import pyoracle as po
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -73,6 +74,31 @@ def test_shards_cover_the_graph_once():
             assert s.graph.in_formats[lf.inputs[0]].byte_offset == g.in_formats[g.filters[gf].inputs[0]].byte_offset
     split = shard_graph(configs.config_c5(), 2, split_outputs=True)
     assert [s.shared_outputs for s in split] == [[0, 1], [0, 1]]
+
+
+def test_compact_shards_reassemble_to_the_whole_graph(oracle_libs):
+    """compact=True: every rank gets an interleaved block of only its channels (one dai device per GPU); slicing
+    the input, running each shard and scattering the outputs back must give the unsharded graph's bytes."""
+    g = configs.config_c3(n_ch=6, L=32, P=3)
+    g.filters[4].outputs, g.filters[4].out_scales = [5], [0.5]      # two filters into output 5: they must stay together
+    taps = configs.synthetic_filters(g, 9)
+    sig = configs.synthetic_signal(g, 9, 7)
+    full = po.BlockDriver("oracle", g)
+    for c, h in enumerate(taps):
+        full.coeff_from_taps(c, h)
+    want = full.run(sig)
+    full.close()
+    got = np.zeros_like(want)
+    shards = shard_graph(g, 3, compact=True)
+    assert sum(s.graph.in_bytes for s in shards) <= g.in_bytes + 3 * 32
+    for s in shards:
+        assert s.graph.in_bytes < g.in_bytes and all(bf.sample_spacing == len(s.inputs) for bf in s.graph.in_formats)
+        d = po.BlockDriver("oracle", s.graph)
+        for c, h in enumerate(taps):
+            d.coeff_from_taps(c, h)
+        s.scatter_output(g, d.run(s.slice_input(g, sig)), got)
+        d.close()
+    assert np.array_equal(got, want)
 
 
 def test_world_size_2_gloo(tmp_path):
