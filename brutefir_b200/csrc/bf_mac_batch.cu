@@ -34,13 +34,17 @@ struct __align__(sizeof(T) * W) LanesB {
     T v[W];
 };
 
+// cp.async with a run-time source size: src_bytes = BYTES copies, src_bytes = 0 writes zeros and does not touch
+// global memory (the "zfill" form) -- predication without a branch.
 template <int BYTES>
-__device__ __forceinline__ void cp_async(void *dst_smem, const void *src)
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src, unsigned int src_bytes)
 {
     if (BYTES == 16) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+                     : "memory");
     } else {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES),
+                     "r"(src_bytes)
                      : "memory");
     }
 }
@@ -136,23 +140,24 @@ __global__ void __launch_bounds__(256, MINB) k_mac_batch2(MacArgs a, int N)
             ny[b] = (T)0;
         }
         if (n > 0) {
-            // producer state: the next step to request
+            // producer state: the next step to request.  Step j needs H[i0 + j] and the delay-line block that joins
+            // the window at step j (ring slot t - i0 - j); step 0's is loaded again although the window already holds
+            // it (one vector per thread and launch) so that every request is the same four copies, no branches.
             const T *hnext = H;
-            int xs = a.t - i0;                  // ring slot of step j's new delay-line block, j = 0 (not loaded: in the window)
+            int xs = a.t - i0;
             xs += (xs < 0) ? R : 0;
+            const T *xnext = X + (size_t)xs * N;
+            const size_t wrap = (size_t)(R - 1) * N;
             int jn = 0;
             auto issue = [&](int stage) {       // request step jn into `stage`; always closes a group
-                if (jn < n) {
-                    cp_async<VB>(stage_ptr(stage, 0), hnext);
-                    cp_async<VB>(stage_ptr(stage, 1), hnext + M);
-                    if (jn > 0) {
-                        const T *xp = X + (size_t)xs * N;
-                        cp_async<VB>(stage_ptr(stage, 2), xp);
-                        cp_async<VB>(stage_ptr(stage, 3), xp + M);
-                    }
-                }
+                const unsigned int sz = jn < n ? (unsigned int)VB : 0u;
+                cp_async<VB>(stage_ptr(stage, 0), hnext, sz);
+                cp_async<VB>(stage_ptr(stage, 1), hnext + M, sz);
+                cp_async<VB>(stage_ptr(stage, 2), xnext, sz);
+                cp_async<VB>(stage_ptr(stage, 3), xnext + M, sz);
                 cp_async_commit();
                 hnext += N;
+                xnext = xs == 0 ? xnext + wrap : xnext - N;
                 xs = xs == 0 ? R - 1 : xs - 1;
                 jn++;
             };
