@@ -59,6 +59,9 @@ class ConfigC(C.Structure):
                 ("device", C.c_int),
                 ("flags", C.c_uint),
                 ("mac_split", C.c_int),
+                ("apply_dither", C.POINTER(C.c_int)),
+                ("sampling_rate", C.c_int),
+                ("max_dither_table_size", C.c_int),
                 ("max_batch", C.c_int)]
 
 

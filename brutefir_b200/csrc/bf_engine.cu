@@ -184,6 +184,9 @@ struct bfcuda_engine {
     std::vector<EvalEntry> h_eval_entries;
     std::vector<MixTerm> h_eval_terms;
     std::vector<int> level_job_first, level_mix_first, level_eval_first;   // [n_levels + 1]
+    // HP-TPDF dither
+    std::vector<int> dither_of_out;     // per output: index into the dithered channels, -1 = not dithered
+    DitherArgs dither;                  // device pointers; n_dither = 0 when nothing is dithered
     bool dirty, xfade_active;
     size_t mac_bytes;           // algorithmic MAC bytes of one block launched alone
     size_t mac_bytes_batch;     // compulsory MAC bytes of one full batch of max_batch blocks
@@ -392,6 +395,9 @@ static void build_tables(bfcuda_engine *e)
         oc.n = 0;
         oc.xf_first = -1;
         oc.shared = std::find(e->shared_out.begin(), e->shared_out.end(), o) != e->shared_out.end() ? 1 : 0;
+        if (e->dither_of_out[o] >= 0) {
+            oc.shared |= 2;
+        }
         bool any_xf = false;
         for (int f = 0; f < F; f++) {
             const FilterState &fs = e->filters[f];
@@ -481,6 +487,103 @@ static int choose_split(const bfcuda_engine *e, int requested)
     return (int)std::max<long>(1, s);
 }
 
+// ---- dither table (dither.c:37-139) -------------------------------------------------------------------------
+// "maximally equidistributed combined Tausworthe generator" (GSL taus) with the default seed, one int8 per sample;
+// channel j starts `spacing` bytes after channel j-1 (10 s of samples, at least 1 s and at least one block).
+static uint32_t tausrand(uint32_t state[3])
+{
+#define BF_TAUSWORTHE(s, a, b, c, d) ((s & c) << d) ^ (((s << a) ^ s) >> b)
+    state[0] = BF_TAUSWORTHE(state[0], 13, 19, (uint32_t)4294967294U, 12);
+    state[1] = BF_TAUSWORTHE(state[1], 2, 25, (uint32_t)4294967288U, 4);
+    state[2] = BF_TAUSWORTHE(state[2], 3, 11, (uint32_t)4294967280U, 17);
+    return state[0] ^ state[1] ^ state[2];
+}
+
+static int setup_dither(bfcuda_engine *e, const struct bfcuda_config *c)
+{
+    e->dither_of_out.assign(std::max(1, e->n_ch[1]), -1);
+    if (c->apply_dither == nullptr) {
+        return 0;
+    }
+    std::vector<DitherChan> chans;
+    for (int o = 0; o < e->n_ch[1]; o++) {
+        const bfcuda_sample_format &sf = e->fmt[1][o].sf;
+        // bfconf.c:3173-3217: no dither on float formats, on more than 16 bit at float_bits 32, on 32 bit formats
+        if (!c->apply_dither[o] || sf.isfloat || (e->rs == 4 && sf.sbytes > 2) || sf.sbytes >= 4) {
+            continue;
+        }
+        e->dither_of_out[o] = (int)chans.size();
+        DitherChan dc;
+        dc.out = o;
+        dc.randtab_ptr = 0;
+        dc.e0 = dc.e1 = 0.0;
+        chans.push_back(dc);
+    }
+    const int n = (int)chans.size();
+    if (n == 0) {
+        return 0;
+    }
+    const int rate = c->sampling_rate > 0 ? c->sampling_rate : 44100;
+    int spacing = 10 * rate;
+    const int minspacing = std::max(rate, e->L);
+    spacing = std::max(spacing, minspacing);
+    if (c->max_dither_table_size > 0 && (long)n * spacing > c->max_dither_table_size) {
+        spacing = c->max_dither_table_size / n;
+    }
+    if (spacing < minspacing) {
+        return fail(BFCUDA_EINVAL, "Maximum dither table size %d bytes is too small, must at least be %d bytes.",
+                    c->max_dither_table_size, n * rate * minspacing);
+    }
+    const size_t size = (size_t)n * spacing + 1;
+    std::vector<int8_t> tab(size);
+    uint32_t st[3];
+    {
+        uint32_t seed = 1;      // tausinit(state, 0): "default seed is 1"
+#define BF_LCG(v) ((69069 * (v)) & 0xFFFFFFFFU)
+        st[0] = BF_LCG(seed);
+        st[1] = BF_LCG(st[0]);
+        st[2] = BF_LCG(st[1]);
+        for (int i = 0; i < 6; i++) {
+            tausrand(st);
+        }
+    }
+    for (size_t i = 0; i < size; i++) {
+        tab[i] = (int8_t)(tausrand(st) & 0x000000FF);
+    }
+    for (int j = 0; j < n; j++) {
+        chans[j].randtab_ptr = j * spacing + 1;
+    }
+    // dither.c:113-131: integer difference -> dither in (-1, +1) plus the +0.5 that makes truncation a mid-tread
+    // requantiser.  Entry 511 (difference +255, which the reference's 511-entry map does not cover) continues the line.
+    std::vector<double> mapd(512);
+    std::vector<float> mapf(512);
+    mapf[0] = -0.5f;
+    mapd[0] = -0.5;
+    for (int k = -255; k < 254; k++) {
+        mapf[k + 256] = (float)(0.5 + 1.0 / 255.0 + 1.0 / 255.0 * (float)k);
+        mapd[k + 256] = 0.5 + 1.0 / 255.0 + 1.0 / 255.0 * (double)k;
+    }
+    mapf[510] = 1.5f;
+    mapd[510] = 1.5;
+    mapf[511] = (float)(1.5 + 1.0 / 255.0);
+    mapd[511] = 1.5 + 1.0 / 255.0;
+    int rc;
+    int8_t *d_tab = nullptr;
+    void *d_map = nullptr;
+    if ((rc = dev_alloc(e, &d_tab, size, false)) != 0) return rc;
+    e->dither.randtab = d_tab;
+    if ((rc = dev_alloc(e, &d_map, 512 * (size_t)e->rs, false)) != 0) return rc;
+    e->dither.randmap = d_map;
+    if ((rc = dev_alloc(e, &e->dither.chans, sizeof(DitherChan) * n, false)) != 0) return rc;
+    CU(cudaMemcpy(d_tab, tab.data(), size, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_map, e->rs == 4 ? (const void *)mapf.data() : (const void *)mapd.data(), 512 * (size_t)e->rs,
+                  cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->dither.chans, chans.data(), sizeof(DitherChan) * n, cudaMemcpyHostToDevice));
+    e->dither.randtab_size = (int)size;
+    e->dither.n_dither = n;
+    return 0;
+}
+
 // ======================================================================================================
 // C ABI
 // ======================================================================================================
@@ -517,7 +620,8 @@ void bfcuda_destroy(bfcuda_engine *e)
     void *ptrs[] = { e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
-                     e->d_keep, e->d_eval_entries, e->d_eval_terms };
+                     e->d_keep, e->d_eval_entries, e->d_eval_terms, e->dither.chans, (void *)e->dither.randtab,
+                     (void *)e->dither.randmap };
     for (void *p : ptrs) {
         if (p != nullptr) {
             cudaFree(p);
@@ -634,6 +738,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->fdl_ring = 2 * e->P + 2 * e->max_batch;
     e->slot_t = 0;
     e->d_xt[0] = e->d_xt[1] = nullptr;
+    memset(&e->dither, 0, sizeof(e->dither));
     e->d_keep = nullptr;
     e->d_eval_entries = nullptr;
     e->d_eval_terms = nullptr;
@@ -847,6 +952,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
                 TRYCU(cudaMemcpy(e->d_fmt[io], f.data(), sizeof(SampleFormat) * f.size(), cudaMemcpyHostToDevice));
             }
         }
+        TRY(setup_dither(e, c));
         TRY(bfcuda_reset_overflow(e));
         e->dirty = true;
         e->xfade_active = false;
@@ -1263,6 +1369,10 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         } else {
             CU(launch_quantise_shared(e->plan, ia, e->s_inv));
         }
+        e->launches++;
+    }
+    if (e->dither.n_dither > 0) {
+        CU(launch_dither(e->plan, ia, e->dither, e->s_inv));
         e->launches++;
     }
     if (timing) {

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32 * WPB) k_pack(InverseArgs a, int L)
         }
         __syncwarp();
         const int c = c0 + lane;
-        if (c < a.n_out) {
+        if (c < a.n_out && !(a.chans[c].shared & 2)) {      // dithered outputs are k_dither's
             const SampleFormat f = a.fmt[c];
             const size_t stride = (size_t)f.sample_spacing * f.bytes;
             uint8_t *p = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset + (size_t)n0 * stride;

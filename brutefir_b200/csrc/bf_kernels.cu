@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(256) k_quantise_shared(InverseArgs a, int L)
 {
     const int o = blockIdx.x, blk = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
     __shared__ QuantStats wstats[32];
-    if (!a.chans[o].shared) {
+    if (a.chans[o].shared != 1) {      // not shared, or dithered (k_dither's job)
         return;
     }
     const SampleFormat f = a.fmt[o];
@@ -815,6 +815,113 @@ __global__ void __launch_bounds__(1024, 1) k_eval(EvalArgs a, const T *__restric
             dst[M + k] = im;
         });
         __syncthreads();
+    }
+}
+
+// ======================================================================================================
+// k_dither -- real2raw with HP-TPDF dither and error feedback
+// ======================================================================================================
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_dither(InverseArgs a, DitherArgs d, int L)
+{
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    if (j >= d.n_dither) {
+        return;
+    }
+    DitherChan st = d.chans[j];
+    const int o = st.out;
+    const SampleFormat f = a.fmt[o];
+    const T *map = reinterpret_cast<const T *>(d.randmap) + 256;
+    const size_t stride = (size_t)f.sample_spacing * f.bytes;
+    const int bits_n = f.sbytes << 3;
+    const int32_t imin = (int32_t)(-((uint64_t)1 << (bits_n - 1)));
+    const int32_t imax = (int32_t)(((uint64_t)1 << (bits_n - 1)) - 1);
+    const T rmin = (T)imin, rmax = (T)imax;
+    // this lane is the only writer of its channel's counters: the reference's sequential bookkeeping, literally
+    Overflow of = a.overflow[o];
+    unsigned int status = 0;
+    T e0 = (T)st.e0, e1 = (T)st.e1;
+
+    for (int blk = 0; blk < a.batch; blk++) {
+        // dither_preloop_real2int_hp_tpdf, dither.h:28-38.  On a wrap the reference copies the last used table byte
+        // into slot 0 so that the differenced sequence continues; here the table is read-only and the byte travels
+        // in a register.
+        int8_t prev;
+        if (st.randtab_ptr + L >= d.randtab_size) {
+            prev = d.randtab[st.randtab_ptr - 1];
+            st.randtab_ptr = 1;
+        } else {
+            prev = d.randtab[st.randtab_ptr - 1];
+        }
+        const int8_t *tab = d.randtab + st.randtab_ptr;
+        st.randtab_ptr += L;
+        const T *src = reinterpret_cast<const T *>(a.out_time) + ((size_t)blk * a.n_out + o) * L;
+        uint8_t *raw = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset;
+        for (int n = 0; n < L; n++) {
+            T real_sample = src[n];
+            // real2raw.h:24-42
+            if (!isfinite((double)real_sample)) {
+                status |= BF_STATUS_NONFINITE;
+            }
+            if (a.safety_limit != 0.0 && ((double)real_sample < -a.safety_limit * of.max ||
+                                          (double)real_sample > a.safety_limit * of.max)) {
+                status |= BF_STATUS_SAFETY;
+            }
+            // dither_funs.h:20-33: error feedback {1, -1}, then dither + the 0.5 offset from the map
+            real_sample = add_rn(real_sample, sub_rn(e0, e1));
+            e1 = e0;
+            const int8_t cur = tab[n];
+            const T dithered = add_rn(real_sample, map[(int)cur - (int)prev]);
+            prev = cur;
+            int32_t sample;
+            if (dithered < (T)0) {
+                if (dithered <= rmin) {
+                    sample = imin;
+                    of.n_overflows++;
+                    if ((double)real_sample < -of.largest) {
+                        of.largest = (double)-dithered;
+                    }
+                } else {
+                    sample = (int32_t)dithered;
+                    sample--;
+                    if (sample < -of.intlargest) {
+                        of.intlargest = -sample;
+                    }
+                }
+            } else {
+                if (dithered > rmax) {
+                    sample = imax;
+                    of.n_overflows++;
+                    if ((double)real_sample > of.largest) {
+                        of.largest = (double)dithered;
+                    }
+                } else {
+                    sample = (int32_t)dithered;
+                    if (sample > of.intlargest) {
+                        of.intlargest = sample;
+                    }
+                }
+            }
+            e0 = sub_rn(real_sample, (T)sample);
+            uint64_t bits = (uint64_t)(uint32_t)sample;
+            if (f.bytes < 4) {
+                bits &= ((uint64_t)1 << (8 * f.bytes)) - 1;
+            }
+            if (f.swap && f.bytes > 1) {
+                bits = swap_bytes(bits, f.bytes);
+            }
+            store_raw_le(raw + (size_t)n * stride, bits, f.bytes);
+        }
+    }
+    st.e0 = (double)e0;
+    st.e1 = (double)e1;
+    d.chans[j] = st;
+    a.overflow[o].n_overflows = of.n_overflows;
+    a.overflow[o].intlargest = of.intlargest;
+    a.overflow[o].largest = of.largest;
+    if (status != 0) {
+        atomicOr(a.status, status);
     }
 }
 
@@ -1153,6 +1260,18 @@ cudaError_t launch_eval(const FftPlan &plan, const EvalArgs &a, cudaStream_t s)
 {
     if (a.n_entries == 0) return cudaSuccess;
     BF_FFT_DISPATCH(plan, k_eval, a.n_entries, s, a, (const T *)plan.tw, plan.N / 2);
+}
+
+cudaError_t launch_dither(const FftPlan &plan, const InverseArgs &a, const DitherArgs &d, cudaStream_t s)
+{
+    if (d.n_dither == 0) return cudaSuccess;
+    const int grid = (d.n_dither + 31) / 32;
+    if (plan.realsize == 4) {
+        k_dither<float><<<grid, 32, 0, s>>>(a, d, plan.N / 2);
+    } else {
+        k_dither<double><<<grid, 32, 0, s>>>(a, d, plan.N / 2);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_quantise_shared(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)

@@ -49,7 +49,8 @@ struct OutChan {
     int first;
     int n;
     int xf_first;   // -1 = no crossfade this block
-    int shared;     // 1 = summed across ranks before quantisation: stop after the time-domain store
+    int shared;     // bit 0: summed across ranks before quantisation; bit 1: dithered (k_dither quantises it);
+                    // either bit: the inverse stage / k_pack stop after the time-domain store
 };
 
 struct FftPlan {
@@ -187,7 +188,23 @@ struct InverseArgs {
 cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
 
-// quantise + pack out_time rows of the channels with chans[o].shared (after the cross-rank sum)
+// HP-TPDF dither with first-order error feedback (dither.c, dither.h:28-38, dither_funs.h:7-68): sequential per
+// channel, one lane per dithered output walks its L samples (and the blocks of a batch) in order.
+struct DitherChan {         // device-resident state of one dithered output (struct dither_state, dither.h:17-22)
+    int out;                // output channel
+    int randtab_ptr;
+    double e0, e1;          // error feedback state sf[0..1] / sd[0..1], kept in the real type's precision
+};
+struct DitherArgs {
+    DitherChan *chans;      // [n_dither]
+    const int8_t *randtab;  // dither_randtab
+    const void *randmap;    // 512 reals: map[d + 256] for d = randtab[n] - randtab[n-1]
+    int randtab_size;
+    int n_dither;
+};
+cudaError_t launch_dither(const FftPlan &plan, const InverseArgs &a, const DitherArgs &d, cudaStream_t s);
+
+// quantise + pack out_time rows of the channels with chans[o].shared == 1 (after the cross-rank sum)
 cudaError_t launch_quantise_shared(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
 
 // coefficient preprocessing (convolver_coeffs2cbuf, fftw_convolver.c:526-573): taps[b][L] -> H block

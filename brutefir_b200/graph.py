@@ -52,6 +52,8 @@ class FilterGraph:
     coeff_n_blocks: List[int]
     safety_limit: float = 0.0
     sampling_rate: int = 48000
+    apply_dither: Sequence[bool] | None = None      # per output channel (`dither: true` of its device)
+    max_dither_table_size: int = 0
 
     @property
     def n_fft(self) -> int:
@@ -134,6 +136,11 @@ class FilterGraph:
         cfg.device = device
         cfg.flags = flags
         cfg.mac_split = mac_split
+        if self.apply_dither is not None:
+            assert len(self.apply_dither) == len(self.out_formats)
+            cfg.apply_dither = C.cast(int_array([int(bool(v)) for v in self.apply_dither]), C.POINTER(C.c_int))
+        cfg.sampling_rate = self.sampling_rate
+        cfg.max_dither_table_size = self.max_dither_table_size
         cfg.max_batch = max_batch
         return cfg, keep
 

@@ -114,6 +114,12 @@ struct bfcuda_config {
     unsigned int flags;         /* BFCUDA_FLAG_* */
     int mac_split;              /* 0 = automatic; 1 = never split the partition sum (reference summation order);
                                    S > 1 = split it S ways */
+    const int *apply_dither;    /* per output channel: dither requested (`dither: true` of its device, bfconf.c:3173-3217);
+                                   NULL = none.  Like bfconf, the engine silently drops the request for float formats,
+                                   for more than 16 bit at realsize 4 and for 32 bit formats.  HP-TPDF dither with
+                                   first-order error feedback, dither_funs.h:7-68: a sequential recurrence per channel. */
+    int sampling_rate;          /* only sizes the dither table (dither.c:75-96); 0 = 44100 */
+    int max_dither_table_size;  /* bfconf->max_dither_table_size, 0 = no limit */
     int max_batch;              /* 0/1 = block by block (the reference's schedule).  B > 1 (<= 8 at realsize 4, <= 4 at
                                    realsize 8) lets bfcuda_process_blocks* take up to B consecutive blocks per call:
                                    offline / file-to-file throughput mode.  Results are bit-identical to B single

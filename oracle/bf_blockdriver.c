@@ -31,6 +31,7 @@
 #ifdef DRV_REFERENCE
 #include "convolver.h"      /* the reference's header, found via -I/root/reference */
 #include "bfconf.h"
+#include "dither.h"
 #define CV(name) convolver_##name
 #define DRV(name) bfref_##name
 #define CV_MIXMODE_INPUT CONVOLVER_MIXMODE_INPUT
@@ -94,6 +95,7 @@ struct drv {
     void **input_freqcbuf, **output_freqcbuf;
     void *(*input_timecbuf)[2];
     cv_overflow *overflow;
+    void **dither_state;            /* per output: struct dither_state * (bfconf->dither_state), NULL = no dither */
     unsigned int blockcounter;
     int curbuf;
     int n_threads;
@@ -293,6 +295,40 @@ DRV(create)(const struct bfcuda_config *c, int n_threads, struct drv **out)
     d->output_freqcbuf = calloc(d->n_ch[OUT], sizeof(void *));
     d->debug_time = calloc(d->n_ch[OUT], sizeof(void *));
     d->overflow = calloc(d->n_ch[OUT], sizeof(cv_overflow));
+    d->dither_state = calloc(d->n_ch[OUT] + 1, sizeof(void *));
+    if (c->apply_dither != NULL) {
+        /* bfconf.c:3173-3238: which outputs are dithered, then one table for all of them */
+        int j = 0, rate = c->sampling_rate > 0 ? c->sampling_rate : 44100;
+        int *which = calloc(d->n_ch[OUT] + 1, sizeof(int));
+        for (n = 0; n < d->n_ch[OUT]; n++) {
+            const cv_buffer_format *b = &d->bf[OUT][n];
+            if (!c->apply_dither[n] || b->sf.isfloat || (d->rs == 4 && b->sf.sbytes > 2) || b->sf.sbytes >= 4) {
+                continue;
+            }
+            which[j++] = n;
+        }
+        if (j > 0) {
+#ifdef DRV_REFERENCE
+            struct dither_state **st = calloc(j, sizeof(*st));
+            if (!dither_init(j, rate, d->rs, c->max_dither_table_size, d->L, st)) {
+                return -1;
+            }
+            for (n = 0; n < j; n++) {
+                d->dither_state[which[n]] = st[n];
+            }
+            free(st);
+#else
+            struct orc_dither_state *st = calloc(j, sizeof(*st));
+            if (!orc_dither_init(j, rate, d->rs, c->max_dither_table_size, d->L, st)) {
+                return -1;
+            }
+            for (n = 0; n < j; n++) {
+                d->dither_state[which[n]] = &st[n];
+            }
+#endif
+        }
+        free(which);
+    }
     for (n = 0; n < d->n_ch[OUT]; n++) {
         d->output_freqcbuf[n] = drv_alloc(d->cbufsize);
         d->debug_time[n] = drv_alloc(d->cbufsize);
@@ -642,7 +678,8 @@ inverse_part(struct drv *d, int t, uint8_t *outbuf)
         }
         CV(freq2time)(d->output_freqcbuf[n], d->timebuf[t]);
         memcpy(d->debug_time[n], d->timebuf[t], (size_t)d->L * d->rs);
-        CV(cbuf2raw)(d->timebuf[t], outbuf, &d->bf[OUT][n], 0, NULL, &d->overflow[n]);
+        CV(cbuf2raw)(d->timebuf[t], outbuf, &d->bf[OUT][n], d->dither_state[n] != NULL, d->dither_state[n],
+                     &d->overflow[n]);     /* bfrun.c:1930-1935 */
     }
 }
 
@@ -758,6 +795,45 @@ void DRV(cv_raw2cbuf)(void *raw, void *cbuf, void *next, const struct bfcuda_buf
     f.sample_spacing = bf->sample_spacing; f.byte_offset = bf->byte_offset;
     CV(raw2cbuf)(raw, cbuf, next, &f, NULL, NULL);
 }
+/* per-call dither: cv_dither_init builds the table and n states (dither_init, dither.c:75-139), cv_cbuf2raw_dither
+ * is convolver_cbuf2raw with apply_dither = true on state `index` */
+#ifdef DRV_REFERENCE
+static struct dither_state *g_cv_dither[BFCUDA_MAXCHANNELS];
+#else
+static struct orc_dither_state g_cv_dither[BFCUDA_MAXCHANNELS];
+#endif
+
+int DRV(cv_dither_init)(int n_channels, int sample_rate, int realsize, int max_size, int max_samples_per_loop)
+{
+    if (n_channels < 1 || n_channels > BFCUDA_MAXCHANNELS) {
+        return 0;
+    }
+#ifdef DRV_REFERENCE
+    return dither_init(n_channels, sample_rate, realsize, max_size, max_samples_per_loop, g_cv_dither) ? 1 : 0;
+#else
+    return orc_dither_init(n_channels, sample_rate, realsize, max_size, max_samples_per_loop, g_cv_dither);
+#endif
+}
+
+void DRV(cv_cbuf2raw_dither)(void *cbuf, void *out, const struct bfcuda_buffer_format *bf,
+                             struct bfcuda_overflow *of, int index)
+{
+    cv_buffer_format f;
+    cv_overflow o;
+    f.sf.isfloat = bf->sf.isfloat; f.sf.swap = bf->sf.swap; f.sf.bytes = bf->sf.bytes;
+    f.sf.sbytes = bf->sf.sbytes; f.sf.scale = bf->sf.scale; f.sf.format = bf->sf.format;
+    f.sample_spacing = bf->sample_spacing; f.byte_offset = bf->byte_offset;
+    o.n_overflows = of->n_overflows; o.intlargest = of->intlargest; o.largest = of->largest;
+    o.max = of->max;
+#ifdef DRV_REFERENCE
+    CV(cbuf2raw)(cbuf, out, &f, 1, g_cv_dither[index], &o);
+#else
+    CV(cbuf2raw)(cbuf, out, &f, 1, &g_cv_dither[index], &o);
+#endif
+    of->n_overflows = o.n_overflows; of->intlargest = o.intlargest; of->largest = o.largest;
+    of->max = o.max;
+}
+
 void DRV(cv_cbuf2raw)(void *cbuf, void *out, const struct bfcuda_buffer_format *bf,
                       struct bfcuda_overflow *of)
 {

@@ -46,6 +46,115 @@ orc_alloc(size_t size)
     return p;
 }
 
+/* ---- dither.c / dither.h ------------------------------------------------------------------------------------ */
+static int8_t *g_dither_randtab;
+static int g_dither_randtab_size;
+static void *g_dither_randmap;
+
+/* dither.c:37-73: "maximally equidistributed combined Tausworthe generator" (GSL's taus), default seed */
+static uint32_t
+orc_tausrand(uint32_t state[3])
+{
+#define ORC_TAUSWORTHE(s, a, b, c, d) ((s & c) << d) ^ (((s << a) ^ s) >> b)
+    state[0] = ORC_TAUSWORTHE(state[0], 13, 19, (uint32_t)4294967294U, 12);
+    state[1] = ORC_TAUSWORTHE(state[1], 2, 25, (uint32_t)4294967288U, 4);
+    state[2] = ORC_TAUSWORTHE(state[2], 3, 11, (uint32_t)4294967280U, 17);
+    return state[0] ^ state[1] ^ state[2];
+}
+
+static void
+orc_tausinit(uint32_t state[3], uint32_t seed)
+{
+    int i;
+    if (seed == 0) {
+        seed = 1;
+    }
+#define ORC_LCG(n) ((69069 * n) & 0xFFFFFFFFU)
+    state[0] = ORC_LCG(seed);
+    state[1] = ORC_LCG(state[0]);
+    state[2] = ORC_LCG(state[1]);
+    for (i = 0; i < 6; i++) {
+        orc_tausrand(state);
+    }
+}
+
+/* dither.c:75-139.  RANDTAB_SPACING 10 s, MIN_RANDTAB_SPACING 1 s (dither.c:19-21).  Returns 0 on failure.
+ * NB the reference's map has 511 entries for differences -256..254, but two int8 values can differ by +255
+ * (-128 followed by 127): the reference then reads one element past its allocation.  Here the map has that
+ * 512th entry and it holds the linear continuation 1.5 + 1/255; tests keep away from such pairs. */
+int
+orc_dither_init(int n_channels, int sample_rate, int realsize, int max_size, int max_samples_per_loop,
+                struct orc_dither_state *states)
+{
+    int n, spacing = 10 * sample_rate, minspacing;
+    uint32_t st[3];
+
+    minspacing = (1 * sample_rate > max_samples_per_loop) ? 1 * sample_rate : max_samples_per_loop;
+    if (spacing < minspacing) {
+        spacing = minspacing;
+    }
+    if (max_size > 0 && n_channels * spacing > max_size) {
+        spacing = max_size / n_channels;
+    }
+    if (spacing < minspacing) {
+        fprintf(stderr, "Maximum dither table size %d bytes is too small, must at least be %d bytes.\n", max_size,
+                n_channels * sample_rate * minspacing);
+        return 0;
+    }
+    g_dither_randtab_size = n_channels * spacing + 1;
+    orc_tausinit(st, 0);
+    free(g_dither_randtab);
+    g_dither_randtab = orc_alloc((size_t)g_dither_randtab_size);
+    for (n = 0; n < g_dither_randtab_size; n++) {
+        g_dither_randtab[n] = (int8_t)(orc_tausrand(st) & 0x000000FF);
+    }
+    {
+        static void *map_base;
+        free(map_base);
+        map_base = orc_alloc((size_t)realsize * 512);
+        g_dither_randmap = (uint8_t *)map_base + 256 * realsize;
+    }
+    if (realsize == 4) {
+        ((float *)g_dither_randmap)[-256] = -0.5;
+        for (n = -255; n < 254; n++) {
+            ((float *)g_dither_randmap)[n] = 0.5 + 1.0 / 255.0 + 1.0 / 255.0 * (float)n;
+        }
+        ((float *)g_dither_randmap)[254] = 1.5;
+        ((float *)g_dither_randmap)[255] = 1.5 + 1.0 / 255.0;
+    } else {
+        ((double *)g_dither_randmap)[-256] = -0.5;
+        for (n = -255; n < 254; n++) {
+            ((double *)g_dither_randmap)[n] = 0.5 + 1.0 / 255.0 + 1.0 / 255.0 * (double)n;
+        }
+        ((double *)g_dither_randmap)[254] = 1.5;
+        ((double *)g_dither_randmap)[255] = 1.5 + 1.0 / 255.0;
+    }
+    for (n = 0; n < n_channels; n++) {
+        memset(&states[n], 0, sizeof(states[n]));
+        states[n].randtab_ptr = n * spacing + 1;
+    }
+    return 1;
+}
+
+/* dither.h:28-38 */
+static void
+orc_dither_preloop(struct orc_dither_state *state, int samples_per_loop)
+{
+    if (state->randtab_ptr + samples_per_loop >= g_dither_randtab_size) {
+        g_dither_randtab[0] = g_dither_randtab[state->randtab_ptr - 1];
+        state->randtab_ptr = 1;
+    }
+    state->randtab = &g_dither_randtab[state->randtab_ptr];
+    state->randtab_ptr += samples_per_loop;
+}
+
+const int8_t *
+orc_dither_table(int *size)
+{
+    *size = g_dither_randtab_size;
+    return g_dither_randtab;
+}
+
 #define REAL float
 #define SFX f
 #define ORC_REAL_IS_FLOAT 1
@@ -139,24 +248,23 @@ orc_raw2cbuf(void *rawbuf, void *cbuf, void *next_cbuf, struct orc_buffer_format
     memcpy((uint8_t *)cbuf + (size_t)g_n_fft2 * g_realsize, next_cbuf, (size_t)g_n_fft2 * g_realsize);
 }
 
-/* fftw_convolver.c:482-518, dither-off branches only (north_star: dither off). */
+/* fftw_convolver.c:482-518 */
 void
 orc_cbuf2raw(void *cbuf, void *outbuf, struct orc_buffer_format *bf, int apply_dither,
              void *dither_state, struct orc_overflow *overflow)
 {
     uint8_t *raw = (uint8_t *)outbuf + bf->byte_offset;
-    (void)dither_state;
+    struct orc_dither_state *ds = NULL;
     if (apply_dither && !bf->sf.isfloat) {
-        fprintf(stderr, "oracle: dither is outside the restated path\n");
-        orc_fail(1);
-        return;
+        ds = dither_state;
+        orc_dither_preloop(ds, g_n_fft2);
     }
     if (g_realsize == 4) {
         orc_real2rawf(raw, cbuf, bf->sf.sbytes << 3, bf->sf.bytes, bf->sf.isfloat,
-                      bf->sample_spacing, bf->sf.swap, g_n_fft2, overflow);
+                      bf->sample_spacing, bf->sf.swap, g_n_fft2, overflow, ds);
     } else {
         orc_real2rawd(raw, cbuf, bf->sf.sbytes << 3, bf->sf.bytes, bf->sf.isfloat,
-                      bf->sample_spacing, bf->sf.swap, g_n_fft2, overflow);
+                      bf->sample_spacing, bf->sf.swap, g_n_fft2, overflow, ds);
     }
 }
 

@@ -68,6 +68,8 @@ class _Lib:
         fn("cv_cbufsize", I)
         fn("cv_raw2cbuf", None, V, V, V, C.POINTER(_abi.BufferFormatC))
         fn("cv_cbuf2raw", None, V, V, C.POINTER(_abi.BufferFormatC), C.POINTER(_abi.OverflowC))
+        fn("cv_dither_init", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+        fn("cv_cbuf2raw_dither", None, V, V, C.POINTER(_abi.BufferFormatC), C.POINTER(_abi.OverflowC), C.c_int)
         fn("cv_time2freq", None, V, V)
         fn("cv_freq2time", None, V, V)
         fn("cv_mixnscale", None, C.POINTER(V), V, C.POINTER(D), I, I)
@@ -137,6 +139,13 @@ class Convolver:
 
     def cbuf2raw(self, cbuf, out, bf, overflow: _abi.OverflowC):
         self.l.cv_cbuf2raw(_ptr(cbuf), _ptr(out), C.byref(buffer_format_c(bf)), C.byref(overflow))
+
+    def dither_init(self, n_channels, sample_rate, max_size=0):
+        """dither_init (dither.c:75-139) for the per-call cbuf2raw_dither; one table per library."""
+        assert self.l.cv_dither_init(n_channels, sample_rate, self.realsize, max_size, self.L) == 1
+
+    def cbuf2raw_dither(self, cbuf, out, bf, overflow: _abi.OverflowC, index: int):
+        self.l.cv_cbuf2raw_dither(_ptr(cbuf), _ptr(out), C.byref(buffer_format_c(bf)), C.byref(overflow), index)
 
     def time2freq(self, x):
         out = self.new()

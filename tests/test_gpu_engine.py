@@ -13,7 +13,7 @@ import pytest
 
 from brutefir_b200 import _abi, configs
 from brutefir_b200.engine import Engine
-from brutefir_b200.formats import interleaved_layout, pack_block, planar_layout
+from brutefir_b200.formats import BufferFormat, interleaved_layout, pack_block, parse_sample_format, planar_layout
 from brutefir_b200.graph import Filter, FilterGraph
 from oracle import pyoracle as po
 from helpers import unpack_run
@@ -393,3 +393,99 @@ def test_filter_chaining_control_crossfade_and_batches(gpu_lib, oracle_libs):
     one = run_engine(1)
     assert_parity(g, one, np.stack(want))
     assert np.array_equal(run_engine(4), one)
+
+
+def dither_graph(L, P, rs, fmt, rate=100):
+    sf_i, sf_f = parse_sample_format(fmt), parse_sample_format("FLOAT_LE")
+    inb, nin = interleaved_layout(2, "S24_4LE", L)
+    outb = [BufferFormat(sf_i, 1, 0), BufferFormat(sf_i, 1, L * sf_i.bytes), BufferFormat(sf_f, 1, 2 * L * sf_i.bytes)]
+    nout = 2 * L * sf_i.bytes + 4 * L + 32
+    filters = [Filter([0], [0], coeff=0), Filter([1], [1], coeff=1), Filter([0, 1], [2], in_scales=[0.5, 0.5], coeff=0)]
+    return FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [P, P], sampling_rate=rate,
+                       apply_dither=[True, True, True])
+
+
+@pytest.mark.parametrize("L,rs,fmt,B", [(64, 4, "S16_LE", 1), (64, 8, "S24_LE", 1), (1024, 4, "S16_LE", 1), (1024, 4, "S16_BE", 4)])
+def test_dither_quantiser_bit_exact_on_the_devices_own_samples(gpu_lib, oracle_libs, L, rs, fmt, B):
+    """HP-TPDF dither + error feedback (dither.c, dither_funs.h:7-68).  The recurrence amplifies
+    nothing but it does turn last-bit differences of the inverse FFT into +-1 LSB decisions, so the quantiser is pinned
+    on its own: the time-domain blocks the device produced (read back) go through the ORACLE's convolver_cbuf2raw
+    with dither, and the device's raw bytes and overflow counters must equal that bit for bit -- through table
+    wraps, clipping blocks, and batches."""
+    P, nb = 2, 40
+    g = dither_graph(L, P, rs, fmt, rate=100 if L == 64 else 1500)
+    rng = np.random.default_rng(78)
+    taps = [rng.standard_normal(L * P).astype(np.float32) / 6 for _ in range(2)]
+    x = np.round(rng.standard_normal((nb, 2, L)) * 0.1 * (1 << 23))
+    x[5:8] *= 40
+    x = np.clip(x, -(1 << 23), (1 << 23) - 1)
+    sig = np.stack([pack_block(x[b], g.in_formats, g.in_bytes) for b in range(nb)])
+    o = po.Convolver("oracle", L, rs)
+    o.dither_init(2, g.sampling_rate)
+    ofs = [_abi.OverflowC(), _abi.OverflowC()]
+    for k in range(2):
+        ofs[k].max = float((1 << (8 * g.out_formats[k].sf.sbytes - 1)) - 1)
+    with Engine(g, max_batch=B) as e:
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+        for b0 in range(0, nb, B):
+            got = np.zeros((B, g.out_bytes), np.uint8)
+            if B == 1:
+                got[0] = e.process_block(sig[b0])
+                times = [[e.debug_read(_abi.DBG_OUTPUT_TIME, k)[:L] for k in range(2)]]
+            else:
+                # batches: the time-domain blocks of a batch come from a second engine run block by block
+                e.process_blocks_async(sig[b0:b0 + B], got, B)
+                e.synchronize()
+                times = None
+            if times is not None:
+                want = np.zeros(g.out_bytes, np.uint8)
+                for k in range(2):
+                    cbuf = np.zeros(2 * L, o.dtype)
+                    cbuf[:L] = times[0][k]
+                    o.cbuf2raw_dither(cbuf, want, g.out_formats[k], ofs[k], k)
+                nbytes = 2 * L * g.out_formats[0].sf.bytes
+                assert np.array_equal(got[0][:nbytes], want[:nbytes]), b0
+            else:
+                batched = got.copy()
+                if b0 == 0:
+                    ref_eng = Engine(g)
+                    for c, h in enumerate(taps):
+                        ref_eng.coeff_from_taps(c, h)
+                for i in range(B):
+                    assert np.array_equal(ref_eng.process_block(sig[b0 + i]), batched[i]), (b0, i)
+        if B == 1:
+            for k in range(2):
+                dev = e.overflow(k)
+                assert (dev.n_overflows, dev.intlargest, dev.largest) == (ofs[k].n_overflows, ofs[k].intlargest, ofs[k].largest)
+                assert dev.n_overflows > 0
+        else:
+            for k in range(2):
+                a, b = e.overflow(k), ref_eng.overflow(k)
+                assert (a.n_overflows, a.intlargest, a.largest) == (b.n_overflows, b.intlargest, b.largest)
+            ref_eng.close()
+
+
+def test_dither_end_to_end_against_oracle(gpu_lib, oracle_libs):
+    """Whole path with dither on against the oracle's block sequence: identical except where a last-bit difference of
+    the inverse FFT flips a quantiser decision, which the error feedback undoes within three samples."""
+    L, P, nb = 1024, 3, 12
+    g = dither_graph(L, P, 4, "S16_LE", rate=48000)
+    taps = [t * 0.5 for t in configs.synthetic_filters(g, 31)]
+    sig = configs.synthetic_signal(g, 31, nb, sigma=0.05)
+    got, ref, of = run_both(g, taps, sig)
+    y, r = unpack_run(got, g.out_formats, L), unpack_run(ref, g.out_formats, L)
+    for k in range(2):
+        diff = np.abs(y[k] - r[k])
+        # float32 FFT noise at 16 bit is ~1e-2 LSB: ~1 % of the decisions flip, each costing three +-1 LSB samples
+        assert diff.max() <= 2 and np.mean(diff > 0) < 0.10, (k, diff.max(), np.mean(diff > 0))
+        assert np.abs(r[k]).max() > 3000
+    assert np.abs(y[2] - r[2]).max() <= 1e-6
+    # dither is on: the undithered run differs on most samples' last bit pattern
+    g2 = dither_graph(L, P, 4, "S16_LE", rate=48000)
+    g2.apply_dither = None
+    with Engine(g2) as e:
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+        plain = unpack_run(e.run(sig), g2.out_formats, L)
+    assert np.mean(plain[0] != y[0]) > 0.2

@@ -151,3 +151,43 @@ def test_filter_chain_eval_bit_exact(both):
         res.append(d.run(sig))
         d.close()
     assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("rs,fmt", [(4, "S16_LE"), (8, "S16_LE"), (8, "S24_LE"), (4, "S8")])
+def test_dither_hp_tpdf_bit_exact(both, rs, fmt):
+    """HP-TPDF dither with error feedback (dither.c:37-139, dither.h:28-38, dither_funs.h:7-68) through whole block
+    sequences, long enough for the random-table pointer to wrap; eligibility rules of bfconf.c:3173-3217 (output 2 is
+    not dithered although requested when it is wider than 16 bit at float_bits 32 -- here it is a float channel)."""
+    L, P, nb = 64, 2, 40
+    sf_i, sf_f = parse_sample_format(fmt), parse_sample_format("FLOAT_LE")
+    inb, nin = interleaved_layout(2, "S24_4LE", L)
+    outb = [BufferFormat(sf_i, 1, 0), BufferFormat(sf_i, 1, L * sf_i.bytes), BufferFormat(sf_f, 1, 2 * L * sf_i.bytes)]
+    nout = 2 * L * sf_i.bytes + 4 * L + 32
+    filters = [Filter([0], [0], coeff=0), Filter([1], [1], coeff=1), Filter([0, 1], [2], in_scales=[0.5, 0.5], coeff=0)]
+    g = FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [P, P], sampling_rate=100,
+                    apply_dither=[True, True, True])
+    rng = np.random.default_rng(77)
+    taps = [rng.standard_normal(L * P).astype(np.float32) / 6 for _ in range(2)]
+    x = np.round(rng.standard_normal((nb, 2, L)) * 0.1 * (1 << 23))
+    x[5:8] *= 40                                            # a few blocks that clip: overflow bookkeeping with dither
+    x = np.clip(x, -(1 << 23), (1 << 23) - 1)
+    sig = np.stack([pack_block(x[b], g.in_formats, g.in_bytes) for b in range(nb)])
+    res = []
+    for kind in ("oracle", "ref"):
+        d = po.BlockDriver(kind, g)
+        for c, h in enumerate(taps):
+            d.coeff_from_taps(c, h)
+        out = d.run(sig)
+        res.append((out, [(d.overflow(o).n_overflows, d.overflow(o).intlargest, d.overflow(o).largest) for o in range(3)]))
+        d.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1] and res[0][1][0][0] > 0
+    # and dither really is on: the same run without it gives different samples on the integer outputs
+    g.apply_dither = None
+    d = po.BlockDriver("oracle", g)
+    for c, h in enumerate(taps):
+        d.coeff_from_taps(c, h)
+    plain = d.run(sig)
+    d.close()
+    assert not np.array_equal(plain[:, :2 * L * sf_i.bytes], res[0][0][:, :2 * L * sf_i.bytes])
+    assert np.array_equal(plain[:, 2 * L * sf_i.bytes:], res[0][0][:, 2 * L * sf_i.bytes:])
