@@ -261,13 +261,6 @@ template <typename T> struct Vec16;
 template <> struct Vec16<float> { typedef float4 type; };
 template <> struct Vec16<double> { typedef double2 type; };
 
-// W reals of type T as one vector register group
-template <typename T, int W> struct VecN;
-template <> struct VecN<float, 4> { typedef float4 type; };
-template <> struct VecN<float, 2> { typedef float2 type; };
-template <> struct VecN<double, 2> { typedef double2 type; };
-template <> struct VecN<double, 1> { typedef double type; };
-
 // streaming loads: read-only path, do not allocate in L1 (every operand byte is used once)
 template <typename V>
 __device__ __forceinline__ V ldg_stream(const V *p)
@@ -444,202 +437,6 @@ __global__ void __launch_bounds__(256) k_split_reduce(MacArgs a, int N)
         }
     }
     *reinterpret_cast<V *>(y0) = *reinterpret_cast<V *>(&acc);
-}
-
-// ======================================================================================================
-// k_mac_batch -- B consecutive audio blocks per launch, coefficient and delay-line spectra reused in
-// registers across the batch
-//
-// Output block t+b needs  sum_i FDL[t+b-i] (*) H[i].  Walking the partitions i upwards with B accumulators, step
-// i uses ONE coefficient vector H[i] for all B blocks and the window FDL[t-i .. t-i+B-1], which differs from the
-// previous step's window by one new slot.  So a step costs two 16-byte vector pairs of traffic for B complex
-// vector MACs instead of 2 B: the HBM traffic of a batch is rs*N*(P + (P+B-1) + B) per filter instead of
-// B*rs*N*(2P+1), while every output block still accumulates its partitions in ascending order with the
-// reference's roundings -- results are bit-identical to B single-block launches.
-// The window lives in registers and is rotated by unrolling the partition loop B times; loads run D = 2 steps
-// ahead of their use.
-// ======================================================================================================
-
-struct TagTrue { static constexpr bool value = true; };
-struct TagFalse { static constexpr bool value = false; };
-
-template <typename T, int W, int B, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_mac_batch(MacArgs a, int N)
-{
-    constexpr int D = 2;
-    typedef typename VecN<T, W>::type V;
-    typedef Lanes<T, W> L;
-    const int M = N >> 1;
-    const int vecs = M / W;
-    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long)a.n_jobs * vecs) {
-        return;
-    }
-    const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
-    const MacJob jb = a.jobs[job];
-    const int z = blockIdx.y;
-    const int R = a.ring;
-    const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * R * N + (size_t)v * W;
-    auto xslot = [&](int s) -> const T * {      // s in (-R, 2R)
-        s += (s < 0) ? R : 0;
-        s -= (s >= R) ? R : 0;
-        return X + (size_t)s * N;
-    };
-
-    L are[B], aim[B];
-#pragma unroll
-    for (int b = 0; b < B; b++) {
-#pragma unroll
-        for (int l = 0; l < W; l++) {
-            are[b].v[l] = (T)0;
-            aim[b].v[l] = (T)0;
-        }
-    }
-
-    if (jb.hbase < 0) {
-        if (z == 0) {
-            const T fr = (T)(1.0 / (T)N);
-#pragma unroll
-            for (int b = 0; b < B; b++) {
-                if (b < a.batch) {
-                    const T *xp = xslot(a.t + b);
-                    const L xr = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(xp)));
-                    const L xi = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(xp + M)));
-#pragma unroll
-                    for (int l = 0; l < W; l++) {
-                        const T s = ((v * W + l) & 1) ? -fr : fr;     // sign by bin parity (W may be odd)
-                        are[b].v[l] = mul_rn(xr.v[l], s);
-                        aim[b].v[l] = mul_rn(xi.v[l], s);
-                    }
-                }
-            }
-        }
-    } else {
-        const int chunk = (jb.n_parts + a.split - 1) / a.split;
-        const int i0 = z * chunk;
-        const int i1 = min(jb.n_parts, i0 + chunk);
-        const T *H = reinterpret_cast<const T *>(a.H) + (size_t)jb.hbase * N + (size_t)v * W;
-        T dc[B], ny[B];
-        V wr[B], wi[B];         // window: logical block b of step i sits in physical slot (b - (i - i0)) mod B
-        V ph_r[D], ph_i[D], px_r[D], px_i[D];
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-            dc[b] = (T)0;
-            ny[b] = (T)0;
-        }
-        if (i0 < i1) {
-#pragma unroll
-            for (int b = 0; b < B; b++) {
-                const T *xp = xslot(a.t + b - i0);
-                wr[b] = ldg_stream(reinterpret_cast<const V *>(xp));
-                wi[b] = ldg_stream(reinterpret_cast<const V *>(xp + M));
-            }
-#pragma unroll
-            for (int d = 0; d < D; d++) {
-                if (i0 + d < i1) {
-                    const T *hp = H + (size_t)(i0 + d) * N;
-                    ph_r[d] = ldg_stream(reinterpret_cast<const V *>(hp));
-                    ph_i[d] = ldg_stream(reinterpret_cast<const V *>(hp + M));
-                    if (d > 0) {
-                        const T *xp = xslot(a.t - (i0 + d));
-                        px_r[d] = ldg_stream(reinterpret_cast<const V *>(xp));
-                        px_i[d] = ldg_stream(reinterpret_cast<const V *>(xp + M));
-                    }
-                }
-            }
-        }
-        // DC and Nyquist ride in lane 0 of the job's first vector and are REAL products (fftw_convfuns.h:546-547):
-        // only the warp that holds that vector carries the two extra accumulators through the loop.
-        const bool has0 = __any_sync(0xffffffffu, v == 0);
-        auto body = [&](auto dcny_tag) {
-            constexpr bool DCNY = decltype(dcny_tag)::value;
-            const T *hnext = H + (size_t)(i0 + D) * N;      // coefficient block of step i + D
-            int xs = a.t - (i0 + D);                        // ring slot of the new delay-line block of step i + D
-            xs += (xs < 0) ? R : 0;
-            xs += (xs < 0) ? R : 0;
-            auto prefetch = [&](int d, int i) {
-                if (i + D < i1) {
-                    const T *xp = X + (size_t)xs * N;
-                    ph_r[d] = ldg_stream(reinterpret_cast<const V *>(hnext));
-                    ph_i[d] = ldg_stream(reinterpret_cast<const V *>(hnext + M));
-                    px_r[d] = ldg_stream(reinterpret_cast<const V *>(xp));
-                    px_i[d] = ldg_stream(reinterpret_cast<const V *>(xp + M));
-                }
-                hnext += N;
-                xs = xs == 0 ? R - 1 : xs - 1;
-            };
-            if (i0 < i1) {
-                // first partition of the range: convolver_convolve, a plain product (peeled so that the main
-                // loop carries no assign/accumulate branch -- its unrolled body must stay in the instruction cache)
-                const L cr = as_lanes<T, W>(ph_r[0]), ci = as_lanes<T, W>(ph_i[0]);
-                prefetch(0, i0);
-#pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const L br = as_lanes<T, W>(wr[b]), bi = as_lanes<T, W>(wi[b]);
-#pragma unroll
-                    for (int l = 0; l < W; l++) {
-                        cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], are[b].v[l], aim[b].v[l]);
-                    }
-                    if (DCNY) {
-                        dc[b] = mul_rn(br.v[0], cr.v[0]);
-                        ny[b] = mul_rn(bi.v[0], ci.v[0]);
-                    }
-                }
-            }
-            // remaining partitions: convolver_convolve_add.  Step i = base + k has window rotation
-            // u = (i - i0) % B and prefetch slot d = (i - i0) % D; base - i0 = 1 (mod B): compile-time constants.
-            for (int base = i0 + 1; base < i1; base += B) {
-#pragma unroll
-                for (int k = 0; k < B; k++) {
-                    const int i = base + k;
-                    if (i < i1) {
-                        const int u = (k + 1) % B;
-                        const int d = (k + 1) % D;
-                        const L cr = as_lanes<T, W>(ph_r[d]), ci = as_lanes<T, W>(ph_i[d]);
-                        // the block that left the window makes room for the new oldest-partition slot
-                        wr[(B - u) % B] = px_r[d];
-                        wi[(B - u) % B] = px_i[d];
-                        prefetch(d, i);
-#pragma unroll
-                        for (int b = 0; b < B; b++) {
-                            const L br = as_lanes<T, W>(wr[(b - u + B) % B]), bi = as_lanes<T, W>(wi[(b - u + B) % B]);
-#pragma unroll
-                            for (int l = 0; l < W; l++) {
-                                T re, im;
-                                cprod<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l], re, im);
-                                are[b].v[l] = add_rn(are[b].v[l], re);
-                                aim[b].v[l] = add_rn(aim[b].v[l], im);
-                            }
-                            if (DCNY) {
-                                dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
-                                ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
-                            }
-                        }
-                    }
-                }
-            }
-        };
-        if (has0) {
-            body(TagTrue());
-        } else {
-            body(TagFalse());
-        }
-        if (v == 0) {
-#pragma unroll
-            for (int b = 0; b < B; b++) {
-                are[b].v[0] = dc[b];
-                aim[b].v[0] = ny[b];
-            }
-        }
-    }
-#pragma unroll
-    for (int b = 0; b < B; b++) {
-        if (b < a.batch) {
-            T *out = reinterpret_cast<T *>(a.Y) + (((size_t)z * a.batch + b) * a.n_slots + jb.out) * N + (size_t)v * W;
-            *reinterpret_cast<V *>(out) = *reinterpret_cast<V *>(&are[b]);
-            *reinterpret_cast<V *>(out + M) = *reinterpret_cast<V *>(&aim[b]);
-        }
-    }
 }
 
 // ======================================================================================================
@@ -1187,16 +984,6 @@ cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaS
 cudaError_t launch_mac_tma(const FftPlan &plan, const MacArgs &a, cudaStream_t s);   // bf_mac_tma.cu
 cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_t s); // bf_mac_batch.cu
 
-static bool mac_batch_v1()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("BFCUDA_MAC_BATCH_V1");
-        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-    }
-    return v == 1;
-}
-
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
     if (a.n_jobs == 0) return cudaSuccess;
@@ -1206,27 +993,8 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
     const int W = 16 / plan.realsize;
     const long threads = (long)a.n_jobs * (plan.N / 2 / W);
     dim3 grid((unsigned int)((threads + 255) / 256), a.split);
-    if (a.batch > 1 && !mac_batch_v1()) {
-        return launch_mac_batch2(plan, a, s);
-    }
     if (a.batch > 1) {
-        // Instantiations: (lanes per thread W, batch B, resident blocks per SM).  Larger batches use narrower
-        // vectors so that B accumulators + the B-slot window stay within 128 registers (2 blocks of 256
-        // threads per SM) and the unrolled loop stays inside the instruction cache.  A batch smaller than B
-        // leaves the surplus accumulators unused (their window slots are still read, always inside the ring).
-        const int M = plan.N / 2;
-        auto blocks = [&](int w) { return dim3((unsigned int)(((long)a.n_jobs * (M / w) + 255) / 256), a.split); };
-        if (plan.realsize == 4) {
-            if (a.batch <= 2) k_mac_batch<float, 4, 2, 2><<<blocks(4), 256, 0, s>>>(a, plan.N);
-            else if (a.batch <= 4) k_mac_batch<float, 4, 4, 2><<<blocks(4), 256, 0, s>>>(a, plan.N);
-            else if (a.batch <= 8) k_mac_batch<float, 2, 8, 2><<<blocks(2), 256, 0, s>>>(a, plan.N);
-            else return cudaErrorInvalidValue;
-        } else {
-            if (a.batch <= 2) k_mac_batch<double, 2, 2, 2><<<blocks(2), 256, 0, s>>>(a, plan.N);
-            else if (a.batch <= 4) k_mac_batch<double, 1, 4, 2><<<blocks(1), 256, 0, s>>>(a, plan.N);
-            else return cudaErrorInvalidValue;
-        }
-        return cudaGetLastError();
+        return launch_mac_batch2(plan, a, s);      // bf_mac_batch.cu
     }
     if (plan.realsize == 4) {
         k_mac<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
