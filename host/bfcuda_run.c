@@ -18,6 +18,12 @@
  *               the files are read and written (offline mode; bit-identical output, several times the throughput)
  *     taps.f32: raw little-endian float32 (float64 with -r 64) taps, one filter after the other, L*P each
  *               ("dirac" = unit pulses, the reference's "dirac pulse" coefficient, bfconf.c:1905-1913)
+ *     -f fmt  : format of the coefficient file, as the `format:` field of a coeff section (bfconf.c:783-812,
+ *               load_coeff bfconf.c:1867-2030): "text" (one number per line, real_read bfconf.c:1725-1766) or a
+ *               sample format name (raw_read bfconf.c:1780-1821: converted like raw2real and multiplied by the
+ *               format's scale); default FLOAT_LE / FLOAT64_LE by -r
+ *     -a dB   : `attenuation:` of the coeff sections (scale = 10^(-dB/20), bfconf.c:778-781)
+ *     -k bytes: `skip:` bytes at the start of the coefficient file (bfconf.c:1886-1893)
  */
 #include <errno.h>
 #include <math.h>
@@ -92,6 +98,9 @@ main(int argc, char *argv[])
 {
     int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, device = 0, batch = 1, a;
     const char *fin = "S24_4LE", *fout = "S24_4LE", *coeff_path = "dirac", *in_path = NULL, *out_path = NULL;
+    const char *coeff_fmt = NULL;
+    double attenuation_db = 0.0;
+    long coeff_skip = 0;
     struct bfcuda_sample_format sf_in, sf_out;
     struct bfcuda_buffer_format *bf_in, *bf_out;
     struct bfcuda_filter *filters;
@@ -116,6 +125,9 @@ main(int argc, char *argv[])
         else if (!strcmp(argv[a], "-i") && a + 1 < argc) fin = argv[++a];
         else if (!strcmp(argv[a], "-o") && a + 1 < argc) fout = argv[++a];
         else if (!strcmp(argv[a], "-c") && a + 1 < argc) coeff_path = argv[++a];
+        else if (!strcmp(argv[a], "-f") && a + 1 < argc) coeff_fmt = argv[++a];
+        else if (!strcmp(argv[a], "-a") && a + 1 < argc) attenuation_db = atof(argv[++a]);
+        else if (!strcmp(argv[a], "-k") && a + 1 < argc) coeff_skip = atol(argv[++a]);
         else if (!strcmp(argv[a], "-m")) matrix = 1;
         else if (!strcmp(argv[a], "-b")) bench = 1;
         else if (!strcmp(argv[a], "-B") && a + 1 < argc) batch = atoi(argv[++a]);
@@ -163,24 +175,67 @@ main(int argc, char *argv[])
     CHECK(bfcuda_create(&cfg, &eng));
     CHECK(bfcuda_get_info(eng, &info));
 
-    /* coefficients: load_coeff (bfconf.c:1867-2030) for the raw and "dirac pulse" cases */
+    /* coefficients: load_coeff (bfconf.c:1867-2030) for "dirac pulse", text and raw sample formats */
     {
         size_t taps = (size_t)L * P;
         void *h = calloc(taps, rs);
         FILE *cf = NULL;
-        if (strcmp(coeff_path, "dirac") != 0 && (cf = fopen(coeff_path, "rb")) == NULL) {
-            DIE("Could not open \"%s\" for reading.", coeff_path);
+        const int is_text = coeff_fmt != NULL && strcasecmp(coeff_fmt, "text") == 0;
+        const double scale = pow(10.0, -attenuation_db / 20.0);      /* FROM_DB(-attenuation), bfconf.c:781 */
+        struct bfcuda_sample_format csf;
+        if (!is_text && parse_format(coeff_fmt != NULL ? coeff_fmt : (rs == 4 ? "FLOAT_LE" : "FLOAT64_LE"), &csf) != 0) {
+            DIE("Unknown coefficient format \"%s\".", coeff_fmt);
+        }
+        if (strcmp(coeff_path, "dirac") != 0) {
+            if ((cf = fopen(coeff_path, is_text ? "rt" : "rb")) == NULL) {
+                DIE("Could not open \"%s\" for reading.", coeff_path);
+            }
+            if (coeff_skip > 0 && (fseek(cf, coeff_skip, SEEK_SET) != 0 || ftell(cf) != coeff_skip)) {
+                DIE("Failed to skip %ld bytes of file \"%s\".", coeff_skip, coeff_path);
+            }
         }
         for (f = 0; f < n_filters; f++) {
-            if (cf != NULL) {
-                memset(h, 0, taps * rs);
-                if (fread(h, rs, taps, cf) == 0) DIE("\"%s\" holds fewer than %d filters.", coeff_path, n_filters);
-            } else if (rs == 4) {
-                ((float *)h)[0] = 1.0f;
+            size_t got = 0;
+            memset(h, 0, taps * rs);
+            if (cf == NULL) {
+                if (rs == 4) ((float *)h)[0] = 1.0f; else ((double *)h)[0] = 1.0;
+                got = taps;
+            } else if (is_text) {
+                char line[1024];
+                while (got < taps && fgets(line, sizeof(line) - 1, cf) != NULL) {      /* real_read */
+                    char *s0 = line, *e0;
+                    double v;
+                    while (*s0 == ' ' || *s0 == '\t') s0++;
+                    if (*s0 == '\n' || *s0 == '\0') continue;
+                    v = strtod(s0, &e0);
+                    if (e0 == s0) DIE("Parse error in file %s: invalid floating point number.", coeff_path);
+                    if (rs == 4) ((float *)h)[got] = (float)v; else ((double *)h)[got] = v;
+                    got++;
+                }
             } else {
-                ((double *)h)[0] = 1.0;
+                unsigned char raw[8];
+                while (got < taps && fread(raw, csf.bytes, 1, cf) == 1) {               /* raw_read + raw2real */
+                    double v;
+                    int i;
+                    unsigned char le[8];
+                    for (i = 0; i < csf.bytes; i++) le[i] = csf.swap ? raw[csf.bytes - 1 - i] : raw[i];
+                    if (csf.isfloat) {
+                        if (csf.bytes == 4) { float t; memcpy(&t, le, 4); v = (double)t; }
+                        else { memcpy(&v, le, 8); }
+                    } else {
+                        int32_t q = 0;
+                        for (i = 0; i < csf.bytes; i++) q |= (int32_t)((uint32_t)le[i] << (8 * (i + 4 - csf.bytes)));
+                        v = (double)(q >> (8 * (4 - csf.bytes)));       /* sign-extending shift, raw2real.h:106-142 */
+                    }
+                    /* the integer is converted unscaled into the real type, then multiplied by sf.scale in the real
+                     * type (bfconf.c:1807-1818) */
+                    if (rs == 4) ((float *)h)[got] = (float)v * (float)csf.scale;
+                    else ((double *)h)[got] = v * csf.scale;
+                    got++;
+                }
             }
-            CHECK(bfcuda_coeff_from_taps(eng, f, h, (int)taps, 1.0));
+            if (got == 0) DIE("\"%s\" holds fewer than %d filters.", coeff_path, n_filters);
+            CHECK(bfcuda_coeff_from_taps(eng, f, h, (int)taps, scale));
         }
         if (cf != NULL) fclose(cf);
         free(h);

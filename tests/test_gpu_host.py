@@ -53,3 +53,42 @@ def test_c_host_streams_files_like_bfio_file(gpu_lib, oracle_libs, tmp_path):
     assert r.returncode == 0, r.stderr
     out2 = np.frombuffer((tmp_path / "out2.raw").read_bytes(), np.uint8)
     assert np.array_equal(out2, padded)
+
+
+def test_c_host_coefficient_file_formats(gpu_lib, oracle_libs, tmp_path):
+    """load_coeff's file formats (bfconf.c:1725-1821, 1867-2030) in the C host: text (one number per line, blank lines
+    skipped), raw integer samples scaled by the format's scale, `skip:` and `attenuation:`; short files are zero
+    extended to whole blocks."""
+    exe = os.path.join(ROOT, "host", "bfcuda_run")
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True).returncode == 0
+    L, P, n = 256, 4, 2
+    g = configs.diagonal_graph(n, L, P, 4, "S24_4LE")
+    sig = configs.synthetic_signal(g, 23, 7, sigma=0.02)
+    (tmp_path / "in.raw").write_bytes(sig.tobytes())
+    rng = np.random.default_rng(23)
+
+    def run_host(extra, taps, scale):
+        r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P)] + extra +
+                           [str(tmp_path / "in.raw"), str(tmp_path / "out.raw")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        out = np.frombuffer((tmp_path / "out.raw").read_bytes(), np.uint8).reshape(7, g.out_bytes)
+        d = po.BlockDriver("oracle", g)
+        for c, h in enumerate(taps):
+            d.coeff_from_taps(c, h, scale)
+        ref = d.run(sig)
+        d.close()
+        assert np.abs(unpack_run(ref, g.out_formats, L)).max() > 1e4
+        assert np.abs(unpack_run(out, g.out_formats, L) - unpack_run(ref, g.out_formats, L)).max() <= 1
+
+    # text: the second filter is short (zero extended); blank lines and leading blanks are skipped
+    t0 = (rng.standard_normal(L * P) / 8).astype(np.float32)
+    t1 = (rng.standard_normal(L * P) / 8).astype(np.float32)
+    t1[300:] = 0
+    lines = ["  %.9e" % v for v in t0] + [""] + ["\t%.9e" % v for v in t1[:300]] + ["0.0"] * (L * P - 300)
+    (tmp_path / "taps.txt").write_text("\n".join(lines) + "\n")
+    run_host(["-c", str(tmp_path / "taps.txt"), "-f", "text"], [t0, t1], 1.0)
+    # raw S16_BE behind a 44-byte header, 6 dB attenuation
+    q = rng.integers(-8000, 8000, size=(2, L * P)).astype(">i2")
+    (tmp_path / "taps.s16").write_bytes(b"H" * 44 + q.tobytes())
+    taps = [(q[c].astype(np.float32) * np.float32(2.0 ** -15)).astype(np.float32) for c in range(2)]
+    run_host(["-c", str(tmp_path / "taps.s16"), "-f", "S16_BE", "-k", "44", "-a", "6.0"], taps, 10.0 ** (-6.0 / 20.0))
