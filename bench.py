@@ -182,26 +182,29 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
-    import torch
-    import torch.distributed as dist
     from brutefir_b200 import _abi
     from brutefir_b200.engine import Engine, PinnedBuffer
     from brutefir_b200.sharding import shard_graph
 
+    # The data path has no collective (diagonal graph: every rank owns its filters, inputs and outputs), so the only
+    # inter-rank traffic of this program is the timing barrier and the max-over-ranks of the measured times: that
+    # control plane runs over gloo on the host.  (Initialising an NCCL communicator here costs the host-buffer path
+    # up to 80 us per step at 4-8 ranks -- measured with tools/e2e_multi.py -- for nothing; NCCL is used where the
+    # path really exchanges data, bfcuda_comm_* for outputs fed from several ranks, tools/multi_gpu_check.py.)
     distributed = world > 1
-    torch.cuda.set_device(local_rank)
     if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
 
     def barrier():
         if distributed:
             dist.barrier()
-        torch.cuda.synchronize()
 
     def max_over_ranks(v):
         if not distributed:
             return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        t = torch.tensor([v], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -275,6 +278,9 @@ def main():
         e2e_ms = eng.timer_stop()
         eng.synchronize()
         barrier()
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"[rank {rank}] B={B} e2e {1e3 * e2e_ms / steps:.1f} us/step, device-resident {1e3 * ms / steps:.1f} us/step",
+                  file=sys.stderr, flush=True)
         e2e_step = max_over_ranks(e2e_ms / steps)
         lat = []
         for i in range(min(40, steps)):
