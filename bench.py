@@ -49,7 +49,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "m8"],
+                    help="c3 = the headline configuration; c2 / c4 = BASELINE configs[1] / [3]; m8 = 8 x 8 matrix of the "
+                         "headline filter shape (64 filters, every input feeds 8 of them: shared delay lines)")
+    ap.add_argument("--no-sharing", action="store_true", help="give every filter its own delay line (A/B for m8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=8,
                     help="audio blocks per step (1 = the reference's block-by-block schedule; the streaming figures are "
@@ -59,7 +62,7 @@ def parse_args():
 
 def workload_graph(name):
     from brutefir_b200 import configs
-    return {"c2": configs.config_c2, "c3": configs.config_c3, "c4": configs.config_c4}[name]()
+    return {"c2": configs.config_c2, "c3": configs.config_c3, "c4": configs.config_c4, "m8": configs.config_matrix}[name]()
 
 
 def workload_config(name, graph, n_gpus):
@@ -163,7 +166,7 @@ def main():
     cfg = workload_config(args.workload, graph, world)
     block_s = graph.block_seconds()
     gtap_unit = graph.gtap_mac_per_realtime()
-    cid = int(args.workload[1])
+    cid = int(args.workload[1]) if args.workload[0] == "c" else 8
 
     if args.impl == "reference":
         if rank != 0:
@@ -230,7 +233,7 @@ def main():
 
     def measure(B, steps, warmup, sample_clocks):
         """One engine with max_batch = B; a step = B consecutive audio blocks in one call."""
-        eng = Engine(sub, device=local_rank, flags=0, max_batch=B)
+        eng = Engine(sub, device=local_rank, flags=_abi.FLAG_NO_STREAM_SHARING if args.no_sharing else 0, max_batch=B)
         for c in sorted({f.coeff for f in sub.filters if f.coeff >= 0}):
             eng.coeff_from_taps(c, taps[c])
         nbuf = 3
@@ -247,6 +250,7 @@ def main():
         for _ in range(graph.n_blocks // B + 1):
             eng.process_blocks_device(B)
         eng.synchronize()
+        info = eng.info()       # after the first block: delay lines that several filters share are merged by now
 
         # ---- device-resident timing -----------------------------------------------------------------
         for _ in range(max(3, warmup)):
@@ -358,7 +362,7 @@ def main():
                "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
                "engine": {"mac_split": info.mac_split, "kernels_per_step": info.kernels_per_block, "max_batch": B,
                           "device": info.device_name.decode(), "device_bytes": info.device_bytes,
-                          "filters_on_rank0": len(sub.filters)}}
+                          "filters_on_rank0": len(sub.filters), "delay_line_rings": info.n_streams}}
         eng.close()
         for b in pin_in + pin_out:
             b.free()

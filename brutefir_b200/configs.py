@@ -50,6 +50,16 @@ def config_c1_chained(realsize: int = 4) -> FilterGraph:
     return FilterGraph(L, P, realsize, inb, outb, nin, nout, filters, [P] * 6, sampling_rate=44100)
 
 
+def config_matrix(n: int = 8, realsize: int = 4, fmt: str = "S24_4LE", L: int = 8192, P: int = 128) -> FilterGraph:
+    """n x n crosstalk / room-correction matrix of the headline shape: n inputs, n outputs, n*n filters of L*P taps,
+    output o = sum over inputs i of filter (o, i).  Every input feeds n filters with the same scale and delay, so their
+    delay lines are one and the same (xtc_config's topology, /root/reference/xtc_config:28-50, scaled up)."""
+    inb, nin = interleaved_layout(n, fmt, L)
+    outb, nout = interleaved_layout(n, fmt, L)
+    filters = [Filter([i], [o], out_scales=[1.0 / n], coeff=o * n + i) for o in range(n) for i in range(n)]
+    return FilterGraph(L, P, realsize, inb, outb, nin, nout, filters, [P] * (n * n))
+
+
 def config_c2(realsize: int = 4) -> FilterGraph:
     return diagonal_graph(2, 4096, 16, realsize, "FLOAT_LE")
 

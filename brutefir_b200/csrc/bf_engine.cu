@@ -108,6 +108,12 @@ struct FilterState {
     std::vector<double> fscale;
     int level;                      // 0 = fed by inputs only; 1 + max level of the sources otherwise
     int eval;                       // index of its evaluated source mix (row n_in + eval of xin), -1 = none
+    // Delay-line sharing: filters fed by the same single input with the same scale and block delay have
+    // bit-identical delay lines, so they share one ring ("input spectra reused across filters").
+    int stream;                     // ring this filter's delay line lives in (its own index, or a lower filter's)
+    int key_ch, key_delay;          // the sharing key the ring was last written under: input, delay, rounded scale
+    double key_scale;
+    long key_since;                 // block count at which the key last changed (-1 = unchanged since creation)
     int coeff, prevcoeff, delayblocks;
 };
 
@@ -164,7 +170,10 @@ struct bfcuda_engine {
     std::vector<MixStream> h_mix_streams;
     std::vector<MixTerm> h_mix_terms;
     std::vector<MacJob> h_jobs;
-    std::vector<OutChan> h_chans;
+    std::vector<OutChan> h_chans;       // what the inverse stage reads
+    std::vector<OutChan> h_mixes;       // the filter terms of every output (k_out_mix)
+    OutChan *d_mixes;
+    bool any_out_mix;
     std::vector<MixTerm> h_out_terms;
     std::vector<int> shared_out;
     std::vector<std::pair<int, int>> delay_fixups;     // (filter, old delay) of delay changes not yet applied to the ring
@@ -178,6 +187,8 @@ struct bfcuda_engine {
     MixTerm *d_out_terms;
     // filter -> filter chaining: per level, the ranges of MAC jobs, mix streams and evaluations
     int n_eval, n_vin, n_levels;
+    long merge_check_at;        // block count at which update_streams() should look for mergeable rings again, -1 = never
+    int n_rings;                // delay-line rings in use (distinct streams; < n_filters when filters share)
     void *d_keep;
     EvalEntry *d_eval_entries;
     MixTerm *d_eval_terms;
@@ -260,6 +271,94 @@ static int coeff_blocks_used(const bfcuda_engine *e, int coeff, int delay)
     return e->coeff_n_blocks[coeff];
 }
 
+static char *ring_ptr(const bfcuda_engine *e, int stream)
+{
+    return (char *)e->d_fdl + rs_bytes(e, (size_t)stream * e->fdl_ring * e->N);
+}
+
+static bool shareable(const bfcuda_engine *e, const FilterState &fs)
+{
+    return !(e->flags & BFCUDA_FLAG_NO_STREAM_SHARING) && fs.eval < 0 && fs.ch[0].size() == 1;
+}
+
+// Keep the ring assignment consistent with the control snapshot, at a block boundary (before the tables are built
+// and before any delay fix-up).  A filter whose key (input, scale, delay) changed leaves the ring it shared and
+// takes a copy of it -- its history up to now IS that ring; if it was the ring's owner the remaining users move to a
+// copy of their own.  Filters whose keys are equal and have been for longer than any slot lives (or since creation)
+// hold identical delay lines and are merged again, no copy needed.
+static int update_streams(bfcuda_engine *e)
+{
+    const int F = e->n_filters;
+    const size_t ring_bytes = rs_bytes(e, (size_t)e->fdl_ring * e->N);
+    for (int f = 0; f < F; f++) {
+        FilterState &fs = e->filters[f];
+        if (fs.ch[0].size() != 1 || fs.eval >= 0) {
+            continue;
+        }
+        const int ch = fs.ch[0][0], delay = clamp_delay(e, fs.delayblocks);
+        const double sc = round_to_real(e, fs.scale[0][0] * e->fmt[0][ch].sf.scale);
+        if (ch == fs.key_ch && delay == fs.key_delay && sc == fs.key_scale) {
+            continue;
+        }
+        const bool first_snapshot = fs.key_ch < 0;
+        // key changed: separate f from the ring it shares
+        std::vector<int> users;
+        for (int u = 0; u < F; u++) {
+            if (u != f && e->filters[u].stream == fs.stream) {
+                users.push_back(u);
+            }
+        }
+        if (!users.empty()) {
+            if (fs.stream != f) {
+                CU(cudaMemcpyAsync(ring_ptr(e, f), ring_ptr(e, fs.stream), ring_bytes, cudaMemcpyDeviceToDevice, e->stream));
+                fs.stream = f;
+            } else {
+                const int g = users[0];     // lowest index: the new owner
+                CU(cudaMemcpyAsync(ring_ptr(e, g), ring_ptr(e, f), ring_bytes, cudaMemcpyDeviceToDevice, e->stream));
+                for (int u : users) {
+                    e->filters[u].stream = g;
+                }
+            }
+        }
+        fs.key_ch = ch;
+        fs.key_delay = delay;
+        fs.key_scale = sc;
+        fs.key_since = first_snapshot ? -1 : (long)e->t;
+    }
+    // merge rings that have become identical
+    const long horizon = 2L * e->P + 2L * e->max_batch;     // no slot written before t - horizon is ever read again
+    for (int f = 0; f < F; f++) {
+        FilterState &fs = e->filters[f];
+        if (!shareable(e, fs) || fs.stream != f) {
+            continue;       // only ring owners look for an older twin; their followers move with them
+        }
+        const bool settled_f = fs.key_since < 0 || (long)e->t - fs.key_since >= horizon;
+        for (int g = 0; g < f && settled_f; g++) {
+            const FilterState &gs = e->filters[g];
+            const bool settled_g = gs.key_since < 0 || (long)e->t - gs.key_since >= horizon;
+            if (shareable(e, gs) && gs.stream == g && settled_g && gs.key_ch == fs.key_ch &&
+                gs.key_delay == fs.key_delay && gs.key_scale == fs.key_scale) {
+                for (int u = 0; u < F; u++) {
+                    if (e->filters[u].stream == f) {
+                        e->filters[u].stream = g;
+                    }
+                }
+                break;
+            }
+        }
+    }
+    // a ring that is not settled yet may become mergeable later: look again then
+    e->merge_check_at = -1;
+    for (int f = 0; f < F; f++) {
+        const FilterState &fs = e->filters[f];
+        if (shareable(e, fs) && fs.key_since >= 0 && (long)e->t - fs.key_since < horizon) {
+            const long at = fs.key_since + horizon;
+            e->merge_check_at = e->merge_check_at < 0 ? at : std::min(e->merge_check_at, at);
+        }
+    }
+    return 0;
+}
+
 // Rebuild every per-block table from the control snapshot: the analogue of bfrun.c:1460-1484 plus the
 // scale / slot / coefficient bookkeeping spread over bfrun.c:1566-1600, 1663-1675, 1726-1777, 1847-1854.
 static void build_tables(bfcuda_engine *e)
@@ -272,6 +371,7 @@ static void build_tables(bfcuda_engine *e)
     std::fill(e->h_need_xin.begin(), e->h_need_xin.end(), (e->flags & 4u) ? 1 : 0);
     e->xfade_active = false;
     size_t blocks_h = 0, blocks_x = 0;
+    std::vector<int> stream_parts(std::max(1, F), 0);   // delay-line blocks read per ring (shared rings count once)
 
     e->h_eval_entries.clear();
     e->h_eval_terms.clear();
@@ -336,11 +436,13 @@ static void build_tables(bfcuda_engine *e)
             e->h_mix_terms.push_back(te);
             e->h_mix_streams.push_back(ms);
         } else if (nin == 1) {
-            FwdDest d;
-            d.stream = f;
-            d.delay = delay;
-            d.scale = round_to_real(e, fs.scale[0][0] * e->fmt[0][fs.ch[0][0]].sf.scale);
-            per_ch[fs.ch[0][0]].push_back(d);
+            if (fs.stream == f) {       // the ring's owner writes it; the filters sharing it only read
+                FwdDest d;
+                d.stream = f;
+                d.delay = delay;
+                d.scale = round_to_real(e, fs.scale[0][0] * e->fmt[0][fs.ch[0][0]].sf.scale);
+                per_ch[fs.ch[0][0]].push_back(d);
+            }
         } else if (nin > 1) {
             MixStream ms;
             ms.stream = f;
@@ -357,13 +459,13 @@ static void build_tables(bfcuda_engine *e)
             e->h_mix_streams.push_back(ms);
         }
         MacJob jb;
-        jb.stream = f;
+        jb.stream = fs.stream;
         jb.hbase = fs.coeff < 0 ? -1 : e->coeff_hbase[fs.coeff];
         jb.n_parts = fs.coeff < 0 ? 1 : coeff_blocks_used(e, fs.coeff, delay);
         jb.out = f;
         e->h_jobs.push_back(jb);
         blocks_h += fs.coeff < 0 ? 0 : jb.n_parts;
-        blocks_x += jb.n_parts;
+        stream_parts[fs.stream] = std::max(stream_parts[fs.stream], jb.n_parts);
         if (fs.crossfade && fs.prevcoeff != fs.coeff) {
             // bfrun.c:1726-1736, 1755-1769: the same delay line through the previous coefficients
             MacJob old = jb;
@@ -372,10 +474,22 @@ static void build_tables(bfcuda_engine *e)
             old.out = F + f;
             e->h_jobs.push_back(old);
             blocks_h += fs.prevcoeff < 0 ? 0 : old.n_parts;
-            blocks_x += old.n_parts;
+            stream_parts[fs.stream] = std::max(stream_parts[fs.stream], old.n_parts);
             e->xfade_active = true;
         }
       }
+    }
+    e->n_rings = 0;
+    for (int f = 0; f < F; f++) {
+        blocks_x += stream_parts[f];
+        e->n_rings += stream_parts[f] > 0;
+    }
+    // jobs that read the same ring sit next to each other within their level: their blocks run at the same time and
+    // the second reader of a delay-line block finds it in L2
+    for (int level = 0; level < e->n_levels; level++) {
+        std::stable_sort(e->h_jobs.begin() + e->level_job_first[level],
+                         e->h_jobs.begin() + (level + 1 < e->n_levels ? e->level_job_first[level + 1] : (int)e->h_jobs.size()),
+                         [](const MacJob &a, const MacJob &b) { return a.stream < b.stream; });
     }
     e->level_job_first[e->n_levels] = (int)e->h_jobs.size();
     e->level_mix_first[e->n_levels] = (int)e->h_mix_streams.size();
@@ -424,6 +538,31 @@ static void build_tables(bfcuda_engine *e)
                 e->h_out_terms.push_back(tm);
             }
         }
+        e->h_mixes[o] = oc;
+        e->h_chans[o] = oc;
+    }
+    // Outputs fed by several filters are mixed by k_out_mix into a spectrum of their own (Y slots 2F + o, and
+    // 2F + n_out + o for the old-coefficient mix of a crossfade block); the inverse stage then sees ONE term with scale 1
+    // for them, like for an output with a single filter.
+    e->any_out_mix = false;
+    for (int o = 0; o < e->n_ch[1]; o++) {
+        const OutChan mx = e->h_mixes[o];
+        if (mx.n <= 1) {
+            continue;
+        }
+        e->any_out_mix = true;
+        OutChan oc = mx;
+        MixTerm tm;
+        tm.scale = 1.0;
+        tm.index = 2 * std::max(1, F) + o;
+        oc.first = (int)e->h_out_terms.size();
+        oc.n = 1;
+        e->h_out_terms.push_back(tm);
+        if (mx.xf_first >= 0) {
+            tm.index = 2 * std::max(1, F) + e->n_ch[1] + o;
+            oc.xf_first = (int)e->h_out_terms.size();
+            e->h_out_terms.push_back(tm);
+        }
         e->h_chans[o] = oc;
     }
     // algorithmic MAC traffic, SURVEY.md 8(d): rs * N * (coefficient blocks + delay-line blocks + outputs)
@@ -431,12 +570,12 @@ static void build_tables(bfcuda_engine *e)
     // a batch of B blocks reads every coefficient block once, a window of n_parts + B - 1 delay-line blocks per
     // job, and writes B outputs per job
     const size_t Bm = (size_t)e->max_batch;
-    e->mac_bytes_batch = (size_t)e->rs * e->N * (blocks_h + blocks_x + e->h_jobs.size() * (Bm - 1) + e->h_jobs.size() * Bm);
+    e->mac_bytes_batch = (size_t)e->rs * e->N * (blocks_h + blocks_x + (size_t)e->n_rings * (Bm - 1) + e->h_jobs.size() * Bm);
     e->single_dest = !(e->flags & 4u) && e->h_mix_streams.empty();
     for (int c = 0; c < e->n_ch[0]; c++) {
         e->single_dest = e->single_dest && per_ch[c].size() == 1;
     }
-    e->simple_mix = !e->xfade_active;   // (a split partition sum is reduced right after the MAC)
+    e->simple_mix = !e->xfade_active;   // (split partition sums and multi-filter mixes are reduced by their own kernels)
     for (int o = 0; o < e->n_ch[1]; o++) {
         e->simple_mix = e->simple_mix && e->h_chans[o].n == 1;
     }
@@ -461,6 +600,7 @@ static int upload_tables(bfcuda_engine *e)
     CU(upload_vec(e->d_mix_terms, e->h_mix_terms, e->stream));
     CU(upload_vec(e->d_jobs, e->h_jobs, e->stream));
     CU(upload_vec(e->d_chans, e->h_chans, e->stream));
+    CU(upload_vec(e->d_mixes, e->h_mixes, e->stream));
     CU(upload_vec(e->d_out_terms, e->h_out_terms, e->stream));
     CU(upload_vec(e->d_eval_entries, e->h_eval_entries, e->stream));
     CU(upload_vec(e->d_eval_terms, e->h_eval_terms, e->stream));
@@ -620,7 +760,7 @@ void bfcuda_destroy(bfcuda_engine *e)
     void *ptrs[] = { e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
-                     e->d_keep, e->d_eval_entries, e->d_eval_terms, e->dither.chans, (void *)e->dither.randtab,
+                     e->d_keep, e->d_eval_entries, e->d_eval_terms, e->d_mixes, e->dither.chans, (void *)e->dither.randtab,
                      (void *)e->dither.randmap };
     for (void *p : ptrs) {
         if (p != nullptr) {
@@ -740,10 +880,14 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->d_xt[0] = e->d_xt[1] = nullptr;
     memset(&e->dither, 0, sizeof(e->dither));
     e->d_keep = nullptr;
+    e->d_mixes = nullptr;
+    e->any_out_mix = false;
     e->d_eval_entries = nullptr;
     e->d_eval_terms = nullptr;
     e->n_eval = 0;
     e->n_levels = 1;
+    e->n_rings = 0;
+    e->merge_check_at = -1;
     e->xt_par = 0;
     e->xt_last_nb = 1;
     e->single_dest = e->simple_mix = false;
@@ -819,6 +963,11 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         fs.delayblocks = s.delayblocks;
         fs.level = 0;
         fs.eval = -1;
+        fs.stream = f;
+        fs.key_ch = -1;         // no key yet: update_streams() takes the first snapshot at block 0
+        fs.key_delay = 0;
+        fs.key_scale = 0.0;
+        fs.key_since = -1;
         if (s.n_filters_in > 0) {
             fs.fin.assign(s.filters_in, s.filters_in + s.n_filters_in);
             if (s.fscale != nullptr) {
@@ -915,7 +1064,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
             TRY(dev_alloc(e, &e->d_eval_terms, sizeof(MixTerm) * terms));
         }
         TRY(dev_alloc(e, &e->d_H, rs_bytes(e, (size_t)std::max(1, e->total_coeff_blocks) * N)));
-        e->y_stride = rs_bytes(e, (size_t)e->split * B * 2 * F * N);
+        e->y_stride = rs_bytes(e, (size_t)e->split * B * (2 * F + 2 * (size_t)e->n_ch[1]) * N);
         TRY(dev_alloc(e, &e->d_Y, 2 * e->y_stride));
         TRY(dev_alloc(e, &e->d_out_time, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[1]) * L)));
         TRY(dev_alloc(e, &e->d_scratch, rs_bytes(e, 4 * N)));
@@ -935,13 +1084,16 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
             for (const FilterState &fs : e->filters) {
                 terms += 2 * fs.ch[1].size();
             }
+            terms += 2 * (size_t)e->n_ch[1];
             TRY(dev_alloc(e, &e->d_out_terms, sizeof(MixTerm) * terms));
         }
         TRY(dev_alloc(e, &e->d_jobs, sizeof(MacJob) * 2 * F));
         TRY(dev_alloc(e, &e->d_chans, sizeof(OutChan) * std::max(1, e->n_ch[1])));
+        TRY(dev_alloc(e, &e->d_mixes, sizeof(OutChan) * std::max(1, e->n_ch[1])));
         e->h_dest_first.assign(e->n_ch[0] + 1, 0);
         e->h_need_xin.assign(std::max(1, e->n_ch[0]), 0);
         e->h_chans.assign(e->n_ch[1], OutChan());
+        e->h_mixes.assign(e->n_ch[1], OutChan());
 
         for (int io = 0; io < 2; io++) {
             std::vector<SampleFormat> f(e->n_ch[io]);
@@ -1277,7 +1429,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ma.Y = (char *)e->d_Y + (size_t)par * e->y_stride;
     ma.jobs = e->d_jobs;
     ma.n_jobs = e->level_job_first[1];
-    ma.n_slots = 2 * std::max(1, e->n_filters);
+    ma.n_slots = 2 * std::max(1, e->n_filters) + 2 * e->n_ch[1];
     ma.ring = e->fdl_ring;
     ma.split = e->split;
     ma.t = e->slot_t;
@@ -1342,6 +1494,18 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ia.safety_limit = e->safety_limit;
     ia.fast_fmt = e->fast_fmt[1];
     ia.simple_mix = e->simple_mix ? 1 : 0;
+    if (e->any_out_mix) {
+        OutMixArgs oa;
+        oa.Y = ma.Y;
+        oa.mixes = e->d_mixes;
+        oa.terms = e->d_out_terms;
+        oa.n_out = e->n_ch[1];
+        oa.n_slots = ma.n_slots;
+        oa.z_first = 2 * std::max(1, e->n_filters);
+        oa.batch = nb;
+        CU(launch_out_mix(e->plan, oa, e->s_inv));
+        e->launches++;
+    }
     CU(launch_inverse(e->plan, ia, e->s_inv));
     e->launches += e->n_ch[1] > 0;
     const bool pack_all = e->plan.tw2 != nullptr;   // size-specialised path: real2raw is a kernel of its own
@@ -1414,7 +1578,7 @@ static int apply_delay_fixups(bfcuda_engine *e)
     for (const std::pair<int, int> &fx : e->delay_fixups) {
         const int f = fx.first, d_old = fx.second;
         const int d_new = clamp_delay(e, e->filters[f].delayblocks);
-        char *ring = (char *)e->d_fdl + nb * (size_t)f * R;
+        char *ring = ring_ptr(e, e->filters[f].stream);   // private by now: update_streams() ran first
         const long T = e->slot_t;
         if (d_new < d_old) {
             for (int j = d_new + 1; j < d_old; j++) {
@@ -1441,6 +1605,9 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
     int done = 0;
     while (done < n) {
         int nb = std::min(n - done, e->max_batch);
+        if (e->merge_check_at >= 0 && (long)e->t >= e->merge_check_at) {
+            e->dirty = true;
+        }
         if (e->dirty || e->xfade_active) {
             // the previous launches' MAC and inverse stages (other streams) still read the job / output-mix tables,
             // and a delay fix-up rewrites ring slots the previous MAC reads
@@ -1449,7 +1616,9 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
                 CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[prev], 0));
                 CU(cudaStreamWaitEvent(e->stream, e->ev_inv_done[prev], 0));
             }
-            int frc = apply_delay_fixups(e);
+            int frc = update_streams(e);
+            if (frc != 0) return frc;
+            frc = apply_delay_fixups(e);
             if (frc != 0) return frc;
             build_tables(e);
             int rc = upload_tables(e);
@@ -1724,7 +1893,7 @@ int bfcuda_get_info(bfcuda_engine *e, struct bfcuda_info *info)
     memset(info, 0, sizeof(*info));
     info->n_fft = e->N;
     info->mac_split = e->split;
-    info->n_streams = e->n_filters;
+    info->n_streams = e->n_rings;
     info->kernels_per_block = 3 + (e->level_mix_first.size() > 1 && e->level_mix_first[1] > 0 ? 1 : 0) +
                               3 * (e->n_levels - 1) +
                               (e->plan.tw2 != nullptr ? 2 : (e->shared_out.empty() ? 0 : 1));
@@ -1773,14 +1942,14 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
         }
         const int R = e->fdl_ring;
         const int phys = (int)((((long)e->slot_t - 1 - back + d) % R + R) % R);
-        const char *src = (const char *)e->d_fdl + nb * ((size_t)index * R + phys);
+        const char *src = ring_ptr(e, e->filters[index].stream) + nb * (size_t)phys;
         CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
         CU(cudaMemcpyAsync(dst, e->d_scratch, nb, cudaMemcpyDeviceToHost, e->stream));
         break;
     }
     case BFCUDA_DBG_FILTER_OUTPUT: {
         if (index < 0 || index >= 2 * e->n_filters) return fail(BFCUDA_EINVAL, "filter out of range");
-        const size_t n_slots = 2 * (size_t)std::max(1, e->n_filters);
+        const size_t n_slots = 2 * (size_t)std::max(1, e->n_filters) + 2 * (size_t)e->n_ch[1];
         std::vector<unsigned char> part(nb);
         for (int z = 0; z < 1; z++) {       // partial 0 holds the complete sum (launch_split_reduce)
             // the last block of the most recent launch

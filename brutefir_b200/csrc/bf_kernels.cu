@@ -440,6 +440,42 @@ __global__ void __launch_bounds__(256) k_split_reduce(MacArgs a, int N)
 }
 
 // ======================================================================================================
+// k_out_mix -- mixnscale(OUTPUT) for outputs fed by several filters
+// ======================================================================================================
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_out_mix(OutMixArgs a, int N)
+{
+    constexpr int W = 16 / (int)sizeof(T);
+    typedef typename Vec16<T>::type V;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N / W) {
+        return;
+    }
+    const int o = blockIdx.y, blk = blockIdx.z;
+    const OutChan ch = a.mixes[o];
+    if (ch.n <= 1) {
+        return;         // a single filter: the inverse stage scales it itself
+    }
+    T *Y = reinterpret_cast<T *>(a.Y) + (size_t)blk * a.n_slots * N + (size_t)v * W;
+    for (int pass = 0; pass < (ch.xf_first >= 0 ? 2 : 1); pass++) {
+        const int first = pass == 0 ? ch.first : ch.xf_first;
+        Lanes<T, W> acc;
+        for (int j = 0; j < ch.n; j++) {
+            const MixTerm tm = a.terms[first + j];
+            const Lanes<T, W> y = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(Y + (size_t)tm.index * N)));
+            const T sc = (T)tm.scale;
+#pragma unroll
+            for (int l = 0; l < W; l++) {
+                const T p = mul_rn(y.v[l], sc);
+                acc.v[l] = j == 0 ? p : add_rn(acc.v[l], p);
+            }
+        }
+        *reinterpret_cast<V *>(Y + (size_t)(a.z_first + pass * a.n_out + o) * N) = *reinterpret_cast<V *>(&acc);
+    }
+}
+
+// ======================================================================================================
 // k_inverse
 // ======================================================================================================
 
@@ -1013,6 +1049,19 @@ cudaError_t launch_split_reduce(const FftPlan &plan, const MacArgs &a, cudaStrea
         k_split_reduce<float><<<grid, 256, 0, s>>>(a, plan.N);
     } else {
         k_split_reduce<double><<<grid, 256, 0, s>>>(a, plan.N);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_out_mix(const FftPlan &plan, const OutMixArgs &a, cudaStream_t s)
+{
+    if (a.n_out == 0) return cudaSuccess;
+    const int W = 16 / plan.realsize;
+    dim3 grid((plan.N / W + 255) / 256, a.n_out, a.batch);
+    if (plan.realsize == 4) {
+        k_out_mix<float><<<grid, 256, 0, s>>>(a, plan.N);
+    } else {
+        k_out_mix<double><<<grid, 256, 0, s>>>(a, plan.N);
     }
     return cudaGetLastError();
 }

@@ -184,6 +184,20 @@ struct InverseArgs {
     int fast_fmt;               // as ForwardArgs::fast_fmt, for the outputs
     int simple_mix;             // every output is one filter's output, unsplit partition sum, no crossfade pending
 };
+// mixnscale(OUTPUT) as a kernel of its own (fftw_convfuns.h:268-494, bfrun.c:1847-1868) for outputs fed by several
+// filters: Z[o] = sum_j scale_j Y[slot_j], left to right, written to Y slot z_first + o (and the "old coefficient" mix
+// of a crossfade block to z_first + n_out + o).  The inverse stage then reads ONE spectrum per output with scale 1.
+struct OutMixArgs {
+    void *Y;                    // [batch][n_slots][N] (partition split already reduced)
+    const OutChan *mixes;       // [n_out]: first / n / xf_first of the filter terms; outputs with n <= 1 are skipped
+    const MixTerm *terms;
+    int n_out;
+    int n_slots;
+    int z_first;
+    int batch;
+};
+cudaError_t launch_out_mix(const FftPlan &plan, const OutMixArgs &a, cudaStream_t s);
+
 // size-specialised path: the inverse stage stops at out_time; this quantises / packs ALL channels from it
 cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);

@@ -129,6 +129,8 @@ struct bfcuda_config {
 #define BFCUDA_FLAG_STAGE_TIMING 1u     /* record CUDA events around each stage of every block */
 #define BFCUDA_FLAG_NO_GRAPH 2u         /* (reserved) */
 #define BFCUDA_FLAG_KEEP_INPUT_SPECTRA 4u   /* keep every input's unscaled spectrum for bfcuda_debug_read */
+#define BFCUDA_FLAG_NO_STREAM_SHARING 16u  /* give every filter its own delay line even where several filters are fed by
+                                           the same input with the same scale and delay (they normally share one) */
 #define BFCUDA_FLAG_SERIAL_STAGES 8u    /* do not overlap the stages of consecutive launches (the engine normally runs
                                            launch n+1's forward and launch n-1's inverse stage beside launch n's
                                            multiply-accumulate): stage timings then are each stage running alone */

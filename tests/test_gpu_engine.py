@@ -489,3 +489,68 @@ def test_dither_end_to_end_against_oracle(gpu_lib, oracle_libs):
             e.coeff_from_taps(c, h)
         plain = unpack_run(e.run(sig), g2.out_formats, L)
     assert np.mean(plain[0] != y[0]) > 0.2
+
+
+def matrix_graph(n, L, P, rs, in_scale=1.0):
+    """n inputs x n outputs, one filter per (input, output) pair: every input feeds n filters (crosstalk / room
+    correction matrices, xtc_config's topology scaled up)."""
+    inb, nin = interleaved_layout(n, "S24_4LE", L)
+    outb, nout = interleaved_layout(n, "S24_4LE", L)
+    filters = [Filter([i], [o], in_scales=[in_scale], out_scales=[1.0 / n], coeff=o * n + i, crossfade=(i == 0))
+               for o in range(n) for i in range(n)]
+    return FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [P] * (n * n))
+
+
+@pytest.mark.parametrize("L,P,rs,B", [(64, 6, 4, 1), (1024, 5, 4, 1), (1024, 5, 4, 4), (256, 4, 8, 2)])
+def test_delay_lines_shared_across_filters(gpu_lib, oracle_libs, L, P, rs, B):
+    """Filters fed by the same input with the same scale and delay share one delay line ("input spectra reused across
+    filters"): n rings instead of n^2.  Results must not depend on it -- byte-identical to the engine with sharing off
+    and within tolerance of the oracle -- through run-time changes that split a filter off its ring (input scale,
+    delay), the aliasing fix-ups on the split-off copy, crossfaded coefficient switches, and re-merging once the rings
+    are identical again."""
+    n, nb = 3, 8 * P + 20
+    g = matrix_graph(n, L, P, rs)
+    taps = [t * 0.8 for t in configs.synthetic_filters(g, 41)]
+    sig = configs.synthetic_signal(g, 41, nb, sigma=0.03)
+    script = {3: [(1, dict(coeff=1, in_scales=[0.5]))],                    # filter 1 leaves input 1's ring
+              5: [(0, dict(coeff=4))],                                     # crossfade on a ring owner
+              7: [(3, dict(coeff=3, delayblocks=2))],                      # owner of input 0's ring changes delay
+              9: [(6, dict(coeff=6, delayblocks=2))],                      # ... a follower follows (own ring, fix-ups)
+              12: [(1, dict(coeff=1, in_scales=[1.0]))],                   # back to the common scale: re-merge later
+              14: [(3, dict(coeff=3, delayblocks=0)), (6, dict(coeff=6, delayblocks=0))]}
+
+    def run_engine(flags):
+        rings = []
+        with Engine(g, mac_split=1, max_batch=B, flags=flags) as e:
+            for c, h in enumerate(taps):
+                e.coeff_from_taps(c, h)
+            out = np.zeros((nb, g.out_bytes), np.uint8)
+            b = 0
+            while b < nb:
+                for filt, kw in script.get(b, []):
+                    e.set_control(filt, **kw)
+                k = 1
+                while k < B and b + k < nb and (b + k) not in script:
+                    k += 1
+                e.process_blocks_async(sig[b:b + k], out[b:b + k], k)
+                e.synchronize()
+                rings.append((b, e.info().n_streams))
+                b += k
+        return out, dict(rings)
+
+    shared, rings = run_engine(0)
+    private, rings_off = run_engine(_abi.FLAG_NO_STREAM_SHARING)
+    assert np.array_equal(shared, private)
+    assert rings[0] == n and rings_off[0] == n * n                  # three rings for nine filters
+    assert max(rings.values()) >= n + 3                             # the splits happened ...
+    assert rings[max(rings)] == n                                   # ... and the rings merged again at the end
+    d = po.BlockDriver("oracle", g)
+    for c, h in enumerate(taps):
+        d.coeff_from_taps(c, h)
+    want = []
+    for b in range(nb):
+        for filt, kw in script.get(b, []):
+            d.set_control(filt, **kw)
+        want.append(d.process_block(sig[b]))
+    d.close()
+    assert_parity(g, shared, np.stack(want))
