@@ -345,7 +345,12 @@ def main():
                     "forward_gbs": (len(sub.in_formats) * (graph.filter_length * sub.in_formats[0].sf.bytes + graph.n_fft * graph.realsize) /
                                     (stage_ms[0] * 1e-3) / 1e9) if stage_ms[0] > 0 else None,
                     "inverse_gbs": (len(sub.out_formats) * (graph.filter_length * sub.out_formats[0].sf.bytes + graph.n_fft * graph.realsize) /
-                                    (stage_ms[2] * 1e-3) / 1e9) if stage_ms[2] > 0 else None}}
+                                    (stage_ms[2] * 1e-3) / 1e9) if stage_ms[2] > 0 else None,
+                    # flop side of the same roofline: ~2.5 N log2 N per real transform of N points
+                    "forward_tflops": (len(sub.in_formats) * 2.5 * graph.n_fft * np.log2(graph.n_fft) /
+                                       (stage_ms[0] * 1e-3) / 1e12) if stage_ms[0] > 0 else None,
+                    "inverse_tflops": (len(sub.out_formats) * 2.5 * graph.n_fft * np.log2(graph.n_fft) /
+                                       (stage_ms[2] * 1e-3) / 1e12) if stage_ms[2] > 0 else None}}
         if B > 1:
             roof["note"] = ("one launch covers B blocks and reads every coefficient / delay-line spectrum ONCE for all "
                             "of them (register reuse): algorithmic bytes = rs*N*(P*F + (P+B-1)*U + B*F).  With the "

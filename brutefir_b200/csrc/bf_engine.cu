@@ -2,17 +2,25 @@
 //
 // Host-side state machine that replaces the per-block body of filter_process()
 // (/root/reference/bfrun.c:1420-2083): it keeps the frequency-domain delay lines, coefficient spectra,
-// the run-time control snapshot and the overflow counters in HBM, and turns each audio block into
-// three kernel launches (forward, multiply-accumulate, inverse; see bf_kernels.cu).
+// the run-time control snapshot, dither state and the overflow counters in HBM, and turns each call (one audio
+// block, or a batch of up to eight) into a short chain of kernel launches on three software-pipelined streams:
+//   main   k_unpack -> k_forward2 (or the fused k_forward) [-> k_stream_mix]
+//   s_mac  k_mac / k_mac_batch2 [-> k_split_reduce] [-> per chaining level: k_eval, k_stream_mix, k_mac ...]
+//   s_inv  [k_out_mix ->] k_inverse2 (or k_inverse) [-> ncclAllReduce] -> k_pack [-> k_dither]
 //
-// HBM layout (all "planar" spectra, bf_common.cuh):
-//   H    [sum of coeff blocks][N]      coefficient spectra, pre-scaled by 1/N  (bfconf->coeffs_data)
-//   FDL  [n_streams][P][N]             delay-line rings, slot (t + delay) % P written per block
-//                                      (cbuf[n][n_blocks], bfrun.c:1045, 1273-1287)
-//   Y    [split][2 F][N]               filter outputs (ocbuf[n]); slots F.. hold the "old coefficient"
-//                                      outputs while a crossfade is in progress (crossfadebuf[0])
-//   prev [n_in][L]                     previous input block per channel (input_timecbuf, fftw_convolver.c:180-193)
-//   xin  [n_in][N]                     unscaled input spectra, only for inputs feeding a multi-input mix
+// HBM layout (all "planar" spectra, bf_common.cuh; B = max_batch, ring = 2 P + 2 B):
+//   H        [sum of coeff blocks][N]       coefficient spectra, pre-scaled by 1/N  (bfconf->coeffs_data)
+//   FDL      [F][ring][N]                   delay-line rings, slot (t + delay) % ring written per block
+//                                           (cbuf[n][n_blocks], bfrun.c:1045, 1273-1287); filters with the same
+//                                           input, scale and delay share a ring (update_streams)
+//   Y        [2][split][B][2F + 2 n_out][N] filter outputs (ocbuf[n]), two generations; slots F.. hold the "old
+//                                           coefficient" outputs of a crossfade block (crossfadebuf[0]), the last
+//                                           2 n_out the mixes of outputs fed by several filters (k_out_mix)
+//   xt       [2][B][n_in][L]                unpacked input blocks, two generations (input_timecbuf,
+//                                           fftw_convolver.c:180-193); prev [n_in][L] on the fused path
+//   xin      [B][n_in + n_eval][N]          unscaled spectra of inputs feeding a multi-input mix, and the evaluated
+//                                           outputs of source filters (to_filters chaining)
+//   out_time [B][n_out][L]                  inverse-transform output, LSB units
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math.h>
@@ -145,7 +153,7 @@ struct bfcuda_engine {
     // delay-line ring has a launch of slack); the MAC is the HBM-bound stage, the other two fill its gaps and tail.
     // `s_in` / `s_out` carry the host<->device copies of the streaming interface (double-buffered raw blocks).
     cudaStream_t stream, s_mac, s_inv, s_in, s_out;
-    cudaEvent_t ev_h2d[2], ev_fwd[2], ev_d2h[2], ev_mac, ev_inv;
+    cudaEvent_t ev_h2d[2], ev_fwd[2], ev_d2h[2], ev_inv;
     cudaEvent_t ev_fwd_done[2], ev_mac_done[2], ev_inv_done[2], ev_join;  // per launch parity
     unsigned int launch_no;     // launches enqueued so far
     size_t y_stride;            // bytes between the two generations of Y
@@ -368,7 +376,7 @@ static void build_tables(bfcuda_engine *e)
     e->h_mix_streams.clear();
     e->h_mix_terms.clear();
     e->h_jobs.clear();
-    std::fill(e->h_need_xin.begin(), e->h_need_xin.end(), (e->flags & 4u) ? 1 : 0);
+    std::fill(e->h_need_xin.begin(), e->h_need_xin.end(), (e->flags & BFCUDA_FLAG_KEEP_INPUT_SPECTRA) ? 1 : 0);
     e->xfade_active = false;
     size_t blocks_h = 0, blocks_x = 0;
     std::vector<int> stream_parts(std::max(1, F), 0);   // delay-line blocks read per ring (shared rings count once)
@@ -571,7 +579,7 @@ static void build_tables(bfcuda_engine *e)
     // job, and writes B outputs per job
     const size_t Bm = (size_t)e->max_batch;
     e->mac_bytes_batch = (size_t)e->rs * e->N * (blocks_h + blocks_x + (size_t)e->n_rings * (Bm - 1) + e->h_jobs.size() * Bm);
-    e->single_dest = !(e->flags & 4u) && e->h_mix_streams.empty();
+    e->single_dest = !(e->flags & BFCUDA_FLAG_KEEP_INPUT_SPECTRA) && e->h_mix_streams.empty();
     for (int c = 0; c < e->n_ch[0]; c++) {
         e->single_dest = e->single_dest && per_ch[c].size() == 1;
     }
@@ -778,7 +786,7 @@ void bfcuda_destroy(bfcuda_engine *e)
         }
     }
     for (cudaEvent_t ev : { e->ev_h2d[0], e->ev_h2d[1], e->ev_fwd[0], e->ev_fwd[1], e->ev_d2h[0], e->ev_d2h[1],
-                            e->ev_mac, e->ev_inv, e->ev_fwd_done[0], e->ev_fwd_done[1], e->ev_mac_done[0],
+                            e->ev_inv, e->ev_fwd_done[0], e->ev_fwd_done[1], e->ev_mac_done[0],
                             e->ev_mac_done[1], e->ev_inv_done[0], e->ev_inv_done[1], e->ev_join }) {
         if (ev) cudaEventDestroy(ev);
     }
@@ -906,7 +914,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->launch_no = 0;
     e->y_stride = 0;
     e->ev_h2d[0] = e->ev_h2d[1] = e->ev_fwd[0] = e->ev_fwd[1] = e->ev_d2h[0] = e->ev_d2h[1] = nullptr;
-    e->ev_mac = e->ev_inv = nullptr;
+    e->ev_inv = nullptr;
     e->io_count = 0;
     e->comm = nullptr;
     e->n_ranks = 1;
@@ -1022,7 +1030,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         TRYCU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
         TRYCU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
         for (cudaEvent_t *ev : { &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_fwd[0], &e->ev_fwd[1], &e->ev_d2h[0],
-                                 &e->ev_d2h[1], &e->ev_mac, &e->ev_inv, &e->ev_fwd_done[0], &e->ev_fwd_done[1],
+                                 &e->ev_d2h[1], &e->ev_inv, &e->ev_fwd_done[0], &e->ev_fwd_done[1],
                                  &e->ev_mac_done[0], &e->ev_mac_done[1], &e->ev_inv_done[0], &e->ev_inv_done[1],
                                  &e->ev_join }) {
             TRYCU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
@@ -1919,7 +1927,7 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
     const size_t nb = rs_bytes(e, e->N);
     switch (what) {
     case BFCUDA_DBG_INPUT_SPECTRUM: {
-        if (!(e->flags & 4u)) return fail(BFCUDA_EINVAL, "input spectra are only kept with flag 4 (debug)");
+        if (!(e->flags & BFCUDA_FLAG_KEEP_INPUT_SPECTRA)) return fail(BFCUDA_EINVAL, "input spectra are only kept with flag 4 (debug)");
         if (index < 0 || index >= e->n_ch[0]) return fail(BFCUDA_EINVAL, "input channel out of range");
         const char *src = (const char *)e->d_xin + nb * index;
         CU(launch_permute(e->plan, src, e->d_scratch, 1, PLANAR_TO_HC, e->stream));
