@@ -22,6 +22,9 @@ from brutefir_b200.formats import BufferFormat, interleaved_layout, pack_block, 
 from brutefir_b200.graph import Filter, FilterGraph  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
 
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_golden import golden_graph_c, golden_graph_d  # noqa: E402
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
 
@@ -107,6 +110,36 @@ def golden_blocks():
         outs.append(d.process_block(sig[b]))
     out["b_sig"], out["b_taps0"], out["b_taps1"] = sig, taps[0], taps[1]
     out["b_out"] = np.stack(outs)
+    d.close()
+    # (c) filter -> filter chaining (bench1_config's topology plus a third level and source multipliers)
+    g = golden_graph_c()
+    rng = np.random.default_rng(778)
+    taps = [rng.standard_normal(g.filter_length * n).astype(np.float32) / 6 for n in g.coeff_n_blocks]
+    x = np.round(rng.standard_normal((12, 2, g.filter_length)) * 0.05 * (1 << 23))
+    sig = np.stack([pack_block(x[b], g.in_formats, g.in_bytes) for b in range(12)])
+    d = po.BlockDriver("ref", g)
+    for c, h in enumerate(taps):
+        d.coeff_from_taps(c, h)
+    out["c_sig"] = sig
+    for c, h in enumerate(taps):
+        out[f"c_taps{c}"] = h
+    out["c_out"] = d.run(sig)
+    d.close()
+    # (d) HP-TPDF dither with error feedback on 16-bit outputs, through a table wrap and clipping blocks
+    g = golden_graph_d()
+    rng = np.random.default_rng(779)
+    taps = [rng.standard_normal(g.filter_length * 2).astype(np.float32) / 6 for _ in range(2)]
+    x = np.round(rng.standard_normal((36, 2, g.filter_length)) * 0.1 * (1 << 23))
+    x[5:8] *= 40
+    x = np.clip(x, -(1 << 23), (1 << 23) - 1)
+    sig = np.stack([pack_block(x[b], g.in_formats, g.in_bytes) for b in range(36)])
+    d = po.BlockDriver("ref", g)
+    for c, h in enumerate(taps):
+        d.coeff_from_taps(c, h)
+    out["d_sig"], out["d_taps0"], out["d_taps1"] = sig, taps[0], taps[1]
+    out["d_out"] = d.run(sig)
+    out["d_overflow"] = np.array([[d.overflow(o).n_overflows, d.overflow(o).intlargest, d.overflow(o).largest]
+                                  for o in range(2)])
     d.close()
     return out
 

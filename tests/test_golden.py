@@ -67,6 +67,27 @@ def golden_graph_b():
     return g
 
 
+def golden_graph_c():
+    """to_filters chaining: four input-fed filters, two fed by them, one fed by those (bfrun.c:1603-1660)."""
+    L, P = 32, 3
+    inb, nin = interleaved_layout(2, "S24_4LE", L)
+    outb, nout = interleaved_layout(3, "S24_4LE", L)
+    filters = [Filter([0], [], coeff=2), Filter([0], [], coeff=3), Filter([1], [2], coeff=4), Filter([1], [], coeff=5),
+               Filter([], [0], coeff=0, from_filters=[0, 3], fscales=[1.0, -0.5]),
+               Filter([1], [1], in_scales=[0.25], coeff=1, from_filters=[1, 2], delayblocks=1),
+               Filter([], [2], out_scales=[0.5], coeff=-1, from_filters=[4, 5], fscales=[0.5, 0.25])]
+    return FilterGraph(L, P, 4, inb, outb, nin, nout, filters, [P, P, 2, P, 1, P])
+
+
+def golden_graph_d():
+    """dither: true on two S16_LE outputs (dither.c, dither_funs.h:7-68); small table so that it wraps."""
+    L, P = 64, 2
+    inb, nin = interleaved_layout(2, "S24_4LE", L)
+    outb, nout = interleaved_layout(2, "S16_LE", L)
+    return FilterGraph(L, P, 4, inb, outb, nin, nout, [Filter([0], [0], coeff=0), Filter([1], [1], coeff=1)], [P, P],
+                       sampling_rate=100, apply_dither=[True, True])
+
+
 def run_golden_b(engine_like, sig):
     outs = []
     for b in range(16):
@@ -90,4 +111,17 @@ def test_block_sequences_against_reference_vectors(oracle_libs, blk):
     d.coeff_from_taps(0, blk["b_taps0"])
     d.coeff_from_taps(1, blk["b_taps1"])
     assert np.array_equal(run_golden_b(d, blk["b_sig"]), blk["b_out"])
+    d.close()
+    gc = golden_graph_c()
+    d = po.BlockDriver("oracle", gc)
+    for c in range(len(gc.coeff_n_blocks)):
+        d.coeff_from_taps(c, blk[f"c_taps{c}"])
+    assert np.array_equal(d.run(blk["c_sig"]), blk["c_out"])
+    d.close()
+    d = po.BlockDriver("oracle", golden_graph_d())
+    d.coeff_from_taps(0, blk["d_taps0"])
+    d.coeff_from_taps(1, blk["d_taps1"])
+    assert np.array_equal(d.run(blk["d_sig"]), blk["d_out"])
+    assert [[d.overflow(o).n_overflows, d.overflow(o).intlargest, d.overflow(o).largest] for o in range(2)] == \
+        blk["d_overflow"].tolist()
     d.close()
