@@ -126,3 +126,30 @@ def test_c1_bench1_config_graph_on_the_device(gpu_lib, oracle_libs):
         got, ref = unpack_run(e.run(sig), g.out_formats, L), unpack_run(d.run(sig), g.out_formats, L)
         d.close()
     assert np.abs(ref).max() > 1e4 and np.abs(got - ref).max() <= 2 and np.mean(np.abs(got - ref) > 1) < 1e-4
+
+
+def test_c3_batched_pipeline_equals_block_by_block_at_full_size(gpu_lib):
+    """The headline mode of bench.py (8 blocks per call, three software-pipelined stage streams) at the full
+    64 x 1 048 576-tap size: byte-identical to the block-by-block engine, random filters on a few channels and shifted
+    unit impulses elsewhere, 24 blocks through host buffers."""
+    g = configs.config_c3()
+    L, P = g.filter_length, g.n_blocks
+    sig = configs.synthetic_signal(g, 3, 24, sigma=0.02)
+    outs = []
+    for B in (1, 8):
+        with Engine(g, max_batch=B) as e:
+            for c in range(64):
+                if c % 16 == 5:
+                    r = np.random.default_rng(35 + c)       # same taps for both engines
+                    h = (r.standard_normal(L * P) * np.exp(-np.arange(L * P) / (L * P / 4.0)) * 3e-3).astype(np.float32)
+                else:
+                    h = np.zeros(L * P, np.float32)
+                    h[(c * 977) % (L * 3)] = 1.0
+                e.coeff_from_taps(c, h)
+            out = np.zeros((24, g.out_bytes), np.uint8)
+            for b0 in range(0, 24, B):
+                e.process_blocks_async(sig[b0:b0 + B], out[b0:b0 + B], B)
+            e.synchronize()
+            outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(unpack_run(outs[0], g.out_formats, L)).max() > 1e4
