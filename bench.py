@@ -330,7 +330,7 @@ def main():
         compulsory = info.mac_bytes_per_batch if B > 1 else info.mac_bytes_per_block
         achieved = compulsory / (mac_ms_launch * 1e-3) / 1e9 if mac_ms_launch > 0 else 0.0
         survey = info.mac_bytes_per_block * B / (mac_ms_launch * 1e-3) / 1e9 if mac_ms_launch > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "k_mac" if B == 1 else f"k_mac_batch (B={B})", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "k_mac" if B == 1 else f"k_mac_batch2 (B={B})", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic.get(f"{args.workload}_n{world}_b{B}"),
                 "peak_source": peak_source, "algorithmic_bytes_per_launch": compulsory, "kernel_ms": mac_ms_launch,
                 "blocks_per_launch": B,
