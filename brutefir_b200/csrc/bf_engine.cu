@@ -626,7 +626,7 @@ static int choose_split(const bfcuda_engine *e, int requested)
     // is enough there.)
     int lanes = 16 / e->rs;
     if (e->max_batch > 1) {
-        lanes = e->rs == 4 ? (e->max_batch <= 4 ? 4 : 2) : (e->max_batch <= 2 ? 2 : 1);
+        lanes = e->rs == 4 ? (e->max_batch <= 4 ? 4 : (e->max_batch <= 8 ? 2 : 1)) : (e->max_batch <= 2 ? 2 : 1);
     }
     const long threads = (long)std::max(1, e->n_filters) * (e->N / 2 / lanes);
     const long target = (long)e->sm_count * (e->max_batch > 1 ? 256 : 512);
@@ -812,8 +812,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     if (c->n_blocks < 1) {
         return fail(BFCUDA_EINVAL, "Invalid number of blocks %d.", c->n_blocks);
     }
-    if (c->max_batch > (c->realsize == 4 ? 8 : 4)) {
-        return fail(BFCUDA_EINVAL, "max_batch %d exceeds %d", c->max_batch, c->realsize == 4 ? 8 : 4);
+    if (c->max_batch > (c->realsize == 4 ? 16 : 4)) {
+        return fail(BFCUDA_EINVAL, "max_batch %d exceeds %d", c->max_batch, c->realsize == 4 ? 16 : 4);
     }
     if (c->n_channels[0] < 0 || c->n_channels[0] > BFCUDA_MAXCHANNELS || c->n_channels[1] < 0 ||
         c->n_channels[1] > BFCUDA_MAXCHANNELS || c->n_filters < 0 || c->n_filters > BFCUDA_MAXFILTERS) {

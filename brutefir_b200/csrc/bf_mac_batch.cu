@@ -26,6 +26,7 @@ namespace bf {
 template <typename T, int W> struct VecB;
 template <> struct VecB<float, 4> { typedef float4 type; };
 template <> struct VecB<float, 2> { typedef float2 type; };
+template <> struct VecB<float, 1> { typedef float type; };
 template <> struct VecB<double, 2> { typedef double2 type; };
 template <> struct VecB<double, 1> { typedef double type; };
 
@@ -321,6 +322,7 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
         if (a.batch <= 2) return launch_one<float, 4, 2, 4>(a, plan.N, s);
         if (a.batch <= 4) return launch_one<float, 4, 4, 4>(a, plan.N, s);
         if (a.batch <= 8) return launch_one<float, 2, 8, 8>(a, plan.N, s);
+        if (a.batch <= 16) return launch_one<float, 1, 16, 16>(a, plan.N, s);
         return cudaErrorInvalidValue;
     }
     if (a.batch <= 2) return launch_one<double, 2, 2, 4>(a, plan.N, s);

@@ -120,7 +120,7 @@ struct bfcuda_config {
                                    first-order error feedback, dither_funs.h:7-68: a sequential recurrence per channel. */
     int sampling_rate;          /* only sizes the dither table (dither.c:75-96); 0 = 44100 */
     int max_dither_table_size;  /* bfconf->max_dither_table_size, 0 = no limit */
-    int max_batch;              /* 0/1 = block by block (the reference's schedule).  B > 1 (<= 8 at realsize 4, <= 4 at
+    int max_batch;              /* 0/1 = block by block (the reference's schedule).  B > 1 (<= 16 at realsize 4, <= 4 at
                                    realsize 8) lets bfcuda_process_blocks* take up to B consecutive blocks per call:
                                    offline / file-to-file throughput mode.  Results are bit-identical to B single
                                    calls; the I/O delay grows by the batch (not for real-time use). */

@@ -299,7 +299,7 @@ def test_errors_and_limits(gpu_lib):
         assert err.value.code == -5             # NaN/Inf in the output: the reference abort()s
 
 
-@pytest.mark.parametrize("rs,B", [(4, 2), (4, 4), (4, 8), (8, 3), (8, 4)])
+@pytest.mark.parametrize("rs,B", [(4, 2), (4, 4), (4, 8), (4, 16), (8, 3), (8, 4)])
 def test_batched_launches_are_bit_identical_to_block_by_block(gpu_lib, oracle_libs, rs, B):
     """max_batch > 1 (offline throughput mode): up to B blocks per launch, coefficient and delay-line spectra
     reused in registers across the batch.  Every output byte and every overflow counter must equal the
