@@ -5,9 +5,10 @@ Workload (configs[2], "c3"): 64 inputs -> 64 outputs, 64 filters of 1 048 576 ta
 8192 x 128, 48 kHz, float_bits 32, S24_4LE interleaved I/O, dither off, synthetic white noise and random
 unit-energy filters.  A "step" is one call of the hot path -- raw2real -> FFT -> delay-line MAC over all
 partitions -> IFFT -> real2raw -- over --batch consecutive audio blocks (8192 samples on every channel =
-170.67 ms of audio each).  --batch 8 (default) is the offline / file-to-file mode the reference's own
-benchmark configs run in (bfio_file, no real-time constraint); --batch 1 is the reference's block-by-block
-schedule and is ALWAYS measured too and reported under "streaming" (with the SURVEY.md 8(d) roofline).
+170.67 ms of audio each).  The default (8 blocks; 16 when a rank holds 16 filters or fewer) is the offline /
+file-to-file mode the reference's own benchmark configs run in (bfio_file, no real-time constraint); --batch 1 is
+the reference's block-by-block schedule and is ALWAYS measured too and reported under "streaming" (with the
+SURVEY.md 8(d) roofline).
 
   value   realtime multiple with the raw input block already resident in HBM (device-timed, CUDA events on
           the engine's stream), whole job over all ranks
@@ -54,9 +55,10 @@ def parse_args():
                          "headline filter shape (64 filters, every input feeds 8 of them: shared delay lines)")
     ap.add_argument("--no-sharing", action="store_true", help="give every filter its own delay line (A/B for m8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=8,
-                    help="audio blocks per step (1 = the reference's block-by-block schedule; the streaming figures are "
-                         "always measured and reported under 'streaming' as well)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="audio blocks per step.  0 (default) = 8, or 16 when a rank holds 16 filters or fewer (small "
+                         "shards amortise their per-step launch cost over more blocks); 1 = the reference's "
+                         "block-by-block schedule (its figures are always measured and reported under 'streaming' too)")
     return ap.parse_args()
 
 
@@ -373,7 +375,7 @@ def main():
             b.free()
         return res
 
-    B = max(1, args.batch)
+    B = args.batch if args.batch >= 1 else (8 if len(sub.filters) > 16 else 16)
     head = measure(B, args.steps, args.warmup, True)
     stream = head if B == 1 else measure(1, max(args.steps, 50), args.warmup, False)
 
