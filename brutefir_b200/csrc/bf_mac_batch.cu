@@ -180,9 +180,11 @@ __global__ void __launch_bounds__(256, MINB) k_mac_batch2(MacArgs a, int N)
             const size_t wrap = (size_t)(R - 1) * N;
             int jn = 0;
             auto issue = [&](int stage) {       // request step jn into `stage`; always closes a group
-                const unsigned int sz = jn < n ? (unsigned int)VB : 0u;
-                cp_async<VB>(stage_ptr(stage, 0), hnext, sz);
-                cp_async<VB>(stage_ptr(stage, 1), hnext + M, sz);
+                const bool live = jn < n;
+                const unsigned int sz = live ? (unsigned int)VB : 0u;
+                const T *hp = live ? hnext : H;     // a zero-size copy reads nothing, but keep its address in bounds anyway
+                cp_async<VB>(stage_ptr(stage, 0), hp, sz);
+                cp_async<VB>(stage_ptr(stage, 1), hp + M, sz);
                 cp_async<VB>(stage_ptr(stage, 2), xnext, sz);
                 cp_async<VB>(stage_ptr(stage, 3), xnext + M, sz);
                 cp_async_commit();
