@@ -98,16 +98,24 @@ __device__ __forceinline__ typename Pair<T>::type cprod_pair(T br, T bi, T cr, T
 struct DcTrue { static constexpr bool value = true; };
 struct DcFalse { static constexpr bool value = false; };
 
+// Threads per block.  (The work is a power of two of identical threads, the machine 148 SMs: 1024 blocks of 256 on 296
+// slots are 3.46 "waves" at the headline shape.  Measured: 64, 128 and 256 threads per block take the same time -- the
+// blocks of the partial last wave run alone on their SMs and correspondingly faster.)
+#ifndef BF_MAC_BATCH_THREADS
+#define BF_MAC_BATCH_THREADS 256
+#endif
+constexpr int MBT = BF_MAC_BATCH_THREADS;
+
 template <typename T, int W, int B, int S, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_mac_batch2(MacArgs a, int N)
+__global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 {
     static_assert(S % B == 0, "the unrolled body must cover whole window rotations");
     constexpr int VB = W * (int)sizeof(T);
     typedef typename VecB<T, W>::type V;
     typedef LanesB<T, W> L;
     extern __shared__ __align__(16) unsigned char mac_ring[];
-    V *ring = reinterpret_cast<V *>(mac_ring) + threadIdx.x;       // [S][4][256] vectors, this thread's column
-    auto stage_ptr = [&](int stage, int op) -> V * { return ring + (stage * 4 + op) * 256; };
+    V *ring = reinterpret_cast<V *>(mac_ring) + threadIdx.x;       // [S][4][MBT] vectors, this thread's column
+    auto stage_ptr = [&](int stage, int op) -> V * { return ring + (stage * 4 + op) * MBT; };
 
     const int M = N >> 1;
     const int vecs = M / W;
@@ -295,12 +303,13 @@ __global__ void __launch_bounds__(256, MINB) k_mac_batch2(MacArgs a, int N)
 template <typename T, int W, int B, int S>
 static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
 {
-    constexpr size_t smem = (size_t)S * 4 * 256 * W * sizeof(T);
+    constexpr size_t smem = (size_t)S * 4 * MBT * W * sizeof(T);
+    constexpr int MINB = 512 / MBT;     // 512 threads per SM at 128 registers
     static bool configured[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem);
         if (err != cudaSuccess) {
             return err;
@@ -310,8 +319,8 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
         }
     }
     const long threads = (long)a.n_jobs * (N / 2 / W);
-    dim3 grid((unsigned int)((threads + 255) / 256), a.split);
-    k_mac_batch2<T, W, B, S, 2><<<grid, 256, smem, s>>>(a, N);
+    dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split);
+    k_mac_batch2<T, W, B, S, MINB><<<grid, MBT, smem, s>>>(a, N);
     return cudaGetLastError();
 }
 
