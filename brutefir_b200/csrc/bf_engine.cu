@@ -1502,6 +1502,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ia.safety_limit = e->safety_limit;
     ia.fast_fmt = e->fast_fmt[1];
     ia.simple_mix = e->simple_mix ? 1 : 0;
+    ia.any_xfade = e->xfade_active ? 1 : 0;
     if (e->any_out_mix) {
         OutMixArgs oa;
         oa.Y = ma.Y;

@@ -18,6 +18,8 @@
 // Radix sequence for M = 2^m, 10 <= m <= 14: one radix-16 pass from registers, then as many further
 // radix-16 passes as needed to make the rest a power of 8, then radix-8 passes:
 //   m = 10: 16 8 8      m = 11: 16 16 8      m = 12: 16 16 16      m = 13: 16 8 8 8      m = 14: 16 16 8 8
+// and the two small sizes that are such products, m = 7: 16 8 and m = 8: 16 16 (8 / 16 threads per transform,
+// 32 / 16 transforms per block).
 //
 // All functions are per thread ("tid"), synchronisation is the caller's job, and the file compiles as
 // plain C++ (tests/host_emul/emul_fft2.cpp runs the phases of all threads in lock step).
@@ -41,9 +43,16 @@ struct alignas(2 * sizeof(T)) cpx {
 
 template <int LOG2M>
 struct Fft2 {
-    static_assert(LOG2M >= 10 && LOG2M <= 14, "specialised FFT sizes: 1024 <= M <= 16384");
+    static_assert(LOG2M == 7 || LOG2M == 8 || (LOG2M >= 10 && LOG2M <= 14),
+                  "specialised FFT sizes: M = 128, 256, 1024 .. 16384 (products of radix 16 and 8 passes)");
     static constexpr int M = 1 << LOG2M;
     static constexpr int NT = M / 16;                   // threads per transform
+    // Small transforms share a block: SUBS transforms side by side, each in its own region of shared memory, all
+    // walking the same passes in lock step (the block-wide barriers serve them all).  Regions are 8 elements apart
+    // from a multiple of the bank period so that two 8-thread transforms in one half-warp do not collide.
+    static constexpr int SUBS = NT >= 256 ? 1 : 256 / NT;
+    static constexpr int CTA = NT * SUBS;               // threads per block
+    static constexpr int SUB_STRIDE = M + (SUBS > 1 ? 8 : 0);
     static constexpr int REST = LOG2M - 4;
     static constexpr int N16 = (REST % 3 == 0) ? 0 : (REST % 3 == 1 ? 1 : 2);
     static constexpr int N8 = (REST - 4 * N16) / 3;

@@ -38,7 +38,7 @@ struct BlockSync2 {
 template <int LOG2M, bool TWS>
 struct Smem2 {
     typedef Fft2<LOG2M> F;
-    static constexpr size_t data_bytes = (size_t)F::M * sizeof(cpx<float>);
+    static constexpr size_t data_bytes = (size_t)F::SUBS * F::SUB_STRIDE * sizeof(cpx<float>);
     static constexpr size_t tw_bytes = TWS ? (size_t)F::TW_TOTAL * sizeof(cpx<float>) : 0;
     static constexpr size_t stats_off = data_bytes + tw_bytes;
     static constexpr size_t bar_off = stats_off + 32 * sizeof(QuantStats);
@@ -258,63 +258,74 @@ __device__ __forceinline__ void load_frame(const ForwardArgs &a, int item, int t
 }
 
 template <int LOG2M, bool SINGLE, bool TWS>
-__global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_forward2(ForwardArgs a, const cpx<float> *__restrict__ tw_global)
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_forward2(ForwardArgs a, const cpx<float> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, N = 2 * F::M;
     constexpr bool PREFETCH = F::NT < 1024;     // 1024 threads leave 64 registers: no room to hold the next frame
     extern __shared__ __align__(128) unsigned char smem2[];
-    cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2);
-    const int tid = threadIdx.x;
-    const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, tid);
+    const int tid = threadIdx.x % F::NT, sub = threadIdx.x / F::NT;     // thread of its transform, transform of the block
+    cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2) + sub * F::SUB_STRIDE;
+    const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, threadIdx.x);
     const int total = a.n_in * a.batch;
+    const int stride = (int)gridDim.x * F::SUBS;
     float *fdl = reinterpret_cast<float *>(a.fdl);
     const int ring = a.ring;
 
     cpx<float> v[16];
-    int item = blockIdx.x;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        v[q].x = 0.f;
+        v[q].y = 0.f;
+    }
+    int item = (int)blockIdx.x * F::SUBS + sub;
     if (item < total) {
         load_frame<LOG2M>(a, item, tid, v);
     }
     wait_twiddles<LOG2M, TWS>(smem2);
-    for (; item < total; item += gridDim.x) {
-        const int c = item % a.n_in, blk = item / a.n_in;
-        if (!PREFETCH && item != (int)blockIdx.x) {
+    // every transform of the block takes the same number of turns (the barriers are block wide); one without an item
+    // left runs on whatever its registers hold and stores nothing
+    for (int base = (int)blockIdx.x * F::SUBS; base < total; base += stride, item += stride) {
+        const bool active = item < total;
+        const int c = active ? item % a.n_in : 0, blk = active ? item / a.n_in : 0;
+        if (!PREFETCH && active && base != (int)blockIdx.x * F::SUBS) {
             load_frame<LOG2M>(a, item, tid, v);
         }
         fft2_complex<float, LOG2M, false, false>(s, tw, tid, v, BlockSync2());
         // the next transform's samples travel while this one's spectrum is split and stored
-        if (PREFETCH && item + (int)gridDim.x < total) {
-            load_frame<LOG2M>(a, item + gridDim.x, tid, v);
+        if (PREFETCH && item + stride < total) {
+            load_frame<LOG2M>(a, item + stride, tid, v);
         }
-        const int d0 = a.dest_first[c], d1 = a.dest_first[c + 1];
-        const int t = a.t + blk;
-        if (SINGLE) {
-            // one filter per input: one destination, hoisted out of the bin loop
-            const FwdDest ds = a.dests[d0];
-            float *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
-            const float sc = (float)ds.scale;
-            fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
-                dst[k] = mul_rn(re, sc);
-                dst[M + k] = mul_rn(im, sc);
-            });
-        } else {
-            float *xin = (a.xin != nullptr && a.need_xin[c])
-                             ? reinterpret_cast<float *>(a.xin) + ((size_t)blk * a.n_vin + c) * N : nullptr;
-            const FwdDest *dests = a.dests;
-            fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
-                if (xin != nullptr) {
-                    xin[k] = re;
-                    xin[M + k] = im;
-                }
-                for (int d = d0; d < d1; d++) {
-                    const FwdDest ds = dests[d];
-                    float *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
-                    const float sc = (float)ds.scale;
+        if (active) {
+            const int d0 = a.dest_first[c], d1 = a.dest_first[c + 1];
+            const int t = a.t + blk;
+            if (SINGLE) {
+                // one filter per input: one destination, hoisted out of the bin loop
+                const FwdDest ds = a.dests[d0];
+                float *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
+                const float sc = (float)ds.scale;
+                fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
                     dst[k] = mul_rn(re, sc);
                     dst[M + k] = mul_rn(im, sc);
-                }
-            });
+                });
+            } else {
+                float *xin = (a.xin != nullptr && a.need_xin[c])
+                                 ? reinterpret_cast<float *>(a.xin) + ((size_t)blk * a.n_vin + c) * N : nullptr;
+                const FwdDest *dests = a.dests;
+                fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
+                    if (xin != nullptr) {
+                        xin[k] = re;
+                        xin[M + k] = im;
+                    }
+                    for (int d = d0; d < d1; d++) {
+                        const FwdDest ds = dests[d];
+                        float *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
+                        const float sc = (float)ds.scale;
+                        dst[k] = mul_rn(re, sc);
+                        dst[M + k] = mul_rn(im, sc);
+                    }
+                });
+            }
         }
         __syncthreads();        // the split phase has finished reading shared memory
     }
@@ -328,7 +339,7 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_forward2(ForwardArgs a, 
 // (the usual block): one scaled spectrum per transform, and the next transform's spectrum is fetched while this
 // one's samples are stored.
 template <int LOG2M, bool SIMPLE, bool TWS>
-__global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, const cpx<float> *__restrict__ tw_global)
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_inverse2(InverseArgs a, const cpx<float> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, L = F::M, N = 2 * F::M, NT = F::NT;
@@ -336,10 +347,12 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, 
     constexpr int BPT = 16 / RL, HALF = RL / 2;      // butterflies per thread, valid outputs per butterfly
     constexpr bool PREFETCH = F::NT < 1024;
     extern __shared__ __align__(128) unsigned char smem2[];
-    cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2);
-    const int tid = threadIdx.x;
-    const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, tid);
+    const int tid = threadIdx.x % NT, sub = threadIdx.x / NT;
+    cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2) + sub * F::SUB_STRIDE;
+    const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, threadIdx.x);
     const int total = a.n_out * a.batch;
+    const int stride = (int)gridDim.x * F::SUBS;
+    const int first_item = (int)blockIdx.x * F::SUBS;
     const int zstride = a.batch * a.n_slots;        // Y slots between two partial sums of the split
     cpx<float> v[16];
 
@@ -362,8 +375,14 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, 
         }
     };
 
+    // Every transform of the block takes the same number of turns (block-wide barriers); one without an item left
+    // transforms whatever its registers hold and stores nothing.
     if (SIMPLE) {
         float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            x[i] = 0.f;
+        }
         float sc = 0.f;
         auto fetch = [&](int item) {
             const int o = item % a.n_out, blk = item / a.n_out;
@@ -372,14 +391,14 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, 
             sc = (float)tm.scale;
             fft2_merge_fetch<float, LOG2M>(tid, x, [&](int i) { return __ldg(y + i); });
         };
-        int item = blockIdx.x;
+        int item = first_item + sub;
         if (item < total) {
             fetch(item);
         }
         wait_twiddles<LOG2M, TWS>(smem2);
-        for (; item < total; item += gridDim.x) {
-            const int o = item % a.n_out, blk = item / a.n_out;
-            if (!PREFETCH && item != (int)blockIdx.x) {
+        for (int base = first_item; base < total; base += stride, item += stride) {
+            const bool active = item < total;
+            if (!PREFETCH && active && base != first_item) {
                 fetch(item);
             }
 #pragma unroll
@@ -394,25 +413,34 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, 
             }
             __syncthreads();        // everybody holds its inputs: pass 0 may overwrite
             fft2_complex<float, LOG2M, true, true>(s, tw, tid, v, BlockSync2());
-            if (PREFETCH && item + (int)gridDim.x < total) {
-                fetch(item + gridDim.x);
+            const int o = active ? item % a.n_out : 0, blk = active ? item / a.n_out : 0;
+            if (PREFETCH && item + stride < total) {
+                fetch(item + stride);
             }
-            store_time(o, blk, nullptr);
+            if (active) {
+                store_time(o, blk, nullptr);
+            }
             __syncthreads();        // the last pass has finished reading shared memory
         }
     } else {
         cpx<float> keep[BPT * HALF];
         wait_twiddles<LOG2M, TWS>(smem2);
-        for (int item = blockIdx.x; item < total; item += gridDim.x) {
-            const int o = item % a.n_out, blk = item / a.n_out;
+        // a launch that contains a crossfading output runs two transforms for EVERY item (same turn count for all
+        // transforms of a block); items without a crossfade transform their mix twice and use the second
+        const int npass = a.any_xfade ? 2 : 1;
+        int item = first_item + sub;
+        for (int base = first_item; base < total; base += stride, item += stride) {
+            const bool active = item < total;
+            const int o = active ? item % a.n_out : 0, blk = active ? item / a.n_out : 0;
             const OutChan ch = a.chans[o];
             const float *Y = reinterpret_cast<const float *>(a.Y) + (size_t)blk * a.n_slots * N;
-            const int npass = ch.xf_first >= 0 ? 2 : 1;
             for (int pass = 0; pass < npass; pass++) {
-                const int term0 = (npass == 2 && pass == 0) ? ch.xf_first : ch.first;
-                fft2_merge_load<float, LOG2M>(s, tw, tid, [&](int i) {
-                    return mix_terms<float>(Y, a.terms, term0, ch.n, zstride, a.split, N, i);
-                });
+                const int term0 = (ch.xf_first >= 0 && pass + 1 < npass) ? ch.xf_first : ch.first;
+                if (active) {
+                    fft2_merge_load<float, LOG2M>(s, tw, tid, [&](int i) {
+                        return mix_terms<float>(Y, a.terms, term0, ch.n, zstride, a.split, N, i);
+                    });
+                }
                 __syncthreads();
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
@@ -431,7 +459,9 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::NT, 1) k_inverse2(InverseArgs a, 
                 }
                 __syncthreads();    // the last pass has finished reading shared memory
             }
-            store_time(o, blk, npass == 2 ? keep : nullptr);
+            if (active) {
+                store_time(o, blk, (npass == 2 && ch.xf_first >= 0) ? keep : nullptr);
+            }
         }
     }
 }
@@ -449,7 +479,7 @@ bool fft2_supported(int N, int realsize)
     if (e != nullptr && atoi(e) != 0) {
         return false;
     }
-    return N == 2048 || N == 4096 || N == 8192 || N == 16384 || N == 32768;
+    return N == 256 || N == 512 || N == 2048 || N == 4096 || N == 8192 || N == 16384 || N == 32768;
 }
 
 template <int LOG2M>
@@ -472,6 +502,8 @@ cudaError_t fft2_plan_create(FftPlan *plan)
         return cudaSuccess;
     }
     switch (plan->N) {
+    case 256: return make_table<7>(&plan->tw2);
+    case 512: return make_table<8>(&plan->tw2);
     case 2048: return make_table<10>(&plan->tw2);
     case 4096: return make_table<11>(&plan->tw2);
     case 8192: return make_table<12>(&plan->tw2);
@@ -528,12 +560,12 @@ static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, 
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_forward2<LOG2M, SINGLE, TWS>, F::NT, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_forward2<LOG2M, SINGLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
-    const int total = a.n_in * a.batch;
+    const int total = (a.n_in * a.batch + F::SUBS - 1) / F::SUBS;      // blocks needed: SUBS transforms each
     const int grid = total < resident[dev] ? total : resident[dev];
-    k_forward2<LOG2M, SINGLE, TWS><<<grid, F::NT, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    k_forward2<LOG2M, SINGLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
     return cudaGetLastError();
 }
 
@@ -547,17 +579,19 @@ static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, 
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_inverse2<LOG2M, SIMPLE, TWS>, F::NT, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_inverse2<LOG2M, SIMPLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
-    const int total = a.n_out * a.batch;
+    const int total = (a.n_out * a.batch + F::SUBS - 1) / F::SUBS;
     const int grid = total < resident[dev] ? total : resident[dev];
-    k_inverse2<LOG2M, SIMPLE, TWS><<<grid, F::NT, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    k_inverse2<LOG2M, SIMPLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
     return cudaGetLastError();
 }
 
 #define BF_FFT2_SIZES(FN, FLAG, ...)                                                   \
     switch (plan.N) {                                                                  \
+    case 256: return FN<7, FLAG, true>(__VA_ARGS__);                                   \
+    case 512: return FN<8, FLAG, true>(__VA_ARGS__);                                   \
     case 2048: return FN<10, FLAG, true>(__VA_ARGS__);                                 \
     case 4096: return FN<11, FLAG, true>(__VA_ARGS__);                                 \
     case 8192: return FN<12, FLAG, true>(__VA_ARGS__);                                 \

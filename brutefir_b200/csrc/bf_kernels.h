@@ -183,6 +183,7 @@ struct InverseArgs {
     double safety_limit;
     int fast_fmt;               // as ForwardArgs::fast_fmt, for the outputs
     int simple_mix;             // every output is one filter's output, unsplit partition sum, no crossfade pending
+    int any_xfade;              // some output of this launch crossfades (two transforms per output, bf_fft2_kernels.cu)
 };
 // mixnscale(OUTPUT) as a kernel of its own (fftw_convfuns.h:268-494, bfrun.c:1847-1868) for outputs fed by several
 // filters: Z[o] = sum_j scale_j Y[slot_j], left to right, written to Y slot z_first + o (and the "old coefficient" mix

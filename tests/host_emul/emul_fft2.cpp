@@ -188,6 +188,8 @@ static int conflicts()
 int main()
 {
     int bad = 0;
+    bad += check<float, 7>(2e-6);
+    bad += check<float, 8>(2e-6);
     bad += check<float, 10>(2e-6);
     bad += check<float, 11>(2e-6);
     bad += check<float, 12>(2e-6);
