@@ -18,8 +18,8 @@
 // Radix sequence for M = 2^m, 10 <= m <= 14: one radix-16 pass from registers, then as many further
 // radix-16 passes as needed to make the rest a power of 8, then radix-8 passes:
 //   m = 10: 16 8 8      m = 11: 16 16 8      m = 12: 16 16 16      m = 13: 16 8 8 8      m = 14: 16 16 8 8
-// and the two small sizes that are such products, m = 7: 16 8 and m = 8: 16 16 (8 / 16 threads per transform,
-// 32 / 16 transforms per block).
+// and below that m = 6: 16 4, m = 7: 16 8, m = 8: 16 16, m = 9: 16 8 4 (4 .. 32 threads per transform, 64 .. 8
+// transforms per block).
 //
 // All functions are per thread ("tid"), synchronisation is the caller's job, and the file compiles as
 // plain C++ (tests/host_emul/emul_fft2.cpp runs the phases of all threads in lock step).
@@ -43,8 +43,7 @@ struct alignas(2 * sizeof(T)) cpx {
 
 template <int LOG2M>
 struct Fft2 {
-    static_assert(LOG2M == 7 || LOG2M == 8 || (LOG2M >= 10 && LOG2M <= 14),
-                  "specialised FFT sizes: M = 128, 256, 1024 .. 16384 (products of radix 16 and 8 passes)");
+    static_assert(LOG2M >= 6 && LOG2M <= 14, "specialised FFT sizes: 64 <= M <= 16384");
     static constexpr int M = 1 << LOG2M;
     static constexpr int NT = M / 16;                   // threads per transform
     // Small transforms share a block: SUBS transforms side by side, each in its own region of shared memory, all
@@ -54,10 +53,14 @@ struct Fft2 {
     static constexpr int CTA = NT * SUBS;               // threads per block
     static constexpr int SUB_STRIDE = M + (SUBS > 1 ? 8 : 0);
     static constexpr int REST = LOG2M - 4;
-    static constexpr int N16 = (REST % 3 == 0) ? 0 : (REST % 3 == 1 ? 1 : 2);
-    static constexpr int N8 = (REST - 4 * N16) / 3;
-    static constexpr int NP = 1 + N16 + N8;             // passes
-    BF_CE int radix(int p) { return p <= N16 ? 16 : 8; }
+    // radix 16 first, then as many more radix-16 passes as make the rest a power of 8; where that is impossible
+    // (m = 6, 9) one closing radix-4 pass takes the two odd bits
+    static constexpr int N4 = (REST % 3 == 2 && REST < 8) ? 1 : 0;
+    static constexpr int REST8 = REST - 2 * N4;
+    static constexpr int N16 = (REST8 % 3 == 0) ? 0 : (REST8 % 3 == 1 ? 1 : 2);
+    static constexpr int N8 = (REST8 - 4 * N16) / 3;
+    static constexpr int NP = 1 + N16 + N8 + N4;        // passes
+    BF_CE int radix(int p) { return p <= N16 ? 16 : (p <= N16 + N8 ? 8 : 4); }
     BF_CE int ns(int p)                      // points already combined before pass p
     {
         int n = 1;
@@ -232,8 +235,10 @@ BF_HD void cdft(cpx<T> *v)
 {
     if (R == 16) {
         cdft16<T, INV>(v);
-    } else {
+    } else if (R == 8) {
         cdft8<T, INV>(v);
+    } else {
+        cdft4<T, INV>(v[0], v[1], v[2], v[3]);
     }
 }
 

@@ -479,7 +479,7 @@ bool fft2_supported(int N, int realsize)
     if (e != nullptr && atoi(e) != 0) {
         return false;
     }
-    return N == 256 || N == 512 || N == 2048 || N == 4096 || N == 8192 || N == 16384 || N == 32768;
+    return N >= 128 && N <= 32768 && (N & (N - 1)) == 0;
 }
 
 template <int LOG2M>
@@ -502,8 +502,10 @@ cudaError_t fft2_plan_create(FftPlan *plan)
         return cudaSuccess;
     }
     switch (plan->N) {
+    case 128: return make_table<6>(&plan->tw2);
     case 256: return make_table<7>(&plan->tw2);
     case 512: return make_table<8>(&plan->tw2);
+    case 1024: return make_table<9>(&plan->tw2);
     case 2048: return make_table<10>(&plan->tw2);
     case 4096: return make_table<11>(&plan->tw2);
     case 8192: return make_table<12>(&plan->tw2);
@@ -590,8 +592,10 @@ static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, 
 
 #define BF_FFT2_SIZES(FN, FLAG, ...)                                                   \
     switch (plan.N) {                                                                  \
+    case 128: return FN<6, FLAG, true>(__VA_ARGS__);                                   \
     case 256: return FN<7, FLAG, true>(__VA_ARGS__);                                   \
     case 512: return FN<8, FLAG, true>(__VA_ARGS__);                                   \
+    case 1024: return FN<9, FLAG, true>(__VA_ARGS__);                                  \
     case 2048: return FN<10, FLAG, true>(__VA_ARGS__);                                 \
     case 4096: return FN<11, FLAG, true>(__VA_ARGS__);                                 \
     case 8192: return FN<12, FLAG, true>(__VA_ARGS__);                                 \

@@ -30,7 +30,7 @@ def test_device_fft2_on_host(tmp_path):
     and the bank-conflict check of every shared-memory access pattern."""
     r = build_and_run(tmp_path, "emul_fft2.cpp", [])
     assert r.returncode == 0, r.stdout
-    assert "FAIL" not in r.stdout and r.stdout.count("ok") == 16
+    assert "FAIL" not in r.stdout and r.stdout.count("ok") == 18
 
 
 def test_device_sample_conversion_on_host(tmp_path, oracle_libs):
