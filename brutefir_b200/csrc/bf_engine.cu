@@ -1591,6 +1591,12 @@ static int apply_delay_fixups(bfcuda_engine *e)
         const long T = e->slot_t;
         if (d_new < d_old) {
             for (int j = d_new + 1; j < d_old; j++) {
+                if ((long)e->t + j - P < 0) {
+                    // a partition older than the first block: the reference never reads it (its partition loop stops
+                    // at the number of blocks processed so far, procblocks, bfrun.c:1567-1571, 1745); here those
+                    // slots are simply still zero and must stay so
+                    continue;
+                }
                 CU(cudaMemcpyAsync(ring + nb * (size_t)phys(T + j - P), ring + nb * (size_t)phys(T + j), nb,
                                    cudaMemcpyDeviceToDevice, e->stream));
             }

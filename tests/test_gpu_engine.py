@@ -598,3 +598,14 @@ def test_pipelined_stages_equal_serialised_stages(gpu_lib, calls, B):
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "soak_pipeline.py"), str(calls), str(B)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
+
+
+def test_randomised_graphs_against_oracle(gpu_lib, oracle_libs):
+    """tools/fuzz_parity.py: random graphs (mixes, chaining, delays, crossfade, formats, 1..6 partitions), random
+    run-time control scripts, random batch sizes, engine against the oracle under the north_star tolerances.  (It found
+    the early-block case of the delay-change fix-up: partitions older than the first block must stay unread.)"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "fuzz_parity.py"), "40", "7"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "40/40" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
