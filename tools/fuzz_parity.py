@@ -21,8 +21,9 @@ rng = np.random.default_rng(seed)
 INT_FMTS = ["S16_LE", "S24_LE", "S24_4LE", "S24_4BE", "S32_LE"]
 bad = 0
 for case in range(n_cases):
-    L = int(rng.choice([16, 64, 128, 256, 512, 1024, 2048]))
-    P = int(rng.integers(1, 7))
+    big = os.environ.get("FUZZ_BIG") == "1"
+    L = int(rng.choice([1024, 2048, 4096, 8192] if big else [16, 64, 128, 256, 512, 1024, 2048]))
+    P = int(rng.integers(1, 13 if big else 7))
     rs = int(rng.choice([4, 4, 8]))
     n_in, n_out = int(rng.integers(1, 5)), int(rng.integers(1, 5))
     fin = str(rng.choice(INT_FMTS + ["FLOAT_LE"]))
@@ -51,7 +52,7 @@ for case in range(n_cases):
     for b in range(2, nblk, int(rng.integers(3, 7))):
         f = int(rng.integers(0, nf))
         script[b] = (f, dict(coeff=int(rng.integers(-1, n_coeffs)), delayblocks=int(rng.integers(0, P))))
-    B = int(rng.choice([1, 1, 2, 4]))
+    B = int(rng.choice([1, 4, 8, 16] if big and rs == 4 else [1, 1, 2, 4]))
     if os.environ.get("FUZZ_B"):
         B = int(os.environ["FUZZ_B"])
     if os.environ.get("FUZZ_ONLY") and case not in [int(x) for x in os.environ["FUZZ_ONLY"].split(",")]:
