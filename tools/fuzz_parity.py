@@ -51,16 +51,24 @@ for case in range(n_cases):
     script = {}
     for b in range(2, nblk, int(rng.integers(3, 7))):
         f = int(rng.integers(0, nf))
-        script[b] = (f, dict(coeff=int(rng.integers(-1, n_coeffs)), delayblocks=int(rng.integers(0, P))))
+        kw = dict(coeff=int(rng.integers(-1, n_coeffs)), delayblocks=int(rng.integers(0, P)))
+        if rng.random() < 0.4 and filters[f].inputs:
+            kw["in_scales"] = [float(rng.choice([1.0, 0.7071067811865476, -0.3183098861837907])) for _ in filters[f].inputs]
+        if rng.random() < 0.3 and filters[f].outputs:
+            kw["out_scales"] = [float(rng.choice([1.0, 0.6180339887498949])) for _ in filters[f].outputs]
+        if rng.random() < 0.3 and filters[f].from_filters:
+            kw["fscales"] = [float(rng.choice([1.0, 0.4342944819032518])) for _ in filters[f].from_filters]
+        script[b] = (f, kw)
+    split = int(rng.choice([1, 1, 0, 3]))
     B = int(rng.choice([1, 4, 8, 16] if big and rs == 4 else [1, 1, 2, 4]))
     if os.environ.get("FUZZ_B"):
         B = int(os.environ["FUZZ_B"])
     if os.environ.get("FUZZ_ONLY") and case not in [int(x) for x in os.environ["FUZZ_ONLY"].split(",")]:
         continue
-    desc = f"case {case}: L={L} P={P} rs={rs} in={n_in}x{fin} out={n_out}x{fout} filters={nf} B={B}"
+    desc = f"case {case}: L={L} P={P} rs={rs} in={n_in}x{fin} out={n_out}x{fout} filters={nf} B={B} split={split}"
     try:
         d = po.BlockDriver("oracle", g)
-        with Engine(g, mac_split=1, max_batch=B) as e:
+        with Engine(g, mac_split=split, max_batch=B) as e:
             for c, h in enumerate(taps):
                 e.coeff_from_taps(c, h)
                 d.coeff_from_taps(c, h)
@@ -87,7 +95,7 @@ for case in range(n_cases):
         if sf.isfloat:
             tol = 1e-6 if rs == 4 or sf.bytes == 4 else 1e-12
         elif rs == 8:
-            tol = 0.0
+            tol = 0.0 if split == 1 else 1.0     # a split partition sum is a different summation tree
         else:
             tol = max(1.0, 4 * 2.0 ** -23 * peak)       # 1 LSB where float32 resolves it, a few ulp above
         ok = diff <= tol
