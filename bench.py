@@ -195,7 +195,7 @@ def main():
     # inter-rank traffic of this program is the timing barrier and the max-over-ranks of the measured times: that
     # control plane runs over gloo on the host.  (Initialising an NCCL communicator here costs the host-buffer path
     # up to 80 us per step at 4-8 ranks -- measured with tools/e2e_multi.py -- for nothing; NCCL is used where the
-    # path really exchanges data, bfcuda_comm_* for outputs fed from several ranks, tools/multi_gpu_check.py.)
+    # path really exchanges data, bfcuda_comm_* for outputs fed from several ranks, tests/checks/multi_gpu_check.py.)
     distributed = world > 1
     if distributed:
         import torch

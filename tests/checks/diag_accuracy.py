@@ -1,11 +1,11 @@
 """GPU vs oracle vs float64 truth: who is how far from what, per config (LSB @24 bit)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from brutefir_b200 import configs
 from brutefir_b200.engine import Engine
 from oracle import pyoracle as po
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from helpers import unpack_run
 
 def truth(x, h):

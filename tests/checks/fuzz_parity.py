@@ -3,9 +3,9 @@ counts from 1), random run-time control scripts, random batch sizes -- engine ag
 north_star tolerances.  Scales are irrational on purpose: with a unit pulse ("coeff: -1") and a scale like 0.5 or 0.7
 integer samples land exactly on .5 (0.7 x 5), where the last bit of the FFT decides the rounding direction in ANY
 implementation.
-Usage: python tools/fuzz_parity.py [n_cases] [seed]"""
+Usage: python tests/checks/fuzz_parity.py [n_cases] [seed]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from brutefir_b200 import configs

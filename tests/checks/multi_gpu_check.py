@@ -4,8 +4,8 @@
       ranks: the time-domain blocks of the shared outputs are summed over NVLink (ncclAllReduce inside the
       engine) before quantisation, with a crossfaded coefficient swap on the way."""
 import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import torch
 import torch.distributed as dist

@@ -1,9 +1,9 @@
 """Soak test of the software-pipelined engine: thousands of asynchronous calls with random run-time control changes
 (coefficients with crossfade, delays, scales), pipelined stages versus BFCUDA_FLAG_SERIAL_STAGES -- the outputs must be
 byte-identical, i.e. no stage ever reads a buffer a neighbouring launch is still writing.
-Usage: python tools/soak_pipeline.py [calls] [B]"""
+Usage: python tests/checks/soak_pipeline.py [calls] [B]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from brutefir_b200 import _abi, configs
 from brutefir_b200.engine import Engine

@@ -589,23 +589,23 @@ def test_delay_lines_shared_across_filters(gpu_lib, oracle_libs, L, P, rs, B):
 
 @pytest.mark.parametrize("calls,B", [(600, 1), (300, 4)])
 def test_pipelined_stages_equal_serialised_stages(gpu_lib, calls, B):
-    """The engine overlaps the stages of consecutive launches on three streams (bf_engine.cu).  tools/soak_pipeline.py
+    """The engine overlaps the stages of consecutive launches on three streams (bf_engine.cu).  tests/checks/soak_pipeline.py
     drives hundreds of asynchronous calls with random coefficient / delay / scale changes, crossfades, chained filters
     and shared delay lines once with the pipeline and once with BFCUDA_FLAG_SERIAL_STAGES: byte-identical outputs at
     every checkpoint, i.e. no stage ever touches a buffer a neighbouring launch still uses."""
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "soak_pipeline.py"), str(calls), str(B)],
+    r = subprocess.run([sys.executable, os.path.join(HERE, "checks", "soak_pipeline.py"), str(calls), str(B)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
 
 
 def test_randomised_graphs_against_oracle(gpu_lib, oracle_libs):
-    """tools/fuzz_parity.py: random graphs (mixes, chaining, delays, crossfade, formats, 1..6 partitions), random
+    """tests/checks/fuzz_parity.py: random graphs (mixes, chaining, delays, crossfade, formats, 1..6 partitions), random
     run-time control scripts, random batch sizes, engine against the oracle under the north_star tolerances.  (It found
     the early-block case of the delay-change fix-up: partitions older than the first block must stay unread.)"""
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "fuzz_parity.py"), "40", "7"],
+    r = subprocess.run([sys.executable, os.path.join(HERE, "checks", "fuzz_parity.py"), "40", "7"],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "40/40" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
