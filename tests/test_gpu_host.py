@@ -92,3 +92,17 @@ def test_c_host_coefficient_file_formats(gpu_lib, oracle_libs, tmp_path):
     (tmp_path / "taps.s16").write_bytes(b"H" * 44 + q.tobytes())
     taps = [(q[c].astype(np.float32) * np.float32(2.0 ** -15)).astype(np.float32) for c in range(2)]
     run_host(["-c", str(tmp_path / "taps.s16"), "-f", "S16_BE", "-k", "44", "-a", "6.0"], taps, 10.0 ** (-6.0 / 20.0))
+
+
+def test_two_gpus_sharded_and_nccl_output_sum(gpu_lib):
+    """tests/checks/multi_gpu_check.py under torchrun on 2 GPUs (skipped on a single-GPU box): the diagonal graph
+    sharded by filter with no exchange, and the xtc topology with the filters of each output split over the ranks --
+    time-domain blocks summed with ncclAllReduce over NVLink before quantisation, through a crossfaded swap."""
+    import sys
+    if gpu_lib.bfcuda_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = os.path.join(ROOT, "tests", "checks", "multi_gpu_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29537", script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
