@@ -47,8 +47,8 @@ UNIT = "x realtime (64ch x 1M-tap @48kHz); Gtap-MAC/s and per-block latency alon
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "m8"],
                     help="c3 = the headline configuration; c2 / c4 = BASELINE configs[1] / [3]; m8 = 8 x 8 matrix of the "
@@ -106,7 +106,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device_index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.lines.append(line.strip())
@@ -269,7 +269,6 @@ def main():
             eng.process_blocks_device(B)
         ms = eng.timer_stop()
         barrier()
-        clocks = sampler.stop() if sampler else None
         _, _, launches = eng.stage_times()
         ms_step = max_over_ranks(ms / steps)
 
@@ -284,6 +283,7 @@ def main():
         e2e_ms = eng.timer_stop()
         eng.synchronize()
         barrier()
+        clocks = sampler.stop() if sampler else None        # sampled over both timed regions
         if os.environ.get("BENCH_DEBUG"):
             print(f"[rank {rank}] B={B} e2e {1e3 * e2e_ms / steps:.1f} us/step, device-resident {1e3 * ms / steps:.1f} us/step",
                   file=sys.stderr, flush=True)
