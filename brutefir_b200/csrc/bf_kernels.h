@@ -160,6 +160,7 @@ struct MacArgs {
     int t;
     int batch;
     int variant;                // 0 = direct streaming loads, 1 = bulk-copy (TMA) staged (batch 1 only)
+    unsigned long long neg_zero2;   // filled in by the batched launcher: two packed -0.0f (bf_mac_batch.cu, BinPairAcc)
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 // With split > 1 the MAC leaves `split` partial sums per output: add them, in order, into partial 0 (the consumers

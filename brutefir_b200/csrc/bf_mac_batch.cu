@@ -16,6 +16,7 @@
 // rotated by unrolling the partition loop.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "bf_kernels.h"
 #include "bf_sample.cuh"
@@ -65,13 +66,20 @@ __device__ __forceinline__ V ldg_once(const V *p)
     return __ldg(p);
 }
 
-// ---- one complex multiply-accumulate, (re, im) pair accumulators ------------------------------------------------
+// ---- one complex multiply-accumulate ------------------------------------------------------------------------------
 // acc += b (*) c with the reference's roundings: four separately rounded products, re = p1 - p2, im = p3 + p4, then
 // the two accumulations (convolver_xmm.c:25-30 / fftw_convfuns.h:548-556).  p1 - p2 is computed as p1 + (-bi) ci:
-// negating a factor negates the rounded product exactly.  For float the four sums are TWO packed instructions
-// (add.rn.f32x2 -> FADD2, new on sm_100): the kernel is FP32-issue bound at B = 8, and this removes a quarter of its
-// floating-point instructions without touching a single rounding.  (The products stay scalar: ptxas contracts a
-// packed mul.rn.f32x2 feeding a packed add into FFMA2, which would drop a rounding.)
+// negating a factor negates the rounded product exactly.  The kernel is FP32-issue bound at B = 8, so the instruction
+// count per complex MAC is what matters; sm_100 has packed FP32 pairs (FADD2, FFMA2) and two ways to use them exactly:
+//
+//  * PairAcc (any type and width): accumulators are (re, im) pairs; the four sums of a MAC are TWO packed adds, the
+//    four products stay scalar -- 6 instructions per MAC (8 unpacked).
+//  * BinPairAcc (float, even W): accumulators pair two neighbouring BINS; the products are packed too -- 4
+//    instructions per MAC.  A packed multiply cannot be written as such: ptxas contracts mul.rn.f32x2 (and an FFMA2
+//    with a literal -0.0 addend) feeding a packed add into one FFMA2, which would drop a rounding.  So the product is
+//    fma.rn.f32x2(x, y, nz) with nz = (-0.0, -0.0) arriving as a KERNEL PARAMETER: the compiler cannot fold what it
+//    does not know, and rn(x*y + -0.0) is rn(x*y) bit for bit for every x*y (including +-0: +0 + -0 = +0,
+//    -0 + -0 = -0 in round-to-nearest; NaN and infinities pass through as in a multiply).
 template <typename T> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };
 template <> struct Pair<double> { typedef double2 type; };
@@ -88,12 +96,115 @@ __device__ __forceinline__ double2 add_pair(double2 a, double2 b)
 }
 __device__ __forceinline__ float2 make_pair(float x, float y) { return make_float2(x, y); }
 __device__ __forceinline__ double2 make_pair(double x, double y) { return make_double2(x, y); }
+// rn(a * b) per half, as FFMA2 with the run-time (-0.0, -0.0) addend
+__device__ __forceinline__ float2 mul_pair_exact(float2 a, float2 b, unsigned long long nz)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(nz));
+    return *reinterpret_cast<float2 *>(&rd);
+}
 
 template <typename T>
 __device__ __forceinline__ typename Pair<T>::type cprod_pair(T br, T bi, T cr, T ci)
 {
     return add_pair(make_pair(mul_rn(br, cr), mul_rn(br, ci)), make_pair(mul_rn(-bi, ci), mul_rn(bi, cr)));
 }
+
+template <typename T, int W>
+struct PairAcc {
+    typedef typename VecB<T, W>::type V;
+    typedef LanesB<T, W> L;
+    typename Pair<T>::type a[W];        // (re, im) per bin
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int l = 0; l < W; l++) {
+            a[l] = make_pair((T)0, (T)0);
+        }
+    }
+    template <bool ADD>
+    __device__ __forceinline__ void step(const V &wr, const V &wi, const V &hr, const V &hi, unsigned long long)
+    {
+        const L br = *reinterpret_cast<const L *>(&wr), bi = *reinterpret_cast<const L *>(&wi);
+        const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
+#pragma unroll
+        for (int l = 0; l < W; l++) {
+            const typename Pair<T>::type p = cprod_pair<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l]);
+            a[l] = ADD ? add_pair(a[l], p) : p;
+        }
+    }
+    __device__ __forceinline__ void set(int l, T re, T im) { a[l] = make_pair(re, im); }
+    __device__ __forceinline__ void get(V &re, V &im) const
+    {
+        L ore, oim;
+#pragma unroll
+        for (int l = 0; l < W; l++) {
+            ore.v[l] = a[l].x;
+            oim.v[l] = a[l].y;
+        }
+        re = *reinterpret_cast<V *>(&ore);
+        im = *reinterpret_cast<V *>(&oim);
+    }
+};
+
+template <int W>
+struct BinPairAcc {
+    static_assert(W % 2 == 0, "pairs of neighbouring bins");
+    typedef typename VecB<float, W>::type V;
+    struct __align__(sizeof(float) * W) H2 {
+        float2 h[W / 2];
+    };
+    float2 re[W / 2], im[W / 2];        // planar, two bins per register pair
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int h = 0; h < W / 2; h++) {
+            re[h] = make_float2(0.0f, 0.0f);
+            im[h] = make_float2(0.0f, 0.0f);
+        }
+    }
+    template <bool ADD>
+    __device__ __forceinline__ void step(const V &wr, const V &wi, const V &hr, const V &hi, unsigned long long nz)
+    {
+        const H2 br = *reinterpret_cast<const H2 *>(&wr), bi = *reinterpret_cast<const H2 *>(&wi);
+        const H2 cr = *reinterpret_cast<const H2 *>(&hr), ci = *reinterpret_cast<const H2 *>(&hi);
+#pragma unroll
+        for (int h = 0; h < W / 2; h++) {
+            const float2 nbi = make_float2(-bi.h[h].x, -bi.h[h].y);     // folds into the operand's negate modifier
+            const float2 pr = add_pair(mul_pair_exact(br.h[h], cr.h[h], nz), mul_pair_exact(nbi, ci.h[h], nz));
+            const float2 pi = add_pair(mul_pair_exact(br.h[h], ci.h[h], nz), mul_pair_exact(bi.h[h], cr.h[h], nz));
+            re[h] = ADD ? add_pair(re[h], pr) : pr;
+            im[h] = ADD ? add_pair(im[h], pi) : pi;
+        }
+    }
+    __device__ __forceinline__ void set(int l, float r, float i)     // l is a compile-time constant at every call site
+    {
+        if (l & 1) {
+            re[l / 2].y = r;
+            im[l / 2].y = i;
+        } else {
+            re[l / 2].x = r;
+            im[l / 2].x = i;
+        }
+    }
+    __device__ __forceinline__ void get(V &r, V &i) const
+    {
+        H2 ore, oim;
+#pragma unroll
+        for (int h = 0; h < W / 2; h++) {
+            ore.h[h] = re[h];
+            oim.h[h] = im[h];
+        }
+        r = *reinterpret_cast<V *>(&ore);
+        i = *reinterpret_cast<V *>(&oim);
+    }
+};
+
+template <typename T, int W> struct AccSel { typedef PairAcc<T, W> type; };
+#ifndef BF_MAC_NO_BINPAIR
+template <> struct AccSel<float, 2> { typedef BinPairAcc<2> type; };
+template <> struct AccSel<float, 4> { typedef BinPairAcc<4> type; };
+#endif
 
 struct DcTrue { static constexpr bool value = true; };
 struct DcFalse { static constexpr bool value = false; };
@@ -134,14 +245,11 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
         return X + (size_t)s * N;
     };
 
-    typedef typename Pair<T>::type P2;
-    P2 acc[B][W];           // (re, im) per block and bin
+    typename AccSel<T, W>::type acc[B];         // one output block's bins each
+    const unsigned long long nz = a.neg_zero2;
 #pragma unroll
     for (int b = 0; b < B; b++) {
-#pragma unroll
-        for (int l = 0; l < W; l++) {
-            acc[b][l] = make_pair((T)0, (T)0);
-        }
+        acc[b].zero();
     }
 
     if (jb.hbase < 0) {
@@ -159,7 +267,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 #pragma unroll
                     for (int l = 0; l < W; l++) {
                         const T s = ((v * W + l) & 1) ? -fr : fr;     // sign by bin parity
-                        acc[b][l] = make_pair(mul_rn(lr.v[l], s), mul_rn(li.v[l], s));
+                        acc[b].set(l, mul_rn(lr.v[l], s), mul_rn(li.v[l], s));
                     }
                 }
             }
@@ -226,12 +334,9 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
                     const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
 #pragma unroll
                     for (int b = 0; b < B; b++) {
-                        const L br = *reinterpret_cast<const L *>(&wr[b]), bi = *reinterpret_cast<const L *>(&wi[b]);
-#pragma unroll
-                        for (int l = 0; l < W; l++) {
-                            acc[b][l] = cprod_pair<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l]);
-                        }
+                        acc[b].template step<false>(wr[b], wi[b], hr, hi, nz);
                         if (DCNY) {
+                            const L br = *reinterpret_cast<const L *>(&wr[b]), bi = *reinterpret_cast<const L *>(&wi[b]);
                             dc[b] = mul_rn(br.v[0], cr.v[0]);
                             ny[b] = mul_rn(bi.v[0], ci.v[0]);
                         }
@@ -255,13 +360,10 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
                             const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
 #pragma unroll
                             for (int b = 0; b < B; b++) {
-                                const L br = *reinterpret_cast<const L *>(&wr[(b - u + B) % B]);
-                                const L bi = *reinterpret_cast<const L *>(&wi[(b - u + B) % B]);
-#pragma unroll
-                                for (int l = 0; l < W; l++) {
-                                    acc[b][l] = add_pair(acc[b][l], cprod_pair<T>(br.v[l], bi.v[l], cr.v[l], ci.v[l]));
-                                }
+                                acc[b].template step<true>(wr[(b - u + B) % B], wi[(b - u + B) % B], hr, hi, nz);
                                 if (DCNY) {
+                                    const L br = *reinterpret_cast<const L *>(&wr[(b - u + B) % B]);
+                                    const L bi = *reinterpret_cast<const L *>(&wi[(b - u + B) % B]);
                                     dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
                                     ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
                                 }
@@ -280,7 +382,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
         if (v == 0) {
 #pragma unroll
             for (int b = 0; b < B; b++) {
-                acc[b][0] = make_pair(dc[b], ny[b]);
+                acc[b].set(0, dc[b], ny[b]);
             }
         }
     }
@@ -288,23 +390,19 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
     for (int b = 0; b < B; b++) {
         if (b < a.batch) {
             T *out = reinterpret_cast<T *>(a.Y) + (((size_t)z * a.batch + b) * a.n_slots + jb.out) * N + (size_t)v * W;
-            L ore, oim;
-#pragma unroll
-            for (int l = 0; l < W; l++) {
-                ore.v[l] = acc[b][l].x;
-                oim.v[l] = acc[b][l].y;
-            }
-            *reinterpret_cast<V *>(out) = *reinterpret_cast<V *>(&ore);
-            *reinterpret_cast<V *>(out + M) = *reinterpret_cast<V *>(&oim);
+            V ore, oim;
+            acc[b].get(ore, oim);
+            *reinterpret_cast<V *>(out) = ore;
+            *reinterpret_cast<V *>(out + M) = oim;
         }
     }
 }
 
-template <typename T, int W, int B, int S>
+template <typename T, int W, int B, int S, int REGS = 128>
 static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
 {
     constexpr size_t smem = (size_t)S * 4 * MBT * W * sizeof(T);
-    constexpr int MINB = 512 / MBT;     // 512 threads per SM at 128 registers
+    constexpr int MINB = 65536 / REGS / MBT;    // 512 threads per SM at 128 registers, 256 at 255
     static bool configured[64];
     int dev = 0;
     cudaGetDevice(&dev);
@@ -320,7 +418,9 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
     }
     const long threads = (long)a.n_jobs * (N / 2 / W);
     dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split);
-    k_mac_batch2<T, W, B, S, MINB><<<grid, MBT, smem, s>>>(a, N);
+    MacArgs args = a;
+    args.neg_zero2 = 0x8000000080000000ull;     // (-0.0f, -0.0f): see BinPairAcc
+    k_mac_batch2<T, W, B, S, MINB><<<grid, MBT, smem, s>>>(args, N);
     return cudaGetLastError();
 }
 
@@ -333,7 +433,10 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
         if (a.batch <= 2) return launch_one<float, 4, 2, 4>(a, plan.N, s);
         if (a.batch <= 4) return launch_one<float, 4, 4, 4>(a, plan.N, s);
         if (a.batch <= 8) return launch_one<float, 2, 8, 8>(a, plan.N, s);
-        if (a.batch <= 16) return launch_one<float, 1, 16, 16>(a, plan.N, s);
+        if (a.batch <= 16) {
+            static const int narrow = getenv("BFCUDA_MAC_B16_NARROW") ? atoi(getenv("BFCUDA_MAC_B16_NARROW")) : 0;
+            return narrow ? launch_one<float, 1, 16, 16>(a, plan.N, s) : launch_one<float, 2, 16, 16, 256>(a, plan.N, s);
+        }
         return cudaErrorInvalidValue;
     }
     if (a.batch <= 2) return launch_one<double, 2, 2, 4>(a, plan.N, s);

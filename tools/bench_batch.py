@@ -5,14 +5,15 @@ import numpy as np
 from brutefir_b200 import configs, _abi
 from brutefir_b200.engine import Engine
 
-g = configs.config_c3()
+F = int(os.environ.get("FILTERS", "64"))       # a rank's share of the 64-filter job on 64 / F GPUs
+g = configs.config_c3() if F == 64 else configs.diagonal_graph(F, 8192, 128, 4, "S24_4LE")
 rng = np.random.default_rng(0)
 taps_n = g.taps_per_filter()
 env = np.exp(-np.arange(taps_n, dtype=np.float32) / (taps_n / 4.0))
 H = [rng.standard_normal(taps_n, dtype=np.float32) * env * 1e-2 for _ in range(4)]
 for B in [int(x) for x in (sys.argv[1:] or ["1", "2", "4", "8"])]:
     with Engine(g, flags=_abi.FLAG_STAGE_TIMING, max_batch=B) as e:
-        for c in range(64):
+        for c in range(F):
             e.coeff_from_taps(c, H[c % 4])
         sig = configs.synthetic_signal(g, 3, B)
         e.upload_inputs(sig)
