@@ -102,7 +102,7 @@ CONVOLVER_SYMBOLS = [
     "convolver_cbuf2raw", "convolver_coeffs2cbuf", "convolver_runtime_coeffs2cbuf",
     "convolver_verify_cbuf", "convolver_debug_dump_cbuf", "convolver_fftplan",
     "convolver_td_block_length", "convolver_td_new", "convolver_td_convolve",
-    "bfcuda_convolver_set_host", "bfcuda_convolver_last_error",
+    "bfcuda_convolver_td_delete", "bfcuda_convolver_set_host", "bfcuda_convolver_last_error",
 ]
 
 _lib = None

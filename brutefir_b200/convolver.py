@@ -152,3 +152,28 @@ def convolver_verify_cbuf(cbufs) -> bool:
 
 def convolver_td_block_length(n_coeffs: int) -> int:
     return _lib().convolver_td_block_length(n_coeffs)
+
+
+def convolver_td_new(coeffs: np.ndarray):
+    """convolver_td_new (convolver.h:140-142): opaque handle or None; coefficients in the convolver's real type."""
+    lib = _lib()
+    lib.convolver_td_new.restype = C.c_void_p
+    lib.convolver_td_new.argtypes = [C.c_void_p, C.c_int]
+    taps = np.ascontiguousarray(coeffs, _dtype())
+    return lib.convolver_td_new(_p(taps), len(taps))
+
+
+def convolver_td_convolve(tdc, overlap_block: np.ndarray):
+    """convolver_td_convolve (convolver.h:144-146): in place on the caller's 2 * block_length reals."""
+    lib = _lib()
+    lib.convolver_td_convolve.restype = None
+    lib.convolver_td_convolve.argtypes = [C.c_void_p, C.c_void_p]
+    assert overlap_block.dtype == _dtype() and overlap_block.flags.c_contiguous
+    lib.convolver_td_convolve(C.c_void_p(tdc), _p(overlap_block))
+
+
+def convolver_td_delete(tdc):
+    lib = _lib()
+    lib.bfcuda_convolver_td_delete.restype = None
+    lib.bfcuda_convolver_td_delete.argtypes = [C.c_void_p]
+    lib.bfcuda_convolver_td_delete(C.c_void_p(tdc))

@@ -16,6 +16,13 @@
 
 using namespace bf;
 
+struct _td_conv_t_ {            // fftw_convolver.c:682-687, device edition
+    FftPlan plan;
+    bool has_plan;              // transforms of 2 and 4 points go through launch_td_small
+    char *d_coeffs, *d_a, *d_b;
+    int blocklen, rs;
+};
+
 namespace {
 
 struct CvContext {
@@ -487,7 +494,7 @@ void *convolver_fftplan(int order, int invert, int inplace)
 
 int convolver_td_block_length(int n_coeffs)
 {
-    // fftw_convolver.c:689-696 / log2.h:28-43: next power of two
+    // fftw_convolver.c:689-696 / log2.h:28-43: next power of two (n_coeffs = 1 is undefined there: 1 << -1; here 1)
     if (n_coeffs < 1) {
         return -1;
     }
@@ -498,17 +505,89 @@ int convolver_td_block_length(int n_coeffs)
     return len;
 }
 
+// The sub-sample-delay convolver (fftw_convolver.c:682-782; caller: delay.c:415-506, 199-tap sinc filters, block
+// length 256).  An object owns its transform plan, its scaled coefficient spectrum and two work buffers on the device.
 td_conv_t *convolver_td_new(void *coeffs, int n_coeffs)
 {
-    (void)coeffs; (void)n_coeffs;
-    cv_fail("bfcuda convolver: the sub-sample-delay convolver (convolver_td_*) is outside the accelerated path");
-    return nullptr;
+    if (!need_ready()) return nullptr;
+    const int blocklen = convolver_td_block_length(n_coeffs);
+    if (blocklen == -1 || coeffs == nullptr) {
+        return nullptr;                                                     // fftw_convolver.c:707-709
+    }
+    const int n = 2 * blocklen, rs = g_cv.rs;
+    if (n >= 8 && !fft_size_supported(n, rs)) {
+        cv_fail("bfcuda convolver: convolver_td_new: %d coefficients need a %d-point transform, above the single-block "
+                "limit", n_coeffs, n);
+        return nullptr;
+    }
+    td_conv_t *tdc = (td_conv_t *)calloc(1, sizeof(td_conv_t));
+    if (tdc == nullptr) {
+        cv_fail("bfcuda convolver: out of memory");
+        return nullptr;
+    }
+    tdc->blocklen = blocklen;
+    tdc->rs = rs;
+    const size_t bytes = (size_t)n * rs;
+    bool ok = cu_ok(cudaMalloc((void **)&tdc->d_coeffs, bytes), "cudaMalloc") &&
+              cu_ok(cudaMalloc((void **)&tdc->d_a, bytes), "cudaMalloc") &&
+              cu_ok(cudaMalloc((void **)&tdc->d_b, bytes), "cudaMalloc");
+    if (ok && n >= 8) {
+        ok = cu_ok(fft_plan_create(&tdc->plan, n, rs), "fft_plan_create");
+        tdc->has_plan = ok;
+    }
+    if (ok) {
+        // [0_blocklen | taps | 0] -> R2HC -> * 1/(2 blocklen)                     fftw_convolver.c:716-732
+        std::vector<char> frame(bytes, 0);
+        memcpy(frame.data() + (size_t)blocklen * rs, coeffs, (size_t)n_coeffs * rs);
+        ok = cu_ok(cudaMemcpyAsync(tdc->d_a, frame.data(), bytes, cudaMemcpyHostToDevice, g_cv.stream), "H2D") &&
+             cu_ok(tdc->has_plan ? launch_r2hc(tdc->plan, tdc->d_a, tdc->d_coeffs, 1, g_cv.stream)
+                                 : launch_td_small(rs, tdc->d_a, tdc->d_coeffs, n, 0, g_cv.stream), "td forward") &&
+             cu_ok(launch_td_scale(rs, tdc->d_coeffs, n, rs == 4 ? (double)(1.0f / (float)n) : 1.0 / (double)n,
+                                   g_cv.stream), "td scale") &&
+             cu_ok(cudaStreamSynchronize(g_cv.stream), "cudaStreamSynchronize");
+    }
+    if (!ok) {
+        bfcuda_convolver_td_delete(tdc);
+        return nullptr;
+    }
+    return tdc;
 }
 
 void convolver_td_convolve(td_conv_t *tdc, void *overlap_block)
 {
-    (void)tdc; (void)overlap_block;
-    cv_fail("bfcuda convolver: the sub-sample-delay convolver (convolver_td_*) is outside the accelerated path");
+    if (!need_ready()) return;
+    if (tdc == nullptr || overlap_block == nullptr) {
+        cv_fail("bfcuda convolver: convolver_td_convolve: null argument");
+        return;
+    }
+    const int n = 2 * tdc->blocklen, rs = tdc->rs;
+    const size_t bytes = (size_t)n * rs;
+    // R2HC, ordered product, HC2R, all in place on the caller's block              fftw_convolver.c:765-781
+    h2d(tdc->d_a, overlap_block, bytes);
+    if (tdc->has_plan) {
+        CVCU(launch_r2hc(tdc->plan, tdc->d_a, tdc->d_b, 1, g_cv.stream));
+    } else {
+        CVCU(launch_td_small(rs, tdc->d_a, tdc->d_b, n, 0, g_cv.stream));
+    }
+    CVCU(launch_td_mul(rs, tdc->d_b, tdc->d_coeffs, n, g_cv.stream));
+    if (tdc->has_plan) {
+        CVCU(launch_hc2r(tdc->plan, tdc->d_b, tdc->d_a, 1, g_cv.stream));
+    } else {
+        CVCU(launch_td_small(rs, tdc->d_b, tdc->d_a, n, 1, g_cv.stream));
+    }
+    d2h(overlap_block, tdc->d_a, bytes);
+    sync();
+}
+
+// Not on the reference surface (it never frees these objects): releases the device memory of a td convolver.
+void bfcuda_convolver_td_delete(td_conv_t *tdc)
+{
+    if (tdc == nullptr) return;
+    if (tdc->has_plan) fft_plan_destroy(&tdc->plan);
+    if (tdc->d_coeffs) cudaFree(tdc->d_coeffs);
+    if (tdc->d_a) cudaFree(tdc->d_a);
+    if (tdc->d_b) cudaFree(tdc->d_b);
+    free(tdc);
 }
 
 }  // extern "C"

@@ -1120,6 +1120,100 @@ cudaError_t launch_hc2r(const FftPlan &plan, const void *in, void *out, int batc
     BF_FFT_DISPATCH(plan, k_hc2r, batch, s, (const T *)in, (T *)out, (const T *)plan.tw, plan.N / 2);
 }
 
+// ---- convolver_td_* pieces (the reference's small ordered-layout convolver, fftw_convolver.c:682-782) -----------
+template <typename T>
+__global__ void __launch_bounds__(256) k_td_scale(T *buf, int n, T scale)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        buf[i] = mul_rn(buf[i], scale);         // fftw_convolver.c:722-732
+    }
+}
+
+// b (*)= c on FFTW's half-complex order, hc[k] = Re X_k, hc[n-k] = Im X_k; DC and Nyquist are real products
+// (convolve_inplace_ordered, fftw_convolver.c:737-763), products and sums separately rounded as compiled there
+template <typename T>
+__global__ void __launch_bounds__(256) k_td_mul(T *b, const T *__restrict__ c, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = n >> 1;
+    if (k > half) {
+        return;
+    }
+    if (k == 0 || k == half) {
+        b[k] = mul_rn(b[k], c[k]);
+        return;
+    }
+    const T br = b[k], bi = b[n - k], cr = c[k], ci = c[n - k];
+    b[k] = add_rn(mul_rn(br, cr), -mul_rn(bi, ci));
+    b[n - k] = add_rn(mul_rn(br, ci), mul_rn(bi, cr));
+}
+
+// n = 2 or 4: X_k = sum_j x_j e^{-2 pi i jk/n} written out (all roots are +-1, +-i); unnormalised both ways like the
+// FFTW_R2HC / FFTW_HC2R plans (fftw_convolver.c:98-126)
+template <typename T>
+__global__ void k_td_small(const T *in, T *out, int n, int dir)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) {
+        return;
+    }
+    if (n == 2) {
+        const T a = in[0], b = in[1];
+        out[0] = add_rn(a, b);
+        out[1] = add_rn(a, -b);
+    } else if (dir == 0) {
+        const T x0 = in[0], x1 = in[1], x2 = in[2], x3 = in[3];
+        const T s02 = add_rn(x0, x2), s13 = add_rn(x1, x3);
+        out[0] = add_rn(s02, s13);              // X_0
+        out[1] = add_rn(x0, -x2);               // Re X_1
+        out[2] = add_rn(s02, -s13);             // X_2 (Nyquist)
+        out[3] = add_rn(x3, -x1);               // Im X_1
+    } else {
+        const T X0 = in[0], R1 = in[1], X2 = in[2], I1 = in[3];
+        const T s = add_rn(X0, X2), d = add_rn(X0, -X2);
+        const T r2 = add_rn(R1, R1), i2 = add_rn(I1, I1);
+        out[0] = add_rn(s, r2);
+        out[1] = add_rn(d, -i2);
+        out[2] = add_rn(s, -r2);
+        out[3] = add_rn(d, i2);
+    }
+}
+
+cudaError_t launch_td_scale(int realsize, void *buf, int n, double scale, cudaStream_t s)
+{
+    const int grid = (n + 255) / 256;
+    if (realsize == 4) {
+        k_td_scale<float><<<grid, 256, 0, s>>>((float *)buf, n, (float)scale);
+    } else {
+        k_td_scale<double><<<grid, 256, 0, s>>>((double *)buf, n, scale);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_td_mul(int realsize, void *buf, const void *coeffs, int n, cudaStream_t s)
+{
+    const int grid = (n / 2 + 1 + 255) / 256;
+    if (realsize == 4) {
+        k_td_mul<float><<<grid, 256, 0, s>>>((float *)buf, (const float *)coeffs, n);
+    } else {
+        k_td_mul<double><<<grid, 256, 0, s>>>((double *)buf, (const double *)coeffs, n);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_td_small(int realsize, const void *in, void *out, int n, int dir, cudaStream_t s)
+{
+    if (n != 2 && n != 4) {
+        return cudaErrorInvalidValue;
+    }
+    if (realsize == 4) {
+        k_td_small<float><<<1, 32, 0, s>>>((const float *)in, (float *)out, n, dir);
+    } else {
+        k_td_small<double><<<1, 32, 0, s>>>((const double *)in, (double *)out, n, dir);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_permute(const FftPlan &plan, const void *src, void *dst, int n_spectra, int mode, cudaStream_t s)
 {
     if (n_spectra == 0) return cudaSuccess;

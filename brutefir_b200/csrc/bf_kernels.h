@@ -243,6 +243,12 @@ cudaError_t launch_cv_mixnscale(const FftPlan &plan, const void *const *in_ptrs,
 cudaError_t launch_cv_convolve(const FftPlan &plan, const void *b, const void *c, void *d, int op,
                                cudaStream_t s);
 cudaError_t launch_cv_dirac(const FftPlan &plan, const void *b, void *d, cudaStream_t s);
+// convolver_td_* (fftw_convolver.c:682-782): ordered half-complex buffers of n reals, n = 2 * blocklen of ANY power of
+// two >= 2.  launch_td_scale: buf *= scale.  launch_td_mul: the in-place ordered product (convolve_inplace_ordered).
+// launch_td_small: n < 8 has no shared-memory transform; forward (dir 0) or inverse (dir 1) DFT by definition.
+cudaError_t launch_td_scale(int realsize, void *buf, int n, double scale, cudaStream_t s);
+cudaError_t launch_td_mul(int realsize, void *buf, const void *coeffs, int n, cudaStream_t s);
+cudaError_t launch_td_small(int realsize, const void *in, void *out, int n, int dir, cudaStream_t s);
 // crossfade ramp over the first L samples (fftw_convolver.c:349-355): nw = old*(1-f n) + nw*f n
 cudaError_t launch_cv_xfade_blend(const FftPlan &plan, const void *old_time, void *new_time, cudaStream_t s);
 cudaError_t launch_cv_raw2real(const FftPlan &plan, const uint8_t *raw, SampleFormat fmt, void *dst,

@@ -58,14 +58,18 @@ void convolver_runtime_coeffs2cbuf(void *src, void *dest);                      
 bool_t convolver_verify_cbuf(void *cbufs[], int n_cbufs);                       /* :116-119 */
 void convolver_debug_dump_cbuf(const char filename[], void *cbufs[], int n_cbufs);     /* :121-126 */
 
-/* On the reference surface but OFF the accelerated path (last paragraph): FFTW plans
- * cannot be handed out (returns NULL), the sub-sample-delay convolver is not provided (td_new returns
- * NULL, td_convolve is a no-op).  Both set bfcuda_convolver_last_error(). */
+/* FFTW plans cannot be handed out: returns NULL and sets bfcuda_convolver_last_error() (there is no FFTW
+ * behind this convolver; the only caller besides the convolver itself is convolver_td_new, below). */
 void *convolver_fftplan(int order, int invert, int inplace);                    /* :128-132 */
+/* The small ordered-layout convolver of the sub-sample delay (fftw_convolver.c:682-782, caller delay.c:415-506):
+ * coefficients and blocks are HOST arrays of `realsize` reals as in the reference; a block is 2 * block_length
+ * reals, convolved in place.  n_coeffs up to 16384 (float) / 8192 (double). */
 typedef struct _td_conv_t_ td_conv_t;
 int convolver_td_block_length(int n_coeffs);                                    /* :137-138 */
 td_conv_t *convolver_td_new(void *coeffs, int n_coeffs);                        /* :140-142 */
 void convolver_td_convolve(td_conv_t *tdc, void *overlap_block);                /* :144-146 */
+/* extension (the reference never frees a td convolver): release its device memory */
+void bfcuda_convolver_td_delete(td_conv_t *tdc);
 
 #ifdef __cplusplus
 }

@@ -866,3 +866,8 @@ int DRV(cv_coeffs2cbuf)(void *taps, int n, double scale, void *dest)
     return CV(coeffs2cbuf)(taps, n, scale, dest) != NULL;
 }
 void DRV(cv_runtime_coeffs2cbuf)(void *src, void *dest) { CV(runtime_coeffs2cbuf)(src, dest); }
+
+/* convolver_td_* (convolver.h:134-146): the small ordered-layout convolver of the sub-sample delay */
+int DRV(cv_td_block_length)(int n_coeffs) { return CV(td_block_length)(n_coeffs); }
+void *DRV(cv_td_new)(void *coeffs, int n_coeffs) { return CV(td_new)(coeffs, n_coeffs); }
+void DRV(cv_td_convolve)(void *tdc, void *overlap_block) { CV(td_convolve)(tdc, overlap_block); }

@@ -385,3 +385,113 @@ orc_verify_cbuf(void *cbufs[], int n_cbufs)
     }
     return 1;
 }
+
+/* ---- the small ordered-layout convolver of the sub-sample delay (fftw_convolver.c:682-782) --------------------- */
+
+struct orc_td {
+    void *plan_fwd, *plan_inv;      /* r2r plans of 2 * blocklen points */
+    void *coeffs;                   /* half-complex spectrum of [0 | taps | 0], scaled by 1 / (2 blocklen) */
+    int blocklen;
+};
+
+/* fftw_convolver.c:689-696 with log2_roof (log2.h:28-43): the next power of two.  (One coefficient is undefined
+ * behaviour there -- log2_roof(1) returns -1 and the result is 1 << -1; here it is a block of one sample.) */
+int
+orc_td_block_length(int n_coeffs)
+{
+    int len = 1;
+    if (n_coeffs < 1) {
+        return -1;
+    }
+    while (len < n_coeffs) {
+        len <<= 1;
+    }
+    return len;
+}
+
+/* fftw_convolver.c:698-734 */
+struct orc_td *
+orc_td_new(void *coeffs, int n_coeffs)
+{
+    const int blocklen = orc_td_block_length(n_coeffs);
+    struct orc_td *td;
+    int n, size;
+
+    if (blocklen == -1) {
+        return NULL;
+    }
+    size = blocklen << 1;
+    td = orc_alloc(sizeof(*td));
+    td->blocklen = blocklen;
+    td->coeffs = orc_alloc((size_t)size * g_realsize);
+    memset(td->coeffs, 0, (size_t)size * g_realsize);
+    memcpy((uint8_t *)td->coeffs + (size_t)blocklen * g_realsize, coeffs, (size_t)n_coeffs * g_realsize);
+    if (g_realsize == 4) {
+        const float scale = 1.0 / (float)size;
+        td->plan_fwd = fftwf_plan_r2r_1d(size, NULL, NULL, FFTW_R2HC, FFTW_MEASURE);
+        td->plan_inv = fftwf_plan_r2r_1d(size, NULL, NULL, FFTW_HC2R, FFTW_MEASURE);
+        fftwf_execute_r2r(td->plan_fwd, td->coeffs, td->coeffs);
+        for (n = 0; n < size; n++) {
+            ((float *)td->coeffs)[n] *= scale;
+        }
+    } else {
+        const double scale = 1.0 / (double)size;
+        td->plan_fwd = fftw_plan_r2r_1d(size, NULL, NULL, FFTW_R2HC, FFTW_MEASURE);
+        td->plan_inv = fftw_plan_r2r_1d(size, NULL, NULL, FFTW_HC2R, FFTW_MEASURE);
+        fftw_execute_r2r(td->plan_fwd, td->coeffs, td->coeffs);
+        for (n = 0; n < size; n++) {
+            ((double *)td->coeffs)[n] *= scale;
+        }
+    }
+    return td;
+}
+
+/* fftw_convolver.c:736-781: forward transform, product on the half-complex order (bin k real part at k, imaginary
+ * part at size - k; DC and Nyquist real), inverse transform, all in place. */
+void
+orc_td_convolve(struct orc_td *td, void *overlap_block)
+{
+    const int size = td->blocklen << 1, half = td->blocklen;
+    int n;
+
+    if (g_realsize == 4) {
+        float *b = overlap_block, *c = td->coeffs;
+        fftwf_execute_r2r(td->plan_fwd, b, b);
+        b[0] *= c[0];
+        for (n = 1; n < half; n++) {
+            const float re = b[n], im = b[size - n];
+            b[n] = re * c[n] - im * c[size - n];
+            b[size - n] = re * c[size - n] + im * c[n];
+        }
+        b[half] *= c[half];
+        fftwf_execute_r2r(td->plan_inv, b, b);
+    } else {
+        double *b = overlap_block, *c = td->coeffs;
+        fftw_execute_r2r(td->plan_fwd, b, b);
+        b[0] *= c[0];
+        for (n = 1; n < half; n++) {
+            const double re = b[n], im = b[size - n];
+            b[n] = re * c[n] - im * c[size - n];
+            b[size - n] = re * c[size - n] + im * c[n];
+        }
+        b[half] *= c[half];
+        fftw_execute_r2r(td->plan_inv, b, b);
+    }
+}
+
+void
+orc_td_free(struct orc_td *td)
+{
+    if (td == NULL) {
+        return;
+    }
+    if (g_realsize == 4) {
+        fftwf_destroy_plan(td->plan_fwd);
+        fftwf_destroy_plan(td->plan_inv);
+    } else {
+        fftw_destroy_plan(td->plan_fwd);
+        fftw_destroy_plan(td->plan_inv);
+    }
+    free(td->coeffs);
+    free(td);
+}

@@ -82,6 +82,9 @@ class _Lib:
         fn("cv_convolve_eval", None, V, V, V)
         fn("cv_coeffs2cbuf", I, V, I, D, V)
         fn("cv_runtime_coeffs2cbuf", None, V, V)
+        fn("cv_td_block_length", I, I)
+        fn("cv_td_new", V, V, I)
+        fn("cv_td_convolve", None, V, V)
 
 
 MAX_LENGTH = 16384
@@ -206,6 +209,20 @@ class Convolver:
         src = np.ascontiguousarray(taps_L, self.dtype)
         self.l.cv_runtime_coeffs2cbuf(_ptr(src), _ptr(out))
         return out
+
+    def td_block_length(self, n_coeffs: int) -> int:
+        return self.l.cv_td_block_length(n_coeffs)
+
+    def td_new(self, taps):
+        """convolver_td_new: an opaque handle (never freed, as in the reference), or None."""
+        taps = np.ascontiguousarray(taps, self.dtype)
+        return self.l.cv_td_new(_ptr(taps), len(taps))
+
+    def td_convolve(self, tdc, overlap_block):
+        """In place on a copy of the 2 * blocklen reals; returns the copy."""
+        blk = np.array(overlap_block, self.dtype)
+        self.l.cv_td_convolve(C.c_void_p(tdc), _ptr(blk))
+        return blk
 
 
 class BlockDriver:

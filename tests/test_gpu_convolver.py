@@ -170,8 +170,34 @@ def test_crossfade_within_fft_tolerance(gpu_lib, oracle_libs, L):
     assert np.abs(g_new - ref).max() <= ulp_tol(np.float32, o.N, 4.0 / np.sqrt(o.N)) * 4
 
 
-def test_off_path_symbols_report_not_supported(gpu_lib):
+def test_fftplan_reports_not_supported(gpu_lib):
     lib = gpu_lib
-    assert cv.convolver_td_block_length(5) == 8 and cv.convolver_td_block_length(0) == -1   # log2.h:28-43
     assert not lib.convolver_fftplan(10, 0, 0)
     assert b"FFTW" in lib.bfcuda_convolver_last_error()
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_td_convolver_matches_oracle(gpu_lib, oracle_libs, rs):
+    """convolver_td_* (convolver.h:134-146; fftw_convolver.c:682-782): the sub-sample delay's small convolver on the
+    device against the oracle, block by block the way delay.c:415-442 slides its [previous | current] frames.
+    Tolerance (north_star): 1e-6 of full scale in float32, 1e-12 in float64 -- full scale = the largest output."""
+    o = init(64, rs)
+    rng = np.random.default_rng(500 + rs)
+    assert cv.convolver_td_block_length(5) == 8 and cv.convolver_td_block_length(0) == -1   # log2.h:28-43
+    assert cv.convolver_td_block_length(199) == 256
+    assert not cv.convolver_td_new(np.zeros(0, o.dtype))
+    for n_coeffs in (1, 2, 3, 5, 31, 199, 256, 1000):
+        B = cv.convolver_td_block_length(n_coeffs)
+        # sinc-like taps of a fractional delay: unit DC gain, decaying tails (delay.c:444-506)
+        k = np.arange(n_coeffs) - (n_coeffs - 1) / 2.0 - 0.37
+        taps = (np.sinc(k) * np.hanning(n_coeffs + 2)[1:-1] if n_coeffs > 2 else rng.standard_normal(n_coeffs)).astype(o.dtype)
+        tg, to = cv.convolver_td_new(taps), o.td_new(taps)
+        assert tg and to
+        x = rng.uniform(-1, 1, 6 * B).astype(o.dtype)
+        for j in range(1, 6):
+            blk = np.ascontiguousarray(x[(j - 1) * B:(j + 1) * B])
+            want = o.td_convolve(to, blk)
+            cv.convolver_td_convolve(tg, blk)
+            fs = max(1.0, np.abs(want).max())
+            assert np.abs(blk - want).max() <= (1e-6 if rs == 4 else 1e-12) * fs, (n_coeffs, j)
+        cv.convolver_td_delete(tg)

@@ -191,3 +191,28 @@ def test_dither_hp_tpdf_bit_exact(both, rs, fmt):
     d.close()
     assert not np.array_equal(plain[:, :2 * L * sf_i.bytes], res[0][0][:, :2 * L * sf_i.bytes])
     assert np.array_equal(plain[:, 2 * L * sf_i.bytes:], res[0][0][:, 2 * L * sf_i.bytes:])
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_td_convolver_bit_exact_and_is_a_linear_convolution(both, rs):
+    """convolver_td_* (fftw_convolver.c:682-782, the sub-sample delay's convolver): the restatement against the
+    reference build bit for bit, and both against the definition -- with the coefficients parked in the second
+    half of the frame, the first blocklen outputs of a [previous | current] block are the linear convolution."""
+    o, r = pair(64, rs)
+    rng = np.random.default_rng(77 + rs)
+    assert [o.td_block_length(n) for n in (0, 1, 2, 3, 199, 256, 257)] == [-1, 1, 2, 4, 256, 256, 512]
+    # one coefficient is undefined in the reference (log2_roof(1) = -1, then 1 << -1; log2.h:28-43): not compared
+    assert [r.td_block_length(n) for n in (0, 2, 3, 199, 256, 257)] == [-1, 2, 4, 256, 256, 512]
+    for n_coeffs in (2, 3, 5, 31, 199, 256):
+        B = o.td_block_length(n_coeffs)
+        taps = rng.standard_normal(n_coeffs).astype(o.dtype)
+        to, tr = o.td_new(taps), r.td_new(taps)
+        assert to and tr
+        x = rng.standard_normal(5 * B).astype(o.dtype)
+        want = np.convolve(x.astype(np.float64), taps.astype(np.float64))
+        for k in range(1, 5):
+            blk = x[(k - 1) * B:(k + 1) * B]
+            yo, yr = o.td_convolve(to, blk), r.td_convolve(tr, blk)
+            assert np.array_equal(yo, yr), (n_coeffs, k)
+            tol = (2e-5 if rs == 4 else 1e-12) * max(1.0, np.abs(want).max())
+            assert np.abs(yo[:B] - want[k * B:(k + 1) * B]).max() <= tol, (n_coeffs, k)
