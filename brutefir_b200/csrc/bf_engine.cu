@@ -123,6 +123,11 @@ struct FilterState {
     double key_scale;
     long key_since;                 // block count at which the key last changed (-1 = unchanged since creation)
     int coeff, prevcoeff, delayblocks;
+    // Exact emulation of the reference's P-slot ring around run-time delay changes (begin_transitions):
+    char *mirror;                   // P slots on the device = the reference's cbuf[filter][0..P) during a transition
+    long trans_until;               // block count at which the ring is regular again, -1 = not in a transition
+    std::vector<long> ref_id;       // [P]    block index whose spectrum each mirror slot holds (-1 = zeros)
+    std::vector<long> eng_id;       // [ring] the same for the slots of the filter's (private) ring
 };
 
 #define TIMING_RING 64
@@ -775,6 +780,11 @@ void bfcuda_destroy(bfcuda_engine *e)
             cudaFree(p);
         }
     }
+    for (FilterState &fs : e->filters) {
+        if (fs.mirror != nullptr) {
+            cudaFree(fs.mirror);
+        }
+    }
     if (e->h_status) cudaFreeHost(e->h_status);
     fft_plan_destroy(&e->plan);
     for (int i = 0; i < 2; i++) {
@@ -976,6 +986,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         fs.key_delay = 0;
         fs.key_scale = 0.0;
         fs.key_since = -1;
+        fs.mirror = nullptr;
+        fs.trans_until = -1;
         if (s.n_filters_in > 0) {
             fs.fin.assign(s.filters_in, s.filters_in + s.n_filters_in);
             if (s.fscale != nullptr) {
@@ -1332,6 +1344,9 @@ static int flush_timing_ring(bfcuda_engine *e)
 //   out_free         : event the inverse stage must wait for (previous read-out of raw_out), or null
 //   fwd_done         : recorded after the forward stage (raw_in may be overwritten afterwards), or null
 // On return e->ev_inv marks the end of the inverse stage.
+static bool in_transition(const bfcuda_engine *e);
+static int transition_repair(bfcuda_engine *e, int level, cudaStream_t stream);
+
 static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw_out, cudaEvent_t in_ready,
                          cudaEvent_t out_free, cudaEvent_t fwd_done)
 {
@@ -1420,6 +1435,11 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         CU(launch_stream_mix(e->plan, sa, e->stream));
         e->launches++;
     }
+    const bool transition = in_transition(e);      // then nb == 1 (enqueue_blocks)
+    if (transition) {
+        int rc = transition_repair(e, 0, e->stream);
+        if (rc != 0) return rc;
+    }
     if (timing) CU(cudaEventRecord(ev[1], e->stream));
     if (fwd_done != nullptr) {
         CU(cudaEventRecord(fwd_done, e->stream));
@@ -1468,6 +1488,10 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         sa.streams = e->d_mix_streams + e->level_mix_first[level];
         sa.n_streams = e->level_mix_first[level + 1] - e->level_mix_first[level];
         CU(launch_stream_mix(e->plan, sa, e->s_mac));
+        if (transition) {
+            int rc = transition_repair(e, level, e->s_mac);
+            if (rc != 0) return rc;
+        }
         ma.jobs = e->d_jobs + e->level_job_first[level];
         ma.n_jobs = e->level_job_first[level + 1] - e->level_job_first[level];
         CU(launch_mac(e->plan, ma, e->s_mac));
@@ -1567,47 +1591,107 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
 }
 
 // A run-time change of a filter's block delay (cfd, bfrun.c:1579-1600).  The reference's ring has exactly P slots,
-// written at (w + delay) % P and read at (t - i) % P, so a change makes it read slots that alias other blocks.  The
-// engine's ring is longer (virtual slot u lives at u % ring, the reference's at u % P), those slots are distinct
-// here, and the aliasing is reproduced ONCE at the block boundary T where the change takes effect:
-//   * decrease d_old -> d_new: the read range grows downwards to T - P + d_new + 1, where the reference finds the
-//     blocks written "ahead" under the old delay: ring[u] = ring[u + P] for u + P in (T + d_new, T + d_old - 1];
-//   * increase d_old -> d_new: virtual slots T + d_old .. T + d_new - 1 are never written, the reference reads the
-//     blocks of one ring turn earlier there: ring[u] = ring[u - P] for those u.
-// After that every read sees what the reference's P-slot ring would hold.  (ring >= 2 P: sources and destinations
-// never share a physical slot.)
-static int apply_delay_fixups(bfcuda_engine *e)
+// written at (w + delay) % P and read at (t - i) % P: after a change it reads slots that alias other blocks -- blocks
+// written "ahead" under a larger old delay, blocks of a ring turn earlier where a larger new delay skips slots -- and
+// changes that follow each other within P blocks stack these effects.  The engine's ring is longer (virtual slot u
+// lives at u % ring, distinct physical slots for what the reference aliases), so for 2 P blocks after a change the
+// filter runs in a TRANSITION: a mirror of P slots is kept that IS the reference's ring (every block the filter's
+// newly written spectrum is copied to mirror[(t + delay) % P]), and before each multiply-accumulate every ring slot the
+// block reads (virtual t - i, i < P - delay, i <= t: the reference stops at the number of blocks processed so far,
+// procblocks, bfrun.c:1567-1571, 1745) is made equal to mirror[(t - i) % P] where the two differ.  Which block a slot
+// holds is tracked on the host (ref_id / eng_id), so only aliasing slots are copied.  After P blocks of constant delay
+// every residue has been rewritten and the mirror equals the plain ring again; the transition is kept for 2 P blocks
+// so that everything a LATER change can still read (P slots back) is regular when its snapshot is taken.  Blocks in
+// a transition are launched one at a time.
+static bool in_transition(const bfcuda_engine *e)
 {
-    if (e->delay_fixups.empty()) {
-        return 0;
-    }
-    const size_t nb = rs_bytes(e, e->N);
-    const int R = e->fdl_ring, P = e->P;
-    auto phys = [&](long u) { return (int)(((u % R) + R) % R); };
-    for (const std::pair<int, int> &fx : e->delay_fixups) {
-        const int f = fx.first, d_old = fx.second;
-        const int d_new = clamp_delay(e, e->filters[f].delayblocks);
-        char *ring = ring_ptr(e, e->filters[f].stream);   // private by now: update_streams() ran first
-        const long T = e->slot_t;
-        if (d_new < d_old) {
-            for (int j = d_new + 1; j < d_old; j++) {
-                if ((long)e->t + j - P < 0) {
-                    // a partition older than the first block: the reference never reads it (its partition loop stops
-                    // at the number of blocks processed so far, procblocks, bfrun.c:1567-1571, 1745); here those
-                    // slots are simply still zero and must stay so
-                    continue;
-                }
-                CU(cudaMemcpyAsync(ring + nb * (size_t)phys(T + j - P), ring + nb * (size_t)phys(T + j), nb,
-                                   cudaMemcpyDeviceToDevice, e->stream));
-            }
-        } else {
-            for (int j = d_old; j < d_new; j++) {
-                CU(cudaMemcpyAsync(ring + nb * (size_t)phys(T + j), ring + nb * (size_t)phys(T + j - P), nb,
-                                   cudaMemcpyDeviceToDevice, e->stream));
-            }
+    for (const FilterState &fs : e->filters) {
+        if (fs.trans_until >= 0) {
+            return true;
         }
     }
+    return false;
+}
+
+static int begin_transitions(bfcuda_engine *e)
+{
+    const size_t nb = rs_bytes(e, e->N);
+    const int R = e->fdl_ring, P = e->P;
+    const long T = (long)e->t;
+    for (FilterState &fs : e->filters) {
+        if (fs.trans_until >= 0 && T >= fs.trans_until) {
+            fs.trans_until = -1;        // regular again
+        }
+    }
+    for (const std::pair<int, int> &fx : e->delay_fixups) {
+        const int f = fx.first, d_old = fx.second;
+        FilterState &fs = e->filters[f];
+        if (clamp_delay(e, fs.delayblocks) == d_old) {
+            continue;       // changed and changed back between two blocks
+        }
+        if (fs.trans_until < 0) {
+            // snapshot: the last P writes went to virtual slots w + d_old (regular), the newest is T - 1 + d_old
+            if (fs.mirror == nullptr) {
+                int rc = dev_alloc(e, &fs.mirror, nb * (size_t)P, false);
+                if (rc != 0) return rc;
+            }
+            const char *ring = ring_ptr(e, fs.stream);     // private by now: update_streams() ran first
+            auto phys = [&](long u) { return (int)((((long)e->slot_t + (u - T)) % R + R) % R); };
+            const long umax = T - 1 + d_old;
+            fs.eng_id.assign((size_t)R, -1);
+            fs.ref_id.assign((size_t)P, -1);
+            for (long u = umax; u > umax - R; u--) {
+                fs.eng_id[(size_t)phys(u)] = u - d_old >= 0 ? u - d_old : -1;
+            }
+            for (long u = umax; u > umax - P; u--) {
+                if (u - d_old < 0) {
+                    continue;
+                }
+                const size_t s = (size_t)(((u % P) + P) % P);
+                fs.ref_id[s] = u - d_old;
+                CU(cudaMemcpyAsync(fs.mirror + nb * s, ring + nb * (size_t)phys(u), nb, cudaMemcpyDeviceToDevice, e->stream));
+            }
+        }
+        fs.trans_until = T + 2L * P;
+    }
     e->delay_fixups.clear();
+    return 0;
+}
+
+// One block (nb = 1) of the filters of `level` that are in a transition, after their delay-line slot of this block has
+// been written and before their partitions are multiplied; `stream` is the stream both of those run on.
+static int transition_repair(bfcuda_engine *e, int level, cudaStream_t stream)
+{
+    const size_t nb = rs_bytes(e, e->N);
+    const int R = e->fdl_ring, P = e->P;
+    const long t = (long)e->t;
+    for (size_t f = 0; f < e->filters.size(); f++) {
+        FilterState &fs = e->filters[f];
+        if (fs.trans_until < 0 || fs.level != level) {
+            continue;
+        }
+        char *ring = ring_ptr(e, fs.stream);
+        auto phys = [&](long u) { return (int)((((long)e->slot_t + (u - t)) % R + R) % R); };
+        const int d = clamp_delay(e, fs.delayblocks);
+        // this block's spectrum: virtual slot t + d, the reference's slot (t + d) % P
+        const size_t sw = (size_t)((t + d) % P);
+        CU(cudaMemcpyAsync(fs.mirror + nb * sw, ring + nb * (size_t)phys(t + d), nb, cudaMemcpyDeviceToDevice, stream));
+        fs.ref_id[sw] = t;
+        fs.eng_id[(size_t)phys(t + d)] = t;
+        for (long i = 0; i < P - d && i <= t; i++) {
+            const long u = t - i;
+            const size_t s = (size_t)(u % P), q = (size_t)phys(u);
+            if (fs.eng_id[q] == fs.ref_id[s]) {
+                continue;
+            }
+            if (fs.ref_id[s] < 0) {
+                CU(cudaMemsetAsync(ring + nb * q, 0, nb, stream));
+            } else {
+                CU(cudaMemcpyAsync(ring + nb * q, fs.mirror + nb * s, nb, cudaMemcpyDeviceToDevice, stream));
+            }
+            fs.eng_id[q] = fs.ref_id[s];
+        }
+    }
     return 0;
 }
 
@@ -1623,9 +1707,10 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
         if (e->merge_check_at >= 0 && (long)e->t >= e->merge_check_at) {
             e->dirty = true;
         }
-        if (e->dirty || e->xfade_active) {
+        const bool transition = in_transition(e);
+        if (e->dirty || e->xfade_active || transition) {
             // the previous launches' MAC and inverse stages (other streams) still read the job / output-mix tables,
-            // and a delay fix-up rewrites ring slots the previous MAC reads
+            // and a delay transition rewrites ring slots the previous MAC reads
             if (e->launch_no >= 1) {
                 const int prev = (int)((e->launch_no - 1) & 1u);
                 CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[prev], 0));
@@ -1633,12 +1718,12 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
             }
             int frc = update_streams(e);
             if (frc != 0) return frc;
-            frc = apply_delay_fixups(e);
+            frc = begin_transitions(e);
             if (frc != 0) return frc;
             build_tables(e);
             int rc = upload_tables(e);
             if (rc != 0) return rc;
-            if (e->xfade_active) {
+            if (e->xfade_active || in_transition(e)) {
                 nb = 1;
             }
         }
@@ -1948,6 +2033,17 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
         // `slot` is the reference's numbering, cbuf[filter][(t + delay) % P] (bfrun.c:1600): the reference's slot s
         // holds the block written at the latest time tau <= t_last with (tau + delay) % P == s; the engine's ring is
         // longer (see bfcuda_create) and keeps that block at (tau + delay) % ring.
+        const FilterState &dfs = e->filters[index];
+        if (dfs.trans_until >= 0) {
+            // in a delay transition the mirror IS the reference's ring (begin_transitions)
+            if (dfs.ref_id[(size_t)slot] < 0) {
+                memset(dst, 0, nb);
+                break;
+            }
+            CU(launch_permute(e->plan, dfs.mirror + nb * (size_t)slot, e->d_scratch, 1, PLANAR_TO_BLOCKED, e->stream));
+            CU(cudaMemcpyAsync(dst, e->d_scratch, nb, cudaMemcpyDeviceToHost, e->stream));
+            break;
+        }
         const int d = clamp_delay(e, e->filters[index].delayblocks);
         const long t_last = (long)e->t - 1;
         const long back = (((t_last + d - slot) % e->P) + e->P) % e->P;

@@ -182,6 +182,59 @@ def test_runtime_control_and_crossfade(gpu_lib, oracle_libs):
     assert_parity(g, np.stack(got), np.stack(ref))
 
 
+@pytest.mark.parametrize("rs,B", [(8, 1), (4, 1), (4, 4)])
+def test_stacked_delay_changes_follow_the_reference_ring(gpu_lib, oracle_libs, rs, B):
+    """Delay changes (cfd) that follow each other within P blocks, up and down, mixed with 'no coefficients': the
+    reference's P-slot ring (written at (t + delay) % P, read at (t - i) % P, bfrun.c:1579-1600, 1745-1754) then
+    reads slots that alias blocks written under EARLIER delays, several changes deep.  The engine's longer ring is
+    repaired from an exact P-slot mirror during such transitions (bf_engine.cu, begin_transitions); float_bits 64
+    must match the oracle bit for bit, and the delay line slot for slot."""
+    L, P = 256, 11
+    inb, nin = interleaved_layout(2, "S24_4LE", L)
+    outb, nout = interleaved_layout(2, "FLOAT64_LE" if rs == 8 else "S24_4LE", L)
+    filters = [Filter([1, 0], [1, 0], coeff=-1, delayblocks=4), Filter([0], [0], coeff=0, delayblocks=2)]
+    g = FilterGraph(L, P, rs, inb, outb, nin, nout, filters, [10, 3])
+    taps = configs.synthetic_filters(g, 31)
+    nblk = 44
+    sig = configs.synthetic_signal(g, 31, nblk, sigma=0.01)
+    script = {2: [(0, dict(coeff=-1, delayblocks=0))], 5: [(0, dict(coeff=0, delayblocks=7))],
+              8: [(0, dict(coeff=-1, delayblocks=10)), (1, dict(coeff=1, delayblocks=9))],
+              11: [(0, dict(coeff=0, delayblocks=0))], 13: [(1, dict(coeff=0, delayblocks=1))],
+              14: [(0, dict(coeff=-1, delayblocks=2))], 17: [(0, dict(coeff=0, delayblocks=3))],
+              20: [(0, dict(coeff=1, delayblocks=6)), (1, dict(coeff=0, delayblocks=10))],
+              23: [(0, dict(coeff=0, delayblocks=7))], 24: [(0, dict(coeff=0, delayblocks=1))],
+              25: [(0, dict(coeff=0, delayblocks=8))], 26: [(1, dict(coeff=0, delayblocks=0))]}
+    with Engine(g, mac_split=1, max_batch=B) as e:
+        d = po.BlockDriver("oracle", g)
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+            d.coeff_from_taps(c, h)
+        ref, got = [], np.zeros((nblk, g.out_bytes), np.uint8)
+        for b in range(nblk):
+            for filt, kw in script.get(b, []):
+                d.set_control(filt, **kw)
+            ref.append(d.process_block(sig[b]))
+        b = 0
+        while b < nblk:
+            for filt, kw in script.get(b, []):
+                e.set_control(filt, **kw)
+            k = 1
+            while k < B and b + k < nblk and (b + k) not in script:
+                k += 1
+            e.process_blocks_async(sig[b:b + k], got[b:b + k], k)
+            b += k
+        e.synchronize()
+        if rs == 8:
+            # the delay lines in the reference's slot numbering, a few blocks after the last change
+            # (which block sits in which slot; the spectra themselves differ by FFT rounding only)
+            for filt in range(2):
+                for slot in range(P):
+                    a, r = e.debug_read(_abi.DBG_DELAYLINE, filt, slot), d.debug_read(_abi.DBG_DELAYLINE, filt, slot)
+                    assert np.abs(a - r).max() <= 1e-12 * max(1.0, np.abs(r).max()), (filt, slot)
+        d.close()
+    assert_parity(g, got, np.stack(ref))
+
+
 def test_golden_block_sequences(gpu_lib):
     """The committed vectors the reference itself produced (tests/golden/make_golden.py), no oracle involved."""
     blk = np.load(os.path.join(HERE, "golden", "blocks.npz"))
