@@ -3,7 +3,10 @@ counts from 1), random run-time control scripts, random batch sizes -- engine ag
 north_star tolerances.  Scales are irrational on purpose: with a unit pulse ("coeff: -1") and a scale like 0.5 or 0.7
 integer samples land exactly on .5 (0.7 x 5), where the last bit of the FFT decides the rounding direction in ANY
 implementation.
-Usage: python tests/checks/fuzz_parity.py [n_cases] [seed]"""
+Usage: python tests/checks/fuzz_parity.py [n_cases] [seed]
+Environment: FUZZ_BIG=1 (partitions of 1024..8192 samples, batches up to 16), FUZZ_PMAX=n (up to n partitions),
+FUZZ_WIDE=1 (up to 70 channels each way and 80 filters),
+FUZZ_B=n (force the batch size), FUZZ_ONLY=i,j (run and explain only these cases)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -23,16 +26,17 @@ bad = 0
 for case in range(n_cases):
     big = os.environ.get("FUZZ_BIG") == "1"
     L = int(rng.choice([1024, 2048, 4096, 8192] if big else [16, 64, 128, 256, 512, 1024, 2048]))
-    P = int(rng.integers(1, 13 if big else 7))
+    P = int(rng.integers(1, int(os.environ.get("FUZZ_PMAX", "12" if big else "6")) + 1))
     rs = int(rng.choice([4, 4, 8]))
-    n_in, n_out = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+    wide = os.environ.get("FUZZ_WIDE") == "1"      # more than one 32-channel tile, many filters per delay-line ring
+    n_in, n_out = (int(rng.integers(1, 71)), int(rng.integers(1, 71))) if wide else (int(rng.integers(1, 5)), int(rng.integers(1, 5)))
     fin = str(rng.choice(INT_FMTS + ["FLOAT_LE"]))
     fout = str(rng.choice(["S24_4LE", "S24_LE", "FLOAT_LE"] if rs == 4 else INT_FMTS + ["FLOAT_LE", "FLOAT64_LE"]))
     inb, nin = (interleaved_layout if rng.random() < 0.7 else planar_layout)(n_in, fin, L)
     outb, nout = (interleaved_layout if rng.random() < 0.7 else planar_layout)(n_out, fout, L)
     n_coeffs = int(rng.integers(1, 4))
     coeff_blocks = [int(rng.integers(1, P + 1)) for _ in range(n_coeffs)]
-    nf = int(rng.integers(1, 7))
+    nf = int(rng.integers(1, 81 if wide else 7))
     filters = []
     for f in range(nf):
         srcs = [int(x) for x in rng.choice(f, size=int(rng.integers(1, min(f, 2) + 1)), replace=False)] if f >= 2 and rng.random() < 0.3 else []
@@ -47,7 +51,8 @@ for case in range(n_cases):
     g = FilterGraph(L, P, rs, inb, outb, nin, nout, filters, coeff_blocks)
     taps = [(rng.standard_normal(L * nb) / (4 * np.sqrt(L * nb / 64))).astype(np.float32 if rs == 4 else np.float64) for nb in coeff_blocks]
     nblk = 3 * P + 8
-    sig = configs.synthetic_signal(g, 100 + case, nblk, sigma=0.01)
+    # wide graphs sum up to dozens of filters per output: keep the peaks where float32 still resolves 1 LSB @24 bit
+    sig = configs.synthetic_signal(g, 100 + case, nblk, sigma=0.001 if wide else 0.01)
     script = {}
     for b in range(2, nblk, int(rng.integers(3, 7))):
         f = int(rng.integers(0, nf))

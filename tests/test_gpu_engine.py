@@ -653,12 +653,15 @@ def test_pipelined_stages_equal_serialised_stages(gpu_lib, calls, B):
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
 
 
-def test_randomised_graphs_against_oracle(gpu_lib, oracle_libs):
-    """tests/checks/fuzz_parity.py: random graphs (mixes, chaining, delays, crossfade, formats, 1..6 partitions), random
-    run-time control scripts, random batch sizes, engine against the oracle under the north_star tolerances.  (It found
-    the early-block case of the delay-change fix-up: partitions older than the first block must stay unread.)"""
+@pytest.mark.parametrize("env,cases,seed", [({}, 40, 7), ({"FUZZ_BIG": "1"}, 24, 9002), ({"FUZZ_PMAX": "24"}, 40, 9010),
+                                            ({"FUZZ_WIDE": "1"}, 24, 9020)])
+def test_randomised_graphs_against_oracle(gpu_lib, oracle_libs, env, cases, seed):
+    """tests/checks/fuzz_parity.py: random graphs (mixes, chaining, delays, crossfade, formats, partition counts from
+    1), random run-time control scripts, random batch sizes, engine against the oracle under the north_star
+    tolerances.  It found the early-block case of delay changes (partitions older than the first block must stay
+    unread) and, at 11-12 partitions (FUZZ_BIG, seed 9002), delay changes stacked within P blocks of each other."""
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(HERE, "checks", "fuzz_parity.py"), "40", "7"],
-                       capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and "40/40" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    r = subprocess.run([sys.executable, os.path.join(HERE, "checks", "fuzz_parity.py"), str(cases), str(seed)],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+    assert r.returncode == 0 and f"{cases}/{cases}" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
