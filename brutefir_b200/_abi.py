@@ -94,6 +94,12 @@ ENGINE_SYMBOLS = [
     "bfcuda_stage_times", "bfcuda_set_serial_stages", "bfcuda_set_stage_timing", "bfcuda_get_info", "bfcuda_debug_read", "bfcuda_comm_unique_id",
     "bfcuda_comm_init", "bfcuda_comm_shared_outputs",
 ]
+class DitherStateC(C.Structure):
+    """struct dither_state (dither.h:17-22) == struct bfcuda_dither_state (include/bfcuda_convolver.h)."""
+    _fields_ = [("randtab_ptr", C.c_int), ("randtab", C.POINTER(C.c_int8)), ("sf", C.c_float * 2),
+                ("sd", C.c_double * 2)]
+
+
 CONVOLVER_SYMBOLS = [
     "convolver_init", "convolver_cbufsize", "convolver_raw2cbuf", "convolver_time2freq",
     "convolver_mixnscale", "convolver_convolve_inplace", "convolver_convolve",
@@ -102,7 +108,8 @@ CONVOLVER_SYMBOLS = [
     "convolver_cbuf2raw", "convolver_coeffs2cbuf", "convolver_runtime_coeffs2cbuf",
     "convolver_verify_cbuf", "convolver_debug_dump_cbuf", "convolver_fftplan",
     "convolver_td_block_length", "convolver_td_new", "convolver_td_convolve",
-    "bfcuda_convolver_td_delete", "bfcuda_convolver_set_host", "bfcuda_convolver_last_error",
+    "bfcuda_convolver_td_delete", "bfcuda_convolver_set_dither_table", "bfcuda_convolver_set_host",
+    "bfcuda_convolver_last_error",
 ]
 
 _lib = None

@@ -133,6 +133,22 @@ def convolver_cbuf2raw(cbuf, outbuf, bf: BufferFormat, apply_dither: bool, overf
     _lib().convolver_cbuf2raw(_p(cbuf), _p(outbuf), C.byref(c), int(apply_dither), None, C.byref(overflow))
 
 
+def set_dither_table(table: np.ndarray):
+    """bfcuda_convolver_set_dither_table: the host's dither_randtab (int8, kept alive and written by the preloop)."""
+    assert table.dtype == np.int8 and table.flags.c_contiguous
+    lib = _lib()
+    lib.bfcuda_convolver_set_dither_table.restype = None
+    lib.bfcuda_convolver_set_dither_table.argtypes = [C.c_void_p, C.c_int]
+    _state["dither_table"] = table
+    lib.bfcuda_convolver_set_dither_table(C.c_void_p(table.ctypes.data), len(table))
+
+
+def convolver_cbuf2raw_dither(cbuf, outbuf, bf: BufferFormat, state: _abi.DitherStateC, overflow: _abi.OverflowC):
+    """convolver_cbuf2raw with apply_dither = true and the channel's struct dither_state."""
+    b = _bf(bf)
+    _lib().convolver_cbuf2raw(_p(cbuf), _p(outbuf), C.byref(b), 1, C.byref(state), C.byref(overflow))
+
+
 def convolver_coeffs2cbuf(coeffs, scale: float, optional_dest: np.ndarray):
     """Returns optional_dest, or None where the reference returns NULL (NaN/Inf among the taps)."""
     coeffs = np.ascontiguousarray(coeffs, _dtype())

@@ -39,12 +39,20 @@ struct CvContext {
     size_t raw_cap;
     Overflow *d_of;
     unsigned int *d_status;
+    // dither (convolver_cbuf2raw with apply_dither)
+    int8_t *d_tab;              // this block's slice of the host's dither table, [previous byte | L bytes]
+    size_t tab_cap;
+    void *d_map;                // 512 reals: dither value per table difference (dither.c:113-131)
+    DitherChan *d_chan;
+    SampleFormat *d_fmt;
 };
 
 CvContext g_cv;
 void (*g_exit_hook)(int) = nullptr;
 int g_quiet = 0;
 double g_safety_limit = 0.0;
+int8_t *g_dither_tab = nullptr;     // the host's dither_randtab / dither_randtab_size
+int g_dither_tab_size = 0;
 char g_cv_err[512] = "";
 
 void cv_exit(int status)
@@ -134,6 +142,125 @@ void h2d(void *dst, const void *src, size_t n) { cu_ok(cudaMemcpyAsync(dst, src,
 void d2h(void *dst, const void *src, size_t n) { cu_ok(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, g_cv.stream), "D2H"); }
 void sync() { cu_ok(cudaStreamSynchronize(g_cv.stream), "cudaStreamSynchronize"); }
 
+// convolver_cbuf2raw with apply_dither (fftw_convolver.c:489-499): the preloop on the host, exactly as
+// dither_preloop_real2int_hp_tpdf (dither.h:28-38) -- it moves the state's table pointer and, on a wrap, copies the
+// last used byte into slot 0 of the HOST's table --, then this block's L + 1 table bytes, the error-feedback state and
+// the samples go to the device, one lane runs the reference's sequential loop (k_dither, dither_funs.h:7-68), and the
+// raw samples, the overflow record and the state come back.
+void cv_cbuf2raw_dither(void *cbuf, void *outbuf, struct bfcuda_buffer_format *bf, struct bfcuda_dither_state *state,
+                        struct bfcuda_overflow *overflow)
+{
+    const int L = g_cv.L, rs = g_cv.rs;
+    if (state == nullptr || g_dither_tab == nullptr) {
+        cv_fail("bfcuda convolver: dither needs the host's table: call bfcuda_convolver_set_dither_table() after "
+                "dither_init(), and pass the channel's struct dither_state");
+        cv_exit(1);
+        return;
+    }
+    if (bf->sf.bytes < 1 || bf->sf.bytes > 4) {
+        fprintf(stderr, "Sample byte size %d is not supported.\n", bf->sf.bytes);   // real2raw.h:245-249
+        cv_exit(1);
+        return;
+    }
+    if (L + 1 >= g_dither_tab_size) {
+        cv_fail("bfcuda convolver: dither table of %d entries is shorter than a block", g_dither_tab_size);
+        cv_exit(1);
+        return;
+    }
+    // dither.h:28-38
+    if (state->randtab_ptr + L >= g_dither_tab_size) {
+        g_dither_tab[0] = g_dither_tab[state->randtab_ptr - 1];
+        state->randtab_ptr = 1;
+    }
+    state->randtab = &g_dither_tab[state->randtab_ptr];
+    state->randtab_ptr += L;
+
+    if (g_cv.d_map == nullptr) {
+        // dither.c:113-131: table difference -> dither in (-1, +1) plus the +0.5 of the mid-tread requantiser
+        std::vector<double> mapd(512);
+        std::vector<float> mapf(512);
+        mapf[0] = -0.5f;
+        mapd[0] = -0.5;
+        for (int k = -255; k < 254; k++) {
+            mapf[k + 256] = (float)(0.5 + 1.0 / 255.0 + 1.0 / 255.0 * (float)k);
+            mapd[k + 256] = 0.5 + 1.0 / 255.0 + 1.0 / 255.0 * (double)k;
+        }
+        mapf[510] = 1.5f;
+        mapd[510] = 1.5;
+        mapf[511] = (float)(1.5 + 1.0 / 255.0);
+        mapd[511] = 1.5 + 1.0 / 255.0;
+        if (!cu_ok(cudaMalloc(&g_cv.d_map, 512 * (size_t)rs), "cudaMalloc") ||
+            !cu_ok(cudaMalloc((void **)&g_cv.d_chan, sizeof(DitherChan)), "cudaMalloc") ||
+            !cu_ok(cudaMalloc((void **)&g_cv.d_fmt, sizeof(SampleFormat)), "cudaMalloc") ||
+            !cu_ok(cudaMemcpy(g_cv.d_map, rs == 4 ? (const void *)mapf.data() : (const void *)mapd.data(),
+                              512 * (size_t)rs, cudaMemcpyHostToDevice), "cudaMemcpy")) {
+            return;
+        }
+    }
+    if (!grow((char **)&g_cv.d_tab, &g_cv.tab_cap, (size_t)L + 1)) return;
+    const size_t span = raw_span(bf);
+    uint8_t *host_raw = (uint8_t *)outbuf + bf->byte_offset;
+    if (!grow((char **)&g_cv.d_raw, &g_cv.raw_cap, span)) return;
+    Overflow of;
+    of.n_overflows = overflow->n_overflows;
+    of.intlargest = overflow->intlargest;
+    of.largest = overflow->largest;
+    of.max = overflow->max;
+    unsigned int status = 0;
+    DitherChan ch;
+    ch.out = 0;
+    ch.randtab_ptr = 1;
+    ch.e0 = rs == 4 ? (double)state->sf[0] : state->sd[0];
+    ch.e1 = rs == 4 ? (double)state->sf[1] : state->sd[1];
+    const SampleFormat fmt = dev_format(bf, 0);
+    h2d(g_cv.d_tab, state->randtab - 1, (size_t)L + 1);
+    h2d(g_cv.d_raw, host_raw, span);    // neighbouring channels' bytes inside the span must survive
+    h2d(g_cv.d_a, cbuf, (size_t)L * rs);
+    h2d(g_cv.d_of, &of, sizeof(of));
+    h2d(g_cv.d_status, &status, sizeof(status));
+    h2d(g_cv.d_chan, &ch, sizeof(ch));
+    h2d(g_cv.d_fmt, &fmt, sizeof(fmt));
+    InverseArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    ia.out_time = g_cv.d_a;
+    ia.raw_out = g_cv.d_raw;
+    ia.fmt = g_cv.d_fmt;
+    ia.overflow = g_cv.d_of;
+    ia.status = g_cv.d_status;
+    ia.n_out = 1;
+    ia.batch = 1;
+    ia.safety_limit = g_safety_limit;
+    DitherArgs da;
+    da.chans = g_cv.d_chan;
+    da.randtab = g_cv.d_tab;
+    da.randmap = g_cv.d_map;
+    da.randtab_size = L + 2;        // never wraps on the device: the host did the preloop
+    da.n_dither = 1;
+    CVCU(launch_dither(g_cv.plan, ia, da, g_cv.stream));
+    d2h(host_raw, g_cv.d_raw, span);
+    d2h(&of, g_cv.d_of, sizeof(of));
+    d2h(&status, g_cv.d_status, sizeof(status));
+    d2h(&ch, g_cv.d_chan, sizeof(ch));
+    sync();
+    overflow->n_overflows = of.n_overflows;
+    overflow->intlargest = of.intlargest;
+    overflow->largest = of.largest;
+    if (rs == 4) {
+        state->sf[0] = (float)ch.e0;
+        state->sf[1] = (float)ch.e1;
+    } else {
+        state->sd[0] = ch.e0;
+        state->sd[1] = ch.e1;
+    }
+    if (status & 1u) {
+        fprintf(stderr, "NaN or Inf values in the output! Bad output. Aborting.\n");    // real2raw.h:27-31
+        cv_exit(-5);
+    } else if (status & 2u) {
+        fprintf(stderr, "Safety limit exceeded on output. Aborting.\n");                // real2raw.h:32-41
+        cv_exit(1);
+    }
+}
+
 // device-side mixnscale over device-resident inputs
 bool dev_mixnscale(char *const in[], const double scales[], int n, char *out, int mode)
 {
@@ -188,6 +315,10 @@ bool_t convolver_init(const char config_filename[], int length, int realsize)
         cudaFree(g_cv.d_of); cudaFree(g_cv.d_status);
         if (g_cv.d_mix) cudaFree(g_cv.d_mix);
         if (g_cv.d_raw) cudaFree(g_cv.d_raw);
+        if (g_cv.d_tab) cudaFree(g_cv.d_tab);
+        if (g_cv.d_map) cudaFree(g_cv.d_map);
+        if (g_cv.d_chan) cudaFree(g_cv.d_chan);
+        if (g_cv.d_fmt) cudaFree(g_cv.d_fmt);
         cudaStreamDestroy(g_cv.stream);
         memset(&g_cv, 0, sizeof(g_cv));
     }
@@ -368,11 +499,9 @@ void convolver_convolve_eval(void *input_cbuf, void *buffer_cbuf, void *output_c
 void convolver_cbuf2raw(void *cbuf, void *outbuf, struct bfcuda_buffer_format *bf, bool_t apply_dither,
                         void *dither_state, struct bfcuda_overflow *overflow)
 {
-    (void)dither_state;
     if (!need_ready()) return;
     if (apply_dither && !bf->sf.isfloat) {
-        cv_fail("bfcuda convolver: dither is outside the accelerated path (north_star: dither off)");
-        cv_exit(1);
+        cv_cbuf2raw_dither(cbuf, outbuf, bf, (struct bfcuda_dither_state *)dither_state, overflow);
         return;
     }
     const bool okf = bf->sf.isfloat ? (bf->sf.bytes == 4 || bf->sf.bytes == 8) : (bf->sf.bytes >= 1 && bf->sf.bytes <= 4);
@@ -482,6 +611,12 @@ void convolver_debug_dump_cbuf(const char filename[], void *cbufs[], int n_cbufs
         }
     }
     fclose(stream);
+}
+
+void bfcuda_convolver_set_dither_table(int8_t *dither_randtab, int dither_randtab_size)
+{
+    g_dither_tab = dither_randtab;
+    g_dither_tab_size = dither_randtab_size;
 }
 
 void *convolver_fftplan(int order, int invert, int inplace)

@@ -20,6 +20,8 @@
 
 #include "bfcuda.h"
 
+#include <stdint.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -35,6 +37,19 @@ typedef int bool_t;     /* defs.h:14 */
  * output calls the exit hook with status -5 where the reference abort()s (real2raw.h:27-31). */
 void bfcuda_convolver_set_host(void (*bf_exit_hook)(int status), int quiet, double safety_limit);
 const char *bfcuda_convolver_last_error(void);
+
+/* Dither (convolver_cbuf2raw with apply_dither, fftw_convolver.c:489-515): the reference's convolver reads two more
+ * host globals, the table dither_init() built -- dither_randtab / dither_randtab_size (dither.c:22-24, used by
+ * dither_preloop_real2int_hp_tpdf, dither.h:28-38).  Hand them over once after dither_init(); the table stays the
+ * host's (the preloop writes its slot 0 on a wrap, exactly as in the reference).  `dither_state` of
+ * convolver_cbuf2raw is the host's struct dither_state, whose layout is: */
+struct bfcuda_dither_state {    /* == struct dither_state, dither.h:17-22 */
+    int randtab_ptr;
+    int8_t *randtab;
+    float sf[2];
+    double sd[2];
+};
+void bfcuda_convolver_set_dither_table(int8_t *dither_randtab, int dither_randtab_size);
 
 /* convolver.h:148-152 -- `config_filename` (FFTW wisdom) is ignored, as the header allows */
 bool_t convolver_init(const char config_filename[], int length, int realsize);

@@ -871,3 +871,23 @@ void DRV(cv_runtime_coeffs2cbuf)(void *src, void *dest) { CV(runtime_coeffs2cbuf
 int DRV(cv_td_block_length)(int n_coeffs) { return CV(td_block_length)(n_coeffs); }
 void *DRV(cv_td_new)(void *coeffs, int n_coeffs) { return CV(td_new)(coeffs, n_coeffs); }
 void DRV(cv_td_convolve)(void *tdc, void *overlap_block) { CV(td_convolve)(tdc, overlap_block); }
+
+/* dither table and per-channel state of the cv_* surface, for tests that hand the SAME table and state to another
+ * implementation: the table (dither_randtab / dither_randtab_size, dither.c:22-24) and a channel's struct dither_state */
+const int8_t *DRV(cv_dither_table)(int *size)
+{
+#ifdef DRV_REFERENCE
+    *size = dither_randtab_size;
+    return dither_randtab;
+#else
+    return orc_dither_table(size);
+#endif
+}
+void *DRV(cv_dither_state)(int index)
+{
+#ifdef DRV_REFERENCE
+    return g_cv_dither[index];
+#else
+    return &g_cv_dither[index];
+#endif
+}

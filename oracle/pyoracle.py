@@ -82,6 +82,8 @@ class _Lib:
         fn("cv_convolve_eval", None, V, V, V)
         fn("cv_coeffs2cbuf", I, V, I, D, V)
         fn("cv_runtime_coeffs2cbuf", None, V, V)
+        fn("cv_dither_table", V, C.POINTER(I))
+        fn("cv_dither_state", V, I)
         fn("cv_td_block_length", I, I)
         fn("cv_td_new", V, V, I)
         fn("cv_td_convolve", None, V, V)
@@ -209,6 +211,17 @@ class Convolver:
         src = np.ascontiguousarray(taps_L, self.dtype)
         self.l.cv_runtime_coeffs2cbuf(_ptr(src), _ptr(out))
         return out
+
+    def dither_table(self) -> np.ndarray:
+        """A copy of the dither table (dither_randtab, dither.c:22-24) after dither_init()."""
+        size = C.c_int(0)
+        ptr = self.l.cv_dither_table(C.byref(size))
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int8)), shape=(size.value,)).copy()
+
+    def dither_state(self, index: int):
+        """(randtab_ptr, sf[2], sd[2]) of channel `index` (struct dither_state, dither.h:17-22)."""
+        st = C.cast(self.l.cv_dither_state(index), C.POINTER(_abi.DitherStateC)).contents
+        return st.randtab_ptr, (st.sf[0], st.sf[1]), (st.sd[0], st.sd[1])
 
     def td_block_length(self, n_coeffs: int) -> int:
         return self.l.cv_td_block_length(n_coeffs)

@@ -10,7 +10,7 @@ import pytest
 
 from brutefir_b200 import _abi
 from brutefir_b200 import convolver as cv
-from brutefir_b200.formats import interleaved_layout, pack_block, parse_sample_format
+from brutefir_b200.formats import BufferFormat, interleaved_layout, pack_block, parse_sample_format
 from oracle import pyoracle as po
 from helpers import ulp_tol
 
@@ -201,3 +201,45 @@ def test_td_convolver_matches_oracle(gpu_lib, oracle_libs, rs):
             fs = max(1.0, np.abs(want).max())
             assert np.abs(blk - want).max() <= (1e-6 if rs == 4 else 1e-12) * fs, (n_coeffs, j)
         cv.convolver_td_delete(tg)
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("fmt", ["S16_LE", "S24_4BE", "S8"])
+def test_cbuf2raw_with_dither_bit_exact(gpu_lib, oracle_libs, rs, fmt):
+    """convolver_cbuf2raw(apply_dither = true) (fftw_convolver.c:489-499; HP-TPDF dither with error feedback,
+    dither_funs.h:7-68, dither.h:28-38): the device quantiser against the oracle on the same time-domain blocks, with
+    the oracle's own dither table and starting state handed to the library the way a host hands over dither_randtab and
+    its struct dither_state -- bytes, overflow record and the state after every block are identical, through a wrap of
+    the table pointer and through clipping blocks."""
+    L, n_ch, rate = 64, 2, 100
+    o = init(L, rs)
+    o.dither_init(n_ch, rate)
+    table = o.dither_table()
+    cv.set_dither_table(table)
+    sf = parse_sample_format(fmt)
+    bf = BufferFormat(sf, 2, sf.bytes)          # second channel of an interleaved pair
+    rng = np.random.default_rng(900 + rs)
+    index = 1
+    ptr, sf0, sd0 = o.dither_state(index)
+    st = _abi.DitherStateC()
+    st.randtab_ptr = ptr
+    st.sf[0], st.sf[1], st.sd[0], st.sd[1] = sf0[0], sf0[1], sd0[0], sd0[1]
+    of_g, of_o = _abi.OverflowC(), _abi.OverflowC()
+    of_g.max = of_o.max = float((1 << (8 * sf.sbytes - 1)) - 1)
+    wraps = 0
+    for blk in range(60):
+        amp = (1 << (8 * sf.sbytes - 1)) * (3.0 if blk in (7, 8, 30) else 0.2)
+        x = np.zeros(2 * L, o.dtype)
+        x[:L] = rng.standard_normal(L) * amp
+        raw_g = np.full(2 * L * sf.bytes, 0x5A, np.uint8)       # the other channel's bytes must survive
+        raw_o = raw_g.copy()
+        before = st.randtab_ptr
+        cv.convolver_cbuf2raw_dither(x, raw_g, bf, st, of_g)
+        o.cbuf2raw_dither(x, raw_o, bf, of_o, index)
+        wraps += st.randtab_ptr < before
+        assert np.array_equal(raw_g, raw_o), blk
+        assert (of_g.n_overflows, of_g.intlargest, of_g.largest) == (of_o.n_overflows, of_o.intlargest, of_o.largest)
+        ptr, sfo, sdo = o.dither_state(index)
+        assert st.randtab_ptr == ptr
+        assert (st.sf[0], st.sf[1]) == sfo if rs == 4 else (st.sd[0], st.sd[1]) == sdo
+    assert wraps >= 1 and of_g.n_overflows > 0
