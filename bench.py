@@ -357,8 +357,8 @@ def main():
             roof["note"] = ("one launch covers B blocks and reads every coefficient / delay-line spectrum ONCE for all "
                             "of them (register reuse): algorithmic bytes = rs*N*(P*F + (P+B-1)*U + B*F).  With the "
                             "per-block formula of SURVEY.md 8(d) times B the same launch rates at "
-                            f"{survey:.0f} GB/s-equivalent ({survey / peak:.2f} of peak); at B = 8 the kernel is FP32-issue "
-                            "bound (8 exactly rounded flop per complex MAC), not HBM bound")
+                            f"{survey:.0f} GB/s-equivalent ({survey / peak:.2f} of peak); at B = 8 the HBM floor and the "
+                            "FP32-pipe floor (8 exactly rounded flop per complex MAC) are within 15 % of each other")
             roof["survey_formula_equivalent_gbs"] = survey
         res = {"batch": B, "value": B * block_s / (ms_step * 1e-3), "ms_per_step": ms_step, "ms_per_block": ms_step / B,
                "gtap_mac_per_s": B * block_s / (ms_step * 1e-3) * gtap_unit,
@@ -375,9 +375,42 @@ def main():
             b.free()
         return res
 
+    def measure_low_latency():
+        """Synchronous per-block call latency of the real-time schedule (BFCUDA_FLAG_LOW_LATENCY): the sum over the
+        partitions 1 .. P-1 of the next block is made while the host waits for that block, so the timed call only
+        multiplies partition 0.  Paced like a real-time host: the engine is idle when the input arrives."""
+        eng = Engine(sub, device=local_rank, flags=_abi.FLAG_LOW_LATENCY, max_batch=1)
+        for c in sorted({f.coeff for f in sub.filters if f.coeff >= 0}):
+            eng.coeff_from_taps(c, taps[c])
+        sig = configs.synthetic_signal(graph, cid, 2)
+        if world > 1:
+            sig = shard.slice_input(graph, sig)
+        pin_in, pin_out = PinnedBuffer(sub.in_bytes), PinnedBuffer(sub.out_bytes)
+        pin_in.array[:] = sig[0].reshape(-1)
+        eng.upload_inputs(sig[:1])
+        for _ in range(graph.n_blocks + 1):
+            eng.process_blocks_device(1)
+        eng.synchronize()
+        lat = []
+        for i in range(40):
+            t0 = time.perf_counter()
+            rc = eng.lib.bfcuda_process_blocks(eng.h, 1, pin_in.array.ctypes.data, pin_out.array.ctypes.data)
+            lat.append(time.perf_counter() - t0)
+            assert rc == 0
+            eng.synchronize()       # the ahead-of-time sum for the next block finishes in the gap between two blocks
+        eng.close()
+        pin_in.free()
+        pin_out.free()
+        return max_over_ranks(float(np.median(lat[5:])) * 1e3)
+
     B = args.batch if args.batch >= 1 else (8 if len(sub.filters) > 16 else 16)
     head = measure(B, args.steps, args.warmup, True)
     stream = head if B == 1 else measure(1, max(args.steps, 50), args.warmup, False)
+    try:
+        low_latency_ms = measure_low_latency()
+    except Exception as exc:        # an extra figure: never takes the headline down with it
+        low_latency_ms = None
+        print(f"low-latency measurement failed: {exc!r}", file=sys.stderr)
 
     cfg["blocks_per_step"] = B
     cfg["schedule"] = ("block by block (the reference's filter_process schedule)" if B == 1 else
@@ -388,6 +421,7 @@ def main():
             "vs_baseline": None, "dtype": "f32" if graph.realsize == 4 else "f64", "data": "synthetic", "config": cfg,
             "gtap_mac_per_s": head["gtap_mac_per_s"], "ms_per_block": head["ms_per_block"],
             "latency_ms_per_block": stream["e2e"]["sync_call_latency_ms"],
+            "latency_ms_per_block_low_latency_schedule": low_latency_ms,
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
             "clocks": head["clocks"], "engine": head["engine"],
             "streaming": {k: stream[k] for k in ("batch", "value", "ms_per_step", "gtap_mac_per_s", "e2e", "roofline",

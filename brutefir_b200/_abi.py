@@ -78,6 +78,7 @@ FLAG_NO_GRAPH = 2
 FLAG_KEEP_INPUT_SPECTRA = 4
 FLAG_SERIAL_STAGES = 8
 FLAG_NO_STREAM_SHARING = 16
+FLAG_LOW_LATENCY = 32
 
 DBG_INPUT_SPECTRUM, DBG_DELAYLINE, DBG_FILTER_OUTPUT, DBG_OUTPUT_TIME = 1, 2, 3, 4
 

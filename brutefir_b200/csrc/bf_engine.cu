@@ -160,6 +160,10 @@ struct bfcuda_engine {
     cudaStream_t stream, s_mac, s_inv, s_in, s_out;
     cudaEvent_t ev_h2d[2], ev_fwd[2], ev_d2h[2], ev_inv;
     cudaEvent_t ev_fwd_done[2], ev_mac_done[2], ev_inv_done[2], ev_join;  // per launch parity
+    // BFCUDA_FLAG_LOW_LATENCY: the sum over partitions 1 .. P-1 of the next block, computed ahead (enqueue_batch)
+    bool low_latency;
+    bool tail_ready;            // Y partial 1 of the next launch's generation holds that sum, made with the current tables
+    cudaEvent_t ev_tail_done;   // end of the most recent ahead-of-time launch (it reads the job table)
     unsigned int launch_no;     // launches enqueued so far
     size_t y_stride;            // bytes between the two generations of Y
     unsigned int io_count;      // blocks submitted through the host-buffer interface
@@ -797,7 +801,7 @@ void bfcuda_destroy(bfcuda_engine *e)
     }
     for (cudaEvent_t ev : { e->ev_h2d[0], e->ev_h2d[1], e->ev_fwd[0], e->ev_fwd[1], e->ev_d2h[0], e->ev_d2h[1],
                             e->ev_inv, e->ev_fwd_done[0], e->ev_fwd_done[1], e->ev_mac_done[0],
-                            e->ev_mac_done[1], e->ev_inv_done[0], e->ev_inv_done[1], e->ev_join }) {
+                            e->ev_mac_done[1], e->ev_inv_done[0], e->ev_inv_done[1], e->ev_join, e->ev_tail_done }) {
         if (ev) cudaEventDestroy(ev);
     }
     for (cudaStream_t st : { e->stream, e->s_mac, e->s_inv, e->s_in, e->s_out }) {
@@ -921,6 +925,9 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         e->ev_fwd_done[i] = e->ev_mac_done[i] = e->ev_inv_done[i] = nullptr;
     }
     e->ev_join = nullptr;
+    e->ev_tail_done = nullptr;
+    e->low_latency = false;
+    e->tail_ready = false;
     e->launch_no = 0;
     e->y_stride = 0;
     e->ev_h2d[0] = e->ev_h2d[1] = e->ev_fwd[0] = e->ev_fwd[1] = e->ev_d2h[0] = e->ev_d2h[1] = nullptr;
@@ -1013,6 +1020,12 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->split = choose_split(e, c->mac_split);
     const char *variant = getenv("BFCUDA_MAC_VARIANT");
     e->mac_variant = variant != nullptr ? atoi(variant) : 0;
+    if ((e->flags & BFCUDA_FLAG_LOW_LATENCY) && e->n_levels == 1 && e->P > 1) {
+        // head = partition 0, tail = the others, one block ahead: a two-way split of uneven halves
+        e->low_latency = true;
+        e->split = 2;
+        e->mac_variant = 0;
+    }
 
     int rc = 0;
 #define TRY(x)                    \
@@ -1044,7 +1057,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         for (cudaEvent_t *ev : { &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_fwd[0], &e->ev_fwd[1], &e->ev_d2h[0],
                                  &e->ev_d2h[1], &e->ev_inv, &e->ev_fwd_done[0], &e->ev_fwd_done[1],
                                  &e->ev_mac_done[0], &e->ev_mac_done[1], &e->ev_inv_done[0], &e->ev_inv_done[1],
-                                 &e->ev_join }) {
+                                 &e->ev_join, &e->ev_tail_done }) {
             TRYCU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         }
         TRYCU(fft_plan_create(&e->plan, e->N, e->rs));
@@ -1188,6 +1201,7 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
 static int check_coeff(bfcuda_engine *e, int coeff, int block)
 {
     if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
+    e->tail_ready = false;      // every coefficient setter comes through here: a sum made ahead of time is stale
     if (coeff < 0 || coeff >= e->n_coeffs) return fail(BFCUDA_EINVAL, "coefficient index %d out of range", coeff);
     if (block < 0 || block >= e->coeff_n_blocks[coeff]) {
         return fail(BFCUDA_EINVAL, "coefficient block %d out of range", block);
@@ -1463,6 +1477,15 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     ma.t = e->slot_t;
     ma.batch = nb;
     ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
+    ma.head = ma.z_first = ma.z_count = 0;
+    const bool ll = e->low_latency && nb == 1;
+    if (ll) {
+        ma.head = 1;
+        if (e->tail_ready) {
+            ma.z_count = 1;     // partial 1 was computed ahead of time: only partition 0 is left
+        }
+    }
+    e->tail_ready = false;
     CU(launch_mac(e->plan, ma, e->s_mac));
     e->launches += ma.n_jobs > 0;
     if (e->split > 1) {
@@ -1578,6 +1601,23 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     }
     CU(cudaEventRecord(e->ev_inv_done[par], e->s_inv));
     CU(cudaEventRecord(e->ev_inv, e->s_inv));
+    if (ll && !e->dirty && !e->xfade_active && !transition && ma.n_jobs > 0) {
+        // The next block's partitions 1 .. P-1 read ring slots that are all written by now: start their sum behind this
+        // block's (short) MAC, into the other generation of Y, which the inverse stage of the previous launch must
+        // have left.  A control change before the next block discards it (enqueue_blocks).
+        MacArgs mt = ma;
+        mt.Y = (char *)e->d_Y + (size_t)(par ^ 1) * e->y_stride;
+        mt.t = (e->slot_t + 1) % e->fdl_ring;
+        mt.z_first = 1;
+        mt.z_count = 1;
+        // ... and not before THIS block's inverse stage is through: the long-running blocks of the sum would hold the
+        // SMs the (short, latency-critical) inverse and packing kernels are waiting for
+        CU(cudaStreamWaitEvent(e->s_mac, e->ev_inv_done[par], 0));
+        CU(launch_mac(e->plan, mt, e->s_mac));
+        CU(cudaEventRecord(e->ev_tail_done, e->s_mac));
+        e->launches++;
+        e->tail_ready = true;
+    }
     e->launch_no++;
 
     // bfrun.c:1838, 2034
@@ -1716,6 +1756,11 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
                 CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[prev], 0));
                 CU(cudaStreamWaitEvent(e->stream, e->ev_inv_done[prev], 0));
             }
+            if (e->low_latency) {
+                // an ahead-of-time launch may still read the job table (no-op while the event was never recorded)
+                CU(cudaStreamWaitEvent(e->stream, e->ev_tail_done, 0));
+                e->tail_ready = false;
+            }
             int frc = update_streams(e);
             if (frc != 0) return frc;
             frc = begin_transitions(e);
@@ -1726,6 +1771,9 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
             if (e->xfade_active || in_transition(e)) {
                 nb = 1;
             }
+        }
+        if (nb != 1) {
+            e->tail_ready = false;      // Y is laid out per batch size
         }
         const bool lastpart = done + nb == n;
         int rc = enqueue_batch(e, nb, raw_in + (size_t)done * e->n_bytes[0], raw_out + (size_t)done * e->n_bytes[1],
@@ -1814,16 +1862,15 @@ int bfcuda_synchronize(bfcuda_engine *e)
 
 int bfcuda_process_block(bfcuda_engine *e, const void *raw_in, void *raw_out)
 {
-    int rc = bfcuda_process_block_async(e, raw_in, raw_out);
-    if (rc != 0) return rc;
-    return bfcuda_synchronize(e);
+    return bfcuda_process_blocks(e, 1, raw_in, raw_out);
 }
 
 int bfcuda_process_blocks(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out)
 {
     int rc = bfcuda_process_blocks_async(e, n_blocks, raw_in, raw_out);
     if (rc != 0) return rc;
-    return bfcuda_synchronize(e);
+    // the call's own read-out, not every stream: in the low-latency schedule the next block's partial sum keeps running
+    return bfcuda_wait_previous(e, 0);
 }
 
 int bfcuda_process_blocks_device(bfcuda_engine *e, int n_blocks)

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
     }
     const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
     const MacJob jb = a.jobs[job];
-    const int z = blockIdx.y;
+    const int z = (int)blockIdx.y + a.z_first;
     const int P = a.ring;       // ring slots per stream
     T *out = reinterpret_cast<T *>(a.Y) + ((size_t)z * a.n_slots + jb.out) * N + (size_t)v * W;
     const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * P * N + (size_t)v * W;
@@ -330,7 +330,13 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
     } else {
         const int chunk = (jb.n_parts + a.split - 1) / a.split;
         int i = z * chunk;
-        const int i1 = min(jb.n_parts, i + chunk);
+        int i1 = min(jb.n_parts, i + chunk);
+        if (a.head > 0) {
+            // uneven two-way split: partial 0 = the first `head` partitions, partial 1 = the others
+            const int h = min(a.head, jb.n_parts);
+            i = z == 0 ? 0 : h;
+            i1 = z == 0 ? h : jb.n_parts;
+        }
         const T *H = reinterpret_cast<const T *>(a.H) + (size_t)jb.hbase * N + (size_t)v * W;
         T dc = (T)0, ny = (T)0;
         if (i < i1) {
@@ -1023,13 +1029,14 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
     if (a.n_jobs == 0) return cudaSuccess;
-    if (a.variant == 1 && a.batch == 1) {
+    if (a.variant == 1 && a.batch == 1 && a.head == 0 && a.z_count == 0) {
         return launch_mac_tma(plan, a, s);
     }
     const int W = 16 / plan.realsize;
     const long threads = (long)a.n_jobs * (plan.N / 2 / W);
-    dim3 grid((unsigned int)((threads + 255) / 256), a.split);
+    dim3 grid((unsigned int)((threads + 255) / 256), a.z_count > 0 ? a.z_count : a.split);
     if (a.batch > 1) {
+        if (a.head > 0 || a.z_count > 0) return cudaErrorInvalidValue;     // block-by-block schedule only
         return launch_mac_batch2(plan, a, s);      // bf_mac_batch.cu
     }
     if (plan.realsize == 4) {

@@ -161,6 +161,10 @@ struct MacArgs {
     int batch;
     int variant;                // 0 = direct streaming loads, 1 = bulk-copy (TMA) staged (batch 1 only)
     unsigned long long neg_zero2;   // filled in by the batched launcher: two packed -0.0f (bf_mac_batch.cu, BinPairAcc)
+    // Uneven two-way split for the low-latency schedule (batch 1, variant 0, split == 2): head > 0 makes partial 0
+    // the partitions [0, head) and partial 1 the rest; z_count > 0 launches only the partials z_first .. z_first +
+    // z_count - 1 (the "rest" is computed one block ahead, bf_engine.cu).
+    int head, z_first, z_count;
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 // With split > 1 the MAC leaves `split` partial sums per output: add them, in order, into partial 0 (the consumers

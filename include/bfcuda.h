@@ -131,6 +131,14 @@ struct bfcuda_config {
 #define BFCUDA_FLAG_KEEP_INPUT_SPECTRA 4u   /* keep every input's unscaled spectrum for bfcuda_debug_read */
 #define BFCUDA_FLAG_NO_STREAM_SHARING 16u  /* give every filter its own delay line even where several filters are fed by
                                            the same input with the same scale and delay (they normally share one) */
+#define BFCUDA_FLAG_LOW_LATENCY 32u     /* real-time schedule for block-by-block calls: the partitions 1 .. P-1 of the NEXT
+                                           block only need spectra that are already in the delay line, so their sum is
+                                           computed right after a block's output has left (while the host waits for the
+                                           next input); when that input arrives only partition 0 is multiplied and the
+                                           two partial sums are added.  The partition sum then is head + tail instead of
+                                           the reference's left-to-right order (like mac_split = 2; within the parity
+                                           tolerances, not bit-identical), the call latency drops by the MAC's time.
+                                           Control changes, crossfades and batches fall back to the full sum. */
 #define BFCUDA_FLAG_SERIAL_STAGES 8u    /* do not overlap the stages of consecutive launches (the engine normally runs
                                            launch n+1's forward and launch n-1's inverse stage beside launch n's
                                            multiply-accumulate): stage timings then are each stage running alone */
