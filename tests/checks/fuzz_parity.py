@@ -6,12 +6,13 @@ implementation.
 Usage: python tests/checks/fuzz_parity.py [n_cases] [seed]
 Environment: FUZZ_BIG=1 (partitions of 1024..8192 samples, batches up to 16), FUZZ_PMAX=n (up to n partitions),
 FUZZ_WIDE=1 (up to 70 channels each way and 80 filters),
+FUZZ_LL=1 (BFCUDA_FLAG_LOW_LATENCY),
 FUZZ_B=n (force the batch size), FUZZ_ONLY=i,j (run and explain only these cases)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
-from brutefir_b200 import configs
+from brutefir_b200 import _abi, configs
 from brutefir_b200.engine import Engine
 from brutefir_b200.formats import interleaved_layout, planar_layout
 from brutefir_b200.graph import Filter, FilterGraph
@@ -65,6 +66,9 @@ for case in range(n_cases):
             kw["fscales"] = [float(rng.choice([1.0, 0.4342944819032518])) for _ in filters[f].from_filters]
         script[b] = (f, kw)
     split = int(rng.choice([1, 1, 0, 3]))
+    ll = os.environ.get("FUZZ_LL") == "1"       # the real-time schedule: head + tail partition sums (a two-way split)
+    if ll:
+        split = 2
     B = int(rng.choice([1, 4, 8, 16] if big and rs == 4 else [1, 1, 2, 4]))
     if os.environ.get("FUZZ_B"):
         B = int(os.environ["FUZZ_B"])
@@ -73,7 +77,7 @@ for case in range(n_cases):
     desc = f"case {case}: L={L} P={P} rs={rs} in={n_in}x{fin} out={n_out}x{fout} filters={nf} B={B} split={split}"
     try:
         d = po.BlockDriver("oracle", g)
-        with Engine(g, mac_split=split, max_batch=B) as e:
+        with Engine(g, mac_split=split, max_batch=B, flags=_abi.FLAG_LOW_LATENCY if ll else 0) as e:
             for c, h in enumerate(taps):
                 e.coeff_from_taps(c, h)
                 d.coeff_from_taps(c, h)

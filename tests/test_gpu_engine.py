@@ -718,7 +718,7 @@ def test_pipelined_stages_equal_serialised_stages(gpu_lib, calls, B):
 
 
 @pytest.mark.parametrize("env,cases,seed", [({}, 40, 7), ({"FUZZ_BIG": "1"}, 24, 9002), ({"FUZZ_PMAX": "24"}, 40, 9010),
-                                            ({"FUZZ_WIDE": "1"}, 24, 9020)])
+                                            ({"FUZZ_WIDE": "1"}, 24, 9020), ({"FUZZ_LL": "1", "FUZZ_B": "1"}, 24, 9031)])
 def test_randomised_graphs_against_oracle(gpu_lib, oracle_libs, env, cases, seed):
     """tests/checks/fuzz_parity.py: random graphs (mixes, chaining, delays, crossfade, formats, partition counts from
     1), random run-time control scripts, random batch sizes, engine against the oracle under the north_star
