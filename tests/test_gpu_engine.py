@@ -389,6 +389,46 @@ def test_coefficient_layouts_round_trip(gpu_lib, oracle_libs):
         assert err.value.code == -5
 
 
+@pytest.mark.parametrize("L,rs,B", [(16384, 4, 1), (16384, 4, 2), (8192, 8, 1)])
+def test_maximum_partition_sizes(gpu_lib, oracle_libs, L, rs, B):
+    """The largest partitions the single-block transforms take: 16384 samples at float_bits 32 (N = 32768, the
+    1024-thread size-specialised kernels with twiddles left in global memory), 8192 at float_bits 64."""
+    g = configs.diagonal_graph(2, L, 2, rs, "S24_4LE")
+    taps = configs.synthetic_filters(g, 51)
+    sig = configs.synthetic_signal(g, 51, 6, sigma=0.01)
+    with Engine(g, mac_split=1, max_batch=B) as e:
+        d = po.BlockDriver("oracle", g)
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+            d.coeff_from_taps(c, h)
+        got = np.zeros((6, g.out_bytes), np.uint8)
+        for b in range(0, 6, B):
+            e.process_blocks_async(sig[b:b + B], got[b:b + B], B)
+        e.synchronize()
+        ref = d.run(sig)
+        d.close()
+    assert_parity(g, got, ref)
+
+
+def test_maximum_channel_and_filter_counts(gpu_lib, oracle_libs):
+    """BF_MAXCHANNELS = BF_MAXFILTERS = 256 (bfmod.h:22-23): 256 inputs, 256 outputs, 256 filters; every fourth
+    filter reads its neighbour's input too and every output but the last is also fed by the next filter."""
+    n, L, P = 256, 64, 2
+    inb, nin = interleaved_layout(n, "S16_LE", L)
+    outb, nout = interleaved_layout(n, "S24_LE", L)
+    filters = []
+    for f in range(n):
+        ins = [f, (f + 1) % n] if f % 4 == 0 else [f]
+        outs = [f] if f == 0 else [f, f - 1]
+        filters.append(Filter(ins, outs, in_scales=[0.5] * len(ins), out_scales=[0.3183098861837907] * len(outs),
+                              coeff=f % 3, delayblocks=f % 2))
+    g = FilterGraph(L, P, 4, inb, outb, nin, nout, filters, [P, 1, P])
+    taps = configs.synthetic_filters(g, 52)
+    sig = configs.synthetic_signal(g, 52, 8, sigma=0.02)
+    got, ref, _ = run_both(g, taps, sig, mac_split=1)
+    assert_parity(g, got, ref)
+
+
 def test_errors_and_limits(gpu_lib):
     g = configs.config_c1_chained()
     g.filters[0].from_filters, g.filters[0].fscales = [4], [1.0]      # a source with a higher index: not topological
