@@ -13,9 +13,11 @@
  *
  *   cc -O2 -Iinclude host/bfcuda_run.c -o host/bfcuda_run -Lbrutefir_b200 -lbfcuda -Wl,-rpath,'$ORIGIN/../brutefir_b200' -lm
  *
- *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] [-B blocks] in.raw out.raw
- *     -B blocks: hand the engine up to `blocks` (<= 8) audio blocks per call and keep two calls in flight while
+ *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] [-l] [-B blocks] in.raw out.raw
+ *     -B blocks: hand the engine up to `blocks` (<= 16) audio blocks per call and keep two calls in flight while
  *               the files are read and written (offline mode; bit-identical output, several times the throughput)
+ *     -l      : the real-time schedule (BFCUDA_FLAG_LOW_LATENCY): block by block, partitions 1 .. P-1 of the next
+ *               block summed ahead of time (half the call latency; partition sums within tolerance, not bit-identical)
  *     taps.f32: raw little-endian float32 (float64 with -r 64) taps, one filter after the other, L*P each
  *               ("dirac" = unit pulses, the reference's "dirac pulse" coefficient, bfconf.c:1905-1913)
  *     -f fmt  : format of the coefficient file, as the `format:` field of a coeff section (bfconf.c:783-812,
@@ -96,7 +98,7 @@ now(void)
 int
 main(int argc, char *argv[])
 {
-    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, device = 0, batch = 1, a;
+    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, low_latency = 0, device = 0, batch = 1, a;
     const char *fin = "S24_4LE", *fout = "S24_4LE", *coeff_path = "dirac", *in_path = NULL, *out_path = NULL;
     const char *coeff_fmt = NULL;
     double attenuation_db = 0.0;
@@ -130,10 +132,11 @@ main(int argc, char *argv[])
         else if (!strcmp(argv[a], "-k") && a + 1 < argc) coeff_skip = atol(argv[++a]);
         else if (!strcmp(argv[a], "-m")) matrix = 1;
         else if (!strcmp(argv[a], "-b")) bench = 1;
+        else if (!strcmp(argv[a], "-l")) low_latency = 1;
         else if (!strcmp(argv[a], "-B") && a + 1 < argc) batch = atoi(argv[++a]);
         else if (in_path == NULL) in_path = argv[a];
         else if (out_path == NULL) out_path = argv[a];
-        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [-B blocks] [in [out]]", argv[0]);
+        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [-l] [-B blocks] [in [out]]", argv[0]);
     }
     if (parse_format(fin, &sf_in) != 0 || parse_format(fout, &sf_out) != 0) DIE("Unknown sample format.");
     rs = realbits / 8;
@@ -170,7 +173,7 @@ main(int argc, char *argv[])
     cfg.n_coeffs = n_filters;
     cfg.coeff_n_blocks = coeff_blocks;
     cfg.device = device;
-    cfg.flags = bench ? BFCUDA_FLAG_STAGE_TIMING : 0;
+    cfg.flags = (bench ? BFCUDA_FLAG_STAGE_TIMING : 0) | (low_latency ? BFCUDA_FLAG_LOW_LATENCY : 0);
     cfg.max_batch = batch;
     CHECK(bfcuda_create(&cfg, &eng));
     CHECK(bfcuda_get_info(eng, &info));

@@ -47,6 +47,14 @@ def test_c_host_streams_files_like_bfio_file(gpu_lib, oracle_libs, tmp_path):
     assert r.returncode == 0, r.stderr
     assert (tmp_path / "out4.raw").read_bytes() == (tmp_path / "out.raw").read_bytes()
 
+    # the real-time schedule (-l): within 1 LSB of the oracle as well
+    r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-i", "S24_4LE", "-o", "S24_4LE", "-l",
+                        "-c", str(tmp_path / "taps.f32"), str(tmp_path / "in.raw"), str(tmp_path / "out_l.raw")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out_l = np.frombuffer((tmp_path / "out_l.raw").read_bytes(), np.uint8).reshape(9, g.out_bytes)
+    assert np.abs(unpack_run(out_l, g.out_formats, L) - unpack_run(ref, g.out_formats, L)).max() <= 1
+
     # "dirac pulse" coefficients: the output file equals the input file (bfconf.c:1905-1913)
     r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-r", "64", str(tmp_path / "in.raw"),
                         str(tmp_path / "out2.raw")], capture_output=True, text=True, timeout=300)
