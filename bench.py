@@ -238,7 +238,7 @@ def main():
         eng = Engine(sub, device=local_rank, flags=_abi.FLAG_NO_STREAM_SHARING if args.no_sharing else 0, max_batch=B)
         for c in sorted({f.coeff for f in sub.filters if f.coeff >= 0}):
             eng.coeff_from_taps(c, taps[c])
-        nbuf = 3
+        nbuf = int(os.environ.get("BENCH_NBUF", "3"))
         sig = configs.synthetic_signal(graph, cid, nbuf * B)
         if world > 1:
             sig = shard.slice_input(graph, sig)
