@@ -193,7 +193,7 @@ struct bfcuda_engine {
     bool any_out_mix;
     std::vector<MixTerm> h_out_terms;
     std::vector<int> shared_out;
-    std::vector<std::pair<int, int>> delay_fixups;     // (filter, old delay) of delay changes not yet applied to the ring
+    std::vector<std::pair<int, int>> delay_fixups;     // (filter, old delay) of delay changes since the last block (begin_transitions)
     FwdDest *d_dests;
     int *d_dest_first;
     uint8_t *d_need_xin;
@@ -299,7 +299,7 @@ static bool shareable(const bfcuda_engine *e, const FilterState &fs)
 }
 
 // Keep the ring assignment consistent with the control snapshot, at a block boundary (before the tables are built
-// and before any delay fix-up).  A filter whose key (input, scale, delay) changed leaves the ring it shared and
+// and before any delay transition starts).  A filter whose key (input, scale, delay) changed leaves the ring it shared and
 // takes a copy of it -- its history up to now IS that ring; if it was the ring's owner the remaining users move to a
 // copy of their own.  Filters whose keys are equal and have been for longer than any slot lives (or since creation)
 // hold identical delay lines and are merged again, no copy needed.
@@ -895,8 +895,9 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->max_batch = c->max_batch < 1 ? 1 : c->max_batch;
     // Ring slots per delay line.  The reference's ring has exactly P (bfrun.c:1045, 1600).  Here: + 2 B - 1 so that
     // launch n+1's forward stage can run beside launch n's MAC, + P - 1 so that a block written "ahead" under the
-    // largest block delay (P - 1) never lands on a slot a running MAC still reads and the one-time aliasing fix-up
-    // of a delay change (apply_delay_fixups) always has distinct source and destination slots.
+    // largest block delay (P - 1) never lands on a slot a running MAC still reads, and every slot a block can read
+    // (P back) stays distinct from the slots being written (what the reference's P-slot ring aliases after a delay
+    // change is reproduced from an exact mirror, begin_transitions).
     e->fdl_ring = 2 * e->P + 2 * e->max_batch;
     e->slot_t = 0;
     e->d_xt[0] = e->d_xt[1] = nullptr;
@@ -1350,7 +1351,7 @@ static int flush_timing_ring(bfcuda_engine *e)
 // Enqueue the kernels of `nb` consecutive blocks as ONE launch per stage (nb <= max_batch; callers make sure
 // no control change or crossfade falls inside): unpack + forward on the main stream, MAC on s_mac, inverse + pack on
 // s_inv, ordered by per-parity events (launch n: p = n & 1):
-//   forward(n)  after MAC(n-2)      -- the ring slots it overwrites were last read there (ring = P + 2B - 1)
+//   forward(n)  after MAC(n-2)      -- the ring slots it overwrites were last read there (ring = 2P + 2B)
 //   MAC(n)      after forward(n) and inverse(n-2)   -- Y[p] is free again
 //   inverse(n)  after MAC(n)
 //   raw_in / raw_out : device raw blocks, block b at + b * n_bytes

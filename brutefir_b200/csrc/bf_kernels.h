@@ -72,9 +72,9 @@ bool fft_size_supported(int N, int realsize);
 // ---- engine kernels --------------------------------------------------------------------------------
 
 // Batching: one launch may process `batch` consecutive audio blocks (grid y = block within the batch).
-// The delay-line ring then has `ring` = P + max_batch - 1 slots per stream, so that the spectra of the
-// later blocks of a batch do not overwrite slots the earlier blocks still read; `t` is the ring slot of
-// the batch's first block (0 <= t < ring).  batch = 1, ring = P is the reference's block-by-block schedule.
+// The delay-line ring has `ring` = 2 P + 2 max_batch slots per stream (bf_engine.cu, bfcuda_create), so that the
+// spectra of the later blocks of a batch -- and of the next launch -- do not overwrite slots the earlier blocks still
+// read; `t` is the ring slot of the batch's first block (0 <= t < ring).
 struct ForwardArgs {
     const uint8_t *raw_in;      // block b at raw_in + b * in_stride
     const SampleFormat *fmt;    // [n_in]

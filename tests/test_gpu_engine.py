@@ -503,7 +503,7 @@ def test_batched_launches_are_bit_identical_to_block_by_block(gpu_lib, oracle_li
         assert got_stats == ref_stats and ref_stats[1][0] > 0
         if split == 1 and B == 2:
             # ... and the block-by-block engine itself follows the reference's P-slot ring through every delay
-            # change (the engine's ring is longer; bf_engine.cu apply_delay_fixups)
+            # change (the engine's ring is longer; bf_engine.cu begin_transitions)
             d = po.BlockDriver("oracle", g)
             for c, h in enumerate(taps):
                 d.coeff_from_taps(c, h, 40.0)
@@ -694,7 +694,7 @@ def test_delay_lines_shared_across_filters(gpu_lib, oracle_libs, L, P, rs, B):
     """Filters fed by the same input with the same scale and delay share one delay line ("input spectra reused across
     filters"): n rings instead of n^2.  Results must not depend on it -- byte-identical to the engine with sharing off
     and within tolerance of the oracle -- through run-time changes that split a filter off its ring (input scale,
-    delay), the aliasing fix-ups on the split-off copy, crossfaded coefficient switches, and re-merging once the rings
+    delay), the delay transition on the split-off copy, crossfaded coefficient switches, and re-merging once the rings
     are identical again."""
     n, nb = 3, 8 * P + 20
     g = matrix_graph(n, L, P, rs)
@@ -703,7 +703,7 @@ def test_delay_lines_shared_across_filters(gpu_lib, oracle_libs, L, P, rs, B):
     script = {3: [(1, dict(coeff=1, in_scales=[0.5]))],                    # filter 1 leaves input 1's ring
               5: [(0, dict(coeff=4))],                                     # crossfade on a ring owner
               7: [(3, dict(coeff=3, delayblocks=2))],                      # owner of input 0's ring changes delay
-              9: [(6, dict(coeff=6, delayblocks=2))],                      # ... a follower follows (own ring, fix-ups)
+              9: [(6, dict(coeff=6, delayblocks=2))],                      # ... a follower follows (own ring, transition)
               12: [(1, dict(coeff=1, in_scales=[1.0]))],                   # back to the common scale: re-merge later
               14: [(3, dict(coeff=3, delayblocks=0)), (6, dict(coeff=6, delayblocks=0))]}
 
