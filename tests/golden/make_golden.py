@@ -67,6 +67,29 @@ def golden_functions():
         out[f"{t}_quant_in"] = q_in
         out[f"{t}_quant_raw"] = raw
         out[f"{t}_quant_overflow"] = np.array([of.n_overflows, of.intlargest, of.largest, of.max])
+        # (a generator of their own, so that the vectors above keep their values)
+        rng2 = np.random.default_rng(4343 + rs)
+        # convolver_td_* (fftw_convolver.c:682-782): 31 taps, block length 32, three sliding [previous | current] frames
+        td_taps = rng2.standard_normal(31).astype(dt)
+        td = cv.td_new(td_taps)
+        x = rng2.standard_normal(4 * 32).astype(dt)
+        out[f"{t}_td_taps"], out[f"{t}_td_in"] = td_taps, x
+        out[f"{t}_td_out"] = np.stack([cv.td_convolve(td, x[k * 32:(k + 2) * 32]) for k in range(3)])
+        # convolver_cbuf2raw with dither (HP-TPDF + error feedback), S16_LE, channel 1 of 2, 40 blocks: the table
+        # pointer wraps (2001 entries at 100 Hz) and block 7 clips
+        cv.dither_init(2, 100)
+        bf16 = BufferFormat(parse_sample_format("S16_LE"), 1, 0)
+        of = _abi.OverflowC(0, 0, 0.0, 32767.0)
+        d_in = rng2.standard_normal((40, 32)) * 3000.0
+        d_in[7] *= 20.0
+        d_in = d_in.astype(dt)
+        raws = []
+        for k in range(40):
+            raw = np.zeros(32 * 2, np.uint8)
+            cv.cbuf2raw_dither(np.concatenate([d_in[k], np.zeros(32, dt)]), raw, bf16, of, 1)
+            raws.append(raw)
+        out[f"{t}_dither_in"], out[f"{t}_dither_raw"] = d_in, np.stack(raws)
+        out[f"{t}_dither_overflow"] = np.array([of.n_overflows, of.intlargest, of.largest, of.max])
     return out
 
 

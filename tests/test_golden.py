@@ -50,6 +50,21 @@ def test_functions_against_reference_vectors(oracle_libs, fn, rs):
     q = raw.view("<i4")[:14]
     assert list(q[:8]) == [0, -1, -2, -3, 1, 2, 4, -3]
     assert q[12] == (1 << 23) - 1 and q[13] == -(1 << 23)
+    # the sub-sample delay's small convolver
+    td = cv.td_new(fn[f"{t}_td_taps"])
+    x = fn[f"{t}_td_in"]
+    for k in range(3):
+        assert np.array_equal(cv.td_convolve(td, x[k * 32:(k + 2) * 32]), fn[f"{t}_td_out"][k])
+    # HP-TPDF dither with error feedback through a wrap of the table pointer and a clipping block
+    cv.dither_init(2, 100)
+    bf16 = BufferFormat(parse_sample_format("S16_LE"), 1, 0)
+    of = _abi.OverflowC(0, 0, 0.0, 32767.0)
+    for k in range(40):
+        raw = np.zeros(32 * 2, np.uint8)
+        cv.cbuf2raw_dither(np.concatenate([fn[f"{t}_dither_in"][k], np.zeros(32, cv.dtype)]), raw, bf16, of, 1)
+        assert np.array_equal(raw, fn[f"{t}_dither_raw"][k]), k
+    assert [of.n_overflows, of.intlargest, of.largest, of.max] == list(fn[f"{t}_dither_overflow"])
+    assert of.n_overflows > 0
 
 
 def golden_graph_a():

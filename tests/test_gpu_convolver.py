@@ -195,7 +195,7 @@ def test_td_convolver_matches_oracle(gpu_lib, oracle_libs, rs):
         assert tg and to
         x = rng.uniform(-1, 1, 6 * B).astype(o.dtype)
         for j in range(1, 6):
-            blk = np.ascontiguousarray(x[(j - 1) * B:(j + 1) * B])
+            blk = x[(j - 1) * B:(j + 1) * B].copy()      # convolved in place: never the stream itself
             want = o.td_convolve(to, blk)
             cv.convolver_td_convolve(tg, blk)
             fs = max(1.0, np.abs(want).max())
@@ -243,3 +243,36 @@ def test_cbuf2raw_with_dither_bit_exact(gpu_lib, oracle_libs, rs, fmt):
         assert st.randtab_ptr == ptr
         assert (st.sf[0], st.sf[1]) == sfo if rs == 4 else (st.sd[0], st.sd[1]) == sdo
     assert wraps >= 1 and of_g.n_overflows > 0
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_td_and_dither_against_reference_vectors(gpu_lib, oracle_libs, rs):
+    """The committed vectors the reference build itself produced (tests/golden/make_golden.py), no oracle in the
+    comparison: convolver_td_* within the float tolerance, the dithered quantiser byte for byte (only the dither TABLE
+    is taken from the oracle library, whose generator the same vectors pin in tests/test_golden.py)."""
+    import os
+    fn = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "functions.npz"))
+    t = f"f{rs * 8}"
+    o = init(32, rs)
+    td = cv.convolver_td_new(fn[f"{t}_td_taps"])
+    assert td
+    x = fn[f"{t}_td_in"]
+    for k in range(3):
+        blk = x[k * 32:(k + 2) * 32].copy()
+        cv.convolver_td_convolve(td, blk)
+        want = fn[f"{t}_td_out"][k]
+        assert np.abs(blk - want).max() <= (1e-6 if rs == 4 else 1e-12) * max(1.0, np.abs(want).max())
+    cv.convolver_td_delete(td)
+    o.dither_init(2, 100)
+    table = o.dither_table()
+    cv.set_dither_table(table)
+    ptr, _, _ = o.dither_state(1)
+    st = _abi.DitherStateC()
+    st.randtab_ptr = ptr
+    bf16 = BufferFormat(parse_sample_format("S16_LE"), 1, 0)
+    of = _abi.OverflowC(0, 0, 0.0, 32767.0)
+    for k in range(40):
+        raw = np.zeros(32 * 2, np.uint8)
+        cv.convolver_cbuf2raw_dither(np.concatenate([fn[f"{t}_dither_in"][k], np.zeros(32, o.dtype)]), raw, bf16, st, of)
+        assert np.array_equal(raw, fn[f"{t}_dither_raw"][k]), k
+    assert [of.n_overflows, of.intlargest, of.largest, of.max] == list(fn[f"{t}_dither_overflow"])
