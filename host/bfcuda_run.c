@@ -13,9 +13,12 @@
  *
  *   cc -O2 -Iinclude host/bfcuda_run.c -o host/bfcuda_run -Lbrutefir_b200 -lbfcuda -Wl,-rpath,'$ORIGIN/../brutefir_b200' -lm
  *
- *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] [-l] [-B blocks] in.raw out.raw
+ *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] [-l] [-t] [-B blocks] in.raw out.raw
  *     -B blocks: hand the engine up to `blocks` (<= 16) audio blocks per call and keep two calls in flight while
  *               the files are read and written (offline mode; bit-identical output, several times the throughput)
+ *     -t      : text files on both sides, bfio_file's `text: true` (bfio_file.c:153-185, 308-420, 509-565): white-space
+ *               separated numbers in, one line per sample frame out ("%+.16e", tab separated); the sample format is
+ *               then FLOAT64_LE as the reference requires
  *     -l      : the real-time schedule (BFCUDA_FLAG_LOW_LATENCY): block by block, partitions 1 .. P-1 of the next
  *               block summed ahead of time (half the call latency; partition sums within tolerance, not bit-identical)
  *     taps.f32: raw little-endian float32 (float64 with -r 64) taps, one filter after the other, L*P each
@@ -95,10 +98,42 @@ now(void)
 #define DIE(...) do { fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); exit(1); } while (0)
 #define CHECK(call) do { int rc__ = (call); if (rc__ != 0) DIE("%s failed (%d): %s", #call, rc__, bfcuda_strerror()); } while (0)
 
+/* bfio_file's text mode (bfio_file.c:308-420): white-space separated numbers, empty lines skipped, one double each.
+ * Returns the bytes filled (a multiple of 8); a token that is not a number is an error as in the reference. */
+static size_t read_text(FILE *in, void *buf, size_t bytes)
+{
+    double *a = buf;
+    size_t i = 0, count = bytes / 8;
+    while (i < count) {
+        int r = fscanf(in, "%lf", &a[i]);
+        if (r == EOF) {
+            break;
+        }
+        if (r != 1) {
+            DIE("File I/O: Read failed: bad text format.");
+        }
+        i++;
+    }
+    return i * 8;
+}
+
+/* bfio_file.c:28, 509-565: "%+.16e" per sample, tabs between the channels of a frame, one frame per line */
+static int write_text(FILE *out, const void *buf, size_t bytes, int channels)
+{
+    const double *a = buf;
+    size_t i, count = bytes / 8;
+    for (i = 0; i < count; i++) {
+        if (fprintf(out, "%+.16e%c", a[i], (i + 1) % (size_t)channels == 0 ? '\n' : '\t') < 0) {
+            return -1;
+        }
+    }
+    return 0;
+}
+
 int
 main(int argc, char *argv[])
 {
-    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, low_latency = 0, device = 0, batch = 1, a;
+    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, low_latency = 0, text_io = 0, fin_set = 0, fout_set = 0, device = 0, batch = 1, a;
     const char *fin = "S24_4LE", *fout = "S24_4LE", *coeff_path = "dirac", *in_path = NULL, *out_path = NULL;
     const char *coeff_fmt = NULL;
     double attenuation_db = 0.0;
@@ -124,8 +159,8 @@ main(int argc, char *argv[])
         else if (!strcmp(argv[a], "-r") && a + 1 < argc) realbits = atoi(argv[++a]);
         else if (!strcmp(argv[a], "-s") && a + 1 < argc) rate = atoi(argv[++a]);
         else if (!strcmp(argv[a], "-d") && a + 1 < argc) device = atoi(argv[++a]);
-        else if (!strcmp(argv[a], "-i") && a + 1 < argc) fin = argv[++a];
-        else if (!strcmp(argv[a], "-o") && a + 1 < argc) fout = argv[++a];
+        else if (!strcmp(argv[a], "-i") && a + 1 < argc) { fin = argv[++a]; fin_set = 1; }
+        else if (!strcmp(argv[a], "-o") && a + 1 < argc) { fout = argv[++a]; fout_set = 1; }
         else if (!strcmp(argv[a], "-c") && a + 1 < argc) coeff_path = argv[++a];
         else if (!strcmp(argv[a], "-f") && a + 1 < argc) coeff_fmt = argv[++a];
         else if (!strcmp(argv[a], "-a") && a + 1 < argc) attenuation_db = atof(argv[++a]);
@@ -133,10 +168,18 @@ main(int argc, char *argv[])
         else if (!strcmp(argv[a], "-m")) matrix = 1;
         else if (!strcmp(argv[a], "-b")) bench = 1;
         else if (!strcmp(argv[a], "-l")) low_latency = 1;
+        else if (!strcmp(argv[a], "-t")) text_io = 1;
         else if (!strcmp(argv[a], "-B") && a + 1 < argc) batch = atoi(argv[++a]);
         else if (in_path == NULL) in_path = argv[a];
         else if (out_path == NULL) out_path = argv[a];
-        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [-l] [-B blocks] [in [out]]", argv[0]);
+        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [-l] [-t] [-B blocks] [in [out]]", argv[0]);
+    }
+    if (text_io) {
+        /* bfio_file.c:165-185: text conversion exists for the native FLOAT64 format only (AUTO selects it) */
+        if ((fin_set && strcmp(fin, "FLOAT64_LE") != 0) || (fout_set && strcmp(fout, "FLOAT64_LE") != 0)) {
+            DIE("File I/O: No support for text conversion of given sample format.");
+        }
+        fin = fout = "FLOAT64_LE";
     }
     if (parse_format(fin, &sf_in) != 0 || parse_format(fout, &sf_out) != 0) DIE("Unknown sample format.");
     rs = realbits / 8;
@@ -263,7 +306,8 @@ main(int argc, char *argv[])
      * the dai double buffers. */
     for (k = 0;; k++) {
         const int s = k % 3;
-        size_t got = fread(raw_in[s], 1, in_bytes * (size_t)batch, in);
+        size_t got = text_io ? read_text(in, raw_in[s], in_bytes * (size_t)batch)
+                             : fread(raw_in[s], 1, in_bytes * (size_t)batch, in);
         if (got == 0) {
             break;
         }
@@ -275,7 +319,8 @@ main(int argc, char *argv[])
         if (k > 0) {
             const int p = (k - 1) % 3;
             CHECK(bfcuda_wait_previous(eng, 1));
-            if (fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
+            if (text_io ? write_text(out, raw_out[p], out_bytes * (size_t)nblk[p], n) != 0
+                        : fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
                 DIE("write failed: %s", strerror(errno));
             }
         }
@@ -284,7 +329,8 @@ main(int argc, char *argv[])
     if (k > 0) {
         const int p = (k - 1) % 3;
         CHECK(bfcuda_synchronize(eng));
-        if (fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
+        if (text_io ? write_text(out, raw_out[p], out_bytes * (size_t)nblk[p], n) != 0
+                    : fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
             DIE("write failed: %s", strerror(errno));
         }
     }

@@ -55,6 +55,24 @@ def test_c_host_streams_files_like_bfio_file(gpu_lib, oracle_libs, tmp_path):
     out_l = np.frombuffer((tmp_path / "out_l.raw").read_bytes(), np.uint8).reshape(9, g.out_bytes)
     assert np.abs(unpack_run(out_l, g.out_formats, L) - unpack_run(ref, g.out_formats, L)).max() <= 1
 
+    # text files on both sides (bfio_file `text: true`, bfio_file.c:153-185, 308-420, 509-565): FLOAT64 samples as
+    # white-space separated numbers in, "%+.16e" tab separated frames out; unit pulses: out == in within 1e-12
+    rng = np.random.default_rng(5)
+    frames = rng.uniform(-1, 1, (3 * L + 17, n))                   # the last block is partial
+    with open(tmp_path / "in.txt", "w") as f:
+        for k, fr in enumerate(frames):
+            f.write(("\t" if k % 2 else " ").join(repr(float(v)) for v in fr) + ("\n\n" if k % 7 == 0 else "\n"))
+    r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-r", "64", "-t", str(tmp_path / "in.txt"),
+                        str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = (tmp_path / "out.txt").read_text().splitlines()
+    assert len(lines) == 4 * L and all(len(ln.split("\t")) == n for ln in lines) and lines[0][0] in "+-"
+    got = np.array([[float(v) for v in ln.split("\t")] for ln in lines])
+    assert np.abs(got[:len(frames)] - frames).max() <= 1e-12 and np.abs(got[len(frames):]).max() <= 1e-12
+    r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-t", "-o", "S16_LE", str(tmp_path / "in.txt"),
+                        str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "No support for text conversion" in r.stderr
+
     # "dirac pulse" coefficients: the output file equals the input file (bfconf.c:1905-1913)
     r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-r", "64", str(tmp_path / "in.raw"),
                         str(tmp_path / "out2.raw")], capture_output=True, text=True, timeout=300)
