@@ -34,6 +34,9 @@ def test_ctypes_structs_match_the_header_layout():
     assert C.sizeof(_abi.SampleFormatC) == 32 and C.sizeof(_abi.BufferFormatC) == 40
     assert C.sizeof(_abi.OverflowC) == 24           # struct bfoverflow, bfmod.h:99-104
     assert _abi.OverflowC.largest.offset == 8 and _abi.OverflowC.max.offset == 16
+    # struct dither_state, dither.h:17-22: int, pointer, float[2], double[2]
+    assert C.sizeof(_abi.DitherStateC) == 40 and _abi.DitherStateC.randtab.offset == 8
+    assert _abi.DitherStateC.sf.offset == 16 and _abi.DitherStateC.sd.offset == 24
 
 
 def test_no_cpu_fallback_without_a_device():
