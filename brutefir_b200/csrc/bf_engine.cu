@@ -1300,7 +1300,23 @@ int bfcuda_set_control(bfcuda_engine *e, int filter, const struct bfcuda_filter_
     if (filter < 0 || filter >= e->n_filters) return fail(BFCUDA_EINVAL, "filter index out of range");
     if (c->coeff >= e->n_coeffs) return fail(BFCUDA_EINVAL, "coefficient index %d out of range", c->coeff);
     FilterState &fs = e->filters[filter];
-    fs.coeff = c->coeff < 0 ? -1 : c->coeff;
+    // The host takes this snapshot for every filter before every block (bfrun.c:1462-1478); mostly nothing has changed,
+    // and then nothing may happen here either: a rebuild of the tables waits for the previous launch's stages and
+    // discards a partition sum made ahead of time.
+    const int new_coeff = c->coeff < 0 ? -1 : c->coeff;
+    bool changed = new_coeff != fs.coeff || c->delayblocks != fs.delayblocks;
+    for (int io = 0; io < 2 && !changed; io++) {
+        if (c->scale[io] != nullptr) {
+            changed = !std::equal(fs.scale[io].begin(), fs.scale[io].end(), c->scale[io]);
+        }
+    }
+    if (!changed && c->fscale != nullptr) {
+        changed = !std::equal(fs.fscale.begin(), fs.fscale.end(), c->fscale);
+    }
+    if (!changed) {
+        return 0;
+    }
+    fs.coeff = new_coeff;
     if (clamp_delay(e, c->delayblocks) != clamp_delay(e, fs.delayblocks)) {
         // remember the delay the ring was last written under (first change since the last block wins)
         bool known = false;

@@ -256,9 +256,12 @@ def test_low_latency_schedule(gpu_lib, oracle_libs, rs):
 
     def run(engine):
         out = np.zeros((nblk, g.out_bytes), np.uint8)
+        cur = {f: dict(coeff=flt.coeff, delayblocks=flt.delayblocks) for f, flt in enumerate(filters)}
         b = 0
         while b < nblk:
             for filt, kw in script.get(b, []):
+                cur[filt] = dict(dict(delayblocks=0), **kw)
+            for filt, kw in cur.items():            # the host's snapshot: every filter, every block (bfrun.c:1462-1478)
                 engine.set_control(filt, **kw)
             if b == 15:
                 engine.coeff_from_taps(1, new_taps)         # between two blocks
