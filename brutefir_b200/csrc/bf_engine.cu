@@ -178,6 +178,8 @@ struct bfcuda_engine {
     Overflow *d_overflow;
     unsigned int *d_status;
     unsigned int *h_status;     // pinned
+    Overflow *h_overflow;       // pinned [n_out]: the overflow records as of the last host-buffer call's read-out
+    bool h_overflow_valid;      // false until such a call has been made (and after a reset / a device-resident call)
     size_t device_bytes;
 
     // tables: host mirrors and device copies
@@ -790,6 +792,7 @@ void bfcuda_destroy(bfcuda_engine *e)
         }
     }
     if (e->h_status) cudaFreeHost(e->h_status);
+    if (e->h_overflow) cudaFreeHost(e->h_overflow);
     fft_plan_destroy(&e->plan);
     for (int i = 0; i < 2; i++) {
         if (e->timer[i]) cudaEventDestroy(e->timer[i]);
@@ -941,6 +944,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->ring_fill = 0;
     e->stage_blocks = e->launches = 0;
     e->h_status = nullptr;
+    e->h_overflow = nullptr;
+    e->h_overflow_valid = false;
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
     memset(e->timer, 0, sizeof(e->timer));
     memset(e->ring, 0, sizeof(e->ring));
@@ -1073,6 +1078,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         }
         TRYCU(cudaMallocHost((void **)&e->h_status, sizeof(unsigned int)));
         *e->h_status = 0;
+        TRYCU(cudaMallocHost((void **)&e->h_overflow, sizeof(Overflow) * (size_t)std::max(1, e->n_ch[1])));
         const size_t B = (size_t)e->max_batch;
         TRY(dev_alloc(e, &e->d_raw[0], B * e->n_bytes[0]));
         TRY(dev_alloc(e, &e->d_raw[1], B * e->n_bytes[1]));
@@ -1177,6 +1183,7 @@ int bfcuda_reset_overflow(bfcuda_engine *e)
         CU(cudaMemcpy(e->d_overflow, of.data(), sizeof(Overflow) * of.size(), cudaMemcpyHostToDevice));
     }
     CU(cudaMemset(e->d_status, 0, sizeof(unsigned int)));
+    e->h_overflow_valid = false;
     return 0;
 }
 
@@ -1185,11 +1192,18 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
     if (e == nullptr || overflow == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     if (out_channel < 0 || out_channel >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
     CU(cudaSetDevice(e->device));
-    for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
-        CU(cudaStreamSynchronize(st));
-    }
     Overflow of;
-    CU(cudaMemcpy(&of, e->d_overflow + out_channel, sizeof(of), cudaMemcpyDeviceToHost));
+    if (e->h_overflow_valid && e->io_count > 0) {
+        // host-buffer interface: the records came back with the most recent call's output -- wait for that read-out
+        // only (no other stream: the next block's ahead-of-time work keeps running), no copy
+        CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u) & 1u]));
+        of = e->h_overflow[out_channel];
+    } else {
+        for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
+            CU(cudaStreamSynchronize(st));
+        }
+        CU(cudaMemcpy(&of, e->d_overflow + out_channel, sizeof(of), cudaMemcpyDeviceToHost));
+    }
     overflow->n_overflows = of.n_overflows;
     overflow->intlargest = of.intlargest;
     overflow->largest = of.largest;
@@ -1846,6 +1860,12 @@ int bfcuda_process_blocks_async(bfcuda_engine *e, int n_blocks, const void *raw_
     CU(cudaStreamWaitEvent(e->s_out, e->ev_inv, 0));
     CU(cudaMemcpyAsync(raw_out, d_out, (size_t)n_blocks * e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_out));
     CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->s_out));
+    if (e->n_ch[1] > 0) {
+        // the peak-meter records travel with the block (bfrun.c:1929-1936 reads them after every block)
+        CU(cudaMemcpyAsync(e->h_overflow, e->d_overflow, sizeof(Overflow) * (size_t)e->n_ch[1], cudaMemcpyDeviceToHost,
+                           e->s_out));
+        e->h_overflow_valid = true;
+    }
     CU(cudaEventRecord(e->ev_d2h[b], e->s_out));
     e->io_count++;
     return 0;
@@ -1897,6 +1917,7 @@ int bfcuda_process_blocks_device(bfcuda_engine *e, int n_blocks)
         return fail(BFCUDA_EINVAL, "n_blocks %d outside 1..max_batch (%d)", n_blocks, e->max_batch);
     }
     CU(cudaSetDevice(e->device));
+    e->h_overflow_valid = false;        // no read-out follows a device-resident call
     return enqueue_blocks(e, n_blocks, e->d_raw[0], e->d_raw[1], nullptr, nullptr, nullptr);
 }
 
