@@ -180,6 +180,7 @@ struct bfcuda_engine {
     unsigned int *h_status;     // pinned
     Overflow *h_overflow;       // pinned [n_out]: the overflow records as of the last host-buffer call's read-out
     bool h_overflow_valid;      // false until such a call has been made (and after a reset / a device-resident call)
+    unsigned int io_waited;     // value of io_count when the host last waited for the most recent call's read-out
     size_t device_bytes;
 
     // tables: host mirrors and device copies
@@ -946,6 +947,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->h_status = nullptr;
     e->h_overflow = nullptr;
     e->h_overflow_valid = false;
+    e->io_waited = 0;
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
     memset(e->timer, 0, sizeof(e->timer));
     memset(e->ring, 0, sizeof(e->ring));
@@ -1191,14 +1193,19 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
 {
     if (e == nullptr || overflow == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     if (out_channel < 0 || out_channel >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
-    CU(cudaSetDevice(e->device));
     Overflow of;
     if (e->h_overflow_valid && e->io_count > 0) {
         // host-buffer interface: the records came back with the most recent call's output -- wait for that read-out
-        // only (no other stream: the next block's ahead-of-time work keeps running), no copy
-        CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u) & 1u]));
+        // only (no other stream: the next block's ahead-of-time work keeps running), no copy; after a synchronous
+        // call not even that (the per-output peak-meter loop of bfrun.c:1929-1936 costs nothing)
+        if (e->io_waited != e->io_count) {
+            CU(cudaSetDevice(e->device));
+            CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u) & 1u]));
+            e->io_waited = e->io_count;
+        }
         of = e->h_overflow[out_channel];
     } else {
+        CU(cudaSetDevice(e->device));
         for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
             CU(cudaStreamSynchronize(st));
         }
@@ -1835,6 +1842,7 @@ static int sync_all(bfcuda_engine *e)
     CU(cudaStreamSynchronize(e->s_mac));
     CU(cudaStreamSynchronize(e->s_inv));
     CU(cudaStreamSynchronize(e->s_out));
+    e->io_waited = e->io_count;
     return 0;
 }
 
@@ -1885,6 +1893,9 @@ int bfcuda_wait_previous(bfcuda_engine *e, int calls_back)
     CU(cudaSetDevice(e->device));
     // the raw blocks are double buffered by call parity; a call's read-out event is re-recorded two calls later
     CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u - (unsigned int)calls_back) & 1u]));
+    if (calls_back == 0) {
+        e->io_waited = e->io_count;
+    }
     return check_status(e);
 }
 

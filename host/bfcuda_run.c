@@ -13,12 +13,16 @@
  *
  *   cc -O2 -Iinclude host/bfcuda_run.c -o host/bfcuda_run -Lbrutefir_b200 -lbfcuda -Wl,-rpath,'$ORIGIN/../brutefir_b200' -lm
  *
- *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] [-l] [-t] [-B blocks] in.raw out.raw
+ *   bfcuda_run -n 2 -L 4096 -P 16 -i S24_4LE -o S24_4LE -c taps.f32 [-r 32] [-s rate] [-m] [-b] [-l] [-t] [-R] [-B blocks] in.raw out.raw
  *     -B blocks: hand the engine up to `blocks` (<= 16) audio blocks per call and keep two calls in flight while
  *               the files are read and written (offline mode; bit-identical output, several times the throughput)
  *     -t      : text files on both sides, bfio_file's `text: true` (bfio_file.c:153-185, 308-420, 509-565): white-space
  *               separated numbers in, one line per sample frame out ("%+.16e", tab separated); the sample format is
  *               then FLOAT64_LE as the reference requires
+ *     -R      : the per-block pattern of filter_process() as INTEGRATION.md section B shows it: control snapshot of
+ *               every filter, ONE synchronous bfcuda_process_block(), the peak-meter read of every output -- timed
+ *               per block (the engine is left to finish its ahead-of-time work between two blocks, as the block
+ *               period of a sound card would); prints the median and the largest call latency
  *     -l      : the real-time schedule (BFCUDA_FLAG_LOW_LATENCY): block by block, partitions 1 .. P-1 of the next
  *               block summed ahead of time (half the call latency; partition sums within tolerance, not bit-identical)
  *     taps.f32: raw little-endian float32 (float64 with -r 64) taps, one filter after the other, L*P each
@@ -133,7 +137,7 @@ static int write_text(FILE *out, const void *buf, size_t bytes, int channels)
 int
 main(int argc, char *argv[])
 {
-    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, low_latency = 0, text_io = 0, fin_set = 0, fout_set = 0, device = 0, batch = 1, a;
+    int n = 2, L = 4096, P = 16, realbits = 32, rate = 48000, matrix = 0, bench = 0, low_latency = 0, text_io = 0, fin_set = 0, fout_set = 0, realtime = 0, device = 0, batch = 1, a;
     const char *fin = "S24_4LE", *fout = "S24_4LE", *coeff_path = "dirac", *in_path = NULL, *out_path = NULL;
     const char *coeff_fmt = NULL;
     double attenuation_db = 0.0;
@@ -169,10 +173,11 @@ main(int argc, char *argv[])
         else if (!strcmp(argv[a], "-b")) bench = 1;
         else if (!strcmp(argv[a], "-l")) low_latency = 1;
         else if (!strcmp(argv[a], "-t")) text_io = 1;
+        else if (!strcmp(argv[a], "-R")) realtime = 1;
         else if (!strcmp(argv[a], "-B") && a + 1 < argc) batch = atoi(argv[++a]);
         else if (in_path == NULL) in_path = argv[a];
         else if (out_path == NULL) out_path = argv[a];
-        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [-l] [-t] [-B blocks] [in [out]]", argv[0]);
+        else DIE("usage: %s [-n ch] [-L len] [-P blocks] [-r 32|64] [-s rate] [-i fmt] [-o fmt] [-c taps|dirac] [-m] [-b] [-l] [-t] [-R] [-B blocks] [in [out]]", argv[0]);
     }
     if (text_io) {
         /* bfio_file.c:165-185: text conversion exists for the native FLOAT64 format only (AUTO selects it) */
@@ -304,6 +309,60 @@ main(int argc, char *argv[])
     /* Call k is submitted, then call k-1's output (complete while call k runs) is written: the file I/O of the
      * reference's input / output processes overlapped with the filter process, with three buffer sets instead of
      * the dai double buffers. */
+    if (realtime) {
+        /* filter_process()'s per-block sequence, bfrun.c:1462-1478 (snapshot), 1494-2006 (the block), 1929-1936 (meter) */
+        double *lat = NULL, sum = 0.0;
+        long n_lat = 0, cap = 0, i, j;
+        for (;;) {
+            struct bfcuda_overflow of;
+            double c0, c1;
+            size_t got = text_io ? read_text(in, raw_in[0], in_bytes) : fread(raw_in[0], 1, in_bytes, in);
+            if (got == 0) {
+                break;
+            }
+            if (got < in_bytes) {
+                memset((char *)raw_in[0] + got, 0, in_bytes - got);
+            }
+            c0 = now();
+            for (f = 0; f < n_filters; f++) {
+                struct bfcuda_filter_control fc;
+                memset(&fc, 0, sizeof(fc));
+                fc.coeff = filters[f].coeff;
+                fc.delayblocks = filters[f].delayblocks;
+                fc.scale[BFCUDA_IN] = filters[f].scale[BFCUDA_IN];
+                fc.scale[BFCUDA_OUT] = filters[f].scale[BFCUDA_OUT];
+                CHECK(bfcuda_set_control(eng, f, &fc));
+            }
+            CHECK(bfcuda_process_block(eng, raw_in[0], raw_out[0]));
+            for (c = 0; c < n; c++) {
+                CHECK(bfcuda_get_overflow(eng, c, &of));
+            }
+            c1 = now();
+            if (n_lat == cap) {
+                cap = cap ? 2 * cap : 1024;
+                lat = realloc(lat, (size_t)cap * sizeof(*lat));
+                if (lat == NULL) DIE("out of memory");
+            }
+            lat[n_lat++] = c1 - c0;
+            if (text_io ? write_text(out, raw_out[0], out_bytes, n) != 0 : fwrite(raw_out[0], 1, out_bytes, out) != out_bytes) {
+                DIE("write failed: %s", strerror(errno));
+            }
+            CHECK(bfcuda_synchronize(eng));     /* the block period passes */
+            blocks++;
+        }
+        for (i = 1; i < n_lat; i++) {           /* insertion sort: a few thousand entries at most */
+            double v = lat[i];
+            for (j = i - 1; j >= 0 && lat[j] > v; j--) lat[j + 1] = lat[j];
+            lat[j + 1] = v;
+        }
+        for (i = 0; i < n_lat; i++) sum += lat[i];
+        if (n_lat > 0) {
+            fprintf(stderr, "per-block call latency (snapshot + block + meter): median %.3f ms, mean %.3f ms, max %.3f ms over %ld blocks\n",
+                    1e3 * lat[n_lat / 2], 1e3 * sum / (double)n_lat, 1e3 * lat[n_lat - 1], n_lat);
+        }
+        free(lat);
+        k = 0;
+    } else
     for (k = 0;; k++) {
         const int s = k % 3;
         size_t got = text_io ? read_text(in, raw_in[s], in_bytes * (size_t)batch)

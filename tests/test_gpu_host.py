@@ -55,6 +55,16 @@ def test_c_host_streams_files_like_bfio_file(gpu_lib, oracle_libs, tmp_path):
     out_l = np.frombuffer((tmp_path / "out_l.raw").read_bytes(), np.uint8).reshape(9, g.out_bytes)
     assert np.abs(unpack_run(out_l, g.out_formats, L) - unpack_run(ref, g.out_formats, L)).max() <= 1
 
+    # filter_process()'s per-block pattern (-R: snapshot of every filter, one synchronous block, peak meter of every
+    # output) on the real-time schedule: same samples within 1 LSB, and the latency line is printed
+    r = subprocess.run([exe, "-n", str(n), "-L", str(L), "-P", str(P), "-i", "S24_4LE", "-o", "S24_4LE", "-l", "-R",
+                        "-c", str(tmp_path / "taps.f32"), str(tmp_path / "in.raw"), str(tmp_path / "out_r.raw")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "per-block call latency" in r.stderr
+    out_r = np.frombuffer((tmp_path / "out_r.raw").read_bytes(), np.uint8).reshape(9, g.out_bytes)
+    assert np.abs(unpack_run(out_r, g.out_formats, L) - unpack_run(ref, g.out_formats, L)).max() <= 1
+
     # text files on both sides (bfio_file `text: true`, bfio_file.c:153-185, 308-420, 509-565): FLOAT64 samples as
     # white-space separated numbers in, "%+.16e" tab separated frames out; unit pulses: out == in within 1e-12
     rng = np.random.default_rng(5)
