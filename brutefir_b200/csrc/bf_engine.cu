@@ -196,7 +196,7 @@ struct bfcuda_engine {
     bool any_out_mix;
     std::vector<MixTerm> h_out_terms;
     std::vector<int> shared_out;
-    std::vector<std::pair<int, int>> delay_fixups;     // (filter, old delay) of delay changes since the last block (begin_transitions)
+    std::vector<std::pair<int, int>> delay_changes;     // (filter, old delay) of delay changes since the last block (begin_transitions)
     FwdDest *d_dests;
     int *d_dest_first;
     uint8_t *d_need_xin;
@@ -1341,11 +1341,11 @@ int bfcuda_set_control(bfcuda_engine *e, int filter, const struct bfcuda_filter_
     if (clamp_delay(e, c->delayblocks) != clamp_delay(e, fs.delayblocks)) {
         // remember the delay the ring was last written under (first change since the last block wins)
         bool known = false;
-        for (const std::pair<int, int> &fx : e->delay_fixups) {
+        for (const std::pair<int, int> &fx : e->delay_changes) {
             known = known || fx.first == filter;
         }
         if (!known) {
-            e->delay_fixups.push_back(std::make_pair(filter, clamp_delay(e, fs.delayblocks)));
+            e->delay_changes.push_back(std::make_pair(filter, clamp_delay(e, fs.delayblocks)));
         }
     }
     fs.delayblocks = c->delayblocks;
@@ -1701,7 +1701,7 @@ static int begin_transitions(bfcuda_engine *e)
             fs.trans_until = -1;        // regular again
         }
     }
-    for (const std::pair<int, int> &fx : e->delay_fixups) {
+    for (const std::pair<int, int> &fx : e->delay_changes) {
         const int f = fx.first, d_old = fx.second;
         FilterState &fs = e->filters[f];
         if (clamp_delay(e, fs.delayblocks) == d_old) {
@@ -1732,7 +1732,7 @@ static int begin_transitions(bfcuda_engine *e)
         }
         fs.trans_until = T + 2L * P;
     }
-    e->delay_fixups.clear();
+    e->delay_changes.clear();
     return 0;
 }
 
