@@ -93,7 +93,7 @@ ENGINE_SYMBOLS = [
     "bfcuda_upload_inputs", "bfcuda_download_outputs",
     "bfcuda_host_alloc", "bfcuda_host_free", "bfcuda_timer_start", "bfcuda_timer_stop",
     "bfcuda_stage_times", "bfcuda_set_serial_stages", "bfcuda_set_stage_timing", "bfcuda_get_info", "bfcuda_debug_read", "bfcuda_comm_unique_id",
-    "bfcuda_comm_init", "bfcuda_comm_shared_outputs",
+    "bfcuda_comm_init", "bfcuda_comm_shared_outputs", "bfcuda_host_alloc_near", "bfcuda_copy_baseline",
 ]
 class DitherStateC(C.Structure):
     """struct dither_state (dither.h:17-22) == struct bfcuda_dither_state (include/bfcuda_convolver.h)."""
@@ -135,6 +135,10 @@ def load_library() -> C.CDLL:
     lib.bfcuda_host_alloc.restype = C.c_void_p
     lib.bfcuda_host_alloc.argtypes = [C.c_size_t]
     lib.bfcuda_host_free.argtypes = [C.c_void_p]
+    lib.bfcuda_host_alloc_near.restype = C.c_void_p
+    lib.bfcuda_host_alloc_near.argtypes = [C.c_int, C.c_size_t]
+    lib.bfcuda_copy_baseline.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.bfcuda_create.argtypes = [C.POINTER(ConfigC), C.POINTER(C.c_void_p)]
     lib.bfcuda_destroy.argtypes = [C.c_void_p]
     lib.bfcuda_destroy.restype = None

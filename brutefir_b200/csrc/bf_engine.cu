@@ -28,6 +28,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -177,8 +179,13 @@ struct bfcuda_engine {
     bool single_dest, simple_mix;   // ForwardArgs::single_dest / InverseArgs::simple_mix of the current tables
     Overflow *d_overflow;
     unsigned int *d_status;
-    unsigned int *h_status;     // pinned
-    Overflow *h_overflow;       // pinned [n_out]: the overflow records as of the last host-buffer call's read-out
+    unsigned int *h_status;     // pinned: status word of the device-resident / download path
+    // Host-buffer calls: the overflow records [n_out] and the status word as of the END of call k are snapshotted on
+    // the device behind its last kernel (s_inv) and read out with its output block, double buffered by call parity --
+    // call k+1's inverse stage may already be updating d_overflow / d_status while call k's read-out runs.
+    char *d_snap[2];
+    char *h_snap[2];            // pinned
+    size_t snap_bytes, snap_status_off;
     bool h_overflow_valid;      // false until such a call has been made (and after a reset / a device-resident call)
     unsigned int io_waited;     // value of io_count when the host last waited for the most recent call's read-out
     size_t device_bytes;
@@ -638,7 +645,7 @@ static int choose_split(const bfcuda_engine *e, int requested)
     // is enough there.)
     int lanes = 16 / e->rs;
     if (e->max_batch > 1) {
-        lanes = e->rs == 4 ? (e->max_batch <= 4 ? 4 : (e->max_batch <= 8 ? 2 : 1)) : (e->max_batch <= 2 ? 2 : 1);
+        lanes = mac_batch_lanes(e->rs, e->max_batch, std::max(1, e->n_filters), e->N);     // the launcher's own table
     }
     const long threads = (long)std::max(1, e->n_filters) * (e->N / 2 / lanes);
     const long target = (long)e->sm_count * (e->max_batch > 1 ? 256 : 512);
@@ -778,7 +785,7 @@ void bfcuda_destroy(bfcuda_engine *e)
         g_nccl.CommDestroy(e->comm);
     }
     void *ptrs[] = { e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
-                     e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_status, e->d_dests, e->d_dest_first,
+                     e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
                      e->d_keep, e->d_eval_entries, e->d_eval_terms, e->d_mixes, e->dither.chans, (void *)e->dither.randtab,
                      (void *)e->dither.randmap };
@@ -793,7 +800,10 @@ void bfcuda_destroy(bfcuda_engine *e)
         }
     }
     if (e->h_status) cudaFreeHost(e->h_status);
-    if (e->h_overflow) cudaFreeHost(e->h_overflow);
+    for (int i = 0; i < 2; i++) {
+        if (e->h_snap[i]) cudaFreeHost(e->h_snap[i]);
+        if (e->d_snap[i]) cudaFree(e->d_snap[i]);
+    }
     fft_plan_destroy(&e->plan);
     for (int i = 0; i < 2; i++) {
         if (e->timer[i]) cudaEventDestroy(e->timer[i]);
@@ -830,8 +840,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     if (c->n_blocks < 1) {
         return fail(BFCUDA_EINVAL, "Invalid number of blocks %d.", c->n_blocks);
     }
-    if (c->max_batch > (c->realsize == 4 ? 16 : 4)) {
-        return fail(BFCUDA_EINVAL, "max_batch %d exceeds %d", c->max_batch, c->realsize == 4 ? 16 : 4);
+    if (c->max_batch > (c->realsize == 4 ? 16 : 8)) {
+        return fail(BFCUDA_EINVAL, "max_batch %d exceeds %d", c->max_batch, c->realsize == 4 ? 16 : 8);
     }
     if (c->n_channels[0] < 0 || c->n_channels[0] > BFCUDA_MAXCHANNELS || c->n_channels[1] < 0 ||
         c->n_channels[1] > BFCUDA_MAXCHANNELS || c->n_filters < 0 || c->n_filters > BFCUDA_MAXFILTERS) {
@@ -842,9 +852,14 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
                     c->filter_length, c->realsize, c->realsize == 4 ? 16384 : 8192);
     }
     for (int io = 0; io < 2; io++) {
+        if (c->n_bytes[io] < 0 || (c->n_channels[io] > 0 && c->formats[io] == nullptr)) {
+            return fail(BFCUDA_EINVAL, "%s: negative block size or missing buffer formats", io ? "output" : "input");
+        }
         for (int n = 0; n < c->n_channels[io]; n++) {
             const bfcuda_buffer_format &b = c->formats[io][n];
-            const bool okf = b.sf.isfloat ? (b.sf.bytes == 4 || b.sf.bytes == 8) : (b.sf.bytes >= 1 && b.sf.bytes <= 4);
+            // integer formats: 1 <= sbytes <= bytes <= 4 (bfconf.c:377-472); the clip limits are 2^(8 sbytes - 1)
+            const bool okf = b.sf.isfloat ? (b.sf.bytes == 4 || b.sf.bytes == 8)
+                                          : (b.sf.bytes >= 1 && b.sf.bytes <= 4 && b.sf.sbytes >= 1 && b.sf.sbytes <= b.sf.bytes);
             if (!okf || b.sample_spacing < 1 || b.byte_offset < 0 ||
                 (long)b.byte_offset + ((long)(c->filter_length - 1) * b.sample_spacing + 1) * b.sf.bytes >
                     c->n_bytes[io]) {
@@ -853,6 +868,9 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
                             io ? "output" : "input", n, b.sf.bytes);
             }
         }
+    }
+    if ((c->n_filters > 0 && c->filters == nullptr) || (c->n_coeffs > 0 && c->coeff_n_blocks == nullptr) || c->n_coeffs < 0) {
+        return fail(BFCUDA_EINVAL, "missing filter or coefficient table");
     }
     for (int f = 0; f < c->n_filters; f++) {
         const bfcuda_filter &s = c->filters[f];
@@ -867,6 +885,9 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
             return fail(BFCUDA_EINVAL, "filter %d: coefficient index %d out of range", f, s.coeff);
         }
         for (int io = 0; io < 2; io++) {
+            if (s.n_channels[io] < 0 || (s.n_channels[io] > 0 && (s.channels[io] == nullptr || s.scale[io] == nullptr))) {
+                return fail(BFCUDA_EINVAL, "filter %d: missing channel or scale array", f);
+            }
             for (int i = 0; i < s.n_channels[io]; i++) {
                 if (s.channels[io][i] < 0 || s.channels[io][i] >= c->n_channels[io]) {
                     return fail(BFCUDA_EINVAL, "filter %d: channel index out of range", f);
@@ -945,7 +966,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->ring_fill = 0;
     e->stage_blocks = e->launches = 0;
     e->h_status = nullptr;
-    e->h_overflow = nullptr;
+    e->h_snap[0] = e->h_snap[1] = e->d_snap[0] = e->d_snap[1] = nullptr;
     e->h_overflow_valid = false;
     e->io_waited = 0;
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
@@ -1080,7 +1101,13 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         }
         TRYCU(cudaMallocHost((void **)&e->h_status, sizeof(unsigned int)));
         *e->h_status = 0;
-        TRYCU(cudaMallocHost((void **)&e->h_overflow, sizeof(Overflow) * (size_t)std::max(1, e->n_ch[1])));
+        e->snap_status_off = sizeof(Overflow) * (size_t)std::max(1, e->n_ch[1]);
+        e->snap_bytes = e->snap_status_off + 16;
+        for (int i = 0; i < 2; i++) {
+            TRYCU(cudaMallocHost((void **)&e->h_snap[i], e->snap_bytes));
+            memset(e->h_snap[i], 0, e->snap_bytes);
+            TRY(dev_alloc(e, &e->d_snap[i], e->snap_bytes));
+        }
         const size_t B = (size_t)e->max_batch;
         TRY(dev_alloc(e, &e->d_raw[0], B * e->n_bytes[0]));
         TRY(dev_alloc(e, &e->d_raw[1], B * e->n_bytes[1]));
@@ -1110,8 +1137,13 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         TRY(dev_alloc(e, &e->d_Y, 2 * e->y_stride));
         TRY(dev_alloc(e, &e->d_out_time, rs_bytes(e, B * (size_t)std::max(1, e->n_ch[1]) * L)));
         TRY(dev_alloc(e, &e->d_scratch, rs_bytes(e, 4 * N)));
-        TRY(dev_alloc(e, &e->d_overflow, sizeof(Overflow) * std::max(1, e->n_ch[1])));
-        TRY(dev_alloc(e, &e->d_status, sizeof(unsigned int)));
+        {
+            // the overflow records and the status word share one allocation: one copy snapshots both
+            char *blob = nullptr;
+            TRY(dev_alloc(e, &blob, e->snap_bytes));
+            e->d_overflow = reinterpret_cast<Overflow *>(blob);
+            e->d_status = reinterpret_cast<unsigned int *>(blob + e->snap_status_off);
+        }
         TRY(dev_alloc(e, &e->d_dests, sizeof(FwdDest) * F));
         TRY(dev_alloc(e, &e->d_dest_first, sizeof(int) * (e->n_ch[0] + 1)));
         TRY(dev_alloc(e, &e->d_need_xin, (size_t)std::max(1, e->n_ch[0])));
@@ -1203,7 +1235,7 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
             CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u) & 1u]));
             e->io_waited = e->io_count;
         }
-        of = e->h_overflow[out_channel];
+        of = reinterpret_cast<const Overflow *>(e->h_snap[(e->io_count - 1u) & 1u])[out_channel];
     } else {
         CU(cudaSetDevice(e->device));
         for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
@@ -1219,6 +1251,20 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
 }
 
 // ---- coefficients ------------------------------------------------------------------------------------
+
+// The multiply-accumulate of the most recent launch (s_mac), and in the low-latency schedule the ahead-of-time sum,
+// may still be reading d_H when a run-time coefficient update arrives: order the update (on e->stream) behind them so
+// that a block sees a coefficient set either wholly old or wholly new (bfrun.c:1462-1478 snapshots per block).
+static int wait_coeff_readers(bfcuda_engine *e)
+{
+    if (e->launch_no >= 1) {
+        CU(cudaStreamWaitEvent(e->stream, e->ev_mac_done[(e->launch_no - 1) & 1u], 0));
+    }
+    if (e->low_latency) {
+        CU(cudaStreamWaitEvent(e->stream, e->ev_tail_done, 0));
+    }
+    return 0;
+}
 
 static int check_coeff(bfcuda_engine *e, int coeff, int block)
 {
@@ -1262,6 +1308,11 @@ int bfcuda_coeff_from_taps(bfcuda_engine *e, int coeff, const void *taps, int n_
     memcpy(padded.data(), taps, n * e->rs);
     void *d_taps = nullptr;
     CU(cudaMalloc(&d_taps, padded.size()));
+    rc = wait_coeff_readers(e);
+    if (rc != 0) {
+        cudaFree(d_taps);
+        return rc;
+    }
     cudaError_t err = cudaMemcpyAsync(d_taps, padded.data(), padded.size(), cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) {
         err = launch_coeff_fft(e->plan, d_taps, nb, scale, e->d_H, e->coeff_hbase[coeff], e->stream);
@@ -1281,8 +1332,10 @@ int bfcuda_coeff_runtime_block(bfcuda_engine *e, int coeff, int block, const voi
     int rc = check_coeff(e, coeff, block);
     if (rc != 0) return rc;
     CU(cudaSetDevice(e->device));
-    // convolver_runtime_coeffs2cbuf (fftw_convolver.c:575-596): no scale, no NaN check.  Stream ordered,
-    // so a running engine picks the new block up at a block boundary.
+    // convolver_runtime_coeffs2cbuf (fftw_convolver.c:575-596): no scale, no NaN check.  Ordered behind the
+    // multiply-accumulate in flight, so a running engine picks the new block up at a block boundary.
+    rc = wait_coeff_readers(e);
+    if (rc != 0) return rc;
     CU(cudaMemcpyAsync(e->d_scratch, taps_L, rs_bytes(e, e->L), cudaMemcpyHostToDevice, e->stream));
     CU(launch_coeff_fft(e->plan, e->d_scratch, 1, 1.0, e->d_H, e->coeff_hbase[coeff] + block, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -1295,6 +1348,8 @@ int bfcuda_coeff_set_block(bfcuda_engine *e, int coeff, int block, const void *c
     if (rc != 0) return rc;
     CU(cudaSetDevice(e->device));
     char *dst = (char *)e->d_H + rs_bytes(e, (size_t)(e->coeff_hbase[coeff] + block) * e->N);
+    rc = wait_coeff_readers(e);
+    if (rc != 0) return rc;
     CU(cudaMemcpyAsync(e->d_scratch, cbuf, rs_bytes(e, e->N), cudaMemcpyHostToDevice, e->stream));
     CU(launch_permute(e->plan, e->d_scratch, dst, 1, BLOCKED_TO_PLANAR, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -1823,9 +1878,8 @@ static int enqueue_blocks(bfcuda_engine *e, int n, uint8_t *raw_in, uint8_t *raw
     return 0;
 }
 
-static int check_status(bfcuda_engine *e)
+static int check_status_word(unsigned int st)
 {
-    const unsigned int st = *e->h_status;
     if (st & 1u) {
         return fail(BFCUDA_ENONFINITE, "NaN or Inf values in the output! Bad output.");
     }
@@ -1833,6 +1887,16 @@ static int check_status(bfcuda_engine *e)
         return fail(BFCUDA_ESAFETY, "Safety limit exceeded on output.");
     }
     return 0;
+}
+
+static int check_status(bfcuda_engine *e)       // the device-resident / download path's word
+{
+    return check_status_word(*e->h_status);
+}
+
+static unsigned int snap_status(const bfcuda_engine *e, unsigned int call)
+{
+    return *reinterpret_cast<const unsigned int *>(e->h_snap[call & 1u] + e->snap_status_off);
 }
 
 static int sync_all(bfcuda_engine *e)
@@ -1865,15 +1929,14 @@ int bfcuda_process_blocks_async(bfcuda_engine *e, int n_blocks, const void *raw_
     CU(cudaEventRecord(e->ev_h2d[b], e->s_in));
     int rc = enqueue_blocks(e, n_blocks, d_in, d_out, e->ev_h2d[b], reuse ? e->ev_d2h[b] : nullptr, e->ev_fwd[b]);
     if (rc != 0) return rc;
+    // the peak-meter records and the status word travel with the block (bfrun.c:1929-1936 reads them after every
+    // block): snapshot them behind this call's last kernel, read the snapshot out with the output
+    CU(cudaMemcpyAsync(e->d_snap[b], e->d_overflow, e->snap_bytes, cudaMemcpyDeviceToDevice, e->s_inv));
+    CU(cudaEventRecord(e->ev_inv, e->s_inv));
     CU(cudaStreamWaitEvent(e->s_out, e->ev_inv, 0));
     CU(cudaMemcpyAsync(raw_out, d_out, (size_t)n_blocks * e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_out));
-    CU(cudaMemcpyAsync(e->h_status, e->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, e->s_out));
-    if (e->n_ch[1] > 0) {
-        // the peak-meter records travel with the block (bfrun.c:1929-1936 reads them after every block)
-        CU(cudaMemcpyAsync(e->h_overflow, e->d_overflow, sizeof(Overflow) * (size_t)e->n_ch[1], cudaMemcpyDeviceToHost,
-                           e->s_out));
-        e->h_overflow_valid = true;
-    }
+    CU(cudaMemcpyAsync(e->h_snap[b], e->d_snap[b], e->snap_bytes, cudaMemcpyDeviceToHost, e->s_out));
+    e->h_overflow_valid = e->n_ch[1] > 0;
     CU(cudaEventRecord(e->ev_d2h[b], e->s_out));
     e->io_count++;
     return 0;
@@ -1892,11 +1955,12 @@ int bfcuda_wait_previous(bfcuda_engine *e, int calls_back)
     }
     CU(cudaSetDevice(e->device));
     // the raw blocks are double buffered by call parity; a call's read-out event is re-recorded two calls later
-    CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u - (unsigned int)calls_back) & 1u]));
+    const unsigned int call = e->io_count - 1u - (unsigned int)calls_back;
+    CU(cudaEventSynchronize(e->ev_d2h[call & 1u]));
     if (calls_back == 0) {
         e->io_waited = e->io_count;
     }
-    return check_status(e);
+    return check_status_word(snap_status(e, call));
 }
 
 int bfcuda_synchronize(bfcuda_engine *e)
@@ -1905,6 +1969,10 @@ int bfcuda_synchronize(bfcuda_engine *e)
     CU(cudaSetDevice(e->device));
     int rc = sync_all(e);
     if (rc != 0) return rc;
+    if (e->io_count > 0) {
+        rc = check_status_word(snap_status(e, e->io_count - 1u));
+        if (rc != 0) return rc;
+    }
     return check_status(e);
 }
 
@@ -1990,6 +2058,79 @@ void *bfcuda_host_alloc(size_t n_bytes)
     }
     memset(p, 0, n_bytes);
     return p;
+}
+
+// Page-locked host memory on the NUMA node the device hangs off (sysfs: /sys/bus/pci/devices/<id>/numa_node): with
+// one process per GPU on a two-socket host, buffers that land on the other socket cross the inter-socket link on every
+// copy.  The node is applied as a PREFERRED memory policy around the allocation (set_mempolicy by syscall number: no
+// libnuma in the image); anything that fails leaves the default placement.
+void *bfcuda_host_alloc_near(int device, size_t n_bytes)
+{
+    int node = -1;
+    char busid[32] = "";
+    if (cudaDeviceGetPCIBusId(busid, (int)sizeof(busid), device) == cudaSuccess) {
+        for (char *c = busid; *c; c++) {
+            if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+        }
+        char path[96];
+        snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", busid);
+        FILE *f = fopen(path, "r");
+        if (f != nullptr) {
+            if (fscanf(f, "%d", &node) != 1) node = -1;
+            fclose(f);
+        }
+    } else {
+        cudaGetLastError();
+    }
+    bool bound = false;
+#ifdef SYS_set_mempolicy
+    if (node >= 0 && node < 64) {
+        unsigned long mask = 1ul << node;
+        bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, 65ul) == 0;
+    }
+#endif
+    void *p = bfcuda_host_alloc(n_bytes);
+#ifdef SYS_set_mempolicy
+    if (bound) {
+        syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+    }
+#endif
+    return p;
+}
+
+// Copy-only baseline of the host-buffer path: `reps` rounds of the H2D copy of n_blocks input blocks and the D2H copy of
+// n_blocks output blocks, on the engine's own copy streams, both directions at once as in the pipelined calls, no
+// kernels.  What the bus / the host side can carry for this engine's block sizes -- with every rank calling it at the
+// same time, what the box can carry.  Reports the wall time of the whole exchange (CUDA events) and the two rates.
+int bfcuda_copy_baseline(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out, int reps, double *ms_per_rep,
+                         double *h2d_gbs, double *d2h_gbs)
+{
+    if (e == nullptr || raw_in == nullptr || raw_out == nullptr || reps < 1) return fail(BFCUDA_EINVAL, "bad argument");
+    if (n_blocks < 1 || n_blocks > e->max_batch) return fail(BFCUDA_EINVAL, "n_blocks outside 1..max_batch");
+    CU(cudaSetDevice(e->device));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
+    const size_t bi = (size_t)n_blocks * e->n_bytes[0], bo = (size_t)n_blocks * e->n_bytes[1];
+    cudaEvent_t ev[4];
+    for (cudaEvent_t &x : ev) CU(cudaEventCreate(&x));
+    CU(cudaEventRecord(ev[0], e->s_in));
+    CU(cudaEventRecord(ev[2], e->s_out));
+    for (int r = 0; r < reps; r++) {
+        CU(cudaMemcpyAsync(r & 1 ? e->d_raw2[0] : e->d_raw[0], raw_in, bi, cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaMemcpyAsync(raw_out, r & 1 ? e->d_raw2[1] : e->d_raw[1], bo, cudaMemcpyDeviceToHost, e->s_out));
+    }
+    CU(cudaEventRecord(ev[1], e->s_in));
+    CU(cudaEventRecord(ev[3], e->s_out));
+    CU(cudaEventSynchronize(ev[1]));
+    CU(cudaEventSynchronize(ev[3]));
+    float m_in = 0.f, m_out = 0.f;
+    CU(cudaEventElapsedTime(&m_in, ev[0], ev[1]));
+    CU(cudaEventElapsedTime(&m_out, ev[2], ev[3]));
+    for (cudaEvent_t &x : ev) cudaEventDestroy(x);
+    if (ms_per_rep) *ms_per_rep = (double)std::max(m_in, m_out) / reps;
+    if (h2d_gbs) *h2d_gbs = m_in > 0.f ? (double)bi * reps / (m_in * 1e-3) / 1e9 : 0.0;
+    if (d2h_gbs) *d2h_gbs = m_out > 0.f ? (double)bo * reps / (m_out * 1e-3) / 1e9 : 0.0;
+    return 0;
 }
 
 void bfcuda_host_free(void *p)

@@ -257,12 +257,15 @@ __device__ __forceinline__ void load_frame(const ForwardArgs &a, int item, int t
     }
 }
 
-template <int LOG2M, bool SINGLE, bool TWS>
-__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_forward2(ForwardArgs a, const cpx<float> *__restrict__ tw_global)
+// MINB = 2 ("light"): two blocks per SM -- 64 registers per thread, so no register prefetch of the next frame, and the
+// twiddle tables stay in global memory / L1 (TWS = false) so that two 64 KB data regions fit one SM.  While one block
+// waits at a pass barrier the other one runs.
+template <int LOG2M, bool SINGLE, bool TWS, int MINB>
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_forward2(ForwardArgs a, const cpx<float> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, N = 2 * F::M;
-    constexpr bool PREFETCH = F::NT < 1024;     // 1024 threads leave 64 registers: no room to hold the next frame
+    constexpr bool PREFETCH = F::NT < 1024 && MINB == 1;    // 64 registers per thread: no room to hold the next frame
     extern __shared__ __align__(128) unsigned char smem2[];
     const int tid = threadIdx.x % F::NT, sub = threadIdx.x / F::NT;     // thread of its transform, transform of the block
     cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2) + sub * F::SUB_STRIDE;
@@ -338,14 +341,14 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_forward2(ForwardArgs a,
 // SIMPLE: every output is fed by exactly one filter, the partition sum is not split and no crossfade is pending
 // (the usual block): one scaled spectrum per transform, and the next transform's spectrum is fetched while this
 // one's samples are stored.
-template <int LOG2M, bool SIMPLE, bool TWS>
-__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_inverse2(InverseArgs a, const cpx<float> *__restrict__ tw_global)
+template <int LOG2M, bool SIMPLE, bool TWS, int MINB>
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs a, const cpx<float> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, L = F::M, N = 2 * F::M, NT = F::NT;
     constexpr int RL = F::radix(F::NP - 1);         // radix of the last pass
     constexpr int BPT = 16 / RL, HALF = RL / 2;      // butterflies per thread, valid outputs per butterfly
-    constexpr bool PREFETCH = F::NT < 1024;
+    constexpr bool PREFETCH = F::NT < 1024 && MINB == 1;
     extern __shared__ __align__(128) unsigned char smem2[];
     const int tid = threadIdx.x % NT, sub = threadIdx.x / NT;
     cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2) + sub * F::SUB_STRIDE;
@@ -552,7 +555,7 @@ static cudaError_t persistent_grid(K kernel, int threads, size_t smem, int total
     return cudaSuccess;
 }
 
-template <int LOG2M, bool SINGLE, bool TWS>
+template <int LOG2M, bool SINGLE, bool TWS, int MINB = 1>
 static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
@@ -562,16 +565,16 @@ static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, 
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_forward2<LOG2M, SINGLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_forward2<LOG2M, SINGLE, TWS, MINB>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
     const int total = (a.n_in * a.batch + F::SUBS - 1) / F::SUBS;      // blocks needed: SUBS transforms each
     const int grid = total < resident[dev] ? total : resident[dev];
-    k_forward2<LOG2M, SINGLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    k_forward2<LOG2M, SINGLE, TWS, MINB><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
     return cudaGetLastError();
 }
 
-template <int LOG2M, bool SIMPLE, bool TWS>
+template <int LOG2M, bool SIMPLE, bool TWS, int MINB = 1>
 static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
@@ -581,12 +584,12 @@ static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, 
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_inverse2<LOG2M, SIMPLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_inverse2<LOG2M, SIMPLE, TWS, MINB>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
     const int total = (a.n_out * a.batch + F::SUBS - 1) / F::SUBS;
     const int grid = total < resident[dev] ? total : resident[dev];
-    k_inverse2<LOG2M, SIMPLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    k_inverse2<LOG2M, SIMPLE, TWS, MINB><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
     return cudaGetLastError();
 }
 
@@ -629,9 +632,22 @@ cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t 
     return cudaGetLastError();
 }
 
+static bool fft2_light()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BFCUDA_FFT2_LIGHT");
+        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 cudaError_t launch_forward2(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
+    if (fft2_light() && plan.N == 16384) {
+        return a.single_dest ? launch_forward2_t<13, true, false, 2>(plan, a, s) : launch_forward2_t<13, false, false, 2>(plan, a, s);
+    }
     if (a.single_dest) {
         BF_FFT2_SIZES(launch_forward2_t, true, plan, a, s)
     }
@@ -641,6 +657,9 @@ cudaError_t launch_forward2(const FftPlan &plan, const ForwardArgs &a, cudaStrea
 cudaError_t launch_inverse2(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
+    if (fft2_light() && plan.N == 16384) {
+        return a.simple_mix ? launch_inverse2_t<13, true, false, 2>(plan, a, s) : launch_inverse2_t<13, false, false, 2>(plan, a, s);
+    }
     if (a.simple_mix) {
         BF_FFT2_SIZES(launch_inverse2_t, true, plan, a, s)
     }

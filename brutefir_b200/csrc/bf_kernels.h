@@ -167,6 +167,8 @@ struct MacArgs {
     int head, z_first, z_count;
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
+// bins per thread the batched kernel will use for such a launch (bf_mac_batch.cu)
+int mac_batch_lanes(int realsize, int batch, int n_jobs, int N);
 // With split > 1 the MAC leaves `split` partial sums per output: add them, in order, into partial 0 (the consumers
 // -- inverse stage, chaining evaluation -- then read one complete spectrum per filter).
 cudaError_t launch_split_reduce(const FftPlan &plan, const MacArgs &a, cudaStream_t s);

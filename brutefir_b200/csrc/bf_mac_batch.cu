@@ -212,12 +212,12 @@ struct DcFalse { static constexpr bool value = false; };
 // Threads per block.  (The work is a power of two of identical threads, the machine 148 SMs: 1024 blocks of 256 on 296
 // slots are 3.46 "waves" at the headline shape.  Measured: 64, 128 and 256 threads per block take the same time -- the
 // blocks of the partial last wave run alone on their SMs and correspondingly faster.)
-#ifndef BF_MAC_BATCH_THREADS
-#define BF_MAC_BATCH_THREADS 256
-#endif
-constexpr int MBT = BF_MAC_BATCH_THREADS;
-
-template <typename T, int W, int B, int S, int MINB>
+//
+// Small shards (8 or 16 filters of a 64-filter job per GPU) do not have a power of two of 256-thread blocks to spread:
+// 8 filters x 4096 bin pairs are 128 blocks for 148 SMs.  They run one bin per thread (W = 1: twice the threads, the
+// (re, im)-pair accumulators PairAcc, scalar products cost the FP32 pipe the same cycles as packed ones) in blocks of
+// 64 threads, which deal out evenly (1024 blocks = 6.9 per SM).  mac_batch_lanes() is the one place that decides.
+template <typename T, int W, int B, int S, int MINB, int MBT>
 __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 {
     static_assert(S % B == 0, "the unrolled body must cover whole window rotations");
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
     }
 }
 
-template <typename T, int W, int B, int S, int REGS = 128>
+template <typename T, int W, int B, int S, int REGS = 128, int MBT = 256>
 static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
 {
     constexpr size_t smem = (size_t)S * 4 * MBT * W * sizeof(T);
@@ -407,7 +407,7 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, MINB, MBT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem);
         if (err != cudaSuccess) {
             return err;
@@ -420,27 +420,53 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
     dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split);
     MacArgs args = a;
     args.neg_zero2 = 0x8000000080000000ull;     // (-0.0f, -0.0f): see BinPairAcc
-    k_mac_batch2<T, W, B, S, MINB><<<grid, MBT, smem, s>>>(args, N);
+    k_mac_batch2<T, W, B, S, MINB, MBT><<<grid, MBT, smem, s>>>(args, N);
     return cudaGetLastError();
 }
 
 // Instantiations: (lanes per thread W, batch B, ring stages S).  Larger batches use narrower vectors so that
 // B accumulators + the B-slot window stay within 128 registers (2 blocks of 256 threads per SM).  A batch smaller
 // than B leaves the surplus accumulators unused (their window slots are still read, always inside the ring).
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v != nullptr ? atoi(v) : dflt;
+}
+
+// Bins per thread of the batched kernel for a launch of `n_jobs` jobs over M = N/2 bins: the one table both the
+// launcher and the engine's split heuristic (choose_split, bf_engine.cu) read.
+int mac_batch_lanes(int realsize, int batch, int n_jobs, int N)
+{
+    const long bins = (long)n_jobs * (N / 2);
+    if (realsize == 4) {
+        if (batch <= 4) return 4;
+        static const int narrow_max = env_int("BFCUDA_MAC_NARROW_MAX_BINS", 16 * 8192);
+        if (batch <= 8) return bins <= narrow_max ? 1 : 2;
+        static const int narrow16 = env_int("BFCUDA_MAC_B16_NARROW", 0);
+        return (narrow16 || bins <= narrow_max) ? 1 : 2;
+    }
+    if (batch <= 2) return 2;
+    return 1;
+}
+
 cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
+    const int lanes = mac_batch_lanes(plan.realsize, a.batch, a.n_jobs, plan.N);
     if (plan.realsize == 4) {
         if (a.batch <= 2) return launch_one<float, 4, 2, 4>(a, plan.N, s);
         if (a.batch <= 4) return launch_one<float, 4, 4, 4>(a, plan.N, s);
-        if (a.batch <= 8) return launch_one<float, 2, 8, 8>(a, plan.N, s);
+        if (a.batch <= 8) {
+            return lanes == 1 ? launch_one<float, 1, 8, 8, 96, 64>(a, plan.N, s) : launch_one<float, 2, 8, 8>(a, plan.N, s);
+        }
         if (a.batch <= 16) {
-            static const int narrow = getenv("BFCUDA_MAC_B16_NARROW") ? atoi(getenv("BFCUDA_MAC_B16_NARROW")) : 0;
-            return narrow ? launch_one<float, 1, 16, 16>(a, plan.N, s) : launch_one<float, 2, 16, 16, 256>(a, plan.N, s);
+            return lanes == 1 ? launch_one<float, 1, 16, 16, 128, 64>(a, plan.N, s)
+                              : launch_one<float, 2, 16, 16, 256>(a, plan.N, s);
         }
         return cudaErrorInvalidValue;
     }
     if (a.batch <= 2) return launch_one<double, 2, 2, 4>(a, plan.N, s);
     if (a.batch <= 4) return launch_one<double, 1, 4, 8>(a, plan.N, s);
+    if (a.batch <= 8) return launch_one<double, 1, 8, 8>(a, plan.N, s);
     return cudaErrorInvalidValue;
 }
 

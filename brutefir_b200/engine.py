@@ -20,10 +20,11 @@ from .graph import FilterGraph
 class PinnedBuffer:
     """Page-locked host memory (bfcuda_host_alloc) viewed as a numpy uint8 array."""
 
-    def __init__(self, n_bytes: int):
+    def __init__(self, n_bytes: int, device: Optional[int] = None):
         lib = _abi.load_library()
         self._lib = lib
-        self.ptr = lib.bfcuda_host_alloc(n_bytes)
+        # device given: on the NUMA node that GPU hangs off (one process per GPU on a multi-socket host)
+        self.ptr = lib.bfcuda_host_alloc(n_bytes) if device is None else lib.bfcuda_host_alloc_near(device, n_bytes)
         if not self.ptr:
             raise MemoryError("bfcuda_host_alloc failed")
         self.n_bytes = n_bytes
@@ -172,6 +173,13 @@ class Engine:
         ms = C.c_double()
         check(self.lib.bfcuda_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def copy_baseline(self, raw_in: np.ndarray, raw_out: np.ndarray, n_blocks: int, reps: int):
+        """(ms per round, H2D GB/s, D2H GB/s) of the host-buffer path's copies alone (no kernels)."""
+        ms, a, b = C.c_double(), C.c_double(), C.c_double()
+        check(self.lib.bfcuda_copy_baseline(self.h, n_blocks, raw_in.ctypes.data, raw_out.ctypes.data, reps,
+                                            C.byref(ms), C.byref(a), C.byref(b)))
+        return ms.value, a.value, b.value
 
     def stage_times(self):
         ms = (C.c_double * 3)()

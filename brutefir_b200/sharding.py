@@ -122,11 +122,27 @@ def shard_graph(graph: FilterGraph, n_ranks: int, split_outputs: bool = False, c
     for f, flt in enumerate(graph.filters):
         for o in flt.outputs:
             feeders.setdefault(o, set()).add(owner[f])
+        for k in flt.from_filters:
+            if owner[k] != owner[f]:
+                # the evaluated output of a source filter never leaves its rank (bfrun.c:1603-1660 runs inside one
+                # filter process; bfconf.c:2234-2298 keeps chained filters together)
+                raise ValueError(f"filter {f} is chained to filter {k} on another rank: chained filters cannot be split")
+    # Outputs fed from several ranks, in GLOBAL channel order.  The engine issues one all-reduce per entry, matched
+    # across ranks by position only (bf_engine.cu), so every rank carries every shared output in the same order -- a
+    # rank without a feeder contributes a row of zeros -- and all ranks issue the same sequence of collectives.
+    shared_global = sorted(o for o, r in feeders.items() if len(r) > 1)
+    dithered = graph.apply_dither is not None and any(graph.apply_dither)
+    if dithered and n_ranks > 1:
+        # A channel's offset into the dither table is its index among the dithered channels (dither.c:75-96); a shard
+        # renumbers its channels, so its sequence would differ from the unsharded (and the reference's) one.  And the
+        # error feedback of a shared output would have to run after the cross-rank sum, on one rank.
+        raise ValueError("sharding a graph with dither enabled is not supported (per-channel dither table offsets "
+                         "follow the global channel numbering)")
     shards = []
     for r in range(n_ranks):
         mine = [f for f in range(len(graph.filters)) if owner[f] == r]
         ins = sorted({c for f in mine for c in graph.filters[f].inputs})
-        outs = sorted({c for f in mine for c in graph.filters[f].outputs})
+        outs = sorted({c for f in mine for c in graph.filters[f].outputs} | set(shared_global))
         # every coefficient set stays addressable by its global index at run time (cfc), so keep them all
         coeffs = list(range(len(graph.coeff_n_blocks)))
         imap = {c: i for i, c in enumerate(ins)}
@@ -146,7 +162,9 @@ def shard_graph(graph: FilterGraph, n_ranks: int, split_outputs: bool = False, c
             out_fmts, out_bytes = _compact_layout(out_fmts, graph.filter_length)
         sub = FilterGraph(graph.filter_length, graph.n_blocks, graph.realsize, in_fmts, out_fmts,
                           in_bytes, out_bytes, local, list(graph.coeff_n_blocks),
-                          safety_limit=graph.safety_limit, sampling_rate=graph.sampling_rate)
-        shared = [omap[o] for o in outs if len(feeders[o]) > 1]
+                          safety_limit=graph.safety_limit, sampling_rate=graph.sampling_rate,
+                          apply_dither=None if graph.apply_dither is None else [graph.apply_dither[o] for o in outs],
+                          max_dither_table_size=graph.max_dither_table_size)
+        shared = [omap[o] for o in shared_global]
         shards.append(Shard(r, sub, mine, ins, outs, coeffs, shared))
     return shards

@@ -120,7 +120,7 @@ struct bfcuda_config {
                                    first-order error feedback, dither_funs.h:7-68: a sequential recurrence per channel. */
     int sampling_rate;          /* only sizes the dither table (dither.c:75-96); 0 = 44100 */
     int max_dither_table_size;  /* bfconf->max_dither_table_size, 0 = no limit */
-    int max_batch;              /* 0/1 = block by block (the reference's schedule).  B > 1 (<= 16 at realsize 4, <= 4 at
+    int max_batch;              /* 0/1 = block by block (the reference's schedule).  B > 1 (<= 16 at realsize 4, <= 8 at
                                    realsize 8) lets bfcuda_process_blocks* take up to B consecutive blocks per call:
                                    offline / file-to-file throughput mode.  Results are bit-identical to B single
                                    calls; the I/O delay grows by the batch (not for real-time use). */
@@ -208,7 +208,14 @@ int bfcuda_download_output(bfcuda_engine *engine, void *raw_out);
 int bfcuda_download_outputs(bfcuda_engine *engine, int n_blocks, void *raw_out);
 
 void *bfcuda_host_alloc(size_t n_bytes);    /* page-locked host memory */
+/* the same, placed on the NUMA node the CUDA device `device` is attached to (multi-GPU hosts: one process per GPU) */
+void *bfcuda_host_alloc_near(int device, size_t n_bytes);
 void bfcuda_host_free(void *p);
+/* Copy-only baseline of the host-buffer path (no kernels): `reps` rounds of "n_blocks input blocks host -> device" and
+ * "n_blocks output blocks device -> host" on the engine's copy streams, both directions concurrently.  Measures what
+ * the bus and the host side can carry for this engine's block sizes (bench.py runs it on all ranks at once). */
+int bfcuda_copy_baseline(bfcuda_engine *engine, int n_blocks, const void *raw_in, void *raw_out, int reps,
+                         double *ms_per_rep, double *h2d_gbs, double *d2h_gbs);
 
 /* ---- measurement ----------------------------------------------------------------------------- */
 

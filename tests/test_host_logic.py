@@ -76,6 +76,53 @@ def test_shards_cover_the_graph_once():
     assert [s.shared_outputs for s in split] == [[0, 1], [0, 1]]
 
 
+@pytest.mark.parametrize("n_ranks", [2, 3, 4])
+def test_split_outputs_every_rank_joins_every_collective(oracle_libs, n_ranks):
+    """Outputs whose feeders sit on SOME ranks only: every rank must still list every shared output, in the same
+    (global) order, because the engine matches its all-reduces across ranks by position.  The cross-rank sum is
+    emulated by adding the ranks' float64 outputs (what ncclAllReduce does to the time-domain rows)."""
+    L, P = 32, 3
+    inb, nin = interleaved_layout(4, "FLOAT64_LE", L)
+    outb, nout = interleaved_layout(3, "FLOAT64_LE", L)
+    filters = [Filter([0], [0], coeff=0), Filter([1], [0], coeff=1), Filter([2], [1], coeff=2), Filter([3], [1], coeff=3),
+               Filter([0], [2], coeff=1)]
+    g = FilterGraph(L, P, 8, inb, outb, nin, nout, filters, [P] * 4)
+    taps = configs.synthetic_filters(g, 7)
+    sig = configs.synthetic_signal(g, 7, 6)
+    full = po.BlockDriver("oracle", g)
+    for c, h in enumerate(taps):
+        full.coeff_from_taps(c, h)
+    want = np.stack([unpack_block(b, g.out_formats, L) for b in full.run(sig)])
+    full.close()
+    shards = shard_graph(g, n_ranks, split_outputs=True, compact=True)
+    n_shared = {len(s.shared_outputs) for s in shards}
+    assert len(n_shared) == 1                                       # same number of collectives on every rank
+    for s in shards:
+        assert [s.outputs[o] for o in s.shared_outputs] == [s0 for s0 in shards[0].outputs if s0 in
+                                                            [shards[0].outputs[o] for o in shards[0].shared_outputs]]
+    got = np.zeros_like(want)
+    for s in shards:
+        d = po.BlockDriver("oracle", s.graph)
+        for c, h in enumerate(taps):
+            d.coeff_from_taps(c, h)
+        y = np.stack([unpack_block(b, s.graph.out_formats, L) for b in d.run(s.slice_input(g, sig))])
+        d.close()
+        for i, o in enumerate(s.outputs):
+            got[:, o] += y[:, i]
+    assert np.abs(got - want).max() <= 1e-12 and np.abs(want).max() > 1e-3
+
+
+def test_sharding_refuses_cross_rank_chains_and_dither():
+    chained = configs.config_c1_chained()
+    with pytest.raises(ValueError):
+        shard_graph(chained, 2, split_outputs=True)
+    g = configs.config_c3(n_ch=4, L=64, P=2, fmt="S16_LE")
+    g.apply_dither = [True] * 4
+    with pytest.raises(ValueError):
+        shard_graph(g, 2)
+    assert shard_graph(g, 1)[0].graph.apply_dither == [True] * 4
+
+
 def test_compact_shards_reassemble_to_the_whole_graph(oracle_libs):
     """compact=True: every rank gets an interleaved block of only its channels (one dai device per GPU); slicing
     the input, running each shard and scattering the outputs back must give the unsharded graph's bytes."""
