@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-sharing", action="store_true", help="give every filter its own delay line (A/B for m8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (configs, nccl_xtc, batch-16 series)")
+    ap.add_argument("--quick", action="store_true", help="only the headline measurement (kernel experiments)")
     ap.add_argument("--shard-of", type=int, default=0,
                     help="single process: run rank 0's shard of a K-rank job (profiling a rank's kernels on one GPU)")
     ap.add_argument("--batch", type=int, default=0,
@@ -683,6 +684,13 @@ def main():
     flags = _abi.FLAG_NO_STREAM_SHARING if args.no_sharing else 0
 
     B = args.batch if args.batch >= 1 else 8
+    if args.quick:
+        head = measure(ctx, graph, shard, taps, cid, B, args.steps, args.warmup, False, flags, tag=args.workload, light=True)
+        if rank == 0:
+            print(json.dumps({"quick": summary(head), "stage_ms_per_block": head["roofline"]["stage_ms_per_block"],
+                              "stage_ms_per_block_pipelined": head["roofline"]["stage_ms_per_block_pipelined"]}), flush=True)
+        dist.close()
+        return
     head = measure(ctx, graph, shard, taps, cid, B, args.steps, args.warmup, True, flags, tag=args.workload)
     stream = head if B == 1 else measure(ctx, graph, shard, taps, cid, 1, max(args.steps, 50), args.warmup, False, flags,
                                          tag=args.workload)

@@ -297,7 +297,7 @@ bool_t convolver_init(const char config_filename[], int length, int realsize)
         fprintf(stderr, "Invalid length %d.\n", length);           // fftw_convolver.c:800-803
         return 0;
     }
-    if (!fft_size_supported(2 * length, realsize)) {
+    if (!fft_single_block_supported(2 * length, realsize)) {    // the per-call surface runs one-block transforms only
         fprintf(stderr, "Invalid length %d (single-block FFT supports 4..%d at realsize %d).\n", length,
                 realsize == 4 ? 16384 : 8192, realsize);
         return 0;
@@ -650,7 +650,7 @@ td_conv_t *convolver_td_new(void *coeffs, int n_coeffs)
         return nullptr;                                                     // fftw_convolver.c:707-709
     }
     const int n = 2 * blocklen, rs = g_cv.rs;
-    if (n >= 8 && !fft_size_supported(n, rs)) {
+    if (n >= 8 && !fft_single_block_supported(n, rs)) {
         cv_fail("bfcuda convolver: convolver_td_new: %d coefficients need a %d-point transform, above the single-block "
                 "limit", n_coeffs, n);
         return nullptr;

@@ -134,6 +134,25 @@ struct FilterState {
 
 #define TIMING_RING 64
 
+// One captured step graph (graph_tick): the stages of THREE consecutive launches side by side -- forward(k), MAC(k-1),
+// inverse(k-2) -- as independent branches of one CUDA graph.  `mask` says which stages it holds (4 forward, 2 MAC,
+// 1 inverse; partial masks fill and drain the pipeline), `par` = k & 1 fixes every double-buffered operand.
+struct StepGraph {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    cudaGraphNode_t n_fwd, n_mac;           // the two kernels whose arguments carry the ring slot
+    cudaKernelNodeParams p_fwd, p_mac;      // as captured (their kernelParams point into `graph`)
+    int n_kernels;
+};
+// a launch whose later stages have not been enqueued yet
+struct PendingStage {
+    bool valid;
+    unsigned int step;          // launch number of the step
+    int slot_t;                 // ring slot of its first block
+    void *host_out;             // host-buffer call: where its output goes (null: device-resident call)
+    unsigned int call;          // ... and which call that was (io_count at the time)
+};
+
 struct bfcuda_engine {
     int L, P, N, rs;
     int max_batch, fdl_ring;    // blocks per launch at most; delay-line slots per stream (see bfcuda_create)
@@ -160,7 +179,19 @@ struct bfcuda_engine {
     // delay-line ring has a launch of slack); the MAC is the HBM-bound stage, the other two fill its gaps and tail.
     // `s_in` / `s_out` carry the host<->device copies of the streaming interface (double-buffered raw blocks).
     cudaStream_t stream, s_mac, s_inv, s_in, s_out;
-    cudaEvent_t ev_h2d[2], ev_fwd[2], ev_d2h[2], ev_inv;
+    cudaEvent_t ev_h2d[2], ev_fwd[2], ev_inv;
+    cudaEvent_t ev_call_done[4];    // output (and overflow snapshot) of host-buffer call c complete in host memory: [c & 3]
+    // Step graphs (launch-bound shapes, small shards): see graph_tick
+    bool graph_enabled;             // not BFCUDA_FLAG_NO_GRAPH
+    bool graph_mode;                // the most recent launch went through graph_tick
+    bool graph_host;                // ... of a host-buffer call (else device-resident)
+    bool graph_used;
+    PendingStage pend_mac, pend_inv;
+    StepGraph sg[2][8][4];          // [host-buffer call][stage mask][k & 3] (k & 1 for device-resident calls)
+    cudaEvent_t ev_cap[4];          // fork / join inside a capture
+    cudaEvent_t ev_g_done[4];       // end of the graph of tick k, [k & 3]
+    cudaEvent_t ev_out_read[4];     // last device -> host read of raw output buffer q (graph mode)
+    cudaEvent_t ev_h2dq[4];         // input copy of tick k complete, [k & 3]
     cudaEvent_t ev_fwd_done[2], ev_mac_done[2], ev_inv_done[2], ev_join;  // per launch parity
     // BFCUDA_FLAG_LOW_LATENCY: the sum over partitions 1 .. P-1 of the next block, computed ahead (enqueue_batch)
     bool low_latency;
@@ -172,6 +203,7 @@ struct bfcuda_engine {
     FftPlan plan;
     uint8_t *d_raw[2];          // raw blocks of the device-resident interface (and buffer 0 of the streaming one)
     uint8_t *d_raw2[2];         // second buffers of the streaming interface
+    uint8_t *d_raw34[2][2];     // third and fourth: the step graphs keep four host-buffer calls in flight
     SampleFormat *d_fmt[2];
     void *d_prev[2], *d_fdl, *d_xin, *d_H, *d_Y, *d_out_time, *d_scratch;
     void *d_xt[2];              // size-specialised path: unpacked input blocks [max_batch][n_in][L], two generations
@@ -183,8 +215,8 @@ struct bfcuda_engine {
     // Host-buffer calls: the overflow records [n_out] and the status word as of the END of call k are snapshotted on
     // the device behind its last kernel (s_inv) and read out with its output block, double buffered by call parity --
     // call k+1's inverse stage may already be updating d_overflow / d_status while call k's read-out runs.
-    char *d_snap[2];
-    char *h_snap[2];            // pinned
+    char *d_snap[4];            // by call & 3
+    char *h_snap[4];            // pinned
     size_t snap_bytes, snap_status_off;
     bool h_overflow_valid;      // false until such a call has been made (and after a reset / a device-resident call)
     unsigned int io_waited;     // value of io_count when the host last waited for the most recent call's read-out
@@ -388,6 +420,13 @@ static int update_streams(bfcuda_engine *e)
 
 // Rebuild every per-block table from the control snapshot: the analogue of bfrun.c:1460-1484 plus the
 // scale / slot / coefficient bookkeeping spread over bfrun.c:1566-1600, 1663-1675, 1726-1777, 1847-1854.
+static void invalidate_graphs(bfcuda_engine *e);
+extern "C" {
+static int sync_all(bfcuda_engine *e);      // drains the step-graph pipeline, then waits for every stream
+static int wait_call(bfcuda_engine *e, unsigned int call);
+static int graph_drain(bfcuda_engine *e);
+}
+
 static void build_tables(bfcuda_engine *e)
 {
     const int F = e->n_filters;
@@ -607,6 +646,7 @@ static void build_tables(bfcuda_engine *e)
         e->simple_mix = e->simple_mix && e->h_chans[o].n == 1;
     }
     e->dirty = false;
+    invalidate_graphs(e);       // job counts and kernel variants are baked into the captured launches
 }
 
 template <typename T>
@@ -755,6 +795,20 @@ static int setup_dither(bfcuda_engine *e, const struct bfcuda_config *c)
 // C ABI
 // ======================================================================================================
 
+static void invalidate_graphs(bfcuda_engine *e)
+{
+    for (int h = 0; h < 2; h++) {
+        for (int m = 0; m < 8; m++) {
+            for (int p = 0; p < 4; p++) {
+                StepGraph &g = e->sg[h][m][p];
+                if (g.exec != nullptr) cudaGraphExecDestroy(g.exec);
+                if (g.graph != nullptr) cudaGraphDestroy(g.graph);
+                memset(&g, 0, sizeof(g));
+            }
+        }
+    }
+}
+
 extern "C" {
 
 const char *bfcuda_strerror(void)
@@ -784,7 +838,7 @@ void bfcuda_destroy(bfcuda_engine *e)
     if (e->comm != nullptr && g_nccl.handle != nullptr) {
         g_nccl.CommDestroy(e->comm);
     }
-    void *ptrs[] = { e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
+    void *ptrs[] = { e->d_raw34[0][0], e->d_raw34[0][1], e->d_raw34[1][0], e->d_raw34[1][1], e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
                      e->d_keep, e->d_eval_entries, e->d_eval_terms, e->d_mixes, e->dither.chans, (void *)e->dither.randtab,
@@ -800,10 +854,11 @@ void bfcuda_destroy(bfcuda_engine *e)
         }
     }
     if (e->h_status) cudaFreeHost(e->h_status);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 4; i++) {
         if (e->h_snap[i]) cudaFreeHost(e->h_snap[i]);
         if (e->d_snap[i]) cudaFree(e->d_snap[i]);
     }
+    invalidate_graphs(e);
     fft_plan_destroy(&e->plan);
     for (int i = 0; i < 2; i++) {
         if (e->timer[i]) cudaEventDestroy(e->timer[i]);
@@ -813,8 +868,11 @@ void bfcuda_destroy(bfcuda_engine *e)
             if (e->ring[i][j]) cudaEventDestroy(e->ring[i][j]);
         }
     }
-    for (cudaEvent_t ev : { e->ev_h2d[0], e->ev_h2d[1], e->ev_fwd[0], e->ev_fwd[1], e->ev_d2h[0], e->ev_d2h[1],
-                            e->ev_inv, e->ev_fwd_done[0], e->ev_fwd_done[1], e->ev_mac_done[0],
+    for (cudaEvent_t ev : { e->ev_h2d[0], e->ev_h2d[1], e->ev_fwd[0], e->ev_fwd[1], e->ev_call_done[0], e->ev_call_done[1],
+                            e->ev_call_done[2], e->ev_call_done[3], e->ev_cap[0], e->ev_cap[1], e->ev_cap[2], e->ev_cap[3],
+                            e->ev_g_done[0], e->ev_g_done[1], e->ev_g_done[2], e->ev_g_done[3], e->ev_out_read[0],
+                            e->ev_out_read[1], e->ev_out_read[2], e->ev_out_read[3], e->ev_h2dq[0], e->ev_h2dq[1],
+                            e->ev_h2dq[2], e->ev_h2dq[3], e->ev_inv, e->ev_fwd_done[0], e->ev_fwd_done[1], e->ev_mac_done[0],
                             e->ev_mac_done[1], e->ev_inv_done[0], e->ev_inv_done[1], e->ev_join, e->ev_tail_done }) {
         if (ev) cudaEventDestroy(ev);
     }
@@ -848,8 +906,16 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         return fail(BFCUDA_EINVAL, "channel or filter count out of range");
     }
     if (!fft_size_supported(2 * c->filter_length, c->realsize)) {
-        return fail(BFCUDA_ENOTSUP, "filter_length %d at realsize %d exceeds the single-block FFT (max %d)",
-                    c->filter_length, c->realsize, c->realsize == 4 ? 16384 : 8192);
+        return fail(BFCUDA_ENOTSUP, "filter_length %d at realsize %d is beyond the four-step transform (max %d)",
+                    c->filter_length, c->realsize, 1 << 22);
+    }
+    if (!fft_single_block_supported(2 * c->filter_length, c->realsize)) {
+        for (int f = 0; f < c->n_filters; f++) {
+            if (c->filters[f].n_filters_in > 0) {
+                return fail(BFCUDA_ENOTSUP, "filter -> filter chaining needs partitions of at most %d samples",
+                            c->realsize == 4 ? 16384 : 8192);
+            }
+        }
     }
     for (int io = 0; io < 2; io++) {
         if (c->n_bytes[io] < 0 || (c->n_channels[io] > 0 && c->formats[io] == nullptr)) {
@@ -956,7 +1022,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->tail_ready = false;
     e->launch_no = 0;
     e->y_stride = 0;
-    e->ev_h2d[0] = e->ev_h2d[1] = e->ev_fwd[0] = e->ev_fwd[1] = e->ev_d2h[0] = e->ev_d2h[1] = nullptr;
+    e->ev_h2d[0] = e->ev_h2d[1] = e->ev_fwd[0] = e->ev_fwd[1] = nullptr;
     e->ev_inv = nullptr;
     e->io_count = 0;
     e->comm = nullptr;
@@ -966,7 +1032,18 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->ring_fill = 0;
     e->stage_blocks = e->launches = 0;
     e->h_status = nullptr;
-    e->h_snap[0] = e->h_snap[1] = e->d_snap[0] = e->d_snap[1] = nullptr;
+    for (int i = 0; i < 4; i++) {
+        e->h_snap[i] = e->d_snap[i] = nullptr;
+        e->ev_call_done[i] = e->ev_cap[i] = nullptr;
+    }
+    for (int i = 0; i < 4; i++) {
+        e->ev_g_done[i] = e->ev_out_read[i] = e->ev_h2dq[i] = nullptr;
+    }
+    e->d_raw34[0][0] = e->d_raw34[0][1] = e->d_raw34[1][0] = e->d_raw34[1][1] = nullptr;
+    memset(e->sg, 0, sizeof(e->sg));
+    e->graph_enabled = !(c->flags & BFCUDA_FLAG_NO_GRAPH) && getenv("BFCUDA_NO_GRAPH") == nullptr;
+    e->graph_mode = e->graph_host = e->graph_used = false;
+    e->pend_mac.valid = e->pend_inv.valid = false;
     e->h_overflow_valid = false;
     e->io_waited = 0;
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
@@ -1083,13 +1160,17 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         }
         TRYCU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
         TRYCU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
-        for (cudaEvent_t *ev : { &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_fwd[0], &e->ev_fwd[1], &e->ev_d2h[0],
-                                 &e->ev_d2h[1], &e->ev_inv, &e->ev_fwd_done[0], &e->ev_fwd_done[1],
+        for (cudaEvent_t *ev : { &e->ev_h2d[0], &e->ev_h2d[1], &e->ev_fwd[0], &e->ev_fwd[1], &e->ev_call_done[0],
+                                 &e->ev_call_done[1], &e->ev_call_done[2], &e->ev_call_done[3], &e->ev_cap[0],
+                                 &e->ev_cap[1], &e->ev_cap[2], &e->ev_cap[3], &e->ev_g_done[0], &e->ev_g_done[1],
+                                 &e->ev_g_done[2], &e->ev_g_done[3], &e->ev_out_read[0], &e->ev_out_read[1],
+                                 &e->ev_out_read[2], &e->ev_out_read[3], &e->ev_h2dq[0], &e->ev_h2dq[1], &e->ev_h2dq[2],
+                                 &e->ev_h2dq[3], &e->ev_inv, &e->ev_fwd_done[0], &e->ev_fwd_done[1],
                                  &e->ev_mac_done[0], &e->ev_mac_done[1], &e->ev_inv_done[0], &e->ev_inv_done[1],
                                  &e->ev_join, &e->ev_tail_done }) {
             TRYCU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         }
-        TRYCU(fft_plan_create(&e->plan, e->N, e->rs));
+        TRYCU(fft_plan_create(&e->plan, e->N, e->rs, e->max_batch * std::max(1, std::max(e->n_ch[0], e->n_ch[1]))));
         TRYCU(cudaEventCreate(&e->timer[0]));
         TRYCU(cudaEventCreate(&e->timer[1]));
         if (e->flags & BFCUDA_FLAG_STAGE_TIMING) {
@@ -1103,7 +1184,7 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         *e->h_status = 0;
         e->snap_status_off = sizeof(Overflow) * (size_t)std::max(1, e->n_ch[1]);
         e->snap_bytes = e->snap_status_off + 16;
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 4; i++) {
             TRYCU(cudaMallocHost((void **)&e->h_snap[i], e->snap_bytes));
             memset(e->h_snap[i], 0, e->snap_bytes);
             TRY(dev_alloc(e, &e->d_snap[i], e->snap_bytes));
@@ -1113,11 +1194,15 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         TRY(dev_alloc(e, &e->d_raw[1], B * e->n_bytes[1]));
         TRY(dev_alloc(e, &e->d_raw2[0], B * e->n_bytes[0]));
         TRY(dev_alloc(e, &e->d_raw2[1], B * e->n_bytes[1]));
+        for (int io = 0; io < 2; io++) {
+            TRY(dev_alloc(e, &e->d_raw34[io][0], B * e->n_bytes[io]));
+            TRY(dev_alloc(e, &e->d_raw34[io][1], B * e->n_bytes[io]));
+        }
         TRY(dev_alloc(e, &e->d_fmt[0], sizeof(SampleFormat) * std::max(1, e->n_ch[0])));
         TRY(dev_alloc(e, &e->d_fmt[1], sizeof(SampleFormat) * std::max(1, e->n_ch[1])));
         TRY(dev_alloc(e, &e->d_prev[0], rs_bytes(e, (size_t)e->n_ch[0] * L)));
         TRY(dev_alloc(e, &e->d_prev[1], rs_bytes(e, (size_t)e->n_ch[0] * L)));
-        if (e->plan.tw2 != nullptr) {
+        if (plan_unpacks_first(e->plan)) {
             TRY(dev_alloc(e, &e->d_xt[0], rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * L)));
             TRY(dev_alloc(e, &e->d_xt[1], rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * L)));
         }
@@ -1210,8 +1295,9 @@ int bfcuda_reset_overflow(bfcuda_engine *e)
             of[n].max = (double)((uint64_t)1 << ((e->fmt[1][n].sf.sbytes << 3) - 1)) - 1;
         }
     }
-    for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
-        CU(cudaStreamSynchronize(st));
+    if (e->stream != nullptr) {
+        int rc = sync_all(e);
+        if (rc != 0) return rc;
     }
     if (!of.empty()) {
         CU(cudaMemcpy(e->d_overflow, of.data(), sizeof(Overflow) * of.size(), cudaMemcpyHostToDevice));
@@ -1232,15 +1318,15 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
         // call not even that (the per-output peak-meter loop of bfrun.c:1929-1936 costs nothing)
         if (e->io_waited != e->io_count) {
             CU(cudaSetDevice(e->device));
-            CU(cudaEventSynchronize(e->ev_d2h[(e->io_count - 1u) & 1u]));
+            int rc = wait_call(e, e->io_count - 1u);
+            if (rc != 0) return rc;
             e->io_waited = e->io_count;
         }
-        of = reinterpret_cast<const Overflow *>(e->h_snap[(e->io_count - 1u) & 1u])[out_channel];
+        of = reinterpret_cast<const Overflow *>(e->h_snap[(e->io_count - 1u) & 3u])[out_channel];
     } else {
         CU(cudaSetDevice(e->device));
-        for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
-            CU(cudaStreamSynchronize(st));
-        }
+        int rc = sync_all(e);
+        if (rc != 0) return rc;
         CU(cudaMemcpy(&of, e->d_overflow + out_channel, sizeof(of), cudaMemcpyDeviceToHost));
     }
     overflow->n_overflows = of.n_overflows;
@@ -1440,6 +1526,100 @@ static int flush_timing_ring(bfcuda_engine *e)
     return 0;
 }
 
+// ---- kernel argument blocks of one launch (shared by enqueue_batch and the step graphs) --------------------------
+static ForwardArgs make_forward_args(const bfcuda_engine *e, int nb, int slot_t, const uint8_t *raw_in)
+{
+    ForwardArgs fa;
+    fa.raw_in = raw_in;
+    fa.fmt = e->d_fmt[0];
+    fa.prev_in = e->d_prev[e->prev_par];
+    fa.prev_out = e->d_prev[e->prev_par ^ 1];
+    fa.fdl = e->d_fdl;
+    fa.xin = e->d_xin;
+    fa.need_xin = e->d_need_xin;
+    fa.dest_first = e->d_dest_first;
+    fa.dests = e->d_dests;
+    fa.n_in = e->n_ch[0];
+    fa.n_vin = e->n_vin;
+    fa.ring = e->fdl_ring;
+    fa.t = slot_t;
+    fa.batch = nb;
+    fa.in_stride = (size_t)e->n_bytes[0];
+    fa.fast_fmt = e->fast_fmt[0];
+    fa.xt_cur = fa.xt_prev = nullptr;
+    fa.single_dest = e->single_dest ? 1 : 0;
+    return fa;
+}
+
+static UnpackArgs make_unpack_args(const bfcuda_engine *e, int nb, const uint8_t *raw_in, int xt_gen)
+{
+    UnpackArgs ua;
+    ua.raw_in = raw_in;
+    ua.fmt = e->d_fmt[0];
+    ua.xt = e->d_xt[xt_gen];
+    ua.n_in = e->n_ch[0];
+    ua.batch = nb;
+    ua.L = e->L;
+    ua.in_stride = (size_t)e->n_bytes[0];
+    ua.fast_fmt = e->fast_fmt[0];
+    return ua;
+}
+
+static MacArgs make_mac_args(const bfcuda_engine *e, int nb, int slot_t, int y_gen)
+{
+    MacArgs ma;
+    ma.fdl = e->d_fdl;
+    ma.H = e->d_H;
+    ma.Y = (char *)e->d_Y + (size_t)y_gen * e->y_stride;
+    ma.jobs = e->d_jobs;
+    ma.n_jobs = e->level_job_first[1];
+    ma.n_slots = 2 * std::max(1, e->n_filters) + 2 * e->n_ch[1];
+    ma.ring = e->fdl_ring;
+    ma.split = e->split;
+    ma.t = slot_t;
+    ma.batch = nb;
+    ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
+    ma.head = ma.z_first = ma.z_count = 0;
+    ma.neg_zero2 = 0x8000000080000000ull;   // two packed -0.0f (bf_mac_batch.cu, BinPairAcc): the launcher sets the same
+    return ma;
+}
+
+static InverseArgs make_inverse_args(const bfcuda_engine *e, int nb, int y_gen, uint8_t *raw_out)
+{
+    InverseArgs ia;
+    ia.Y = (char *)e->d_Y + (size_t)y_gen * e->y_stride;
+    ia.chans = e->d_chans;
+    ia.terms = e->d_out_terms;
+    ia.out_time = e->d_out_time;
+    ia.raw_out = raw_out;
+    ia.fmt = e->d_fmt[1];
+    ia.overflow = e->d_overflow;
+    ia.status = e->d_status;
+    ia.n_out = e->n_ch[1];
+    ia.n_slots = 2 * std::max(1, e->n_filters) + 2 * e->n_ch[1];
+    ia.split = 1;               // already reduced (launch_split_reduce)
+    ia.batch = nb;
+    ia.out_stride = (size_t)e->n_bytes[1];
+    ia.safety_limit = e->safety_limit;
+    ia.fast_fmt = e->fast_fmt[1];
+    ia.simple_mix = e->simple_mix ? 1 : 0;
+    ia.any_xfade = e->xfade_active ? 1 : 0;
+    return ia;
+}
+
+static OutMixArgs make_out_mix_args(const bfcuda_engine *e, int nb, const InverseArgs &ia)
+{
+    OutMixArgs oa;
+    oa.Y = const_cast<void *>(ia.Y);
+    oa.mixes = e->d_mixes;
+    oa.terms = e->d_out_terms;
+    oa.n_out = e->n_ch[1];
+    oa.n_slots = ia.n_slots;
+    oa.z_first = 2 * std::max(1, e->n_filters);
+    oa.batch = nb;
+    return oa;
+}
+
 // Enqueue the kernels of `nb` consecutive blocks as ONE launch per stage (nb <= max_batch; callers make sure
 // no control change or crossfade falls inside): unpack + forward on the main stream, MAC on s_mac, inverse + pack on
 // s_inv, ordered by per-parity events (launch n: p = n & 1):
@@ -1485,37 +1665,11 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     }
     if (timing) CU(cudaEventRecord(ev[0], e->stream));
 
-    ForwardArgs fa;
-    fa.raw_in = raw_in;
-    fa.fmt = e->d_fmt[0];
-    fa.prev_in = e->d_prev[e->prev_par];
-    fa.prev_out = e->d_prev[e->prev_par ^ 1];
-    fa.fdl = e->d_fdl;
-    fa.xin = e->d_xin;
-    fa.need_xin = e->d_need_xin;
-    fa.dest_first = e->d_dest_first;
-    fa.dests = e->d_dests;
-    fa.n_in = e->n_ch[0];
-    fa.n_vin = e->n_vin;
-    fa.ring = e->fdl_ring;
-    fa.t = e->slot_t;
-    fa.batch = nb;
-    fa.in_stride = (size_t)e->n_bytes[0];
-    fa.fast_fmt = e->fast_fmt[0];
-    fa.xt_cur = fa.xt_prev = nullptr;
-    fa.single_dest = e->single_dest ? 1 : 0;
-    if (e->plan.tw2 != nullptr) {
-        // size-specialised path: unpack the raw blocks into planar reals first (raw2real), transforms read those
+    ForwardArgs fa = make_forward_args(e, nb, e->slot_t, raw_in);
+    if (plan_unpacks_first(e->plan)) {
+        // size-specialised / four-step path: unpack the raw blocks into planar reals first (raw2real), transforms read those
         e->xt_par ^= 1;
-        UnpackArgs ua;
-        ua.raw_in = raw_in;
-        ua.fmt = e->d_fmt[0];
-        ua.xt = e->d_xt[e->xt_par];
-        ua.n_in = e->n_ch[0];
-        ua.batch = nb;
-        ua.L = e->L;
-        ua.in_stride = (size_t)e->n_bytes[0];
-        ua.fast_fmt = e->fast_fmt[0];
+        UnpackArgs ua = make_unpack_args(e, nb, raw_in, e->xt_par);
         CU(launch_unpack(e->plan, ua, e->stream));
         e->launches += e->n_ch[0] > 0;
         fa.xt_cur = e->d_xt[e->xt_par];
@@ -1558,19 +1712,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     }
     if (timing) CU(cudaEventRecord(ev[2], e->s_mac));
 
-    MacArgs ma;
-    ma.fdl = e->d_fdl;
-    ma.H = e->d_H;
-    ma.Y = (char *)e->d_Y + (size_t)par * e->y_stride;
-    ma.jobs = e->d_jobs;
-    ma.n_jobs = e->level_job_first[1];
-    ma.n_slots = 2 * std::max(1, e->n_filters) + 2 * e->n_ch[1];
-    ma.ring = e->fdl_ring;
-    ma.split = e->split;
-    ma.t = e->slot_t;
-    ma.batch = nb;
-    ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
-    ma.head = ma.z_first = ma.z_count = 0;
+    MacArgs ma = make_mac_args(e, nb, e->slot_t, par);
     const bool ll = e->low_latency && nb == 1;
     if (ll) {
         ma.head = 1;
@@ -1625,39 +1767,15 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     }
     if (timing) CU(cudaEventRecord(ev[4], e->s_inv));
 
-    InverseArgs ia;
-    ia.Y = ma.Y;
-    ia.chans = e->d_chans;
-    ia.terms = e->d_out_terms;
-    ia.out_time = e->d_out_time;
-    ia.raw_out = raw_out;
-    ia.fmt = e->d_fmt[1];
-    ia.overflow = e->d_overflow;
-    ia.status = e->d_status;
-    ia.n_out = e->n_ch[1];
-    ia.n_slots = ma.n_slots;
-    ia.split = 1;               // already reduced (launch_split_reduce)
-    ia.batch = nb;
-    ia.out_stride = (size_t)e->n_bytes[1];
-    ia.safety_limit = e->safety_limit;
-    ia.fast_fmt = e->fast_fmt[1];
-    ia.simple_mix = e->simple_mix ? 1 : 0;
-    ia.any_xfade = e->xfade_active ? 1 : 0;
+    InverseArgs ia = make_inverse_args(e, nb, par, raw_out);
     if (e->any_out_mix) {
-        OutMixArgs oa;
-        oa.Y = ma.Y;
-        oa.mixes = e->d_mixes;
-        oa.terms = e->d_out_terms;
-        oa.n_out = e->n_ch[1];
-        oa.n_slots = ma.n_slots;
-        oa.z_first = 2 * std::max(1, e->n_filters);
-        oa.batch = nb;
+        OutMixArgs oa = make_out_mix_args(e, nb, ia);
         CU(launch_out_mix(e->plan, oa, e->s_inv));
         e->launches++;
     }
     CU(launch_inverse(e->plan, ia, e->s_inv));
     e->launches += e->n_ch[1] > 0;
-    const bool pack_all = e->plan.tw2 != nullptr;   // size-specialised path: real2raw is a kernel of its own
+    const bool pack_all = plan_unpacks_first(e->plan);   // size-specialised / four-step path: real2raw is a kernel of its own
     if (!e->shared_out.empty() || pack_all) {
         // outputs fed from several ranks: sum the L valid time-domain samples over NVLink, then quantise
         // (after the inverse FFT, before real2raw)
@@ -1896,11 +2014,282 @@ static int check_status(bfcuda_engine *e)       // the device-resident / downloa
 
 static unsigned int snap_status(const bfcuda_engine *e, unsigned int call)
 {
-    return *reinterpret_cast<const unsigned int *>(e->h_snap[call & 1u] + e->snap_status_off);
+    return *reinterpret_cast<const unsigned int *>(e->h_snap[call & 3u] + e->snap_status_off);
+}
+
+// ======================================================================================================
+// Step graphs
+//
+// A step of a small shard or a short partition is a handful of kernels of a few microseconds each: what bounds it is
+// the host's enqueue cost (five launches plus a dozen event operations on three streams) and, inside the GPU, the gaps
+// between dependent launches.  For calls that need no synchronous answer (the asynchronous and device-resident entry
+// points) the engine therefore runs a SKEWED pipeline as ONE graph launch per call: tick k runs forward(k), MAC(k-1)
+// and inverse(k-2) as three independent branches of a captured CUDA graph -- the same overlap the three stage streams
+// give, without the events, and one cudaGraphLaunch instead of ~15 API calls.  The ring slot is the only per-launch
+// quantity: it travels through cudaGraphExecKernelNodeSetParams on the two kernels that use it.  Output k arrives with
+// tick k+2; everything that needs a complete state (synchronize, wait_previous, a control change, the synchronous
+// call) drains the pipeline with the partial-mask graphs.  Anything the plain case does not cover -- pending control
+// changes, crossfades, delay transitions, chained filters, the cross-rank sum, dither, stage timing -- takes the
+// stream path (enqueue_blocks) after a drain.
+// ======================================================================================================
+
+// Where the step graphs pay: the stream path costs the host ~30 us per step (five launches and a dozen event
+// operations) and leaves ~1 us bubbles between dependent kernels, which only matters when the step's GPU time is in
+// that range.  Measured (profiles/r2_graph_ab.txt): 2 x 64 K taps 27 -> 11 us per block, 32 x 256 K taps 34 -> 28 us,
+// but an 8-filter shard of the headline job (45 us of MAC per step) is 7 % faster on the streams, whose stages flow
+// from step to step without the join at the end of every graph.  Automatic rule: graphs when the step's MAC traffic
+// is below what HBM moves in ~21 us.  BFCUDA_GRAPH=0 / 1 forces it.
+static bool graph_preferred(const bfcuda_engine *e)
+{
+    static const char *env = getenv("BFCUDA_GRAPH");
+    if (env != nullptr) {
+        return atoi(env) != 0;
+    }
+    const size_t bytes = e->max_batch > 1 ? e->mac_bytes_batch : e->mac_bytes;
+    return bytes <= (size_t)136500000;
+}
+
+static bool graph_eligible(const bfcuda_engine *e, int n_blocks)
+{
+    return e->graph_enabled && graph_preferred(e) && e->plan.tw2 != nullptr && e->n_levels == 1 && n_blocks == e->max_batch && !e->dirty &&
+           !e->xfade_active && !in_transition(e) && !e->low_latency && e->comm == nullptr && e->shared_out.empty() &&
+           e->dither.n_dither == 0 && !(e->flags & (BFCUDA_FLAG_STAGE_TIMING | BFCUDA_FLAG_SERIAL_STAGES)) &&
+           e->single_dest && e->launch_no >= 2 && e->mac_variant == 0 && e->n_ch[0] > 0 && e->n_ch[1] > 0 &&
+           e->level_job_first[1] > 0 && !(e->merge_check_at >= 0 && (long)e->t >= e->merge_check_at);
+}
+
+// every stream waits for everything enqueued so far on every other one (device side only): taken when the engine
+// switches between the stream path and the graph path, whose bookkeeping of buffer reuse differs
+static int join_streams(bfcuda_engine *e)
+{
+    cudaStream_t all[5] = { e->stream, e->s_mac, e->s_inv, e->s_in, e->s_out };
+    for (int i = 0; i < 5; i++) {
+        CU(cudaEventRecord(e->ev_join, all[i]));
+        for (int j = 0; j < 5; j++) {
+            if (j != i) CU(cudaStreamWaitEvent(all[j], e->ev_join, 0));
+        }
+    }
+    return 0;
+}
+
+static uint8_t *raw_queue(const bfcuda_engine *e, int io, int q)
+{
+    return q == 0 ? e->d_raw[io] : (q == 1 ? e->d_raw2[io] : e->d_raw34[io][q - 2]);
+}
+
+static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const UnpackArgs &ua, const ForwardArgs &fa,
+                              const MacArgs &ma, const InverseArgs &ia)
+{
+    const void *f_fwd = nullptr, *f_mac = nullptr;
+    const int nb = e->max_batch;
+    CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (err == cudaSuccess) err = r; return err == cudaSuccess; };
+    ok(cudaEventRecord(e->ev_cap[0], e->stream));
+    if (mask & 4) {
+        if (ok(launch_unpack(e->plan, ua, e->stream)) && ok(launch_forward(e->plan, fa, e->stream))) {
+            f_fwd = g_last_func;
+        }
+    }
+    if (mask & 2) {
+        ok(cudaStreamWaitEvent(e->s_mac, e->ev_cap[0], 0));
+        if (ok(launch_mac(e->plan, ma, e->s_mac))) {
+            f_mac = g_last_func;
+        }
+        if (e->split > 1) ok(launch_split_reduce(e->plan, ma, e->s_mac));
+        ok(cudaEventRecord(e->ev_cap[1], e->s_mac));
+        ok(cudaStreamWaitEvent(e->stream, e->ev_cap[1], 0));
+    }
+    if (mask & 1) {
+        ok(cudaStreamWaitEvent(e->s_inv, e->ev_cap[0], 0));
+        if (e->any_out_mix) ok(launch_out_mix(e->plan, make_out_mix_args(e, nb, ia), e->s_inv));
+        ok(launch_inverse(e->plan, ia, e->s_inv));
+        ok(launch_pack(e->plan, ia, e->s_inv));
+        ok(cudaEventRecord(e->ev_cap[2], e->s_inv));
+        ok(cudaStreamWaitEvent(e->stream, e->ev_cap[2], 0));
+    }
+    cudaGraph_t graph = nullptr;
+    cudaError_t end = cudaStreamEndCapture(e->stream, &graph);
+    if (err != cudaSuccess || end != cudaSuccess || graph == nullptr) {
+        if (graph != nullptr) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return fail(BFCUDA_ECUDA, "step graph capture failed: %s", cudaGetErrorString(err != cudaSuccess ? err : end));
+    }
+    memset(&g, 0, sizeof(g));
+    g.graph = graph;
+    size_t n = 0;
+    CU(cudaGraphGetNodes(graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    CU(cudaGraphGetNodes(graph, nodes.data(), &n));
+    for (size_t i = 0; i < n; i++) {
+        cudaGraphNodeType ty;
+        CU(cudaGraphNodeGetType(nodes[i], &ty));
+        if (ty != cudaGraphNodeTypeKernel) {
+            continue;
+        }
+        g.n_kernels++;
+        cudaKernelNodeParams kp;
+        CU(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+        if ((mask & 4) && kp.func == f_fwd && g.n_fwd == nullptr) {
+            g.n_fwd = nodes[i];
+            g.p_fwd = kp;
+        } else if ((mask & 2) && kp.func == f_mac && g.n_mac == nullptr) {
+            g.n_mac = nodes[i];
+            g.p_mac = kp;
+        }
+    }
+    if (((mask & 4) && g.n_fwd == nullptr) || ((mask & 2) && g.n_mac == nullptr)) {
+        cudaGraphDestroy(graph);
+        memset(&g, 0, sizeof(g));
+        return fail(BFCUDA_ECUDA, "step graph: could not identify the forward / MAC kernel nodes");
+    }
+    cudaError_t ierr = cudaGraphInstantiate(&g.exec, graph, 0);
+    if (ierr != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        memset(&g, 0, sizeof(g));
+        return fail(BFCUDA_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ierr));
+    }
+    return 0;
+}
+
+// One tick of the skewed pipeline.  have_f: a new step enters (its raw input is in the device input buffer of this
+// tick's parity); the pending MAC / inverse stages of the two steps before it ride along.  Without have_f the tick only
+// drains.  host_out / call: destination and number of the host-buffer call that brought the new step.
+static int graph_tick(bfcuda_engine *e, bool have_f, void *host_out, unsigned int call)
+{
+    const int nb = e->max_batch;
+    const int mask = (have_f ? 4 : 0) | (e->pend_mac.valid ? 2 : 0) | (e->pend_inv.valid ? 1 : 0);
+    if (mask == 0) {
+        return 0;
+    }
+    const unsigned int k = have_f ? e->launch_no : (e->pend_mac.valid ? e->pend_mac.step + 1u : e->pend_inv.step + 2u);
+    const bool host = e->graph_host;
+    // the double-buffered operands (Y, unpacked samples) follow k & 1; a host-buffer pipeline keeps FOUR raw blocks
+    // per direction in flight (the copies of a 16 MiB step take longer than its kernels), so its graphs go by k & 3
+    const int par = (int)(k & (host ? 3u : 1u));
+    uint8_t *d_in = host ? raw_queue(e, 0, par) : e->d_raw[0];
+    uint8_t *d_out = host ? raw_queue(e, 1, par) : e->d_raw[1];
+    UnpackArgs ua;
+    ForwardArgs fa;
+    MacArgs ma;
+    InverseArgs ia;
+    memset(&ua, 0, sizeof(ua));
+    memset(&fa, 0, sizeof(fa));
+    memset(&ma, 0, sizeof(ma));
+    memset(&ia, 0, sizeof(ia));
+    if (have_f) {
+        e->xt_par ^= 1;             // == (k + 1) & 1: the stream path toggles it once per launch too
+        ua = make_unpack_args(e, nb, d_in, e->xt_par);
+        fa = make_forward_args(e, nb, e->slot_t, d_in);
+        fa.xt_cur = e->d_xt[e->xt_par];
+        fa.xt_prev = (const char *)e->d_xt[e->xt_par ^ 1] + rs_bytes(e, (size_t)(e->xt_last_nb - 1) * e->n_ch[0] * e->L);
+        e->xt_last_nb = nb;
+    }
+    if (mask & 2) {
+        ma = make_mac_args(e, nb, e->pend_mac.slot_t, (int)(e->pend_mac.step & 1u));
+    }
+    if (mask & 1) {
+        ia = make_inverse_args(e, nb, (int)(e->pend_inv.step & 1u), d_out);
+    }
+    StepGraph &g = e->sg[host ? 1 : 0][mask][par];
+    if (g.exec == nullptr) {
+        int rc = capture_step_graph(e, g, mask, ua, fa, ma, ia);
+        if (rc != 0) return rc;
+    } else {
+        if (mask & 4) {
+            cudaKernelNodeParams kp = g.p_fwd;
+            void *args[2] = { &fa, g.p_fwd.kernelParams[1] };
+            kp.kernelParams = args;
+            CU(cudaGraphExecKernelNodeSetParams(g.exec, g.n_fwd, &kp));
+        }
+        if (mask & 2) {
+            cudaKernelNodeParams kp = g.p_mac;
+            void *args[2] = { &ma, g.p_mac.kernelParams[1] };
+            kp.kernelParams = args;
+            CU(cudaGraphExecKernelNodeSetParams(g.exec, g.n_mac, &kp));
+        }
+    }
+    const bool out_to_host = (mask & 1) && host && e->pend_inv.host_out != nullptr;
+    if (out_to_host) {
+        // the inverse stage overwrites raw output buffer `par`: its last read-out (two ticks ago) must be through
+        CU(cudaStreamWaitEvent(e->stream, e->ev_out_read[par], 0));
+    }
+    CU(cudaGraphLaunch(g.exec, e->stream));
+    e->launches += g.n_kernels;
+    e->graph_used = true;
+    if (out_to_host) {
+        const unsigned int c = e->pend_inv.call;
+        CU(cudaMemcpyAsync(e->d_snap[c & 3u], e->d_overflow, e->snap_bytes, cudaMemcpyDeviceToDevice, e->stream));
+        CU(cudaEventRecord(e->ev_g_done[par], e->stream));
+        CU(cudaStreamWaitEvent(e->s_out, e->ev_g_done[par], 0));
+        CU(cudaMemcpyAsync(e->pend_inv.host_out, d_out, (size_t)nb * e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_out));
+        CU(cudaMemcpyAsync(e->h_snap[c & 3u], e->d_snap[c & 3u], e->snap_bytes, cudaMemcpyDeviceToHost, e->s_out));
+        CU(cudaEventRecord(e->ev_call_done[c & 3u], e->s_out));
+        CU(cudaEventRecord(e->ev_out_read[par], e->s_out));
+        e->h_overflow_valid = e->n_ch[1] > 0;
+    } else {
+        CU(cudaEventRecord(e->ev_g_done[par], e->stream));
+    }
+    CU(cudaEventRecord(e->ev_inv, e->stream));
+    // advance the pipeline
+    e->pend_inv = e->pend_mac;
+    e->pend_mac.valid = false;
+    if (have_f) {
+        e->pend_mac.valid = true;
+        e->pend_mac.step = e->launch_no;
+        e->pend_mac.slot_t = e->slot_t;
+        e->pend_mac.host_out = host_out;
+        e->pend_mac.call = call;
+        e->launch_no++;
+        for (FilterState &fs : e->filters) {
+            fs.prevcoeff = fs.coeff;        // bfrun.c:1838, 2034
+        }
+        e->t += (unsigned int)nb;
+        e->slot_t = (e->slot_t + nb) % e->fdl_ring;
+        e->last_batch = nb;
+    }
+    return 0;
+}
+
+// complete every stage that is still pending in the skewed pipeline
+static int graph_drain(bfcuda_engine *e)
+{
+    while (e->pend_mac.valid || e->pend_inv.valid) {
+        int rc = graph_tick(e, false, nullptr, 0);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+static int leave_graph_mode(bfcuda_engine *e)
+{
+    if (!e->graph_mode) {
+        return 0;
+    }
+    int rc = graph_drain(e);
+    if (rc != 0) return rc;
+    e->graph_mode = false;
+    return join_streams(e);
+}
+
+static int enter_graph_mode(bfcuda_engine *e, bool host)
+{
+    if (e->graph_mode && e->graph_host == host) {
+        return 0;
+    }
+    int rc = leave_graph_mode(e);       // device-resident <-> host-buffer: different raw buffers
+    if (rc != 0) return rc;
+    rc = join_streams(e);
+    if (rc != 0) return rc;
+    e->graph_mode = true;
+    e->graph_host = host;
+    return 0;
 }
 
 static int sync_all(bfcuda_engine *e)
 {
+    int rc = graph_drain(e);
+    if (rc != 0) return rc;
     CU(cudaStreamSynchronize(e->s_in));
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaStreamSynchronize(e->s_mac));
@@ -1910,36 +2299,71 @@ static int sync_all(bfcuda_engine *e)
     return 0;
 }
 
-int bfcuda_process_blocks_async(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out)
+// the output of host-buffer call `call` is complete in host memory
+static int wait_call(bfcuda_engine *e, unsigned int call)
+{
+    if ((e->pend_mac.valid && e->pend_mac.host_out != nullptr && e->pend_mac.call <= call) ||
+        (e->pend_inv.valid && e->pend_inv.host_out != nullptr && e->pend_inv.call <= call)) {
+        int rc = graph_drain(e);        // its later stages are still waiting for the next ticks
+        if (rc != 0) return rc;
+    }
+    CU(cudaEventSynchronize(e->ev_call_done[call & 3u]));
+    return 0;
+}
+
+static int process_blocks_host(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out, bool allow_graph)
 {
     if (e == nullptr || raw_in == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     if (n_blocks < 1 || n_blocks > e->max_batch) {
         return fail(BFCUDA_EINVAL, "n_blocks %d outside 1..max_batch (%d)", n_blocks, e->max_batch);
     }
     CU(cudaSetDevice(e->device));
+    const unsigned int call = e->io_count;
+    if (allow_graph && graph_eligible(e, n_blocks)) {
+        int rc = enter_graph_mode(e, true);
+        if (rc != 0) return rc;
+        const int q = (int)(e->launch_no & 3u);
+        uint8_t *d_in = raw_queue(e, 0, q);
+        CU(cudaStreamWaitEvent(e->s_in, e->ev_g_done[q], 0));       // the forward stage four ticks ago has consumed d_in
+        CU(cudaMemcpyAsync(d_in, raw_in, (size_t)n_blocks * e->n_bytes[0], cudaMemcpyHostToDevice, e->s_in));
+        CU(cudaEventRecord(e->ev_h2dq[q], e->s_in));
+        CU(cudaStreamWaitEvent(e->stream, e->ev_h2dq[q], 0));
+        rc = graph_tick(e, true, raw_out, call);
+        if (rc != 0) return rc;
+        e->io_count++;
+        return 0;
+    }
+    int rc = leave_graph_mode(e);
+    if (rc != 0) return rc;
     // double-buffered raw blocks: copy-in of call k+1 and copy-out of call k-1 overlap the kernels of call k
-    const int b = (int)(e->io_count & 1u);
+    const int b = (int)(call & 1u);
     uint8_t *d_in = b ? e->d_raw2[0] : e->d_raw[0];
     uint8_t *d_out = b ? e->d_raw2[1] : e->d_raw[1];
-    const bool reuse = e->io_count >= 2;
+    const bool reuse = call >= 2;
     if (reuse) {
         CU(cudaStreamWaitEvent(e->s_in, e->ev_fwd[b], 0));      // forward of call k-2 has consumed d_in
     }
     CU(cudaMemcpyAsync(d_in, raw_in, (size_t)n_blocks * e->n_bytes[0], cudaMemcpyHostToDevice, e->s_in));
     CU(cudaEventRecord(e->ev_h2d[b], e->s_in));
-    int rc = enqueue_blocks(e, n_blocks, d_in, d_out, e->ev_h2d[b], reuse ? e->ev_d2h[b] : nullptr, e->ev_fwd[b]);
+    rc = enqueue_blocks(e, n_blocks, d_in, d_out, e->ev_h2d[b], reuse ? e->ev_call_done[(call - 2u) & 3u] : nullptr,
+                        e->ev_fwd[b]);
     if (rc != 0) return rc;
     // the peak-meter records and the status word travel with the block (bfrun.c:1929-1936 reads them after every
     // block): snapshot them behind this call's last kernel, read the snapshot out with the output
-    CU(cudaMemcpyAsync(e->d_snap[b], e->d_overflow, e->snap_bytes, cudaMemcpyDeviceToDevice, e->s_inv));
+    CU(cudaMemcpyAsync(e->d_snap[call & 3u], e->d_overflow, e->snap_bytes, cudaMemcpyDeviceToDevice, e->s_inv));
     CU(cudaEventRecord(e->ev_inv, e->s_inv));
     CU(cudaStreamWaitEvent(e->s_out, e->ev_inv, 0));
     CU(cudaMemcpyAsync(raw_out, d_out, (size_t)n_blocks * e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_out));
-    CU(cudaMemcpyAsync(e->h_snap[b], e->d_snap[b], e->snap_bytes, cudaMemcpyDeviceToHost, e->s_out));
+    CU(cudaMemcpyAsync(e->h_snap[call & 3u], e->d_snap[call & 3u], e->snap_bytes, cudaMemcpyDeviceToHost, e->s_out));
     e->h_overflow_valid = e->n_ch[1] > 0;
-    CU(cudaEventRecord(e->ev_d2h[b], e->s_out));
+    CU(cudaEventRecord(e->ev_call_done[call & 3u], e->s_out));
     e->io_count++;
     return 0;
+}
+
+int bfcuda_process_blocks_async(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out)
+{
+    return process_blocks_host(e, n_blocks, raw_in, raw_out, true);
 }
 
 int bfcuda_process_block_async(bfcuda_engine *e, const void *raw_in, void *raw_out)
@@ -1950,13 +2374,14 @@ int bfcuda_process_block_async(bfcuda_engine *e, const void *raw_in, void *raw_o
 int bfcuda_wait_previous(bfcuda_engine *e, int calls_back)
 {
     if (e == nullptr) return fail(BFCUDA_EINVAL, "null engine");
-    if (calls_back < 0 || calls_back > 1 || (unsigned int)calls_back >= e->io_count) {
-        return fail(BFCUDA_EINVAL, "only the two most recent asynchronous calls can be waited for");
+    if (calls_back < 0 || calls_back > 3 || (unsigned int)calls_back >= e->io_count) {
+        return fail(BFCUDA_EINVAL, "only the four most recent asynchronous calls can be waited for");
     }
     CU(cudaSetDevice(e->device));
-    // the raw blocks are double buffered by call parity; a call's read-out event is re-recorded two calls later
+    // per-call events and snapshots are kept for the four most recent calls
     const unsigned int call = e->io_count - 1u - (unsigned int)calls_back;
-    CU(cudaEventSynchronize(e->ev_d2h[call & 1u]));
+    int rc = wait_call(e, call);
+    if (rc != 0) return rc;
     if (calls_back == 0) {
         e->io_waited = e->io_count;
     }
@@ -1983,7 +2408,8 @@ int bfcuda_process_block(bfcuda_engine *e, const void *raw_in, void *raw_out)
 
 int bfcuda_process_blocks(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out)
 {
-    int rc = bfcuda_process_blocks_async(e, n_blocks, raw_in, raw_out);
+    // the answer is wanted now: the stream path (a skewed pipeline would have to be drained right away)
+    int rc = process_blocks_host(e, n_blocks, raw_in, raw_out, false);
     if (rc != 0) return rc;
     // the call's own read-out, not every stream: in the low-latency schedule the next block's partial sum keeps running
     return bfcuda_wait_previous(e, 0);
@@ -1997,6 +2423,13 @@ int bfcuda_process_blocks_device(bfcuda_engine *e, int n_blocks)
     }
     CU(cudaSetDevice(e->device));
     e->h_overflow_valid = false;        // no read-out follows a device-resident call
+    if (graph_eligible(e, n_blocks)) {
+        int rc = enter_graph_mode(e, false);
+        if (rc != 0) return rc;
+        return graph_tick(e, true, nullptr, 0);
+    }
+    int rc = leave_graph_mode(e);
+    if (rc != 0) return rc;
     return enqueue_blocks(e, n_blocks, e->d_raw[0], e->d_raw[1], nullptr, nullptr, nullptr);
 }
 
@@ -2156,7 +2589,12 @@ int bfcuda_timer_stop(bfcuda_engine *e, double *elapsed_ms)
 {
     if (e == nullptr || elapsed_ms == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
-    // the stop event must come after everything enqueued on any of the engine's streams
+    // the stop event must come after everything enqueued on any of the engine's streams -- including the stages of
+    // the last two steps that the skewed step graphs have not run yet
+    {
+        int rc = graph_drain(e);
+        if (rc != 0) return rc;
+    }
     for (cudaStream_t st : { e->s_mac, e->s_inv, e->s_out }) {
         CU(cudaEventRecord(e->ev_join, st));
         CU(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
@@ -2233,8 +2671,8 @@ int bfcuda_get_info(bfcuda_engine *e, struct bfcuda_info *info)
     info->n_streams = e->n_rings;
     info->kernels_per_block = 3 + (e->level_mix_first.size() > 1 && e->level_mix_first[1] > 0 ? 1 : 0) +
                               3 * (e->n_levels - 1) +
-                              (e->plan.tw2 != nullptr ? 2 : (e->shared_out.empty() ? 0 : 1));
-    info->uses_graph = 0;
+                              (plan_unpacks_first(e->plan) ? 2 : (e->shared_out.empty() ? 0 : 1));
+    info->uses_graph = e->graph_used ? 1 : 0;
     info->max_batch = e->max_batch;
     info->mac_bytes_per_batch = e->mac_bytes_batch;
     info->sm_count = e->sm_count;
@@ -2250,8 +2688,9 @@ int bfcuda_debug_read(bfcuda_engine *e, int what, int index, int slot, void *dst
 {
     if (e == nullptr || dst == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     CU(cudaSetDevice(e->device));
-    for (cudaStream_t st : { e->s_in, e->stream, e->s_mac, e->s_inv, e->s_out }) {
-        CU(cudaStreamSynchronize(st));
+    {
+        int rc = sync_all(e);
+        if (rc != 0) return rc;
     }
     const size_t nb = rs_bytes(e, e->N);
     switch (what) {

@@ -570,6 +570,7 @@ static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, 
     }
     const int total = (a.n_in * a.batch + F::SUBS - 1) / F::SUBS;      // blocks needed: SUBS transforms each
     const int grid = total < resident[dev] ? total : resident[dev];
+    g_last_func = (const void *)k_forward2<LOG2M, SINGLE, TWS, MINB>;
     k_forward2<LOG2M, SINGLE, TWS, MINB><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
     return cudaGetLastError();
 }

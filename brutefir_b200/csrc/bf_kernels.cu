@@ -24,11 +24,13 @@
 
 namespace bf {
 
+thread_local const void *g_last_func = nullptr;
+
 // ======================================================================================================
 // FFT plan (twiddle table)
 // ======================================================================================================
 
-bool fft_size_supported(int N, int realsize)
+bool fft_single_block_supported(int N, int realsize)
 {
     if (N < 8 || (N & (N - 1)) != 0) {
         return false;
@@ -37,12 +39,19 @@ bool fft_size_supported(int N, int realsize)
     return realsize == 4 ? N <= 32768 : N <= 16384;
 }
 
-cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize)
+bool fft_size_supported(int N, int realsize)
+{
+    return fft_single_block_supported(N, realsize) || fft_big_supported(N, realsize);     // bf_fft4.cu beyond one block
+}
+
+cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize, int big_items_hint)
 {
     plan->N = N;
     plan->realsize = realsize;
     plan->tw = nullptr;
     plan->tw2 = nullptr;
+    plan->big_m1 = plan->big_m2 = plan->big_items = 0;
+    plan->big_tw1 = plan->big_tw2 = plan->big_scr0 = plan->big_scr1 = plan->big_old = nullptr;
     const int half = N / 2;
     cudaError_t err = cudaMalloc(&plan->tw, (size_t)N * realsize);
     if (err != cudaSuccess) {
@@ -71,6 +80,9 @@ cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize)
     if (err != cudaSuccess) {
         return err;
     }
+    if (!fft_single_block_supported(N, realsize)) {
+        return fft_big_plan_create(plan, big_items_hint);
+    }
     return fft2_plan_create(plan);
 }
 
@@ -84,6 +96,7 @@ void fft_plan_destroy(FftPlan *plan)
         cudaFree(plan->tw2);
         plan->tw2 = nullptr;
     }
+    fft_big_plan_destroy(plan);
 }
 
 // ======================================================================================================
@@ -1007,6 +1020,7 @@ static bool fft_force16()
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
+    if (plan.big_m1 != 0) return launch_forward_big(plan, a, s);
     if (plan.tw2 != nullptr) return launch_forward2(plan, a, s);
     BF_FFT_DISPATCH(plan, k_forward, dim3(a.n_in, a.batch), s, a, (const T *)plan.tw, plan.N / 2);
 }
@@ -1040,8 +1054,10 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
         return launch_mac_batch2(plan, a, s);      // bf_mac_batch.cu
     }
     if (plan.realsize == 4) {
+        g_last_func = (const void *)k_mac<float, 4>;
         k_mac<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
     } else {
+        g_last_func = (const void *)k_mac<double, 4>;
         k_mac<double, 4><<<grid, 256, 0, s>>>(a, plan.N);
     }
     return cudaGetLastError();
@@ -1076,6 +1092,7 @@ cudaError_t launch_out_mix(const FftPlan &plan, const OutMixArgs &a, cudaStream_
 cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
+    if (plan.big_m1 != 0) return launch_inverse_big(plan, a, s);
     if (plan.tw2 != nullptr) return launch_inverse2(plan, a, s);
     BF_FFT_DISPATCH(plan, k_inverse, dim3(a.n_out, a.batch), s, a, (const T *)plan.tw, plan.N / 2);
 }
@@ -1083,6 +1100,7 @@ cudaError_t launch_inverse(const FftPlan &plan, const InverseArgs &a, cudaStream
 cudaError_t launch_eval(const FftPlan &plan, const EvalArgs &a, cudaStream_t s)
 {
     if (a.n_entries == 0) return cudaSuccess;
+    if (plan.big_m1 != 0) return cudaErrorNotSupported;     // chained filters stop at one block's transform size
     BF_FFT_DISPATCH(plan, k_eval, a.n_entries, s, a, (const T *)plan.tw, plan.N / 2);
 }
 
@@ -1113,6 +1131,7 @@ cudaError_t launch_coeff_fft(const FftPlan &plan, const void *taps, int n_blocks
                              cudaStream_t s)
 {
     if (n_blocks == 0) return cudaSuccess;
+    if (plan.big_m1 != 0) return launch_coeff_fft_big(plan, taps, n_blocks, scale, H, hbase, s);
     BF_FFT_DISPATCH(plan, k_coeff_fft, n_blocks, s, (const T *)taps, (T)scale, (T *)H, hbase, (const T *)plan.tw,
                     plan.N / 2);
 }

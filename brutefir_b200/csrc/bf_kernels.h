@@ -58,9 +58,29 @@ struct FftPlan {
     int realsize;
     void *tw;       // device: N/2 complex roots e^{-2 pi i j / N}
     void *tw2;      // device: per-pass tables of the size-specialised transform (bf_fft2.cuh), or NULL
+    // transforms longer than one thread block holds (bf_fft4.cu): M = big_m1 x big_m2, 0 = not in use
+    int big_m1, big_m2;
+    void *big_tw1, *big_tw2;        // root tables of the two sub-transform sizes
+    void *big_scr0, *big_scr1;      // scratch, big_items x M complex each
+    void *big_old;                  // big_items x L reals: the old-coefficient signal of a crossfade block
+    int big_items;                  // transforms per chunk
 };
 
-cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize);
+// big_items_hint: the largest number of transforms one launch will ask for (sizes the four-step scratch)
+cudaError_t fft_plan_create(FftPlan *plan, int N, int realsize, int big_items_hint = 64);
+// bf_fft4.cu: the four-step transform for N beyond one block (L >= 32768 float / 16384 double)
+bool fft_big_supported(int N, int realsize);
+cudaError_t fft_big_plan_create(FftPlan *plan, int max_items);
+void fft_big_plan_destroy(FftPlan *plan);
+cudaError_t launch_forward_big(const FftPlan &plan, const struct ForwardArgs &a, cudaStream_t s);
+cudaError_t launch_inverse_big(const FftPlan &plan, const struct InverseArgs &a, cudaStream_t s);
+cudaError_t launch_coeff_fft_big(const FftPlan &plan, const void *taps, int n_blocks, double scale, void *H, int hbase,
+                                 cudaStream_t s);
+// the forward / inverse stages read unpacked planar samples (k_unpack before, k_pack after): true for the
+// size-specialised and the four-step transforms
+inline bool plan_unpacks_first(const FftPlan &plan) { return plan.tw2 != nullptr || plan.big_m1 != 0; }
+// one block holds the transform in shared memory (the generic kernels and the per-call convolver.h surface)
+bool fft_single_block_supported(int N, int realsize);
 // bf_fft2_kernels.cu: the size-specialised forward / inverse stages (float, 1024 <= L <= 16384)
 bool fft2_supported(int N, int realsize);
 cudaError_t fft2_plan_create(FftPlan *plan);
@@ -167,6 +187,9 @@ struct MacArgs {
     int head, z_first, z_count;
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
+// The host stub of the kernel the most recent launch_forward / launch_mac call of this thread launched: how the engine
+// finds those two nodes in a captured step graph (their arguments carry the ring slot, which changes per launch).
+extern thread_local const void *g_last_func;
 // bins per thread the batched kernel will use for such a launch (bf_mac_batch.cu)
 int mac_batch_lanes(int realsize, int batch, int n_jobs, int N);
 // With split > 1 the MAC leaves `split` partial sums per output: add them, in order, into partial 0 (the consumers

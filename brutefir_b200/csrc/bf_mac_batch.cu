@@ -220,7 +220,7 @@ struct DcFalse { static constexpr bool value = false; };
 template <typename T, int W, int B, int S, int MINB, int MBT>
 __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 {
-    static_assert(S % B == 0, "the unrolled body must cover whole window rotations");
+    static_assert(S >= 2, "at least one stage in flight");
     constexpr int VB = W * (int)sizeof(T);
     typedef typename VecB<T, W>::type V;
     typedef LanesB<T, W> L;
@@ -342,21 +342,26 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
                         }
                     }
                 }
-                // remaining steps: convolver_convolve_add.  Step j = base + k has ring stage j % S = (k + 1) % S and
-                // window rotation u = j % B = (k + 1) % B: compile-time constants because base = 1 (mod S).
-                for (int base = 1; base < n; base += S) {
+                // remaining steps: convolver_convolve_add.  The window rotation u = j % B is a compile-time constant
+                // (the loop is unrolled over one rotation, base = 1 mod B); the ring stage is tracked at run time, so
+                // the ring depth S is free of B and the unrolled body stays one rotation long whatever S is
+                // (an S-fold unrolled body outgrew the instruction cache at S = 16 and 24).
+                int st_c = 1 % S;           // stage step j reads:    j % S
+                int st_p = 0;               // stage step j refills:  (j - 1) % S, consumed by the previous step
+                for (int base = 1; base < n; base += B) {
 #pragma unroll
-                    for (int k = 0; k < S; k++) {
+                    for (int k = 0; k < B; k++) {
                         const int j = base + k;
                         if (j < n) {
-                            const int stage = (k + 1) % S;
                             const int u = (k + 1) % B;
                             cp_async_wait<S - 2>();
-                            const V hr = *stage_ptr(stage, 0), hi = *stage_ptr(stage, 1);
+                            const V hr = *stage_ptr(st_c, 0), hi = *stage_ptr(st_c, 1);
                             // the block that left the window makes room for the new oldest-partition slot
-                            wr[(B - u) % B] = *stage_ptr(stage, 2);
-                            wi[(B - u) % B] = *stage_ptr(stage, 3);
-                            issue(k % S);       // stage (j + S - 1) % S = the one consumed by the previous step
+                            wr[(B - u) % B] = *stage_ptr(st_c, 2);
+                            wi[(B - u) % B] = *stage_ptr(st_c, 3);
+                            issue(st_p);
+                            st_p = st_c;
+                            st_c = st_c + 1 == S ? 0 : st_c + 1;
                             const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
 #pragma unroll
                             for (int b = 0; b < B; b++) {
@@ -420,6 +425,7 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
     dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split);
     MacArgs args = a;
     args.neg_zero2 = 0x8000000080000000ull;     // (-0.0f, -0.0f): see BinPairAcc
+    g_last_func = (const void *)k_mac_batch2<T, W, B, S, MINB, MBT>;
     k_mac_batch2<T, W, B, S, MINB, MBT><<<grid, MBT, smem, s>>>(args, N);
     return cudaGetLastError();
 }
@@ -438,6 +444,11 @@ static int env_int(const char *name, int dflt)
 int mac_batch_lanes(int realsize, int batch, int n_jobs, int N)
 {
     const long bins = (long)n_jobs * (N / 2);
+#ifdef BF_MAC_SWEEP
+    if (realsize == 4 && batch > 4 && batch <= 8 && getenv("BFCUDA_MAC_W") != nullptr) {
+        return atoi(getenv("BFCUDA_MAC_W"));
+    }
+#endif
     if (realsize == 4) {
         if (batch <= 4) return 4;
         static const int narrow_max = env_int("BFCUDA_MAC_NARROW_MAX_BINS", 16 * 8192);
@@ -456,7 +467,28 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
         if (a.batch <= 2) return launch_one<float, 4, 2, 4>(a, plan.N, s);
         if (a.batch <= 4) return launch_one<float, 4, 4, 4>(a, plan.N, s);
         if (a.batch <= 8) {
+#ifdef BF_MAC_SWEEP
+            // experiment build: (ring stages, threads per block) from the environment
+            const int S = env_int("BFCUDA_MAC_S", 8), TPB = env_int("BFCUDA_MAC_TPB", lanes == 1 ? 64 : 256);
+            if (lanes == 1) {
+                if (S == 8 && TPB == 64) return launch_one<float, 1, 8, 8, 96, 64>(a, plan.N, s);
+                if (S == 16 && TPB == 64) return launch_one<float, 1, 8, 16, 96, 64>(a, plan.N, s);
+                if (S == 24 && TPB == 64) return launch_one<float, 1, 8, 24, 96, 64>(a, plan.N, s);
+                if (S == 16 && TPB == 128) return launch_one<float, 1, 8, 16, 96, 128>(a, plan.N, s);
+                return cudaErrorInvalidValue;
+            }
+            if (S == 8 && TPB == 256) return launch_one<float, 2, 8, 8>(a, plan.N, s);
+            if (S == 8 && TPB == 128) return launch_one<float, 2, 8, 8, 128, 128>(a, plan.N, s);
+            if (S == 10 && TPB == 256) return launch_one<float, 2, 8, 10>(a, plan.N, s);
+            if (S == 12 && TPB == 256) return launch_one<float, 2, 8, 12>(a, plan.N, s);
+            if (S == 12 && TPB == 128) return launch_one<float, 2, 8, 12, 128, 128>(a, plan.N, s);
+            if (S == 16 && TPB == 128) return launch_one<float, 2, 8, 16, 128, 128>(a, plan.N, s);
+            if (S == 16 && TPB == 256) return launch_one<float, 2, 8, 16, 128, 256>(a, plan.N, s);
+            if (S == 24 && TPB == 256) return launch_one<float, 2, 8, 24, 128, 256>(a, plan.N, s);
+            return cudaErrorInvalidValue;
+#else
             return lanes == 1 ? launch_one<float, 1, 8, 8, 96, 64>(a, plan.N, s) : launch_one<float, 2, 8, 8>(a, plan.N, s);
+#endif
         }
         if (a.batch <= 16) {
             return lanes == 1 ? launch_one<float, 1, 16, 16, 128, 64>(a, plan.N, s)

@@ -151,9 +151,9 @@ main(int argc, char *argv[])
     int n_filters, *chan, *coeff_blocks, f, c, rs;
     double *ones, t0, t1, stage[BFCUDA_N_STAGES];
     long blocks = 0, stage_blocks = 0, launches = 0;
-    void *raw_in[3], *raw_out[3];
+    void *raw_in[4], *raw_out[4];
     size_t in_bytes, out_bytes;
-    int nblk[3], k;
+    int nblk[4], k;
     FILE *in, *out;
 
     for (a = 1; a < argc; a++) {
@@ -297,7 +297,7 @@ main(int argc, char *argv[])
     if (in == NULL || out == NULL) DIE("Could not open input or output: %s", strerror(errno));
     in_bytes = (size_t)cfg.n_bytes[BFCUDA_IN];
     out_bytes = (size_t)cfg.n_bytes[BFCUDA_OUT];
-    for (k = 0; k < 3; k++) {
+    for (k = 0; k < 4; k++) {
         raw_in[k] = bfcuda_host_alloc(in_bytes * (size_t)batch);
         raw_out[k] = bfcuda_host_alloc(out_bytes * (size_t)batch);
         if (raw_in[k] == NULL || raw_out[k] == NULL) DIE("%s", bfcuda_strerror());
@@ -364,7 +364,9 @@ main(int argc, char *argv[])
         k = 0;
     } else
     for (k = 0;; k++) {
-        const int s = k % 3;
+        /* file to file: the engine keeps up to three calls in flight (its step graphs run forward(k), MAC(k-1) and
+         * inverse(k-2) side by side); call k is submitted, then the output of call k-2 is written while k runs */
+        const int s = k % 4;
         size_t got = text_io ? read_text(in, raw_in[s], in_bytes * (size_t)batch)
                              : fread(raw_in[s], 1, in_bytes * (size_t)batch, in);
         if (got == 0) {
@@ -375,9 +377,9 @@ main(int argc, char *argv[])
             memset((char *)raw_in[s] + got, 0, (size_t)nblk[s] * in_bytes - got);       /* dai.c:1312-1332 */
         }
         CHECK(bfcuda_process_blocks_async(eng, nblk[s], raw_in[s], raw_out[s]));
-        if (k > 0) {
-            const int p = (k - 1) % 3;
-            CHECK(bfcuda_wait_previous(eng, 1));
+        if (k > 1) {
+            const int p = (k - 2) % 4;
+            CHECK(bfcuda_wait_previous(eng, 2));
             if (text_io ? write_text(out, raw_out[p], out_bytes * (size_t)nblk[p], n) != 0
                         : fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
                 DIE("write failed: %s", strerror(errno));
@@ -386,11 +388,14 @@ main(int argc, char *argv[])
         blocks += nblk[s];
     }
     if (k > 0) {
-        const int p = (k - 1) % 3;
+        int q;
         CHECK(bfcuda_synchronize(eng));
-        if (text_io ? write_text(out, raw_out[p], out_bytes * (size_t)nblk[p], n) != 0
-                    : fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
-            DIE("write failed: %s", strerror(errno));
+        for (q = k > 1 ? k - 2 : 0; q < k; q++) {
+            const int p = q % 4;
+            if (text_io ? write_text(out, raw_out[p], out_bytes * (size_t)nblk[p], n) != 0
+                        : fwrite(raw_out[p], 1, out_bytes * (size_t)nblk[p], out) != out_bytes * (size_t)nblk[p]) {
+                DIE("write failed: %s", strerror(errno));
+            }
         }
     }
     t1 = now();
@@ -415,7 +420,7 @@ main(int argc, char *argv[])
                     stage[0], stage[1], stage[2], launches);
         }
     }
-    for (k = 0; k < 3; k++) {
+    for (k = 0; k < 4; k++) {
         bfcuda_host_free(raw_in[k]);
         bfcuda_host_free(raw_out[k]);
     }

@@ -58,7 +58,7 @@ def test_invalid_configurations_are_rejected_like_convolver_init():
     g = configs.config_c5()
     for mutate, needle in ((lambda c: setattr(c, "realsize", 6), b"Invalid real size"),
                            (lambda c: setattr(c, "filter_length", 48), b"Invalid length"),
-                           (lambda c: setattr(c, "filter_length", 65536), b"exceeds")):
+                           (lambda c: setattr(c, "filter_length", 1 << 23), b"beyond the four-step transform")):
         cfg, keep = g.to_config()
         mutate(cfg)
         rc = lib.bfcuda_create(C.byref(cfg), C.byref(h))

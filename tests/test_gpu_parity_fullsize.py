@@ -93,7 +93,7 @@ def truth_tail(graph, taps, sig, channels, n_tail):
         n = x.shape[1] + len(h) - 1
         nfft = 1 << int(np.ceil(np.log2(n)))
         y = np.fft.irfft(np.fft.rfft(x[graph.filters[c].inputs[0]], nfft) * np.fft.rfft(h, nfft), nfft)[: x.shape[1]]
-        out[c] = y[-n_tail:] * float(1 << 23)      # LSB units at 24 bit
+        out[c] = y[-n_tail:]                       # integer input samples are LSB units already; unit-energy filters
     return out
 
 
@@ -135,23 +135,51 @@ def test_c3_all_partitions_live_against_the_reference(gpu_lib, oracle_libs, sigm
             assert np.array_equal(first, got)                   # batched == block by block, byte for byte
 
 
-@pytest.mark.parametrize("sigma", [0.01, 0.1])
+@pytest.mark.parametrize("sigma", [0.01, 0.03, 0.1])
 def test_c4_automatic_partition_split_against_the_reference(gpu_lib, oracle_libs, sigma):
+    """32 filters x 256 bins cannot fill 148 SMs, so the engine splits the 1024-deep partition sum (37 ways block by
+    block, 5 ways at 8 blocks per call): a different float32 summation tree than the reference's left-to-right one.
+    Up to -30 dBFS that is invisible (<= 1 LSB, strictly).  At -20 dBFS -- outputs near 2^22 LSB, 1024 float32 terms per
+    bin -- the reference's own rounding noise is several LSB and ANY other order lands elsewhere: measured
+    (profiles/r2_diag_c4.txt) max 4 LSB, 1.2 % of the samples beyond 1 LSB, < 1e-4 beyond 2 LSB.  What is required
+    there: <= 4 LSB, < 2 % beyond 1, < 0.05 % beyond 2, and the GPU no further from the float64 truth than the reference
+    (rms and max).  mac_split = 1 keeps the reference's order (bit-exact MAC stage) and meets the same rule as the
+    headline shape (<= 2 LSB, < 0.05 % beyond 1 at this depth); it is the documented way to ask for it."""
     g = configs.config_c4()
     n_blocks = 1032                                             # P + 8
     taps = fast_unit_energy_filters(g, 2004)
     sig = configs.synthetic_signal(g, 4, n_blocks, sigma=sigma)
     ref = reference_run(g, taps, sig)
-    n_tail = 64 * g.filter_length
+    L = g.filter_length
+    r = unpack_run(ref, g.out_formats, L)
+    assert np.abs(r).max() > 1e4
+    n_tail = 64 * L
     truth = truth_tail(g, taps, sig, [0, 13, 31], n_tail) if sigma > 0.05 else None
+
+    def near_truth(y):
+        for c, t in truth.items():
+            eg, er = y[c, -n_tail:] - t, r[c, -n_tail:] - t
+            assert np.sqrt(np.mean(eg ** 2)) <= 1.05 * np.sqrt(np.mean(er ** 2)), c
+            assert np.abs(eg).max() <= np.abs(er).max() + 0.25, c
+
     for B in (1, 8):
         got, info = engine_run(g, taps, sig, B)
-        assert info.mac_split > 1                               # 32 x 256 bins cannot fill 148 SMs: the sum is split
-        check(g, got, ref, strict=sigma < 0.05, truth=truth, n_tail=n_tail)
-    # and with the split forced off the reference's summation order is kept: still within the same bounds
+        assert info.mac_split > 1                               # the sum is split
+        d = np.abs(unpack_run(got, g.out_formats, L) - r)
+        if sigma < 0.05:
+            assert d.max() <= 1, d.max()
+        else:
+            assert d.max() <= 4 and np.mean(d > 1) < 0.02 and np.mean(d > 2) < 5e-4, (d.max(), np.mean(d > 1), np.mean(d > 2))
+            near_truth(unpack_run(got, g.out_formats, L))
+    # the split forced off: the reference's summation order
     got, info = engine_run(g, taps, sig, 1, mac_split=1)
     assert info.mac_split == 1
-    check(g, got, ref, strict=sigma < 0.05, truth=truth, n_tail=n_tail)
+    d = np.abs(unpack_run(got, g.out_formats, L) - r)
+    if sigma < 0.05:
+        assert d.max() <= 1, d.max()
+    else:
+        assert d.max() <= 2 and np.mean(d > 1) < 5e-4, (d.max(), np.mean(d > 1))
+        near_truth(unpack_run(got, g.out_formats, L))
 
 
 def xtc_setup(L=64, P=64):
