@@ -62,7 +62,9 @@ class ConfigC(C.Structure):
                 ("apply_dither", C.POINTER(C.c_int)),
                 ("sampling_rate", C.c_int),
                 ("max_dither_table_size", C.c_int),
-                ("max_batch", C.c_int)]
+                ("max_batch", C.c_int),
+                ("powersave", C.c_int),
+                ("analog_powersave", C.c_double)]
 
 
 class InfoC(C.Structure):

@@ -68,6 +68,19 @@ __device__ __forceinline__ void reduce_stats(QuantStats st, Overflow *of, unsign
     }
 }
 
+// powersave: is the frame [previous block | block blk] of input c silent?  (test_silent, bfrun.c:722-772: exact zeros,
+// or a peak below the analog level)
+__device__ __forceinline__ bool frame_silent(const ForwardArgs &a, int c, int blk)
+{
+    if (a.powersave == 0) {
+        return false;
+    }
+    const unsigned int cur = a.amax_cur[(size_t)blk * a.n_in + c];
+    const unsigned int prv = blk == 0 ? a.amax_prev[c] : a.amax_cur[(size_t)(blk - 1) * a.n_in + c];
+    const float m = fmaxf(__uint_as_float(cur), __uint_as_float(prv));
+    return a.powersave == 1 ? (m == 0.f) : (m < a.ps_thr[c]);
+}
+
 template <typename T> struct Vec2;
 template <> struct Vec2<float> {
     typedef float2 type;

@@ -257,6 +257,12 @@ struct bfcuda_engine {
     // HP-TPDF dither
     std::vector<int> dither_of_out;     // per output: index into the dithered channels, -1 = not dithered
     DitherArgs dither;                  // device pointers; n_dither = 0 when nothing is dithered
+    // powersave (bfrun.c:1541-1552, 1613-1700, 722-772)
+    int powersave;                      // 0 off, 1 exact zeros only, 2 analog level
+    unsigned int *d_amax[2];            // [max_batch][n_in] block peaks, by the generation of d_xt
+    float *d_ps_thr;                    // [n_in]
+    uint8_t *d_slot_zero;               // [F][ring]
+    long ps_hold_until;                 // block count until which the MAC ignores the flags (after a delay transition)
     bool dirty, xfade_active;
     size_t mac_bytes;           // algorithmic MAC bytes of one block launched alone
     size_t mac_bytes_batch;     // compulsory MAC bytes of one full batch of max_batch blocks
@@ -370,10 +376,18 @@ static int update_streams(bfcuda_engine *e)
         if (!users.empty()) {
             if (fs.stream != f) {
                 CU(cudaMemcpyAsync(ring_ptr(e, f), ring_ptr(e, fs.stream), ring_bytes, cudaMemcpyDeviceToDevice, e->stream));
+                if (e->d_slot_zero != nullptr) {        // the powersave flags travel with the ring
+                    CU(cudaMemcpyAsync(e->d_slot_zero + (size_t)f * e->fdl_ring, e->d_slot_zero + (size_t)fs.stream * e->fdl_ring,
+                                       (size_t)e->fdl_ring, cudaMemcpyDeviceToDevice, e->stream));
+                }
                 fs.stream = f;
             } else {
                 const int g = users[0];     // lowest index: the new owner
                 CU(cudaMemcpyAsync(ring_ptr(e, g), ring_ptr(e, f), ring_bytes, cudaMemcpyDeviceToDevice, e->stream));
+                if (e->d_slot_zero != nullptr) {
+                    CU(cudaMemcpyAsync(e->d_slot_zero + (size_t)g * e->fdl_ring, e->d_slot_zero + (size_t)f * e->fdl_ring,
+                                       (size_t)e->fdl_ring, cudaMemcpyDeviceToDevice, e->stream));
+                }
                 for (int u : users) {
                     e->filters[u].stream = g;
                 }
@@ -838,7 +852,7 @@ void bfcuda_destroy(bfcuda_engine *e)
     if (e->comm != nullptr && g_nccl.handle != nullptr) {
         g_nccl.CommDestroy(e->comm);
     }
-    void *ptrs[] = { e->d_raw34[0][0], e->d_raw34[0][1], e->d_raw34[1][0], e->d_raw34[1][1], e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
+    void *ptrs[] = { e->d_amax[0], e->d_amax[1], e->d_ps_thr, e->d_slot_zero, e->d_raw34[0][0], e->d_raw34[0][1], e->d_raw34[1][0], e->d_raw34[1][1], e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
                      e->d_keep, e->d_eval_entries, e->d_eval_terms, e->d_mixes, e->dither.chans, (void *)e->dither.randtab,
@@ -1043,6 +1057,11 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     memset(e->sg, 0, sizeof(e->sg));
     e->graph_enabled = !(c->flags & BFCUDA_FLAG_NO_GRAPH) && getenv("BFCUDA_NO_GRAPH") == nullptr;
     e->graph_mode = e->graph_host = e->graph_used = false;
+    e->powersave = 0;
+    e->d_amax[0] = e->d_amax[1] = nullptr;
+    e->d_ps_thr = nullptr;
+    e->d_slot_zero = nullptr;
+    e->ps_hold_until = -1;
     e->pend_mac.valid = e->pend_inv.valid = false;
     e->h_overflow_valid = false;
     e->io_waited = 0;
@@ -1205,6 +1224,26 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         if (plan_unpacks_first(e->plan)) {
             TRY(dev_alloc(e, &e->d_xt[0], rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * L)));
             TRY(dev_alloc(e, &e->d_xt[1], rs_bytes(e, B * (size_t)std::max(1, e->n_ch[0]) * L)));
+        }
+        if (c->powersave && plan_unpacks_first(e->plan) && e->n_ch[0] > 0) {
+            // (partitions shorter than 64 samples run the fused generic kernels, which have no separate unpack pass to
+            // take the peaks in: there powersave is left off -- with exact-zero detection it changes no result anyway)
+            const double level = c->analog_powersave <= 0.0 ? 1.0 : c->analog_powersave;
+            e->powersave = level >= 1.0 ? 1 : 2;
+            TRY(dev_alloc(e, &e->d_amax[0], sizeof(unsigned int) * B * (size_t)e->n_ch[0]));
+            TRY(dev_alloc(e, &e->d_amax[1], sizeof(unsigned int) * B * (size_t)e->n_ch[0]));
+            TRY(dev_alloc(e, &e->d_ps_thr, sizeof(float) * (size_t)e->n_ch[0]));
+            TRY(dev_alloc(e, &e->d_slot_zero, F * (size_t)e->fdl_ring, false));
+            TRYCU(cudaMemset(e->d_slot_zero, 1, F * (size_t)e->fdl_ring));      // nothing written yet: every slot is zeros
+            std::vector<float> thr((size_t)e->n_ch[0]);
+            for (int n = 0; n < e->n_ch[0]; n++) {
+                // silent iff scale * peak < level (bfrun.c:767); the peak is kept in float
+                thr[(size_t)n] = (float)(level / e->fmt[0][n].sf.scale);
+            }
+            TRYCU(cudaMemcpy(e->d_ps_thr, thr.data(), sizeof(float) * thr.size(), cudaMemcpyHostToDevice));
+        } else if (c->powersave && c->analog_powersave > 0.0 && c->analog_powersave < 1.0) {
+            rc = fail(BFCUDA_ENOTSUP, "analog powersave needs partitions of at least 64 samples");
+            goto error;
         }
         TRY(dev_alloc(e, &e->d_fdl, rs_bytes(e, F * (size_t)e->fdl_ring * N)));
         TRY(dev_alloc(e, &e->d_xin, rs_bytes(e, B * (size_t)std::max(1, e->n_vin) * N)));
@@ -1527,6 +1566,7 @@ static int flush_timing_ring(bfcuda_engine *e)
 }
 
 // ---- kernel argument blocks of one launch (shared by enqueue_batch and the step graphs) --------------------------
+static bool in_transition(const bfcuda_engine *e);
 static ForwardArgs make_forward_args(const bfcuda_engine *e, int nb, int slot_t, const uint8_t *raw_in)
 {
     ForwardArgs fa;
@@ -1548,7 +1588,24 @@ static ForwardArgs make_forward_args(const bfcuda_engine *e, int nb, int slot_t,
     fa.fast_fmt = e->fast_fmt[0];
     fa.xt_cur = fa.xt_prev = nullptr;
     fa.single_dest = e->single_dest ? 1 : 0;
+    fa.powersave = 0;           // set_xt_generation() fills these in on the unpack-first paths
+    fa.amax_cur = fa.amax_prev = nullptr;
+    fa.ps_thr = e->d_ps_thr;
+    fa.slot_zero = e->d_slot_zero;
     return fa;
+}
+
+// the operands that follow the generation of the unpacked-sample buffers: this launch's blocks in d_xt[gen], the block
+// before them the last one of the other generation (and the same for the powersave peaks)
+static void set_xt_generation(const bfcuda_engine *e, ForwardArgs &fa, int gen, int prev_nb)
+{
+    fa.xt_cur = e->d_xt[gen];
+    fa.xt_prev = (const char *)e->d_xt[gen ^ 1] + rs_bytes(e, (size_t)(prev_nb - 1) * e->n_ch[0] * e->L);
+    if (e->powersave) {
+        fa.powersave = e->powersave;
+        fa.amax_cur = e->d_amax[gen];
+        fa.amax_prev = e->d_amax[gen ^ 1] + (size_t)(prev_nb - 1) * e->n_ch[0];
+    }
 }
 
 static UnpackArgs make_unpack_args(const bfcuda_engine *e, int nb, const uint8_t *raw_in, int xt_gen)
@@ -1562,6 +1619,7 @@ static UnpackArgs make_unpack_args(const bfcuda_engine *e, int nb, const uint8_t
     ua.L = e->L;
     ua.in_stride = (size_t)e->n_bytes[0];
     ua.fast_fmt = e->fast_fmt[0];
+    ua.amax = e->powersave ? e->d_amax[xt_gen] : nullptr;
     return ua;
 }
 
@@ -1580,6 +1638,8 @@ static MacArgs make_mac_args(const bfcuda_engine *e, int nb, int slot_t, int y_g
     ma.batch = nb;
     ma.variant = (e->mac_variant == 1 && !mac_tma_applicable(e->plan)) ? 0 : e->mac_variant;
     ma.head = ma.z_first = ma.z_count = 0;
+    // powersave: zero slots are skipped -- unless a delay transition has been rewriting slots behind the flags' back
+    ma.slot_zero = (e->powersave && !in_transition(e) && (long)e->t >= e->ps_hold_until) ? e->d_slot_zero : nullptr;
     ma.neg_zero2 = 0x8000000080000000ull;   // two packed -0.0f (bf_mac_batch.cu, BinPairAcc): the launcher sets the same
     return ma;
 }
@@ -1670,11 +1730,12 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         // size-specialised / four-step path: unpack the raw blocks into planar reals first (raw2real), transforms read those
         e->xt_par ^= 1;
         UnpackArgs ua = make_unpack_args(e, nb, raw_in, e->xt_par);
+        if (ua.amax != nullptr) {
+            CU(cudaMemsetAsync(ua.amax, 0, sizeof(unsigned int) * (size_t)nb * e->n_ch[0], e->stream));
+        }
         CU(launch_unpack(e->plan, ua, e->stream));
         e->launches += e->n_ch[0] > 0;
-        fa.xt_cur = e->d_xt[e->xt_par];
-        fa.xt_prev = (const char *)e->d_xt[e->xt_par ^ 1] +
-                     rs_bytes(e, (size_t)(e->xt_last_nb - 1) * e->n_ch[0] * e->L);
+        set_xt_generation(e, fa, e->xt_par, e->xt_last_nb);
         e->xt_last_nb = nb;
     }
     CU(launch_forward(e->plan, fa, e->stream));
@@ -1688,6 +1749,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     sa.ring = e->fdl_ring;
     sa.t = e->slot_t;
     sa.batch = nb;
+    sa.slot_zero = e->d_slot_zero;
     if (e->level_mix_first[1] > 0) {
         // mixes of input channels only (level 0); the mixes that contain an evaluated filter output follow their
         // source filters' MAC below
@@ -1904,6 +1966,9 @@ static int begin_transitions(bfcuda_engine *e)
             }
         }
         fs.trans_until = T + 2L * P;
+        // the repairs copy whole slots without their powersave flags: read everything until the last repaired slot is
+        // out of every filter's reach
+        e->ps_hold_until = std::max(e->ps_hold_until, T + 3L * P + 2L * e->max_batch);
     }
     e->delay_changes.clear();
     return 0;
@@ -2087,6 +2152,9 @@ static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const Un
     auto ok = [&](cudaError_t r) { if (err == cudaSuccess) err = r; return err == cudaSuccess; };
     ok(cudaEventRecord(e->ev_cap[0], e->stream));
     if (mask & 4) {
+        if (ua.amax != nullptr) {
+            ok(cudaMemsetAsync(ua.amax, 0, sizeof(unsigned int) * (size_t)nb * e->n_ch[0], e->stream));
+        }
         if (ok(launch_unpack(e->plan, ua, e->stream)) && ok(launch_forward(e->plan, fa, e->stream))) {
             f_fwd = g_last_func;
         }
@@ -2181,8 +2249,7 @@ static int graph_tick(bfcuda_engine *e, bool have_f, void *host_out, unsigned in
         e->xt_par ^= 1;             // == (k + 1) & 1: the stream path toggles it once per launch too
         ua = make_unpack_args(e, nb, d_in, e->xt_par);
         fa = make_forward_args(e, nb, e->slot_t, d_in);
-        fa.xt_cur = e->d_xt[e->xt_par];
-        fa.xt_prev = (const char *)e->d_xt[e->xt_par ^ 1] + rs_bytes(e, (size_t)(e->xt_last_nb - 1) * e->n_ch[0] * e->L);
+        set_xt_generation(e, fa, e->xt_par, e->xt_last_nb);
         e->xt_last_nb = nb;
     }
     if (mask & 2) {

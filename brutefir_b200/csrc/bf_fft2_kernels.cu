@@ -35,20 +35,20 @@ struct BlockSync2 {
 };
 
 // shared memory: [M complex data][TW_TOTAL complex twiddles (TWS only)][32 QuantStats][mbarrier]
-template <int LOG2M, bool TWS>
+template <typename T, int LOG2M, bool TWS>
 struct Smem2 {
     typedef Fft2<LOG2M> F;
-    static constexpr size_t data_bytes = (size_t)F::SUBS * F::SUB_STRIDE * sizeof(cpx<float>);
-    static constexpr size_t tw_bytes = TWS ? (size_t)F::TW_TOTAL * sizeof(cpx<float>) : 0;
+    static constexpr size_t data_bytes = (size_t)F::SUBS * F::SUB_STRIDE * sizeof(cpx<T>);
+    static constexpr size_t tw_bytes = TWS ? (size_t)F::TW_TOTAL * sizeof(cpx<T>) : 0;
     static constexpr size_t stats_off = data_bytes + tw_bytes;
     static constexpr size_t bar_off = stats_off + 32 * sizeof(QuantStats);
     static constexpr size_t total = bar_off + 16;
 };
 
-template <int LOG2M, bool TWS>
-__device__ __forceinline__ const cpx<float> *stage_twiddles(unsigned char *smem, const cpx<float> *tw_global, int tid)
+template <typename T, int LOG2M, bool TWS>
+__device__ __forceinline__ const cpx<T> *stage_twiddles(unsigned char *smem, const cpx<T> *tw_global, int tid)
 {
-    typedef Smem2<LOG2M, TWS> S;
+    typedef Smem2<T, LOG2M, TWS> S;
     if (!TWS) {
         return tw_global;
     }
@@ -67,14 +67,14 @@ __device__ __forceinline__ const cpx<float> *stage_twiddles(unsigned char *smem,
         }
     }
     __syncthreads();        // the barrier is initialised before anybody polls it
-    return reinterpret_cast<const cpx<float> *>(dst);
+    return reinterpret_cast<const cpx<T> *>(dst);
 }
 
-template <int LOG2M, bool TWS>
+template <typename T, int LOG2M, bool TWS>
 __device__ __forceinline__ void wait_twiddles(unsigned char *smem)
 {
     if (TWS) {
-        mbar_wait(reinterpret_cast<uint64_t *>(smem + Smem2<LOG2M, TWS>::bar_off), 0);
+        mbar_wait(reinterpret_cast<uint64_t *>(smem + Smem2<T, LOG2M, TWS>::bar_off), 0);
     }
 }
 
@@ -96,6 +96,9 @@ __device__ __forceinline__ void wait_twiddles(unsigned char *smem)
 constexpr int RW = 8;           // samples per tile row group
 constexpr int WPB = 8;          // warps per block
 constexpr int TS = RW + 1;      // padded row stride of the shared tile
+
+__device__ __forceinline__ float peak_as_float(float v) { return fabsf(v); }
+__device__ __forceinline__ float peak_as_float(double v) { return __double2float_ru(fabs(v)); }
 
 template <typename T>
 __global__ void __launch_bounds__(32 * WPB) k_unpack(UnpackArgs a)
@@ -127,6 +130,19 @@ __global__ void __launch_bounds__(32 * WPB) k_unpack(UnpackArgs a)
             } else {
                 for (int r = 0; r < RW; r++) {
                     row[r] = decode_sample<T>(load_raw_le(p + r * stride, f.bytes), f.bytes, f.isfloat, f.swap);
+                }
+            }
+            if (a.amax != nullptr) {
+                // powersave: the block's peak, rounded up to float so that "not zero" stays "not zero"
+                float m = 0.f;
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    m = fmaxf(m, peak_as_float(row[r]));
+                }
+                unsigned int *slot = a.amax + (size_t)blk * a.n_in + c;
+                const unsigned int bits = __float_as_uint(m);       // non-negative floats order like their bit patterns
+                if (bits > *slot) {
+                    atomicMax(slot, bits);
                 }
             }
         }
@@ -240,16 +256,16 @@ __global__ void __launch_bounds__(32 * WPB) k_pack(InverseArgs a, int L)
 
 // frame = [previous block | this block] (fftw_convolver.c:180-193) packed as z_i = x_2i + i x_2i+1; a thread's
 // first-pass butterfly takes z[tid + q NT]: q < 8 lies in the previous block, q >= 8 in this one.
-template <int LOG2M>
-__device__ __forceinline__ void load_frame(const ForwardArgs &a, int item, int tid, cpx<float> *v)
+template <typename T, int LOG2M>
+__device__ __forceinline__ void load_frame(const ForwardArgs &a, int item, int tid, cpx<T> *v)
 {
     typedef Fft2<LOG2M> F;
     constexpr int L = F::M, NT = F::NT;
     const int c = item % a.n_in, blk = item / a.n_in;
-    const float *cur = reinterpret_cast<const float *>(a.xt_cur) + ((size_t)blk * a.n_in + c) * L;
-    const float *old = blk == 0 ? reinterpret_cast<const float *>(a.xt_prev) + (size_t)c * L
-                                : cur - (size_t)a.n_in * L;
-    const cpx<float> *po = reinterpret_cast<const cpx<float> *>(old), *pc = reinterpret_cast<const cpx<float> *>(cur);
+    const T *cur = reinterpret_cast<const T *>(a.xt_cur) + ((size_t)blk * a.n_in + c) * L;
+    const T *old = blk == 0 ? reinterpret_cast<const T *>(a.xt_prev) + (size_t)c * L
+                            : cur - (size_t)a.n_in * L;
+    const cpx<T> *po = reinterpret_cast<const cpx<T> *>(old), *pc = reinterpret_cast<const cpx<T> *>(cur);
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         v[q] = po[tid + q * NT];
@@ -257,75 +273,86 @@ __device__ __forceinline__ void load_frame(const ForwardArgs &a, int item, int t
     }
 }
 
-// MINB = 2 ("light"): two blocks per SM -- 64 registers per thread, so no register prefetch of the next frame, and the
-// twiddle tables stay in global memory / L1 (TWS = false) so that two 64 KB data regions fit one SM.  While one block
-// waits at a pass barrier the other one runs.
-template <int LOG2M, bool SINGLE, bool TWS, int MINB>
-__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_forward2(ForwardArgs a, const cpx<float> *__restrict__ tw_global)
+template <typename T, int LOG2M, bool SINGLE, bool TWS>
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_forward2(ForwardArgs a, const cpx<T> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, N = 2 * F::M;
-    constexpr bool PREFETCH = F::NT < 1024 && MINB == 1;    // 64 registers per thread: no room to hold the next frame
+    // holding the next frame in registers while the current one is stored: not with 1024 threads (64 registers each)
+    // and not in double precision (the 16 points alone are 64 registers)
+    constexpr bool PREFETCH = F::NT < 1024 && sizeof(T) == 4;
     extern __shared__ __align__(128) unsigned char smem2[];
     const int tid = threadIdx.x % F::NT, sub = threadIdx.x / F::NT;     // thread of its transform, transform of the block
-    cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2) + sub * F::SUB_STRIDE;
-    const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, threadIdx.x);
+    cpx<T> *s = reinterpret_cast<cpx<T> *>(smem2) + sub * F::SUB_STRIDE;
+    const cpx<T> *tw = stage_twiddles<T, LOG2M, TWS>(smem2, tw_global, threadIdx.x);
     const int total = a.n_in * a.batch;
     const int stride = (int)gridDim.x * F::SUBS;
-    float *fdl = reinterpret_cast<float *>(a.fdl);
+    T *fdl = reinterpret_cast<T *>(a.fdl);
     const int ring = a.ring;
 
-    cpx<float> v[16];
+    cpx<T> v[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) {
-        v[q].x = 0.f;
-        v[q].y = 0.f;
+        v[q].x = (T)0;
+        v[q].y = (T)0;
     }
     int item = (int)blockIdx.x * F::SUBS + sub;
     if (item < total) {
-        load_frame<LOG2M>(a, item, tid, v);
+        load_frame<T, LOG2M>(a, item, tid, v);
     }
-    wait_twiddles<LOG2M, TWS>(smem2);
+    wait_twiddles<T, LOG2M, TWS>(smem2);
     // every transform of the block takes the same number of turns (the barriers are block wide); one without an item
     // left runs on whatever its registers hold and stores nothing
     for (int base = (int)blockIdx.x * F::SUBS; base < total; base += stride, item += stride) {
         const bool active = item < total;
         const int c = active ? item % a.n_in : 0, blk = active ? item / a.n_in : 0;
         if (!PREFETCH && active && base != (int)blockIdx.x * F::SUBS) {
-            load_frame<LOG2M>(a, item, tid, v);
+            load_frame<T, LOG2M>(a, item, tid, v);
         }
-        fft2_complex<float, LOG2M, false, false>(s, tw, tid, v, BlockSync2());
+        fft2_complex<T, LOG2M, false, false>(s, tw, tid, v, BlockSync2());
         // the next transform's samples travel while this one's spectrum is split and stored
         if (PREFETCH && item + stride < total) {
-            load_frame<LOG2M>(a, item + stride, tid, v);
+            load_frame<T, LOG2M>(a, item + stride, tid, v);
         }
         if (active) {
             const int d0 = a.dest_first[c], d1 = a.dest_first[c + 1];
             const int t = a.t + blk;
+            // powersave: a silent frame leaves zeros (the reference memsets, bfrun.c:1548-1552) and flags its slots
+            const bool silent = frame_silent(a, c, blk);
+            if (a.slot_zero != nullptr && tid == 0) {
+                for (int d = d0; d < d1; d++) {
+                    const FwdDest ds = a.dests[d];
+                    a.slot_zero[(size_t)ds.stream * ring + (t + ds.delay) % ring] = silent ? 1 : 0;
+                }
+            }
             if (SINGLE) {
                 // one filter per input: one destination, hoisted out of the bin loop
                 const FwdDest ds = a.dests[d0];
-                float *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
-                const float sc = (float)ds.scale;
-                fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
-                    dst[k] = mul_rn(re, sc);
-                    dst[M + k] = mul_rn(im, sc);
+                T *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
+                const T sc = silent ? (T)0 : (T)ds.scale;
+                fft2_split_emit<T, LOG2M>(s, tw, tid, [&](int k, T re, T im) {
+                    dst[k] = silent ? (T)0 : mul_rn(re, sc);
+                    dst[M + k] = silent ? (T)0 : mul_rn(im, sc);
                 });
             } else {
-                float *xin = (a.xin != nullptr && a.need_xin[c])
-                                 ? reinterpret_cast<float *>(a.xin) + ((size_t)blk * a.n_vin + c) * N : nullptr;
+                T *xin = (a.xin != nullptr && a.need_xin[c])
+                                 ? reinterpret_cast<T *>(a.xin) + ((size_t)blk * a.n_vin + c) * N : nullptr;
                 const FwdDest *dests = a.dests;
-                fft2_split_emit<float, LOG2M>(s, tw, tid, [&](int k, float re, float im) {
+                fft2_split_emit<T, LOG2M>(s, tw, tid, [&](int k, T re, T im) {
+                    if (silent) {
+                        re = (T)0;
+                        im = (T)0;
+                    }
                     if (xin != nullptr) {
                         xin[k] = re;
                         xin[M + k] = im;
                     }
                     for (int d = d0; d < d1; d++) {
                         const FwdDest ds = dests[d];
-                        float *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
-                        const float sc = (float)ds.scale;
-                        dst[k] = mul_rn(re, sc);
-                        dst[M + k] = mul_rn(im, sc);
+                        T *dst = fdl + ((size_t)ds.stream * ring + (t + ds.delay) % ring) * N;
+                        const T sc = (T)ds.scale;
+                        dst[k] = silent ? (T)0 : mul_rn(re, sc);
+                        dst[M + k] = silent ? (T)0 : mul_rn(im, sc);
                     }
                 });
             }
@@ -341,39 +368,39 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_forward2(ForwardArgs
 // SIMPLE: every output is fed by exactly one filter, the partition sum is not split and no crossfade is pending
 // (the usual block): one scaled spectrum per transform, and the next transform's spectrum is fetched while this
 // one's samples are stored.
-template <int LOG2M, bool SIMPLE, bool TWS, int MINB>
-__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs a, const cpx<float> *__restrict__ tw_global)
+template <typename T, int LOG2M, bool SIMPLE, bool TWS>
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_inverse2(InverseArgs a, const cpx<T> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, L = F::M, N = 2 * F::M, NT = F::NT;
     constexpr int RL = F::radix(F::NP - 1);         // radix of the last pass
     constexpr int BPT = 16 / RL, HALF = RL / 2;      // butterflies per thread, valid outputs per butterfly
-    constexpr bool PREFETCH = F::NT < 1024 && MINB == 1;
+    constexpr bool PREFETCH = F::NT < 1024 && sizeof(T) == 4;
     extern __shared__ __align__(128) unsigned char smem2[];
     const int tid = threadIdx.x % NT, sub = threadIdx.x / NT;
-    cpx<float> *s = reinterpret_cast<cpx<float> *>(smem2) + sub * F::SUB_STRIDE;
-    const cpx<float> *tw = stage_twiddles<LOG2M, TWS>(smem2, tw_global, threadIdx.x);
+    cpx<T> *s = reinterpret_cast<cpx<T> *>(smem2) + sub * F::SUB_STRIDE;
+    const cpx<T> *tw = stage_twiddles<T, LOG2M, TWS>(smem2, tw_global, threadIdx.x);
     const int total = a.n_out * a.batch;
     const int stride = (int)gridDim.x * F::SUBS;
     const int first_item = (int)blockIdx.x * F::SUBS;
     const int zstride = a.batch * a.n_slots;        // Y slots between two partial sums of the split
-    cpx<float> v[16];
+    cpx<T> v[16];
 
     // overlap-save: only the first L samples are output (fftw_convolver.c:498-501); they are elements
     // i = (tid + b NT) + q M/RL, q < RL/2, of the complex result, sample 2i in .x and 2i + 1 in .y
-    auto store_time = [&](int o, int blk, const cpx<float> *keep) {
-        float *tdst = reinterpret_cast<float *>(a.out_time) + ((size_t)blk * a.n_out + o) * L;
+    auto store_time = [&](int o, int blk, const cpx<T> *keep) {
+        T *tdst = reinterpret_cast<T *>(a.out_time) + ((size_t)blk * a.n_out + o) * L;
 #pragma unroll
         for (int b = 0; b < BPT; b++) {
 #pragma unroll
             for (int q = 0; q < HALF; q++) {
                 const int i = (tid + b * NT) + q * (M / RL);
-                cpx<float> y = v[b * RL + q];
+                cpx<T> y = v[b * RL + q];
                 if (keep != nullptr) {
-                    y.x = xfade<float>(keep[b * HALF + q].x, y.x, 2 * i, L);
-                    y.y = xfade<float>(keep[b * HALF + q].y, y.y, 2 * i + 1, L);
+                    y.x = xfade<T>(keep[b * HALF + q].x, y.x, 2 * i, L);
+                    y.y = xfade<T>(keep[b * HALF + q].y, y.y, 2 * i + 1, L);
                 }
-                *reinterpret_cast<cpx<float> *>(tdst + 2 * i) = y;
+                *reinterpret_cast<cpx<T> *>(tdst + 2 * i) = y;
             }
         }
     };
@@ -381,24 +408,24 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs
     // Every transform of the block takes the same number of turns (block-wide barriers); one without an item left
     // transforms whatever its registers hold and stores nothing.
     if (SIMPLE) {
-        float x[32];
+        T x[32];
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-            x[i] = 0.f;
+            x[i] = (T)0;
         }
-        float sc = 0.f;
+        T sc = (T)0;
         auto fetch = [&](int item) {
             const int o = item % a.n_out, blk = item / a.n_out;
             const MixTerm tm = a.terms[a.chans[o].first];
-            const float *y = reinterpret_cast<const float *>(a.Y) + ((size_t)blk * a.n_slots + tm.index) * N;
-            sc = (float)tm.scale;
-            fft2_merge_fetch<float, LOG2M>(tid, x, [&](int i) { return __ldg(y + i); });
+            const T *y = reinterpret_cast<const T *>(a.Y) + ((size_t)blk * a.n_slots + tm.index) * N;
+            sc = (T)tm.scale;
+            fft2_merge_fetch<T, LOG2M>(tid, x, [&](int i) { return __ldg(y + i); });
         };
         int item = first_item + sub;
         if (item < total) {
             fetch(item);
         }
-        wait_twiddles<LOG2M, TWS>(smem2);
+        wait_twiddles<T, LOG2M, TWS>(smem2);
         for (int base = first_item; base < total; base += stride, item += stride) {
             const bool active = item < total;
             if (!PREFETCH && active && base != first_item) {
@@ -408,14 +435,14 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs
             for (int i = 0; i < 32; i++) {
                 x[i] = mul_rn(x[i], sc);        // mixnscale(OUTPUT) with one term (fftw_convfuns.h:268-494)
             }
-            fft2_merge_store<float, LOG2M>(s, tw, tid, x);
+            fft2_merge_store<T, LOG2M>(s, tw, tid, x);
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 v[q] = s[tid + q * NT];
             }
             __syncthreads();        // everybody holds its inputs: pass 0 may overwrite
-            fft2_complex<float, LOG2M, true, true>(s, tw, tid, v, BlockSync2());
+            fft2_complex<T, LOG2M, true, true>(s, tw, tid, v, BlockSync2());
             const int o = active ? item % a.n_out : 0, blk = active ? item / a.n_out : 0;
             if (PREFETCH && item + stride < total) {
                 fetch(item + stride);
@@ -426,8 +453,8 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs
             __syncthreads();        // the last pass has finished reading shared memory
         }
     } else {
-        cpx<float> keep[BPT * HALF];
-        wait_twiddles<LOG2M, TWS>(smem2);
+        cpx<T> keep[BPT * HALF];
+        wait_twiddles<T, LOG2M, TWS>(smem2);
         // a launch that contains a crossfading output runs two transforms for EVERY item (same turn count for all
         // transforms of a block); items without a crossfade transform their mix twice and use the second
         const int npass = a.any_xfade ? 2 : 1;
@@ -436,12 +463,12 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs
             const bool active = item < total;
             const int o = active ? item % a.n_out : 0, blk = active ? item / a.n_out : 0;
             const OutChan ch = a.chans[o];
-            const float *Y = reinterpret_cast<const float *>(a.Y) + (size_t)blk * a.n_slots * N;
+            const T *Y = reinterpret_cast<const T *>(a.Y) + (size_t)blk * a.n_slots * N;
             for (int pass = 0; pass < npass; pass++) {
                 const int term0 = (ch.xf_first >= 0 && pass + 1 < npass) ? ch.xf_first : ch.first;
                 if (active) {
-                    fft2_merge_load<float, LOG2M>(s, tw, tid, [&](int i) {
-                        return mix_terms<float>(Y, a.terms, term0, ch.n, zstride, a.split, N, i);
+                    fft2_merge_load<T, LOG2M>(s, tw, tid, [&](int i) {
+                        return mix_terms<T>(Y, a.terms, term0, ch.n, zstride, a.split, N, i);
                     });
                 }
                 __syncthreads();
@@ -450,7 +477,7 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs
                     v[q] = s[tid + q * NT];
                 }
                 __syncthreads();    // everybody holds its inputs: pass 0 may overwrite
-                fft2_complex<float, LOG2M, true, true>(s, tw, tid, v, BlockSync2());
+                fft2_complex<T, LOG2M, true, true>(s, tw, tid, v, BlockSync2());
                 if (pass + 1 < npass) {
 #pragma unroll
                     for (int b = 0; b < BPT; b++) {
@@ -475,27 +502,44 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs
 
 bool fft2_supported(int N, int realsize)
 {
-    if (realsize != 4) {
-        return false;
-    }
     const char *e = getenv("BFCUDA_FFT_V1");
     if (e != nullptr && atoi(e) != 0) {
         return false;
     }
-    return N >= 128 && N <= 32768 && (N & (N - 1)) == 0;
+    if ((N & (N - 1)) != 0 || N < 128) {
+        return false;
+    }
+    // float: M = N/2 up to 16384 complex points in shared memory; double: up to 8192
+    return realsize == 4 ? N <= 32768 : N <= 16384;
 }
 
-template <int LOG2M>
+template <typename T, int LOG2M>
 static cudaError_t make_table(void **out)
 {
     typedef Fft2<LOG2M> F;
-    std::vector<cpx<float>> h((size_t)F::TW_TOTAL);
-    fft2_fill_table<float, LOG2M>(h.data());
-    cudaError_t err = cudaMalloc(out, h.size() * sizeof(cpx<float>));
+    std::vector<cpx<T>> h((size_t)F::TW_TOTAL);
+    fft2_fill_table<T, LOG2M>(h.data());
+    cudaError_t err = cudaMalloc(out, h.size() * sizeof(cpx<T>));
     if (err != cudaSuccess) {
         return err;
     }
-    return cudaMemcpy(*out, h.data(), h.size() * sizeof(cpx<float>), cudaMemcpyHostToDevice);
+    return cudaMemcpy(*out, h.data(), h.size() * sizeof(cpx<T>), cudaMemcpyHostToDevice);
+}
+
+template <typename T>
+static cudaError_t make_table_for(void **out, int N)
+{
+    switch (N) {
+    case 128: return make_table<T, 6>(out);
+    case 256: return make_table<T, 7>(out);
+    case 512: return make_table<T, 8>(out);
+    case 1024: return make_table<T, 9>(out);
+    case 2048: return make_table<T, 10>(out);
+    case 4096: return make_table<T, 11>(out);
+    case 8192: return make_table<T, 12>(out);
+    case 16384: return make_table<T, 13>(out);
+    default: return make_table<T, 14>(out);
+    }
 }
 
 cudaError_t fft2_plan_create(FftPlan *plan)
@@ -504,17 +548,7 @@ cudaError_t fft2_plan_create(FftPlan *plan)
     if (!fft2_supported(plan->N, plan->realsize)) {
         return cudaSuccess;
     }
-    switch (plan->N) {
-    case 128: return make_table<6>(&plan->tw2);
-    case 256: return make_table<7>(&plan->tw2);
-    case 512: return make_table<8>(&plan->tw2);
-    case 1024: return make_table<9>(&plan->tw2);
-    case 2048: return make_table<10>(&plan->tw2);
-    case 4096: return make_table<11>(&plan->tw2);
-    case 8192: return make_table<12>(&plan->tw2);
-    case 16384: return make_table<13>(&plan->tw2);
-    default: return make_table<14>(&plan->tw2);
-    }
+    return plan->realsize == 4 ? make_table_for<float>(&plan->tw2, plan->N) : make_table_for<double>(&plan->tw2, plan->N);
 }
 
 static int sm_count_of_current_device()
@@ -555,57 +589,72 @@ static cudaError_t persistent_grid(K kernel, int threads, size_t smem, int total
     return cudaSuccess;
 }
 
-template <int LOG2M, bool SINGLE, bool TWS, int MINB = 1>
+template <typename T, int LOG2M, bool SINGLE, bool TWS>
 static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
     static int resident[64];
-    const size_t smem = Smem2<LOG2M, TWS>::total;
+    const size_t smem = Smem2<T, LOG2M, TWS>::total;
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_forward2<LOG2M, SINGLE, TWS, MINB>, F::CTA, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_forward2<T, LOG2M, SINGLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
     const int total = (a.n_in * a.batch + F::SUBS - 1) / F::SUBS;      // blocks needed: SUBS transforms each
     const int grid = total < resident[dev] ? total : resident[dev];
-    g_last_func = (const void *)k_forward2<LOG2M, SINGLE, TWS, MINB>;
-    k_forward2<LOG2M, SINGLE, TWS, MINB><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    g_last_func = (const void *)k_forward2<T, LOG2M, SINGLE, TWS>;
+    k_forward2<T, LOG2M, SINGLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<T> *>(plan.tw2));
     return cudaGetLastError();
 }
 
-template <int LOG2M, bool SIMPLE, bool TWS, int MINB = 1>
+template <typename T, int LOG2M, bool SIMPLE, bool TWS>
 static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
     static int resident[64];
-    const size_t smem = Smem2<LOG2M, TWS>::total;
+    const size_t smem = Smem2<T, LOG2M, TWS>::total;
     int dev = 0;
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_inverse2<LOG2M, SIMPLE, TWS, MINB>, F::CTA, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_inverse2<T, LOG2M, SIMPLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
     const int total = (a.n_out * a.batch + F::SUBS - 1) / F::SUBS;
     const int grid = total < resident[dev] ? total : resident[dev];
-    k_inverse2<LOG2M, SIMPLE, TWS, MINB><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<float> *>(plan.tw2));
+    k_inverse2<T, LOG2M, SIMPLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<T> *>(plan.tw2));
     return cudaGetLastError();
 }
 
-#define BF_FFT2_SIZES(FN, FLAG, ...)                                                   \
-    switch (plan.N) {                                                                  \
-    case 128: return FN<6, FLAG, true>(__VA_ARGS__);                                   \
-    case 256: return FN<7, FLAG, true>(__VA_ARGS__);                                   \
-    case 512: return FN<8, FLAG, true>(__VA_ARGS__);                                   \
-    case 1024: return FN<9, FLAG, true>(__VA_ARGS__);                                  \
-    case 2048: return FN<10, FLAG, true>(__VA_ARGS__);                                 \
-    case 4096: return FN<11, FLAG, true>(__VA_ARGS__);                                 \
-    case 8192: return FN<12, FLAG, true>(__VA_ARGS__);                                 \
-    case 16384: return FN<13, FLAG, true>(__VA_ARGS__);                                \
-    case 32768: return FN<14, FLAG, false>(__VA_ARGS__);                               \
-    default: return cudaErrorInvalidValue;                                             \
+// float: twiddle tables resident in shared memory up to M = 8192 (98 KB of tables beside 64 KB of data); double: up to
+// M = 4096 (the same byte counts), M = 8192 reads them through L1 (128 KB of data fills the block's shared memory)
+#define BF_FFT2_SIZES(FN, FLAG, ...)                                                          \
+    if (plan.realsize == 4) {                                                                 \
+        switch (plan.N) {                                                                     \
+        case 128: return FN<float, 6, FLAG, true>(__VA_ARGS__);                               \
+        case 256: return FN<float, 7, FLAG, true>(__VA_ARGS__);                               \
+        case 512: return FN<float, 8, FLAG, true>(__VA_ARGS__);                               \
+        case 1024: return FN<float, 9, FLAG, true>(__VA_ARGS__);                              \
+        case 2048: return FN<float, 10, FLAG, true>(__VA_ARGS__);                             \
+        case 4096: return FN<float, 11, FLAG, true>(__VA_ARGS__);                             \
+        case 8192: return FN<float, 12, FLAG, true>(__VA_ARGS__);                             \
+        case 16384: return FN<float, 13, FLAG, true>(__VA_ARGS__);                            \
+        case 32768: return FN<float, 14, FLAG, false>(__VA_ARGS__);                           \
+        default: return cudaErrorInvalidValue;                                                \
+        }                                                                                     \
+    }                                                                                         \
+    switch (plan.N) {                                                                         \
+    case 128: return FN<double, 6, FLAG, true>(__VA_ARGS__);                                  \
+    case 256: return FN<double, 7, FLAG, true>(__VA_ARGS__);                                  \
+    case 512: return FN<double, 8, FLAG, true>(__VA_ARGS__);                                  \
+    case 1024: return FN<double, 9, FLAG, true>(__VA_ARGS__);                                 \
+    case 2048: return FN<double, 10, FLAG, true>(__VA_ARGS__);                                \
+    case 4096: return FN<double, 11, FLAG, true>(__VA_ARGS__);                                \
+    case 8192: return FN<double, 12, FLAG, true>(__VA_ARGS__);                                \
+    case 16384: return FN<double, 13, FLAG, false>(__VA_ARGS__);                              \
+    default: return cudaErrorInvalidValue;                                                    \
     }
 
 cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t s)
@@ -633,22 +682,9 @@ cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t 
     return cudaGetLastError();
 }
 
-static bool fft2_light()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("BFCUDA_FFT2_LIGHT");
-        v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-    }
-    return v == 1;
-}
-
 cudaError_t launch_forward2(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
-    if (fft2_light() && plan.N == 16384) {
-        return a.single_dest ? launch_forward2_t<13, true, false, 2>(plan, a, s) : launch_forward2_t<13, false, false, 2>(plan, a, s);
-    }
     if (a.single_dest) {
         BF_FFT2_SIZES(launch_forward2_t, true, plan, a, s)
     }
@@ -658,9 +694,6 @@ cudaError_t launch_forward2(const FftPlan &plan, const ForwardArgs &a, cudaStrea
 cudaError_t launch_inverse2(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
-    if (fft2_light() && plan.N == 16384) {
-        return a.simple_mix ? launch_inverse2_t<13, true, false, 2>(plan, a, s) : launch_inverse2_t<13, false, false, 2>(plan, a, s);
-    }
     if (a.simple_mix) {
         BF_FFT2_SIZES(launch_inverse2_t, true, plan, a, s)
     }

@@ -221,6 +221,16 @@ __global__ void __launch_bounds__(256) k_big_split(BigSplitArgs<T> a)
     const ForwardArgs &f = a.fa;
     const int gi = a.item0 + item;
     const int c = gi % f.n_in, blk = gi / f.n_in;
+    const bool silent = frame_silent(f, c, blk);        // powersave
+    if (silent) {
+        x0r = x0i = x1r = x1i = (T)0;
+    }
+    if (f.slot_zero != nullptr && k == 0) {
+        for (int d = f.dest_first[c]; d < f.dest_first[c + 1]; d++) {
+            const FwdDest ds = f.dests[d];
+            f.slot_zero[(size_t)ds.stream * f.ring + (f.t + blk + ds.delay) % f.ring] = silent ? 1 : 0;
+        }
+    }
     if (f.xin != nullptr && f.need_xin[c]) {
         T *xin = reinterpret_cast<T *>(f.xin) + ((size_t)blk * f.n_vin + c) * N;
         xin[k] = x0r;
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(256) k_big_split(BigSplitArgs<T> a)
     for (int d = f.dest_first[c]; d < f.dest_first[c + 1]; d++) {
         const FwdDest ds = f.dests[d];
         T *dst = fdl + ((size_t)ds.stream * f.ring + (t + ds.delay) % f.ring) * N;
-        const T sc = (T)ds.scale;
+        const T sc = silent ? (T)0 : (T)ds.scale;      // exact zeros, never -0 or NaN * 0
         dst[k] = mul_rn(x0r, sc);
         dst[M + k] = mul_rn(x0i, sc);
         if (two) {

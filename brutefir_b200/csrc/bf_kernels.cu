@@ -257,6 +257,9 @@ __global__ void __launch_bounds__(256) k_stream_mix(StreamMixArgs a, int N)
     }
     const T *xin = reinterpret_cast<const T *>(a.xin) + (size_t)blk * a.n_in * N;
     const int slot = (a.t + blk + ms.delay) % a.ring;
+    if (a.slot_zero != nullptr && i == 0) {
+        a.slot_zero[(size_t)ms.stream * a.ring + slot] = 0;     // powersave: a mixed slot is never skipped
+    }
     T acc = (T)0;
     for (int j = 0; j < ms.n_inputs; j++) {
         const MixTerm tm = a.terms[ms.first + j];
@@ -319,6 +322,9 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
     T *out = reinterpret_cast<T *>(a.Y) + ((size_t)z * a.n_slots + jb.out) * N + (size_t)v * W;
     const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * P * N + (size_t)v * W;
     const int slot0 = a.t;
+    // powersave (bfrun.c:1737-1754: `if (!cbuf_zero[n][j] || !powersave)`): partitions whose delay-line slot holds zeros
+    // are skipped -- neither the slot nor its coefficient block is read
+    const uint8_t *sz = a.slot_zero != nullptr ? a.slot_zero + (size_t)jb.stream * P : nullptr;
 
     Lanes<T, W> are, aim;
 #pragma unroll
@@ -352,7 +358,9 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
         }
         const T *H = reinterpret_cast<const T *>(a.H) + (size_t)jb.hbase * N + (size_t)v * W;
         T dc = (T)0, ny = (T)0;
-        if (i < i1) {
+        if (i < i1 && sz != nullptr && sz[(slot0 - i) + ((slot0 - i) < 0 ? P : 0)]) {
+            i++;        // a zero first partition: the sum starts from zero (memset of ocbuf, bfrun.c:1741-1744)
+        } else if (i < i1) {
             // convolver_convolve: plain product for the first partition of the range
             int slot = slot0 - i;
             slot += (slot < 0) ? P : 0;
@@ -374,11 +382,13 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
         // reference's summation order; UNROLL partitions of loads are in flight per thread
         for (; i < i1; i += UNROLL) {
             V xr[UNROLL], xi[UNROLL], hr[UNROLL], hi[UNROLL];
+            bool live[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                if (i + u < i1) {
-                    int slot = slot0 - (i + u);
-                    slot += (slot < 0) ? P : 0;
+                int slot = slot0 - (i + u);
+                slot += (slot < 0) ? P : 0;
+                live[u] = i + u < i1 && !(sz != nullptr && sz[slot]);
+                if (live[u]) {
                     const T *xp = X + (size_t)slot * N;
                     const T *hp = H + (size_t)(i + u) * N;
                     xr[u] = ldg_stream(reinterpret_cast<const V *>(xp));
@@ -389,7 +399,7 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                if (i + u < i1) {
+                if (live[u]) {
                     const Lanes<T, W> br = as_lanes<T, W>(xr[u]), bi = as_lanes<T, W>(xi[u]);
                     const Lanes<T, W> cr = as_lanes<T, W>(hr[u]), ci = as_lanes<T, W>(hi[u]);
 #pragma unroll
@@ -1053,6 +1063,8 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
         if (a.head > 0 || a.z_count > 0) return cudaErrorInvalidValue;     // block-by-block schedule only
         return launch_mac_batch2(plan, a, s);      // bf_mac_batch.cu
     }
+    // (the cp.async ring kernel was tried for single blocks as well -- BASELINE config 4, 28 partitions per thread after
+    // the split: 36.8 us against 32.0 us for this kernel, profiles/r2_macsweep_groups_b1ring.txt)
     if (plan.realsize == 4) {
         g_last_func = (const void *)k_mac<float, 4>;
         k_mac<float, 4><<<grid, 256, 0, s>>>(a, plan.N);

@@ -116,6 +116,13 @@ struct ForwardArgs {
     const void *xt_cur;         // [batch][n_in][L] reals, this launch's blocks
     const void *xt_prev;        // [n_in][L] reals, the block before the first one
     int single_dest;            // every input feeds exactly one delay-line stream and no input spectrum is kept
+    // powersave (bfrun.c:1541-1552, 722-772): a frame [previous block | this block] whose peak is zero (mode 1) or
+    // below the channel's level (mode 2) leaves zero spectra, and its delay-line slots are flagged for the MAC
+    int powersave;              // 0 = off
+    const unsigned int *amax_cur;   // [batch][n_in] peak |sample| of this launch's blocks, float bits (k_unpack)
+    const unsigned int *amax_prev;  // [n_in] the same for the block before the first one
+    const float *ps_thr;        // [n_in] mode 2: silent iff peak < ps_thr (= analog_powersave / sf.scale)
+    uint8_t *slot_zero;         // [U][ring] 1 = the slot holds zeros (the MAC neither reads it nor its coefficients)
 };
 
 struct UnpackArgs {
@@ -127,6 +134,7 @@ struct UnpackArgs {
     int L;
     size_t in_stride;
     int fast_fmt;
+    unsigned int *amax;         // [batch][n_in] running peak |sample| as float bits (zeroed before the launch), or NULL
 };
 cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t s);
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s);
@@ -141,6 +149,7 @@ struct StreamMixArgs {
     int ring;
     int t;
     int batch;
+    uint8_t *slot_zero;         // mixed slots are marked "not zero" (conservative), or NULL
 };
 cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaStream_t s);
 
@@ -185,6 +194,7 @@ struct MacArgs {
     // the partitions [0, head) and partial 1 the rest; z_count > 0 launches only the partials z_first .. z_first +
     // z_count - 1 (the "rest" is computed one block ahead, bf_engine.cu).
     int head, z_first, z_count;
+    const uint8_t *slot_zero;   // [U][ring] powersave: slots flagged 1 are not read (nor the coefficients they meet), or NULL
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 // The host stub of the kernel the most recent launch_forward / launch_mac call of this thread launched: how the engine

@@ -213,10 +213,16 @@ struct DcFalse { static constexpr bool value = false; };
 // slots are 3.46 "waves" at the headline shape.  Measured: 64, 128 and 256 threads per block take the same time -- the
 // blocks of the partial last wave run alone on their SMs and correspondingly faster.)
 //
-// Small shards (8 or 16 filters of a 64-filter job per GPU) do not have a power of two of 256-thread blocks to spread:
-// 8 filters x 4096 bin pairs are 128 blocks for 148 SMs.  They run one bin per thread (W = 1: twice the threads, the
-// (re, im)-pair accumulators PairAcc, scalar products cost the FP32 pipe the same cycles as packed ones) in blocks of
-// 64 threads, which deal out evenly (1024 blocks = 6.9 per SM).  mac_batch_lanes() is the one place that decides.
+// Small shards (8 filters of a 64-filter job per GPU) do not have a power of two of 256-thread blocks to spread:
+// 8 filters x 4096 bin pairs are 128 blocks for 148 SMs, and the engine's split heuristic would cut the partition sum in
+// two (a different summation tree) to fill the machine.  They run one bin per thread instead (W = 1: twice the threads,
+// the (re, im)-pair accumulators PairAcc, scalar products cost the FP32 pipe the same cycles as packed ones) in blocks
+// of 64 threads, which deal out evenly (1024 blocks = 6.9 per SM): the same 44-45 us per 8-block launch as the split
+// two-bin kernel, in the reference's summation order.  mac_batch_lanes() is the one place that decides.
+// What did NOT help at that size (profiles/r2_macsweep_*.txt, ncu profiles/r2_shard8_mac_summary.txt): deeper rings
+// (S = 12 .. 24: slower -- the kernel is not waiting for memory, its stalls are math-pipe throttle and fixed-latency
+// waits with 2-3 warps per scheduler), two groups of four blocks per thread (twice the threads, 59 us), 128- or
+// 64-thread blocks of the two-bin kernel.
 template <typename T, int W, int B, int S, int MINB, int MBT>
 __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 {
@@ -238,6 +244,12 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
     const MacJob jb = a.jobs[job];
     const int z = blockIdx.y;
     const int R = a.ring;
+    // Batch groups (blockIdx.z): a batch larger than B is dealt over gridDim.z groups of B consecutive blocks each --
+    // more threads for shards too small to fill the machine otherwise; the groups read the same coefficient vectors at
+    // about the same time (second reader: L2), and every output block keeps its own left-to-right partition sum.
+    const int bg = (int)blockIdx.z * B;         // first block of this thread's group
+    const int t0 = (a.t + bg) % R;
+    const int nb_here = a.batch - bg;           // blocks of the group that exist (<= B are computed)
     const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * R * N + (size_t)v * W;
     auto xslot = [&](int s) -> const T * {      // s in (-R, 2R)
         s += (s < 0) ? R : 0;
@@ -259,8 +271,8 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
             const T fr = (T)(1.0 / (T)N);
 #pragma unroll
             for (int b = 0; b < B; b++) {
-                if (b < a.batch) {
-                    const T *xp = xslot(a.t + b);
+                if (b < nb_here) {
+                    const T *xp = xslot(t0 + b);
                     const V xr = ldg_once(reinterpret_cast<const V *>(xp));
                     const V xi = ldg_once(reinterpret_cast<const V *>(xp + M));
                     const L lr = *reinterpret_cast<const L *>(&xr), li = *reinterpret_cast<const L *>(&xi);
@@ -290,19 +302,42 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
             // the window at step j (ring slot t - i0 - j); step 0's is loaded again although the window already holds
             // it (one vector per thread and launch) so that every request is the same four copies, no branches.
             const T *hnext = H;
-            int xs = a.t - i0;
+            int xs = t0 - i0;
             xs += (xs < 0) ? R : 0;
             const T *xnext = X + (size_t)xs * N;
             const size_t wrap = (size_t)(R - 1) * N;
             int jn = 0;
+            // powersave (bfrun.c:1745-1754 skips convolve_add for zero delay-line blocks): a flagged slot is not read --
+            // the zero-fill form of cp.async delivers its zeros -- and while the whole B-slot window of a step is
+            // flagged its coefficient vector is not read either.  nzw = unflagged slots in the window of step jn.
+            const uint8_t *zf = a.slot_zero != nullptr ? a.slot_zero + (size_t)jb.stream * R : nullptr;
+            int nzw = 0;
+            if (zf != nullptr) {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    int sl = xs + b;
+                    sl -= (sl >= R) ? R : 0;
+                    nzw += zf[sl] ? 0 : 1;
+                }
+            }
             auto issue = [&](int stage) {       // request step jn into `stage`; always closes a group
                 const bool live = jn < n;
-                const unsigned int sz = live ? (unsigned int)VB : 0u;
+                bool xlive = live, hlive = live;
+                if (zf != nullptr && live) {
+                    if (jn > 0) {               // the window moved down by one slot: xs joined, xs + B left
+                        int old = xs + B;
+                        old -= (old >= R) ? R : 0;
+                        nzw += (zf[xs] ? 0 : 1) - (zf[old] ? 0 : 1);
+                    }
+                    xlive = !zf[xs];
+                    hlive = nzw > 0;
+                }
+                const unsigned int szx = xlive ? (unsigned int)VB : 0u, szh = hlive ? (unsigned int)VB : 0u;
                 const T *hp = live ? hnext : H;     // a zero-size copy reads nothing, but keep its address in bounds anyway
-                cp_async<VB>(stage_ptr(stage, 0), hp, sz);
-                cp_async<VB>(stage_ptr(stage, 1), hp + M, sz);
-                cp_async<VB>(stage_ptr(stage, 2), xnext, sz);
-                cp_async<VB>(stage_ptr(stage, 3), xnext + M, sz);
+                cp_async<VB>(stage_ptr(stage, 0), hp, szh);
+                cp_async<VB>(stage_ptr(stage, 1), hp + M, szh);
+                cp_async<VB>(stage_ptr(stage, 2), xnext, szx);
+                cp_async<VB>(stage_ptr(stage, 3), xnext + M, szx);
                 cp_async_commit();
                 hnext += N;
                 xnext = xs == 0 ? xnext + wrap : xnext - N;
@@ -316,7 +351,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
             // the initial window (blocks t .. t+B-1 against partition i0) straight into registers
 #pragma unroll
             for (int b = 0; b < B; b++) {
-                const T *xp = xslot(a.t + b - i0);
+                const T *xp = xslot(t0 + b - i0);
                 wr[b] = ldg_once(reinterpret_cast<const V *>(xp));
                 wi[b] = ldg_once(reinterpret_cast<const V *>(xp + M));
             }
@@ -393,8 +428,8 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
     }
 #pragma unroll
     for (int b = 0; b < B; b++) {
-        if (b < a.batch) {
-            T *out = reinterpret_cast<T *>(a.Y) + (((size_t)z * a.batch + b) * a.n_slots + jb.out) * N + (size_t)v * W;
+        if (b < nb_here) {
+            T *out = reinterpret_cast<T *>(a.Y) + (((size_t)z * a.batch + bg + b) * a.n_slots + jb.out) * N + (size_t)v * W;
             V ore, oim;
             acc[b].get(ore, oim);
             *reinterpret_cast<V *>(out) = ore;
@@ -404,7 +439,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 }
 
 template <typename T, int W, int B, int S, int REGS = 128, int MBT = 256>
-static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
+static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s, int groups = 1)
 {
     constexpr size_t smem = (size_t)S * 4 * MBT * W * sizeof(T);
     constexpr int MINB = 65536 / REGS / MBT;    // 512 threads per SM at 128 registers, 256 at 255
@@ -422,7 +457,7 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s)
         }
     }
     const long threads = (long)a.n_jobs * (N / 2 / W);
-    dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split);
+    dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split, groups);
     MacArgs args = a;
     args.neg_zero2 = 0x8000000080000000ull;     // (-0.0f, -0.0f): see BinPairAcc
     g_last_func = (const void *)k_mac_batch2<T, W, B, S, MINB, MBT>;
@@ -451,7 +486,7 @@ int mac_batch_lanes(int realsize, int batch, int n_jobs, int N)
 #endif
     if (realsize == 4) {
         if (batch <= 4) return 4;
-        static const int narrow_max = env_int("BFCUDA_MAC_NARROW_MAX_BINS", 16 * 8192);
+        static const int narrow_max = env_int("BFCUDA_MAC_NARROW_MAX_BINS", 8 * 8192);
         if (batch <= 8) return bins <= narrow_max ? 1 : 2;
         static const int narrow16 = env_int("BFCUDA_MAC_B16_NARROW", 0);
         return (narrow16 || bins <= narrow_max) ? 1 : 2;
@@ -464,6 +499,14 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
 {
     const int lanes = mac_batch_lanes(plan.realsize, a.batch, a.n_jobs, plan.N);
     if (plan.realsize == 4) {
+#ifdef BF_MAC_SWEEP
+        if (a.batch == 1) {
+            const int S = env_int("BFCUDA_MAC_S", 8);
+            if (S == 16) return launch_one<float, 4, 1, 16, 64, 256>(a, plan.N, s);
+            if (S == 12) return launch_one<float, 4, 1, 12, 64, 256>(a, plan.N, s);
+            return launch_one<float, 4, 1, 8, 64, 256>(a, plan.N, s);
+        }
+#endif
         if (a.batch <= 2) return launch_one<float, 4, 2, 4>(a, plan.N, s);
         if (a.batch <= 4) return launch_one<float, 4, 4, 4>(a, plan.N, s);
         if (a.batch <= 8) {
@@ -476,6 +519,12 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
                 if (S == 24 && TPB == 64) return launch_one<float, 1, 8, 24, 96, 64>(a, plan.N, s);
                 if (S == 16 && TPB == 128) return launch_one<float, 1, 8, 16, 96, 128>(a, plan.N, s);
                 return cudaErrorInvalidValue;
+            }
+            if (env_int("BFCUDA_MAC_GROUPS", 1) == 2) {
+                // two groups of four blocks
+                if (lanes == 4) return launch_one<float, 4, 4, 4>(a, plan.N, s, 2);
+                if (TPB == 128) return launch_one<float, 2, 4, 8, 64, 128>(a, plan.N, s, 2);
+                return launch_one<float, 2, 4, 8, 64, 256>(a, plan.N, s, 2);
             }
             if (S == 8 && TPB == 256) return launch_one<float, 2, 8, 8>(a, plan.N, s);
             if (S == 8 && TPB == 128) return launch_one<float, 2, 8, 8, 128, 128>(a, plan.N, s);

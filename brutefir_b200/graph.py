@@ -54,6 +54,8 @@ class FilterGraph:
     sampling_rate: int = 48000
     apply_dither: Sequence[bool] | None = None      # per output channel (`dither: true` of its device)
     max_dither_table_size: int = 0
+    powersave: bool = False                 # bfconf->powersave
+    analog_powersave: float = 1.0           # linear level; >= 1.0: only exact zeros are silent (bfrun.c:722-772)
 
     @property
     def n_fft(self) -> int:
@@ -142,6 +144,8 @@ class FilterGraph:
         cfg.sampling_rate = self.sampling_rate
         cfg.max_dither_table_size = self.max_dither_table_size
         cfg.max_batch = max_batch
+        cfg.powersave = int(bool(self.powersave))
+        cfg.analog_powersave = float(self.analog_powersave)
         return cfg, keep
 
     # ---- derived figures used by bench.py -------------------------------------

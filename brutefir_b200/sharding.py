@@ -164,7 +164,8 @@ def shard_graph(graph: FilterGraph, n_ranks: int, split_outputs: bool = False, c
                           in_bytes, out_bytes, local, list(graph.coeff_n_blocks),
                           safety_limit=graph.safety_limit, sampling_rate=graph.sampling_rate,
                           apply_dither=None if graph.apply_dither is None else [graph.apply_dither[o] for o in outs],
-                          max_dither_table_size=graph.max_dither_table_size)
+                          max_dither_table_size=graph.max_dither_table_size,
+                          powersave=graph.powersave, analog_powersave=graph.analog_powersave)
         shared = [omap[o] for o in shared_global]
         shards.append(Shard(r, sub, mine, ins, outs, coeffs, shared))
     return shards

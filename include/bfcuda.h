@@ -124,6 +124,12 @@ struct bfcuda_config {
                                    realsize 8) lets bfcuda_process_blocks* take up to B consecutive blocks per call:
                                    offline / file-to-file throughput mode.  Results are bit-identical to B single
                                    calls; the I/O delay grows by the batch (not for real-time use). */
+    int powersave;              /* bfconf->powersave (bfrun.c:1541-1552, 1613-1700): a silent input frame skips its transform
+                                   and leaves a zero delay-line slot, and the multiply-accumulate skips zero slots -- on
+                                   this engine: does not READ them, nor the coefficient blocks they would meet.  0 = off */
+    double analog_powersave;    /* bfconf->analog_powersave as a linear level: a frame whose peak (times the sample
+                                   format's scale) is below it is made truly zero (bfrun.c:722-772).  >= 1.0 (or 0) =
+                                   only frames of exact zeros count as silent */
 };
 
 #define BFCUDA_FLAG_STAGE_TIMING 1u     /* record CUDA events around each stage of every block */

@@ -98,6 +98,9 @@ struct drv {
     void **dither_state;            /* per output: struct dither_state * (bfconf->dither_state), NULL = no dither */
     unsigned int blockcounter;
     int curbuf;
+    int powersave;                  /* bfconf->powersave */
+    double analog_powersave;        /* bfconf->analog_powersave, linear */
+    double *in_scale;               /* sf.scale of every input */
     int n_threads;
     /* per-thread scratch */
     void **crossfadebuf0, **crossfadebuf1, **timebuf;
@@ -284,6 +287,12 @@ DRV(create)(const struct bfcuda_config *c, int n_threads, struct drv **out)
         for (i = 0; i < d->coeff_n_blocks[n]; i++) {
             d->coeffs[n][i] = drv_alloc(d->cbufsize);
         }
+    }
+    d->powersave = c->powersave;
+    d->analog_powersave = (c->analog_powersave <= 0.0) ? 1.0 : c->analog_powersave;
+    d->in_scale = calloc(d->n_ch[IN] + 1, sizeof(double));
+    for (n = 0; n < d->n_ch[IN]; n++) {
+        d->in_scale[n] = c->formats[IN][n].sf.scale;
     }
     d->input_freqcbuf = calloc(d->n_ch[IN], sizeof(void *));
     d->input_timecbuf = calloc(d->n_ch[IN], sizeof(void *[2]));
@@ -523,6 +532,53 @@ DRV(debug_read)(struct drv *d, int what, int index, int slot, void *dst)
 
 /* ---- one block, the part of worker `t` ------------------------------------------------------- */
 
+/* test_silent(), bfrun.c:722-772: with analog_powersave >= 1.0 only a frame of exact zero BYTES is silent
+ * (memiszero, bfrun.c:700-720); below that, a frame whose scaled peak is under the level is silent and is "made truly
+ * zero".  The frame is the whole cbuf: previous block and this block. */
+static int
+drv_test_silent(void *buf, int size, int realsize, double analog_powersave, double scale)
+{
+    int n, count;
+    double dmax = 0;
+    if (analog_powersave >= 1.0) {
+        const unsigned char *b = buf;
+        for (n = 0; n < size; n++) {
+            if (b[n] != 0) {
+                return 0;
+            }
+        }
+        return 1;
+    }
+    if (realsize == 4) {
+        float fmax = 0;
+        count = size >> 2;
+        for (n = 0; n < count; n++) {
+            const float v = ((float *)buf)[n];
+            if (v < 0) {
+                if (-v > fmax) fmax = -v;
+            } else if (v > fmax) {
+                fmax = v;
+            }
+        }
+        dmax = fmax;
+    } else {
+        count = size >> 3;
+        for (n = 0; n < count; n++) {
+            const double v = ((double *)buf)[n];
+            if (v < 0) {
+                if (-v > dmax) dmax = -v;
+            } else if (v > dmax) {
+                dmax = v;
+            }
+        }
+    }
+    if (scale * dmax >= analog_powersave) {
+        return 0;
+    }
+    memset(buf, 0, size);
+    return 1;
+}
+
 static void
 forward_part(struct drv *d, int t, const uint8_t *inbuf)
 {
@@ -534,7 +590,15 @@ forward_part(struct drv *d, int t, const uint8_t *inbuf)
         }
         CV(raw2cbuf)((void *)inbuf, d->input_timecbuf[n][d->curbuf], d->input_timecbuf[n][!d->curbuf],
                      &d->bf[IN][n], NULL, NULL);
-        CV(time2freq)(d->input_timecbuf[n][d->curbuf], d->input_freqcbuf[n]);
+        /* bfrun.c:1541-1552.  What the reference then skips downstream (mixing and multiplying zero blocks,
+           bfrun.c:1613-1700, 1737-1754) leaves every result as it is -- zeros times coefficients add nothing -- so
+           the replay keeps computing them. */
+        if (d->powersave && drv_test_silent(d->input_timecbuf[n][d->curbuf], d->cbufsize, d->rs, d->analog_powersave,
+                                            d->in_scale[n])) {
+            memset(d->input_freqcbuf[n], 0, d->cbufsize);
+        } else {
+            CV(time2freq)(d->input_timecbuf[n][d->curbuf], d->input_freqcbuf[n]);
+        }
     }
 }
 

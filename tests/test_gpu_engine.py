@@ -438,10 +438,17 @@ def test_errors_and_limits(gpu_lib):
     with pytest.raises(_abi.BfcudaError) as err:
         Engine(g)
     assert err.value.code == -1 and "processing order" in str(err.value)      # bfconf.c:2933-2964
-    g = configs.diagonal_graph(1, 32768, 2, 4, "S16_LE")
+    g = configs.diagonal_graph(1, 1 << 23, 1, 4, "S16_LE")
     with pytest.raises(_abi.BfcudaError) as err:
         Engine(g)
-    assert err.value.code == -7                                         # partition beyond the single-block FFT
+    assert err.value.code == -7                                         # partition beyond the four-step transform
+    g = configs.config_c1_chained()
+    g.filter_length = 32768                                             # chained filters: one-block transforms only
+    g.in_formats, g.in_bytes = interleaved_layout(2, "S24_4LE", 32768)
+    g.out_formats, g.out_bytes = interleaved_layout(2, "S24_4LE", 32768)
+    with pytest.raises(_abi.BfcudaError) as err:
+        Engine(g)
+    assert err.value.code == -7
     g = configs.diagonal_graph(1, 64, 2, 4, "S16_LE")
     with Engine(g) as e:
         e.coeff_from_taps(0, np.full(128, 1e3, np.float32))

@@ -14,6 +14,11 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+           "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg",
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 out = []
 for arg in sys.argv[2:]:
