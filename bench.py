@@ -389,7 +389,12 @@ def measure(ctx, graph, shard, taps, cid, B, steps, warmup, sample_clocks=False,
                    "h2d_bytes_per_step": B * sub.in_bytes, "d2h_bytes_per_step": B * sub.out_bytes,
                    "mode": f"pipelined bfcuda_process_blocks_async({B} block(s) per call), pinned host buffers on the GPU's NUMA node",
                    "sync_call_latency_ms": latency_ms, "copy_only": copy_only,
-                   "host_fanout_gather_ms_per_step": fan_ms},
+                   "host_fanout_gather_ms_per_step": fan_ms,
+                   "host_fanout_note": None if fan_ms is None else
+                   "every rank is handed and returns blocks of ITS channels only (one I/O device or file per GPU, the way bfconf "
+                   "configs split channels over devices); if a single interleaved device feeds all GPUs the host must cut the "
+                   "channels apart first -- this figure is that repack (in and out) done by one numpy thread, OUTSIDE the timed "
+                   "e2e loop"},
            "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
            "engine": {"mac_split": info.mac_split, "kernels_per_step": info.kernels_per_block, "max_batch": B,
                       "device": info.device_name.decode(), "device_bytes": info.device_bytes,
@@ -740,11 +745,20 @@ def main():
             dog = threading.Timer(float(os.environ.get("BENCH_NCCL_TIMEOUT", "150")), bail)
             dog.daemon = True
             dog.start()
+            # NCCL writes its version / INFO lines to stdout: send them to stderr while the communicator lives, so that
+            # stdout carries the one JSON line only
+            sys.stdout.flush()
+            saved_stdout = os.dup(1)
+            os.dup2(2, 1)
             try:
                 res = nccl_xtc(ctx)
             except Exception as exc:
                 res = {"error": repr(exc)}
                 print(f"[rank {rank}] nccl_xtc failed: {exc!r}", file=sys.stderr, flush=True)
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved_stdout, 1)
+                os.close(saved_stdout)
             line["nccl_xtc"] = res
             dist.barrier()
             dog.cancel()

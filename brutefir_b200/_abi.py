@@ -64,7 +64,8 @@ class ConfigC(C.Structure):
                 ("max_dither_table_size", C.c_int),
                 ("max_batch", C.c_int),
                 ("powersave", C.c_int),
-                ("analog_powersave", C.c_double)]
+                ("analog_powersave", C.c_double),
+                ("out_physical", C.POINTER(C.c_int))]
 
 
 class InfoC(C.Structure):
@@ -96,6 +97,7 @@ ENGINE_SYMBOLS = [
     "bfcuda_host_alloc", "bfcuda_host_free", "bfcuda_timer_start", "bfcuda_timer_stop",
     "bfcuda_stage_times", "bfcuda_set_serial_stages", "bfcuda_set_stage_timing", "bfcuda_get_info", "bfcuda_debug_read", "bfcuda_comm_unique_id",
     "bfcuda_comm_init", "bfcuda_comm_shared_outputs", "bfcuda_host_alloc_near", "bfcuda_copy_baseline",
+    "bfcuda_set_subdelay", "bfcuda_set_mute",
 ]
 class DitherStateC(C.Structure):
     """struct dither_state (dither.h:17-22) == struct bfcuda_dither_state (include/bfcuda_convolver.h)."""
@@ -149,6 +151,8 @@ def load_library() -> C.CDLL:
     lib.bfcuda_coeff_get_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.bfcuda_coeff_runtime_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.bfcuda_set_control.argtypes = [C.c_void_p, C.c_int, C.POINTER(FilterControlC)]
+    lib.bfcuda_set_subdelay.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.bfcuda_set_mute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.bfcuda_get_overflow.argtypes = [C.c_void_p, C.c_int, C.POINTER(OverflowC)]
     lib.bfcuda_reset_overflow.argtypes = [C.c_void_p]
     lib.bfcuda_process_block.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

@@ -263,6 +263,19 @@ struct bfcuda_engine {
     float *d_ps_thr;                    // [n_in]
     uint8_t *d_slot_zero;               // [F][ring]
     long ps_hold_until;                 // block count until which the MAC ignores the flags (after a delay transition)
+    // virtual -> physical outputs, mute, sub-sample delay (bfrun.c:1503-1526, 1918-2002)
+    std::vector<int> out_rep;           // per output: the member of its physical channel that is quantised (itself: alone)
+    std::vector<VirtGroup> h_groups;
+    std::vector<int> h_members;
+    VirtGroup *d_groups;
+    int *d_members;
+    bool any_group;                     // some physical channel carries several virtual outputs
+    std::vector<uint8_t> h_muted[2];
+    uint8_t *d_muted[2];
+    bool any_muted[2];
+    std::vector<SubdelayChan> h_sd[2];  // channels with a sub-sample delay filter
+    SubdelayChan *d_sd_chans[2];
+    void *d_sd_taps[2], *d_sd_hist[2];  // [n_ch][BF_SUBDELAY_MAX_TAPS] taps, [n_ch][BF_SUBDELAY_MAX_TAPS - 1] history
     bool dirty, xfade_active;
     size_t mac_bytes;           // algorithmic MAC bytes of one block launched alone
     size_t mac_bytes_batch;     // compulsory MAC bytes of one full batch of max_batch blocks
@@ -592,6 +605,9 @@ static void build_tables(bfcuda_engine *e)
         if (e->dither_of_out[o] >= 0) {
             oc.shared |= 2;
         }
+        if (!e->out_rep.empty() && e->out_rep[(size_t)o] != o) {
+            oc.shared |= 4;     // mixed into another virtual output's physical channel (k_virt_mix), never packed
+        }
         bool any_xf = false;
         for (int f = 0; f < F; f++) {
             const FilterState &fs = e->filters[f];
@@ -852,7 +868,8 @@ void bfcuda_destroy(bfcuda_engine *e)
     if (e->comm != nullptr && g_nccl.handle != nullptr) {
         g_nccl.CommDestroy(e->comm);
     }
-    void *ptrs[] = { e->d_amax[0], e->d_amax[1], e->d_ps_thr, e->d_slot_zero, e->d_raw34[0][0], e->d_raw34[0][1], e->d_raw34[1][0], e->d_raw34[1][1], e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
+    void *ptrs[] = { e->d_groups, e->d_members, e->d_muted[0], e->d_muted[1], e->d_sd_chans[0], e->d_sd_chans[1], e->d_sd_taps[0],
+                     e->d_sd_taps[1], e->d_sd_hist[0], e->d_sd_hist[1], e->d_amax[0], e->d_amax[1], e->d_ps_thr, e->d_slot_zero, e->d_raw34[0][0], e->d_raw34[0][1], e->d_raw34[1][0], e->d_raw34[1][1], e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
                      e->d_keep, e->d_eval_entries, e->d_eval_terms, e->d_mixes, e->dither.chans, (void *)e->dither.randtab,
@@ -1057,6 +1074,15 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     memset(e->sg, 0, sizeof(e->sg));
     e->graph_enabled = !(c->flags & BFCUDA_FLAG_NO_GRAPH) && getenv("BFCUDA_NO_GRAPH") == nullptr;
     e->graph_mode = e->graph_host = e->graph_used = false;
+    e->d_groups = nullptr;
+    e->d_members = nullptr;
+    e->any_group = false;
+    for (int io = 0; io < 2; io++) {
+        e->d_muted[io] = nullptr;
+        e->any_muted[io] = false;
+        e->d_sd_chans[io] = nullptr;
+        e->d_sd_taps[io] = e->d_sd_hist[io] = nullptr;
+    }
     e->powersave = 0;
     e->d_amax[0] = e->d_amax[1] = nullptr;
     e->d_ps_thr = nullptr;
@@ -1302,6 +1328,60 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
                 TRYCU(cudaMemcpy(e->d_fmt[io], f.data(), sizeof(SampleFormat) * f.size(), cudaMemcpyHostToDevice));
             }
         }
+        // virtual -> physical outputs (bfconf->virt2phys[OUT], n_virtperphys): group the outputs by physical id
+        e->out_rep.resize((size_t)std::max(1, e->n_ch[1]));
+        for (int io = 0; io < 2; io++) {
+            e->h_muted[io].assign((size_t)std::max(1, e->n_ch[io]), 0);
+            TRY(dev_alloc(e, &e->d_muted[io], (size_t)std::max(1, e->n_ch[io])));
+        }
+        {
+            std::vector<char> seen((size_t)std::max(1, e->n_ch[1]), 0);
+            for (int o = 0; o < e->n_ch[1]; o++) {
+                e->out_rep[(size_t)o] = o;
+                if (seen[(size_t)o]) {
+                    continue;
+                }
+                VirtGroup g;
+                g.first = (int)e->h_members.size();
+                g.n = 0;
+                for (int q = o; q < e->n_ch[1]; q++) {
+                    if (q == o || (c->out_physical != nullptr && c->out_physical[q] == c->out_physical[o])) {
+                        const bfcuda_buffer_format &a = e->fmt[1][o], &b = e->fmt[1][q];
+                        if (a.byte_offset != b.byte_offset || a.sample_spacing != b.sample_spacing || a.sf.bytes != b.sf.bytes ||
+                            a.sf.sbytes != b.sf.sbytes || a.sf.isfloat != b.sf.isfloat || a.sf.swap != b.sf.swap) {
+                            rc = fail(BFCUDA_EINVAL, "outputs %d and %d share a physical channel but not a buffer format", o, q);
+                            goto error;
+                        }
+                        seen[(size_t)q] = 1;
+                        e->h_members.push_back(q);
+                        g.n++;
+                    }
+                }
+                for (int j = 0; j < g.n; j++) {
+                    e->out_rep[(size_t)e->h_members[(size_t)(g.first + j)]] = e->h_members[(size_t)(g.first + g.n - 1)];
+                }
+                e->any_group = e->any_group || g.n > 1;
+                e->h_groups.push_back(g);
+            }
+            if (e->any_group) {
+                if (!plan_unpacks_first(e->plan)) {
+                    rc = fail(BFCUDA_ENOTSUP, "several outputs on one physical channel need partitions of at least 64 samples");
+                    goto error;
+                }
+                for (int o = 0; o < e->n_ch[1]; o++) {
+                    if (c->apply_dither != nullptr && c->apply_dither[o] && e->out_rep[(size_t)o] != o) {
+                        rc = fail(BFCUDA_ENOTSUP, "dither on a physical channel that carries several virtual outputs");
+                        goto error;
+                    }
+                }
+            }
+            TRY(dev_alloc(e, &e->d_groups, sizeof(VirtGroup) * std::max<size_t>(1, e->h_groups.size())));
+            TRY(dev_alloc(e, &e->d_members, sizeof(int) * std::max<size_t>(1, e->h_members.size())));
+            if (!e->h_groups.empty()) {
+                TRYCU(cudaMemcpy(e->d_groups, e->h_groups.data(), sizeof(VirtGroup) * e->h_groups.size(), cudaMemcpyHostToDevice));
+                TRYCU(cudaMemcpy(e->d_members, e->h_members.data(), sizeof(int) * e->h_members.size(), cudaMemcpyHostToDevice));
+            }
+        }
         TRY(setup_dither(e, c));
         TRY(bfcuda_reset_overflow(e));
         e->dirty = true;
@@ -1350,6 +1430,8 @@ int bfcuda_get_overflow(bfcuda_engine *e, int out_channel, struct bfcuda_overflo
 {
     if (e == nullptr || overflow == nullptr) return fail(BFCUDA_EINVAL, "null argument");
     if (out_channel < 0 || out_channel >= e->n_ch[1]) return fail(BFCUDA_EINVAL, "output channel out of range");
+    // the virtual outputs of one physical channel share its record (bfrun.c:1994-1998)
+    out_channel = e->out_rep.empty() ? out_channel : e->out_rep[(size_t)out_channel];
     Overflow of;
     if (e->h_overflow_valid && e->io_count > 0) {
         // host-buffer interface: the records came back with the most recent call's output -- wait for that read-out
@@ -1541,6 +1623,65 @@ int bfcuda_set_control(bfcuda_engine *e, int filter, const struct bfcuda_filter_
     return 0;
 }
 
+int bfcuda_set_mute(bfcuda_engine *e, int io, int channel, int muted)
+{
+    if (e == nullptr || (io != 0 && io != 1)) return fail(BFCUDA_EINVAL, "bad argument");
+    if (channel < 0 || channel >= e->n_ch[io]) return fail(BFCUDA_EINVAL, "channel out of range");
+    if (!plan_unpacks_first(e->plan)) return fail(BFCUDA_ENOTSUP, "mute needs partitions of at least 64 samples");
+    if ((e->h_muted[io][(size_t)channel] != 0) == (muted != 0)) {
+        return 0;
+    }
+    CU(cudaSetDevice(e->device));
+    int rc = sync_all(e);       // the flags are read by launches in flight: change them between blocks
+    if (rc != 0) return rc;
+    e->h_muted[io][(size_t)channel] = muted ? 1 : 0;
+    e->any_muted[io] = false;
+    for (uint8_t m : e->h_muted[io]) {
+        e->any_muted[io] = e->any_muted[io] || m != 0;
+    }
+    CU(cudaMemcpy(e->d_muted[io], e->h_muted[io].data(), e->h_muted[io].size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int bfcuda_set_subdelay(bfcuda_engine *e, int io, int channel, const void *taps, int n_taps)
+{
+    if (e == nullptr || (io != 0 && io != 1)) return fail(BFCUDA_EINVAL, "bad argument");
+    if (channel < 0 || channel >= e->n_ch[io]) return fail(BFCUDA_EINVAL, "channel out of range");
+    if (taps != nullptr && (n_taps < 1 || n_taps > BF_SUBDELAY_MAX_TAPS)) {
+        return fail(BFCUDA_EINVAL, "sub-sample delay filter of %d taps (1..%d)", n_taps, BF_SUBDELAY_MAX_TAPS);
+    }
+    if (!plan_unpacks_first(e->plan)) return fail(BFCUDA_ENOTSUP, "sub-sample delay needs partitions of at least 64 samples");
+    CU(cudaSetDevice(e->device));
+    int rc = sync_all(e);
+    if (rc != 0) return rc;
+    const size_t nch = (size_t)std::max(1, e->n_ch[io]);
+    if (e->d_sd_taps[io] == nullptr) {
+        if ((rc = dev_alloc(e, &e->d_sd_taps[io], rs_bytes(e, nch * BF_SUBDELAY_MAX_TAPS))) != 0) return rc;
+        if ((rc = dev_alloc(e, &e->d_sd_hist[io], rs_bytes(e, nch * (BF_SUBDELAY_MAX_TAPS - 1)))) != 0) return rc;
+        if ((rc = dev_alloc(e, &e->d_sd_chans[io], sizeof(SubdelayChan) * nch)) != 0) return rc;
+    }
+    std::vector<SubdelayChan> &list = e->h_sd[io];
+    for (size_t i = 0; i < list.size(); i++) {
+        if (list[i].ch == channel) {
+            list.erase(list.begin() + (long)i);
+            break;
+        }
+    }
+    if (taps != nullptr) {
+        SubdelayChan sc;
+        sc.ch = channel;
+        sc.tap_first = channel * BF_SUBDELAY_MAX_TAPS;
+        sc.n_taps = n_taps;
+        list.push_back(sc);
+        CU(cudaMemcpy((char *)e->d_sd_taps[io] + rs_bytes(e, (size_t)sc.tap_first), taps, rs_bytes(e, (size_t)n_taps),
+                      cudaMemcpyHostToDevice));
+    }
+    if (!list.empty()) {
+        CU(cudaMemcpy(e->d_sd_chans[io], list.data(), sizeof(SubdelayChan) * list.size(), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
 // ---- the block step ------------------------------------------------------------------------------------
 
 static int flush_timing_ring(bfcuda_engine *e)
@@ -1620,6 +1761,7 @@ static UnpackArgs make_unpack_args(const bfcuda_engine *e, int nb, const uint8_t
     ua.in_stride = (size_t)e->n_bytes[0];
     ua.fast_fmt = e->fast_fmt[0];
     ua.amax = e->powersave ? e->d_amax[xt_gen] : nullptr;
+    ua.muted = e->any_muted[0] ? e->d_muted[0] : nullptr;
     return ua;
 }
 
@@ -1665,6 +1807,20 @@ static InverseArgs make_inverse_args(const bfcuda_engine *e, int nb, int y_gen, 
     ia.simple_mix = e->simple_mix ? 1 : 0;
     ia.any_xfade = e->xfade_active ? 1 : 0;
     return ia;
+}
+
+static SubdelayArgs make_subdelay_args(const bfcuda_engine *e, int io, void *data, int nb)
+{
+    SubdelayArgs sa;
+    sa.data = data;
+    sa.chans = e->d_sd_chans[io];
+    sa.taps = e->d_sd_taps[io];
+    sa.hist = e->d_sd_hist[io];
+    sa.n_chans = (int)e->h_sd[io].size();
+    sa.n_ch = e->n_ch[io];
+    sa.batch = nb;
+    sa.L = e->L;
+    return sa;
 }
 
 static OutMixArgs make_out_mix_args(const bfcuda_engine *e, int nb, const InverseArgs &ia)
@@ -1735,6 +1891,11 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         }
         CU(launch_unpack(e->plan, ua, e->stream));
         e->launches += e->n_ch[0] > 0;
+        if (!e->h_sd[0].empty()) {
+            // the postprocess hook of convolver_raw2cbuf: delay_subsample_update on the new samples (bfrun.c:1503-1526)
+            CU(launch_subdelay(e->plan, make_subdelay_args(e, 0, ua.xt, nb), e->stream));
+            e->launches++;
+        }
         set_xt_generation(e, fa, e->xt_par, e->xt_last_nb);
         e->xt_last_nb = nb;
     }
@@ -1837,6 +1998,24 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     }
     CU(launch_inverse(e->plan, ia, e->s_inv));
     e->launches += e->n_ch[1] > 0;
+    if (!e->h_sd[1].empty()) {
+        // bfrun.c:1918-1925: delay_subsample_update on the output block, before mixing and quantisation
+        CU(launch_subdelay(e->plan, make_subdelay_args(e, 1, e->d_out_time, nb), e->s_inv));
+        e->launches++;
+    }
+    if (e->any_group || e->any_muted[1]) {
+        VirtMixArgs va;
+        va.out_time = e->d_out_time;
+        va.groups = e->d_groups;
+        va.members = e->d_members;
+        va.muted = e->any_muted[1] ? e->d_muted[1] : nullptr;
+        va.n_groups = (int)e->h_groups.size();
+        va.n_out = e->n_ch[1];
+        va.batch = nb;
+        va.L = e->L;
+        CU(launch_virt_mix(e->plan, va, e->s_inv));
+        e->launches++;
+    }
     const bool pack_all = plan_unpacks_first(e->plan);   // size-specialised / four-step path: real2raw is a kernel of its own
     if (!e->shared_out.empty() || pack_all) {
         // outputs fed from several ranks: sum the L valid time-domain samples over NVLink, then quantise
@@ -2120,7 +2299,8 @@ static bool graph_eligible(const bfcuda_engine *e, int n_blocks)
            !e->xfade_active && !in_transition(e) && !e->low_latency && e->comm == nullptr && e->shared_out.empty() &&
            e->dither.n_dither == 0 && !(e->flags & (BFCUDA_FLAG_STAGE_TIMING | BFCUDA_FLAG_SERIAL_STAGES)) &&
            e->single_dest && e->launch_no >= 2 && e->mac_variant == 0 && e->n_ch[0] > 0 && e->n_ch[1] > 0 &&
-           e->level_job_first[1] > 0 && !(e->merge_check_at >= 0 && (long)e->t >= e->merge_check_at);
+           e->level_job_first[1] > 0 && !(e->merge_check_at >= 0 && (long)e->t >= e->merge_check_at) &&
+           e->h_sd[0].empty() && e->h_sd[1].empty() && !e->any_group && !e->any_muted[0] && !e->any_muted[1];
 }
 
 // every stream waits for everything enqueued so far on every other one (device side only): taken when the engine

@@ -132,6 +132,12 @@ __global__ void __launch_bounds__(32 * WPB) k_unpack(UnpackArgs a)
                     row[r] = decode_sample<T>(load_raw_le(p + r * stride, f.bytes), f.bytes, f.isfloat, f.swap);
                 }
             }
+            if (a.muted != nullptr && a.muted[c]) {
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    row[r] = (T)0;          // a muted input reads as silence (bfrun.c:1523-1525)
+                }
+            }
             if (a.amax != nullptr) {
                 // powersave: the block's peak, rounded up to float so that "not zero" stays "not zero"
                 float m = 0.f;
@@ -183,7 +189,7 @@ __global__ void __launch_bounds__(32 * WPB) k_pack(InverseArgs a, int L)
         }
         __syncwarp();
         const int c = c0 + lane;
-        if (c < a.n_out && !(a.chans[c].shared & 2)) {      // dithered outputs are k_dither's
+        if (c < a.n_out && !(a.chans[c].shared & 6)) {      // dithered outputs are k_dither's; bit 2: mixed into another channel
             const SampleFormat f = a.fmt[c];
             const size_t stride = (size_t)f.sample_spacing * f.bytes;
             uint8_t *p = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset + (size_t)n0 * stride;

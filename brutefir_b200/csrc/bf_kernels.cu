@@ -788,6 +788,110 @@ __global__ void __launch_bounds__(32) k_dither(InverseArgs a, DitherArgs d, int 
 }
 
 // ======================================================================================================
+// k_subdelay, k_virt_mix -- sub-sample delay and virtual -> physical output mixing on the engine path
+// ======================================================================================================
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_subdelay(SubdelayArgs a)
+{
+    constexpr int CH = 1024;            // samples per chunk
+    __shared__ T tile[BF_SUBDELAY_MAX_TAPS - 1 + CH];
+    __shared__ T taps[BF_SUBDELAY_MAX_TAPS];
+    const SubdelayChan sc = a.chans[blockIdx.x];
+    const int H = sc.n_taps - 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    T *hist = reinterpret_cast<T *>(a.hist) + (size_t)sc.ch * (BF_SUBDELAY_MAX_TAPS - 1);     // kept per channel across filter changes
+    for (int k = tid; k < sc.n_taps; k += nt) {
+        taps[k] = reinterpret_cast<const T *>(a.taps)[sc.tap_first + k];
+    }
+    for (int k = tid; k < H; k += nt) {
+        tile[k] = hist[k];              // the last H inputs before this launch, oldest first
+    }
+    __syncthreads();
+    for (int blk = 0; blk < a.batch; blk++) {
+        T *x = reinterpret_cast<T *>(a.data) + ((size_t)blk * a.n_ch + sc.ch) * a.L;
+        for (int n0 = 0; n0 < a.L; n0 += CH) {
+            const int cn = min(CH, a.L - n0);
+            for (int n = tid; n < cn; n += nt) {
+                tile[H + n] = x[n0 + n];
+            }
+            __syncthreads();
+            for (int n = tid; n < cn; n += nt) {
+                // y[n] = sum_k h[k] x[n - k]; tile[H + n - k] is input n - k of this chunk (or history)
+                T acc = (T)0;
+                for (int k = 0; k <= H; k++) {
+                    acc += taps[k] * tile[H + n - k];
+                }
+                x[n0 + n] = acc;
+            }
+            __syncthreads();
+            // the last H inputs of what the tile holds become the history of the next chunk (H may exceed cn)
+            T keep[(BF_SUBDELAY_MAX_TAPS - 1 + 255) / 256];
+            int q = 0;
+            for (int k = tid; k < H; k += nt, q++) {
+                keep[q] = tile[cn + k];
+            }
+            __syncthreads();
+            q = 0;
+            for (int k = tid; k < H; k += nt, q++) {
+                tile[k] = keep[q];
+            }
+            __syncthreads();
+        }
+    }
+    for (int k = tid; k < H; k += nt) {
+        hist[k] = tile[k];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_virt_mix(VirtMixArgs a)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= a.L) {
+        return;
+    }
+    const VirtGroup g = a.groups[blockIdx.y];
+    T *base = reinterpret_cast<T *>(a.out_time) + (size_t)blockIdx.z * a.n_out * a.L + n;
+    // mixbuf = first unmuted member; mixbuf += the others, in channel order (bfrun.c:1955-1981); all muted: zeros
+    T acc = (T)0;
+    bool filled = false;
+    for (int j = 0; j < g.n; j++) {
+        const int o = a.members[g.first + j];
+        if (a.muted != nullptr && a.muted[o]) {
+            continue;
+        }
+        const T v = base[(size_t)o * a.L];
+        acc = filled ? add_rn(acc, v) : v;
+        filled = true;
+    }
+    base[(size_t)a.members[g.first + g.n - 1] * a.L] = acc;
+}
+
+cudaError_t launch_subdelay(const FftPlan &plan, const SubdelayArgs &a, cudaStream_t s)
+{
+    if (a.n_chans == 0) return cudaSuccess;
+    if (plan.realsize == 4) {
+        k_subdelay<float><<<a.n_chans, 256, 0, s>>>(a);
+    } else {
+        k_subdelay<double><<<a.n_chans, 256, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_virt_mix(const FftPlan &plan, const VirtMixArgs &a, cudaStream_t s)
+{
+    if (a.n_groups == 0) return cudaSuccess;
+    dim3 grid((a.L + 255) / 256, a.n_groups, a.batch);
+    if (plan.realsize == 4) {
+        k_virt_mix<float><<<grid, 256, 0, s>>>(a);
+    } else {
+        k_virt_mix<double><<<grid, 256, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+// ======================================================================================================
 // coefficient preprocessing and plain transforms
 // ======================================================================================================
 

@@ -50,7 +50,8 @@ struct OutChan {
     int n;
     int xf_first;   // -1 = no crossfade this block
     int shared;     // bit 0: summed across ranks before quantisation; bit 1: dithered (k_dither quantises it);
-                    // either bit: the inverse stage / k_pack stop after the time-domain store
+                    // bit 2: a virtual output mixed into another one's physical channel (k_virt_mix): never packed;
+                    // any bit: the inverse stage / k_pack stop after the time-domain store
 };
 
 struct FftPlan {
@@ -135,6 +136,7 @@ struct UnpackArgs {
     size_t in_stride;
     int fast_fmt;
     unsigned int *amax;         // [batch][n_in] running peak |sample| as float bits (zeroed before the launch), or NULL
+    const uint8_t *muted;       // [n_in] muted inputs read as zeros (bfrun.c:1523-1525), or NULL
 };
 cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t s);
 cudaError_t launch_forward(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s);
@@ -258,6 +260,41 @@ struct DitherArgs {
     int n_dither;
 };
 cudaError_t launch_dither(const FftPlan &plan, const InverseArgs &a, const DitherArgs &d, cudaStream_t s);
+
+// Sub-sample delay (delay_subsample_update, delay.c:415-442, the postprocess hook of convolver_raw2cbuf, bfrun.c:1503-1526,
+// and the output side, bfrun.c:1918-1925): the reference pushes the L new samples of a channel through its td convolver
+// in overlap-save blocks -- a causal FIR over the channel's stream, y[n] = sum_k h[k] x[n - k], with the windowed-sinc taps
+// of the channel's current delay step.  Here: that FIR in place on the unpacked samples / the inverse transform's output,
+// one thread block per delayed channel (the blocks of a batch in order; `hist` carries the last n_taps - 1 inputs).
+struct SubdelayChan {
+    int ch;             // channel (row of the sample buffer)
+    int tap_first;      // first tap in `taps`
+    int n_taps;         // <= BF_SUBDELAY_MAX_TAPS
+};
+#define BF_SUBDELAY_MAX_TAPS 1025
+struct SubdelayArgs {
+    void *data;                 // [batch][n_ch][L] reals, filtered in place
+    const SubdelayChan *chans;  // [n_chans]
+    const void *taps;           // reals
+    void *hist;                 // [n_ch][BF_SUBDELAY_MAX_TAPS - 1] reals, row = channel
+    int n_chans, n_ch, batch, L;
+};
+cudaError_t launch_subdelay(const FftPlan &plan, const SubdelayArgs &a, cudaStream_t s);
+
+// Several virtual outputs on one physical channel (bfrun.c:1937-2002): their time-domain blocks are added sample by
+// sample, in channel order, muted ones left out, into the row of the group's last member, which alone is quantised;
+// a group of one only serves the mute.
+struct VirtGroup {
+    int first, n;       // members[first .. first + n): virtual output channels, ascending
+};
+struct VirtMixArgs {
+    void *out_time;             // [batch][n_out][L]
+    const VirtGroup *groups;
+    const int *members;
+    const uint8_t *muted;       // [n_out]
+    int n_groups, n_out, batch, L;
+};
+cudaError_t launch_virt_mix(const FftPlan &plan, const VirtMixArgs &a, cudaStream_t s);
 
 // quantise + pack out_time rows of the channels with chans[o].shared == 1 (after the cross-rank sum)
 cudaError_t launch_quantise_shared(const FftPlan &plan, const InverseArgs &a, cudaStream_t s);

@@ -110,6 +110,17 @@ class Engine:
             c.fscale = C.cast(farr, C.POINTER(C.c_double))
         check(self.lib.bfcuda_set_control(self.h, filt, C.byref(c)))
 
+    def set_subdelay(self, io: int, channel: int, taps=None):
+        """Sub-sample delay FIR of one channel (taps = the windowed sinc of its delay step), None = off."""
+        if taps is None:
+            check(self.lib.bfcuda_set_subdelay(self.h, io, channel, None, 0))
+        else:
+            t = np.ascontiguousarray(taps, self.dtype)
+            check(self.lib.bfcuda_set_subdelay(self.h, io, channel, t.ctypes.data, len(t)))
+
+    def set_mute(self, io: int, channel: int, muted: bool):
+        check(self.lib.bfcuda_set_mute(self.h, io, channel, 1 if muted else 0))
+
     def overflow(self, out_channel: int) -> _abi.OverflowC:
         o = _abi.OverflowC()
         check(self.lib.bfcuda_get_overflow(self.h, out_channel, C.byref(o)))

@@ -56,6 +56,7 @@ class FilterGraph:
     max_dither_table_size: int = 0
     powersave: bool = False                 # bfconf->powersave
     analog_powersave: float = 1.0           # linear level; >= 1.0: only exact zeros are silent (bfrun.c:722-772)
+    out_physical: Sequence[int] | None = None   # virt2phys[OUT]: outputs with equal ids share a physical channel
 
     @property
     def n_fft(self) -> int:
@@ -146,6 +147,9 @@ class FilterGraph:
         cfg.max_batch = max_batch
         cfg.powersave = int(bool(self.powersave))
         cfg.analog_powersave = float(self.analog_powersave)
+        if self.out_physical is not None:
+            assert len(self.out_physical) == len(self.out_formats)
+            cfg.out_physical = C.cast(int_array(list(self.out_physical)), C.POINTER(C.c_int))
         return cfg, keep
 
     # ---- derived figures used by bench.py -------------------------------------

@@ -130,6 +130,12 @@ struct bfcuda_config {
     double analog_powersave;    /* bfconf->analog_powersave as a linear level: a frame whose peak (times the sample
                                    format's scale) is below it is made truly zero (bfrun.c:722-772).  >= 1.0 (or 0) =
                                    only frames of exact zeros count as silent */
+    const int *out_physical;    /* per virtual output channel: its physical channel, bfconf->virt2phys[OUT].  Outputs with
+                                   the same id are added sample by sample in the time domain, in channel order, and
+                                   quantised once (bfrun.c:1937-2002); they must carry the same buffer format, and they
+                                   share one overflow record.  NULL = every output has a physical channel of its own.
+                                   (Several virtual INPUTS on one physical channel need nothing: give them the same
+                                   buffer format.) */
 };
 
 #define BFCUDA_FLAG_STAGE_TIMING 1u     /* record CUDA events around each stage of every block */
@@ -174,6 +180,16 @@ int bfcuda_coeff_runtime_block(bfcuda_engine *engine, int coeff, int block, cons
 /* ---- control --------------------------------------------------------------------------------- */
 
 int bfcuda_set_control(bfcuda_engine *engine, int filter, const struct bfcuda_filter_control *control);
+/* Sub-sample delay of one channel (io = BFCUDA_IN: the postprocess hook of convolver_raw2cbuf, bfrun.c:1503-1526;
+ * BFCUDA_OUT: before mixing and quantisation, bfrun.c:1918-1925).  `taps` are the n_taps = 2 * sdf_length + 1 reals
+ * (engine precision) of the windowed sinc of the channel's current delay step -- what the host's unchanged delay.c /
+ * firwindow.c hand to convolver_td_new (delay.c:486-499); the engine applies them as the causal FIR the td convolver
+ * computes.  taps == NULL switches the channel's sub-sample delay off.  Takes effect at the next block; filter history
+ * is kept across changes like delay.c's `rest`.  n_taps <= 1025. */
+int bfcuda_set_subdelay(bfcuda_engine *engine, int io, int channel, const void *taps, int n_taps);
+/* Mute of a virtual channel (icomm->ismuted, bfrun.c:1510-1525, 1953): a muted input reads as silence, a muted output
+ * contributes nothing to its physical channel. */
+int bfcuda_set_mute(bfcuda_engine *engine, int io, int channel, int muted);
 int bfcuda_get_overflow(bfcuda_engine *engine, int out_channel, struct bfcuda_overflow *overflow);
 int bfcuda_reset_overflow(bfcuda_engine *engine);
 

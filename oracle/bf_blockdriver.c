@@ -101,6 +101,13 @@ struct drv {
     int powersave;                  /* bfconf->powersave */
     double analog_powersave;        /* bfconf->analog_powersave, linear */
     double *in_scale;               /* sf.scale of every input */
+    /* virtual -> physical outputs, mute, sub-sample delay (bfrun.c:1503-1526, 1918-2002) */
+    int *out_phys;                  /* bfconf->virt2phys[OUT], NULL = 1:1 */
+    unsigned char *muted[2];        /* icomm->ismuted */
+    void **sd_filter[2];            /* per channel: td convolver of its sub-sample delay (subdelay_filter[subdelay]) */
+    void **sd_rest[2];              /* per channel: input_sd_rest / output_sd_rest */
+    int *sd_blocksize[2];
+    void *mixbuf;
     int n_threads;
     /* per-thread scratch */
     void **crossfadebuf0, **crossfadebuf1, **timebuf;
@@ -288,6 +295,18 @@ DRV(create)(const struct bfcuda_config *c, int n_threads, struct drv **out)
             d->coeffs[n][i] = drv_alloc(d->cbufsize);
         }
     }
+    for (io = 0; io < 2; io++) {
+        d->muted[io] = calloc(d->n_ch[io] + 1, 1);
+        d->sd_filter[io] = calloc(d->n_ch[io] + 1, sizeof(void *));
+        d->sd_rest[io] = calloc(d->n_ch[io] + 1, sizeof(void *));
+        d->sd_blocksize[io] = calloc(d->n_ch[io] + 1, sizeof(int));
+    }
+    d->out_phys = NULL;
+    if (c->out_physical != NULL) {
+        d->out_phys = malloc(sizeof(int) * (d->n_ch[OUT] + 1));
+        memcpy(d->out_phys, c->out_physical, sizeof(int) * d->n_ch[OUT]);
+    }
+    d->mixbuf = drv_alloc((size_t)d->L * d->rs);
     d->powersave = c->powersave;
     d->analog_powersave = (c->analog_powersave <= 0.0) ? 1.0 : c->analog_powersave;
     d->in_scale = calloc(d->n_ch[IN] + 1, sizeof(double));
@@ -497,6 +516,39 @@ DRV(set_control)(struct drv *d, int filter, const struct bfcuda_filter_control *
 }
 
 int
+DRV(set_mute)(struct drv *d, int io, int channel, int muted)
+{
+    if (io < 0 || io > 1 || channel < 0 || channel >= d->n_ch[io]) {
+        return -1;
+    }
+    d->muted[io][channel] = muted ? 1 : 0;
+    return 0;
+}
+
+/* taps: the windowed sinc of the channel's delay step (what delay_subsample_init hands to convolver_td_new,
+   delay.c:486-499); NULL switches the channel's sub-sample delay off */
+int
+DRV(set_subdelay)(struct drv *d, int io, int channel, void *taps, int n_taps)
+{
+    if (io < 0 || io > 1 || channel < 0 || channel >= d->n_ch[io]) {
+        return -1;
+    }
+    if (taps == NULL) {
+        d->sd_filter[io][channel] = NULL;
+        return 0;
+    }
+    d->sd_blocksize[io][channel] = CV(td_block_length)(n_taps);
+    if (d->L % d->sd_blocksize[io][channel] != 0) {
+        return -1;      /* "Incompatible fragment/filter sizes", delay.c:465-469 */
+    }
+    d->sd_filter[io][channel] = CV(td_new)(taps, n_taps);
+    if (d->sd_rest[io][channel] == NULL) {
+        d->sd_rest[io][channel] = drv_alloc((size_t)d->sd_blocksize[io][channel] * d->rs);
+    }
+    return 0;
+}
+
+int
 DRV(get_overflow)(struct drv *d, int out_channel, struct bfcuda_overflow *of)
 {
     if (out_channel < 0 || out_channel >= d->n_ch[OUT]) {
@@ -579,6 +631,41 @@ drv_test_silent(void *buf, int size, int realsize, double analog_powersave, doub
     return 1;
 }
 
+/* delay_subsample_update(), delay.c:415-442, on the td convolver of the channel's current delay step */
+struct drv_sd_params {
+    struct drv *d;
+    int io, ch;
+};
+
+static void
+drv_subsample_update(struct drv *d, int io, int ch, void *buf)
+{
+    const int bs = d->sd_blocksize[io][ch];
+    const size_t blocksize = (size_t)bs * d->rs;
+    unsigned char *cbuffer, *rest = d->sd_rest[io][ch];
+    size_t i;
+    if (d->sd_filter[io][ch] == NULL) {
+        return;
+    }
+    cbuffer = malloc(blocksize << 1);
+    for (i = 0; i < (size_t)d->L * d->rs; i += blocksize) {
+        memcpy(cbuffer, rest, blocksize);
+        memcpy(cbuffer + blocksize, (unsigned char *)buf + i, blocksize);
+        memcpy(rest, cbuffer + blocksize, blocksize);
+        CV(td_convolve)(d->sd_filter[io][ch], cbuffer);
+        memcpy((unsigned char *)buf + i, cbuffer, blocksize);
+    }
+    free(cbuffer);
+}
+
+static void
+drv_apply_subdelay(void *realbuf, int n_samples, void *arg)     /* bfrun.c:971-984 */
+{
+    struct drv_sd_params *p = arg;
+    (void)n_samples;
+    drv_subsample_update(p->d, p->io, p->ch, realbuf);
+}
+
 static void
 forward_part(struct drv *d, int t, const uint8_t *inbuf)
 {
@@ -588,8 +675,24 @@ forward_part(struct drv *d, int t, const uint8_t *inbuf)
         if (d->in_fft_thread[n] != t) {
             continue;
         }
-        CV(raw2cbuf)((void *)inbuf, d->input_timecbuf[n][d->curbuf], d->input_timecbuf[n][!d->curbuf],
-                     &d->bf[IN][n], NULL, NULL);
+        {
+            struct drv_sd_params sp;
+            sp.d = d;
+            sp.io = IN;
+            sp.ch = n;
+            if (d->muted[IN][n]) {
+                /* bfrun.c:1523-1525: a muted virtual input is converted from a block of zeros */
+                const cv_buffer_format *bf = &d->bf[IN][n];
+                const size_t span = (size_t)bf->byte_offset + ((size_t)(d->L - 1) * bf->sample_spacing + 1) * bf->sf.bytes;
+                void *zeros = calloc(1, span);
+                CV(raw2cbuf)(zeros, d->input_timecbuf[n][d->curbuf], d->input_timecbuf[n][!d->curbuf],
+                             &d->bf[IN][n], drv_apply_subdelay, &sp);
+                free(zeros);
+            } else {
+                CV(raw2cbuf)((void *)inbuf, d->input_timecbuf[n][d->curbuf], d->input_timecbuf[n][!d->curbuf],
+                             &d->bf[IN][n], drv_apply_subdelay, &sp);
+            }
+        }
         /* bfrun.c:1541-1552.  What the reference then skips downstream (mixing and multiplying zero blocks,
            bfrun.c:1613-1700, 1737-1754) leaves every result as it is -- zeros times coefficients add nothing -- so
            the replay keeps computing them. */
@@ -735,12 +838,68 @@ static void
 inverse_part(struct drv *d, int t, uint8_t *outbuf)
 {
     int n;
+    if (d->out_phys != NULL) {
+        /* bfrun.c:1937-2002: the virtual outputs of one physical channel are added in the time domain, in channel
+           order, muted ones left out, and quantised once; all of it on one worker (the reference keeps the outputs of a
+           physical channel in one process as well) */
+        int i, k, filled;
+        if (t != 0) {
+            return;
+        }
+        for (n = 0; n < d->n_ch[OUT]; n++) {
+            int first = 1, last = n;
+            for (k = 0; k < d->n_ch[OUT]; k++) {
+                if (d->out_phys[k] == d->out_phys[n]) {
+                    if (k < n) first = 0;
+                    last = k;
+                }
+            }
+            if (!first) {
+                continue;       /* handled with the first member of its group */
+            }
+            filled = 0;
+            for (k = n; k <= last; k++) {
+                if (d->out_phys[k] != d->out_phys[n]) {
+                    continue;
+                }
+                CV(freq2time)(d->output_freqcbuf[k], d->timebuf[0]);
+                drv_subsample_update(d, OUT, k, d->timebuf[0]);
+                memcpy(d->debug_time[k], d->timebuf[0], (size_t)d->L * d->rs);
+                if (d->muted[OUT][k]) {
+                    continue;
+                }
+                if (!filled) {
+                    memcpy(d->mixbuf, d->timebuf[0], (size_t)d->L * d->rs);
+                } else if (d->rs == 4) {
+                    for (i = 0; i < d->L; i++) ((float *)d->mixbuf)[i] += ((float *)d->timebuf[0])[i];
+                } else {
+                    for (i = 0; i < d->L; i++) ((double *)d->mixbuf)[i] += ((double *)d->timebuf[0])[i];
+                }
+                filled = 1;
+            }
+            if (!filled) {
+                memset(d->mixbuf, 0, (size_t)d->L * d->rs);
+            }
+            CV(cbuf2raw)(d->mixbuf, outbuf, &d->bf[OUT][last], d->dither_state[last] != NULL, d->dither_state[last],
+                         &d->overflow[last]);
+            for (k = n; k <= last; k++) {
+                if (d->out_phys[k] == d->out_phys[n]) {
+                    d->overflow[k] = d->overflow[last];     /* bfrun.c:1994-1998 */
+                }
+            }
+        }
+        return;
+    }
     /* bfrun.c:1877-1936 */
     for (n = 0; n < d->n_ch[OUT]; n++) {
         if (d->out_fft_thread[n] != t) {
             continue;
         }
         CV(freq2time)(d->output_freqcbuf[n], d->timebuf[t]);
+        drv_subsample_update(d, OUT, n, d->timebuf[t]);     /* bfrun.c:1918-1925 */
+        if (d->muted[OUT][n]) {
+            memset(d->timebuf[t], 0, (size_t)d->L * d->rs);    /* (the reference mutes 1:1 outputs in dai.c) */
+        }
         memcpy(d->debug_time[n], d->timebuf[t], (size_t)d->L * d->rs);
         CV(cbuf2raw)(d->timebuf[t], outbuf, &d->bf[OUT][n], d->dither_state[n] != NULL, d->dither_state[n],
                      &d->overflow[n]);     /* bfrun.c:1930-1935 */

@@ -58,6 +58,8 @@ class _Lib:
         fn("coeff_get_block", I, V, I, I, V)
         fn("coeff_runtime_block", I, V, I, I, V)
         fn("set_control", I, V, I, C.POINTER(_abi.FilterControlC))
+        fn("set_mute", I, V, I, I, I)
+        fn("set_subdelay", I, V, I, I, V, I)
         fn("get_overflow", I, V, I, C.POINTER(_abi.OverflowC))
         fn("debug_read", I, V, I, I, I, V)
         fn("run", D, V, I, V, C.c_size_t, V, C.c_size_t)
@@ -292,6 +294,16 @@ class BlockDriver:
             keep.append(farr)
             c.fscale = C.cast(farr, C.POINTER(C.c_double))
         assert self.l.set_control(self.h, filt, C.byref(c)) == 0
+
+    def set_mute(self, io, channel, muted):
+        assert self.l.set_mute(self.h, io, channel, 1 if muted else 0) == 0
+
+    def set_subdelay(self, io, channel, taps=None):
+        if taps is None:
+            assert self.l.set_subdelay(self.h, io, channel, None, 0) == 0
+        else:
+            t = np.ascontiguousarray(taps, self.dtype)
+            assert self.l.set_subdelay(self.h, io, channel, _ptr(t), len(t)) == 0
 
     def process_block(self, raw_in: np.ndarray) -> np.ndarray:
         out = np.zeros(self.graph.out_bytes, np.uint8)
