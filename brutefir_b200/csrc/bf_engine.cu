@@ -1337,10 +1337,10 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
         {
             std::vector<char> seen((size_t)std::max(1, e->n_ch[1]), 0);
             for (int o = 0; o < e->n_ch[1]; o++) {
-                e->out_rep[(size_t)o] = o;
                 if (seen[(size_t)o]) {
                     continue;
                 }
+                e->out_rep[(size_t)o] = o;
                 VirtGroup g;
                 g.first = (int)e->h_members.size();
                 g.n = 0;

@@ -33,7 +33,15 @@
  *               format's scale); default FLOAT_LE / FLOAT64_LE by -r
  *     -a dB   : `attenuation:` of the coeff sections (scale = 10^(-dB/20), bfconf.c:778-781)
  *     -k bytes: `skip:` bytes at the start of the coefficient file (bfconf.c:1886-1893)
+ *     -K blocks: `blocks:` of the coeff sections (bfconf.c:823-826, 2827-2831): the coefficient sets are K <= P partitions long
+ *     -f processed: the file holds the sets already in the convolver's processed layout, K blocks of
+ *               convolver_cbufsize() bytes each per filter (COEFF_FORMAT_PROCESSED, bfconf.c:1924-1957)
+ *     -c shm:ID/OFFSET/BLOCKS[,ID/OFFSET/BLOCKS...]: processed blocks in System V shared memory segments, as
+ *               `filename: ID/OFFSET/BLOCKS` with `shared_mem: true` (bfconf.c:795-815, get_sharedmem bfconf.c:1825-1865);
+ *               the parts are concatenated and must hold n_filters * K blocks
  */
+#include <sys/ipc.h>
+#include <sys/shm.h>
 #include <errno.h>
 #include <math.h>
 #include <stdio.h>
@@ -142,6 +150,7 @@ main(int argc, char *argv[])
     const char *coeff_fmt = NULL;
     double attenuation_db = 0.0;
     long coeff_skip = 0;
+    int coeff_nblocks = 0;
     struct bfcuda_sample_format sf_in, sf_out;
     struct bfcuda_buffer_format *bf_in, *bf_out;
     struct bfcuda_filter *filters;
@@ -169,6 +178,7 @@ main(int argc, char *argv[])
         else if (!strcmp(argv[a], "-f") && a + 1 < argc) coeff_fmt = argv[++a];
         else if (!strcmp(argv[a], "-a") && a + 1 < argc) attenuation_db = atof(argv[++a]);
         else if (!strcmp(argv[a], "-k") && a + 1 < argc) coeff_skip = atol(argv[++a]);
+        else if (!strcmp(argv[a], "-K") && a + 1 < argc) coeff_nblocks = atoi(argv[++a]);
         else if (!strcmp(argv[a], "-m")) matrix = 1;
         else if (!strcmp(argv[a], "-b")) bench = 1;
         else if (!strcmp(argv[a], "-l")) low_latency = 1;
@@ -214,8 +224,9 @@ main(int argc, char *argv[])
         filters[f].channels[BFCUDA_OUT] = &chan[2 * f + 1];
         filters[f].scale[BFCUDA_IN] = filters[f].scale[BFCUDA_OUT] = ones;
         filters[f].coeff = f;
-        coeff_blocks[f] = P;
+        coeff_blocks[f] = coeff_nblocks > 0 ? coeff_nblocks : P;        /* bfconf.c:2827-2831 */
     }
+    if (coeff_nblocks > P) DIE("Too many blocks in coeff 0.");
     cfg.n_filters = n_filters;
     cfg.filters = filters;
     cfg.n_coeffs = n_filters;
@@ -226,9 +237,47 @@ main(int argc, char *argv[])
     CHECK(bfcuda_create(&cfg, &eng));
     CHECK(bfcuda_get_info(eng, &info));
 
+    /* coefficients already in the convolver's processed layout: a file of blocks, or System V shared memory
+       (COEFF_FORMAT_PROCESSED, bfconf.c:1924-1957; get_sharedmem, bfconf.c:1825-1865) */
+    if ((coeff_fmt != NULL && strcasecmp(coeff_fmt, "processed") == 0) || strncmp(coeff_path, "shm:", 4) == 0) {
+        const int K = coeff_blocks[0];
+        const size_t cbufsize = (size_t)2 * L * rs;        /* convolver_cbufsize(), fftw_convolver.c:520-524 */
+        const size_t want = (size_t)n_filters * K;
+        size_t have = 0;
+        if (strncmp(coeff_path, "shm:", 4) == 0) {
+            const char *p = coeff_path + 4;
+            while (*p != '\0') {
+                int id, off, nb, used = 0;
+                unsigned char *seg;
+                if (sscanf(p, "%d/%d/%d%n", &id, &off, &nb, &used) != 3) DIE("bad shared memory spec \"%s\"", coeff_path);
+                if ((seg = shmat(id, NULL, SHM_RDONLY)) == (void *)-1) {
+                    DIE("Failed to attach to shared memory with id %d: %s.", id, strerror(errno));
+                }
+                if ((off & 31) != 0) DIE("Shared memory pointer with id %d and offset %d is not aligned at a 32 byte boundary.", id, off);
+                for (f = 0; f < nb && have < want; f++, have++) {
+                    CHECK(bfcuda_coeff_set_block(eng, (int)(have / K), (int)(have % K), seg + off + (size_t)f * cbufsize));
+                }
+                shmdt(seg);
+                p += used;
+                if (*p == ',') p++;
+            }
+        } else {
+            FILE *pf = fopen(coeff_path, "rb");
+            void *blk = malloc(cbufsize);
+            if (pf == NULL) DIE("Could not open \"%s\" for reading.", coeff_path);
+            if (coeff_skip > 0) fseek(pf, coeff_skip, SEEK_SET);
+            while (have < want && fread(blk, 1, cbufsize, pf) == cbufsize) {
+                CHECK(bfcuda_coeff_set_block(eng, (int)(have / K), (int)(have % K), blk));
+                have++;
+            }
+            fclose(pf);
+            free(blk);
+        }
+        if (have != want) DIE("Shared memory block count mismatch in coeff %d.", (int)(have / K));
+    } else
     /* coefficients: load_coeff (bfconf.c:1867-2030) for "dirac pulse", text and raw sample formats */
     {
-        size_t taps = (size_t)L * P;
+        size_t taps = (size_t)L * coeff_blocks[0];
         void *h = calloc(taps, rs);
         FILE *cf = NULL;
         const int is_text = coeff_fmt != NULL && strcasecmp(coeff_fmt, "text") == 0;

@@ -142,3 +142,86 @@ def test_two_gpus_sharded_and_nccl_output_sum(gpu_lib):
                         "--master-addr", "127.0.0.1", "--master-port", "29537", script],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("matrix", [False, True])
+@pytest.mark.parametrize("gpus,B", [(2, 1), (3, 4)])
+def test_multi_gpu_c_host_equals_the_single_engine_host(gpu_lib, tmp_path, matrix, gpus, B):
+    """host/bfcuda_multi.c: load_balance_filters' grouping (bfconf.c:2227-2318) dealt over `gpus` engines from plain C
+    (engine k on device k modulo the devices present), per-engine blocks of its own channels, host fan-out and
+    gather -- byte-identical to the single-engine host on the same files."""
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L, P, n = 256, 5, 6
+    rng = np.random.default_rng(77)
+    n_filters = n * n if matrix else n
+    taps = (rng.standard_normal((n_filters, L * P)) * np.exp(-np.arange(L * P) / (L * P / 4.0)) * 0.05).astype("<f4")
+    g = configs.diagonal_graph(n, L, P, 4, "S24_4LE")
+    sig = configs.synthetic_signal(g, 22, 11, sigma=0.02)
+    (tmp_path / "in.raw").write_bytes(sig.tobytes()[: sig.size - 500])
+    (tmp_path / "taps.f32").write_bytes(taps.tobytes())
+    common = ["-n", str(n), "-L", str(L), "-P", str(P), "-c", str(tmp_path / "taps.f32")] + (["-m"] if matrix else [])
+    one = subprocess.run([os.path.join(ROOT, "host", "bfcuda_run")] + common + [str(tmp_path / "in.raw"), str(tmp_path / "one.raw")],
+                         capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0, one.stderr
+    many = subprocess.run([os.path.join(ROOT, "host", "bfcuda_multi"), "-g", str(gpus), "-B", str(B)] + common +
+                          [str(tmp_path / "in.raw"), str(tmp_path / "many.raw")], capture_output=True, text=True, timeout=300)
+    assert many.returncode == 0, many.stderr
+    a, b = (tmp_path / "one.raw").read_bytes(), (tmp_path / "many.raw").read_bytes()
+    assert len(a) == len(b) == 11 * g.out_bytes and a == b
+    assert np.abs(unpack_run(np.frombuffer(a, np.uint8).reshape(11, -1), g.out_formats, L)).max() > 1e4
+
+
+def test_c_host_processed_and_shared_memory_coefficients(gpu_lib, tmp_path):
+    """`blocks:` (-K), the "processed" coefficient format and System V shared-memory coefficients of load_coeff
+    (bfconf.c:823-826, 1924-1957, 1825-1865) in the C host: the same bytes as loading the taps."""
+    import ctypes
+    from brutefir_b200.engine import Engine
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "host")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = os.path.join(ROOT, "host", "bfcuda_run")
+    L, P, K, n = 256, 6, 4, 2
+    g = configs.diagonal_graph(n, L, P, 4, "S24_4LE", coeff_blocks=K)
+    taps = configs.synthetic_filters(g, 27)
+    sig = configs.synthetic_signal(g, 27, 10, sigma=0.02)
+    (tmp_path / "in.raw").write_bytes(sig.tobytes())
+    (tmp_path / "taps.f32").write_bytes(np.concatenate(taps).astype("<f4").tobytes())
+    common = [exe, "-n", str(n), "-L", str(L), "-P", str(P), "-K", str(K)]
+    r = subprocess.run(common + ["-c", str(tmp_path / "taps.f32"), str(tmp_path / "in.raw"), str(tmp_path / "a.raw")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    # the processed blocks, in the reference's layout, from an engine that loaded the same taps
+    with Engine(g) as e:
+        for c, h in enumerate(taps):
+            e.coeff_from_taps(c, h)
+        blocks = np.concatenate([e.coeff_get_block(c, b) for c in range(n) for b in range(K)]).astype("<f4")
+    (tmp_path / "proc.bin").write_bytes(blocks.tobytes())
+    r = subprocess.run(common + ["-f", "processed", "-c", str(tmp_path / "proc.bin"), str(tmp_path / "in.raw"),
+                                 str(tmp_path / "b.raw")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "a.raw").read_bytes() == (tmp_path / "b.raw").read_bytes()
+    # ... and the same blocks in two System V shared memory segments (filename: ID/OFFSET/BLOCKS, shared_mem: true)
+    libc = ctypes.CDLL(None, use_errno=True)
+    libc.shmat.restype = ctypes.c_void_p
+    libc.shmat.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    libc.shmdt.argtypes = [ctypes.c_void_p]
+    raw = blocks.tobytes()
+    half = (n * K // 2) * 2 * L * 4
+    ids = []
+    try:
+        spec = []
+        for part, off in ((raw[:half], 64), (raw[half:], 0)):
+            shmid = libc.shmget(0, len(part) + off, 0o1000 | 0o600)        # IPC_PRIVATE, IPC_CREAT
+            assert shmid >= 0, ctypes.get_errno()
+            ids.append(shmid)
+            p = libc.shmat(shmid, None, 0)
+            ctypes.memmove(p + off, part, len(part))
+            libc.shmdt(p)
+            spec.append(f"{shmid}/{off}/{len(part) // (2 * L * 4)}")
+        r = subprocess.run(common + ["-c", "shm:" + ",".join(spec), str(tmp_path / "in.raw"), str(tmp_path / "c.raw")],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+    finally:
+        for shmid in ids:
+            libc.shmctl(shmid, 0, None)       # IPC_RMID
+    assert (tmp_path / "a.raw").read_bytes() == (tmp_path / "c.raw").read_bytes()
