@@ -223,7 +223,8 @@ struct DcFalse { static constexpr bool value = false; };
 // (S = 12 .. 24: slower -- the kernel is not waiting for memory, its stalls are math-pipe throttle and fixed-latency
 // waits with 2-3 warps per scheduler), two groups of four blocks per thread (twice the threads, 59 us), 128- or
 // 64-thread blocks of the two-bin kernel.
-template <typename T, int W, int B, int S, int MINB, int MBT>
+// PS: powersave instantiation (zero delay-line slots are not read); kept apart so that the plain kernel carries none of it
+template <typename T, int W, int B, int S, int MINB, int MBT, bool PS>
 __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 {
     static_assert(S >= 2, "at least one stage in flight");
@@ -310,9 +311,9 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
             // powersave (bfrun.c:1745-1754 skips convolve_add for zero delay-line blocks): a flagged slot is not read --
             // the zero-fill form of cp.async delivers its zeros -- and while the whole B-slot window of a step is
             // flagged its coefficient vector is not read either.  nzw = unflagged slots in the window of step jn.
-            const uint8_t *zf = a.slot_zero != nullptr ? a.slot_zero + (size_t)jb.stream * R : nullptr;
+            const uint8_t *zf = PS ? a.slot_zero + (size_t)jb.stream * R : nullptr;
             int nzw = 0;
-            if (zf != nullptr) {
+            if (PS) {
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     int sl = xs + b;
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
             auto issue = [&](int stage) {       // request step jn into `stage`; always closes a group
                 const bool live = jn < n;
                 bool xlive = live, hlive = live;
-                if (zf != nullptr && live) {
+                if (PS && live) {
                     if (jn > 0) {               // the window moved down by one slot: xs joined, xs + B left
                         int old = xs + B;
                         old -= (old >= R) ? R : 0;
@@ -438,8 +439,8 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
     }
 }
 
-template <typename T, int W, int B, int S, int REGS = 128, int MBT = 256>
-static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s, int groups = 1)
+template <typename T, int W, int B, int S, int REGS, int MBT, bool PS>
+static cudaError_t launch_one_ps(const MacArgs &a, int N, cudaStream_t s, int groups)
 {
     constexpr size_t smem = (size_t)S * 4 * MBT * W * sizeof(T);
     constexpr int MINB = 65536 / REGS / MBT;    // 512 threads per SM at 128 registers, 256 at 255
@@ -447,7 +448,7 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s, int group
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, MINB, MBT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, MINB, MBT, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem);
         if (err != cudaSuccess) {
             return err;
@@ -460,9 +461,16 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s, int group
     dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split, groups);
     MacArgs args = a;
     args.neg_zero2 = 0x8000000080000000ull;     // (-0.0f, -0.0f): see BinPairAcc
-    g_last_func = (const void *)k_mac_batch2<T, W, B, S, MINB, MBT>;
-    k_mac_batch2<T, W, B, S, MINB, MBT><<<grid, MBT, smem, s>>>(args, N);
+    g_last_func = (const void *)k_mac_batch2<T, W, B, S, MINB, MBT, PS>;
+    k_mac_batch2<T, W, B, S, MINB, MBT, PS><<<grid, MBT, smem, s>>>(args, N);
     return cudaGetLastError();
+}
+
+template <typename T, int W, int B, int S, int REGS = 128, int MBT = 256>
+static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s, int groups = 1)
+{
+    return a.slot_zero != nullptr ? launch_one_ps<T, W, B, S, REGS, MBT, true>(a, N, s, groups)
+                                  : launch_one_ps<T, W, B, S, REGS, MBT, false>(a, N, s, groups);
 }
 
 // Instantiations: (lanes per thread W, batch B, ring stages S).  Larger batches use narrower vectors so that
