@@ -142,6 +142,7 @@ struct StepGraph {
     cudaGraphExec_t exec;
     cudaGraphNode_t n_fwd, n_mac;           // the two kernels whose arguments carry the ring slot
     cudaKernelNodeParams p_fwd, p_mac;      // as captured (their kernelParams point into `graph`)
+    cudaGraphNode_t n_h2d, n_d2h, n_snap;   // mode 2: the copy nodes whose host side changes per call
     int n_kernels;
 };
 // a launch whose later stages have not been enqueued yet
@@ -184,10 +185,11 @@ struct bfcuda_engine {
     // Step graphs (launch-bound shapes, small shards): see graph_tick
     bool graph_enabled;             // not BFCUDA_FLAG_NO_GRAPH
     bool graph_mode;                // the most recent launch went through graph_tick
-    bool graph_host;                // ... of a host-buffer call (else device-resident)
+    int graph_host;                 // ... 0: of a device-resident call; 1: host buffers, copies on the copy streams around
+                                    // the graph; 2: host buffers, copies INSIDE the graph (small pinned blocks)
     bool graph_used;
     PendingStage pend_mac, pend_inv;
-    StepGraph sg[2][8][4];          // [host-buffer call][stage mask][k & 3] (k & 1 for device-resident calls)
+    StepGraph sg[3][8][4];          // [graph_host mode][stage mask][k & 3] (k & 1 unless mode 1)
     cudaEvent_t ev_cap[4];          // fork / join inside a capture
     cudaEvent_t ev_g_done[4];       // end of the graph of tick k, [k & 3]
     cudaEvent_t ev_out_read[4];     // last device -> host read of raw output buffer q (graph mode)
@@ -718,7 +720,13 @@ static int choose_split(const bfcuda_engine *e, int requested)
         lanes = mac_batch_lanes(e->rs, e->max_batch, std::max(1, e->n_filters), e->N);     // the launcher's own table
     }
     const long threads = (long)std::max(1, e->n_filters) * (e->N / 2 / lanes);
-    const long target = (long)e->sm_count * (e->max_batch > 1 ? 256 : 512);
+    long target = (long)e->sm_count * (e->max_batch > 1 ? 256 : 512);
+    if (e->max_batch > 1 && threads < target) {
+        // once the sum has to be split anyway, split it far enough for ~4 warps per scheduler: the batched kernel's
+        // throughput at low occupancy follows the warp count (32 x 256 bins x 1024 partitions: 62 us per 8 blocks with
+        // 5 partials)
+        target = (long)e->sm_count * 512;
+    }
     long s = (target + threads - 1) / threads;
     s = std::min<long>(s, std::max(1, e->P / 8));
     return (int)std::max<long>(1, s);
@@ -827,7 +835,7 @@ static int setup_dither(bfcuda_engine *e, const struct bfcuda_config *c)
 
 static void invalidate_graphs(bfcuda_engine *e)
 {
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < 3; h++) {
         for (int m = 0; m < 8; m++) {
             for (int p = 0; p < 4; p++) {
                 StepGraph &g = e->sg[h][m][p];
@@ -1073,7 +1081,8 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->d_raw34[0][0] = e->d_raw34[0][1] = e->d_raw34[1][0] = e->d_raw34[1][1] = nullptr;
     memset(e->sg, 0, sizeof(e->sg));
     e->graph_enabled = !(c->flags & BFCUDA_FLAG_NO_GRAPH) && getenv("BFCUDA_NO_GRAPH") == nullptr;
-    e->graph_mode = e->graph_host = e->graph_used = false;
+    e->graph_mode = e->graph_used = false;
+    e->graph_host = 0;
     e->d_groups = nullptr;
     e->d_members = nullptr;
     e->any_group = false;
@@ -2322,8 +2331,9 @@ static uint8_t *raw_queue(const bfcuda_engine *e, int io, int q)
     return q == 0 ? e->d_raw[io] : (q == 1 ? e->d_raw2[io] : e->d_raw34[io][q - 2]);
 }
 
+// host_in / host_out / host_snap: mode 2 only (copies inside the graph), else null
 static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const UnpackArgs &ua, const ForwardArgs &fa,
-                              const MacArgs &ma, const InverseArgs &ia)
+                              const MacArgs &ma, const InverseArgs &ia, const void *host_in, void *host_out, void *host_snap)
 {
     const void *f_fwd = nullptr, *f_mac = nullptr;
     const int nb = e->max_batch;
@@ -2332,6 +2342,9 @@ static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const Un
     auto ok = [&](cudaError_t r) { if (err == cudaSuccess) err = r; return err == cudaSuccess; };
     ok(cudaEventRecord(e->ev_cap[0], e->stream));
     if (mask & 4) {
+        if (host_in != nullptr) {
+            ok(cudaMemcpyAsync(const_cast<uint8_t *>(ua.raw_in), host_in, (size_t)nb * e->n_bytes[0], cudaMemcpyHostToDevice, e->stream));
+        }
         if (ua.amax != nullptr) {
             ok(cudaMemsetAsync(ua.amax, 0, sizeof(unsigned int) * (size_t)nb * e->n_ch[0], e->stream));
         }
@@ -2353,6 +2366,10 @@ static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const Un
         if (e->any_out_mix) ok(launch_out_mix(e->plan, make_out_mix_args(e, nb, ia), e->s_inv));
         ok(launch_inverse(e->plan, ia, e->s_inv));
         ok(launch_pack(e->plan, ia, e->s_inv));
+        if (host_out != nullptr) {
+            ok(cudaMemcpyAsync(host_out, ia.raw_out, (size_t)nb * e->n_bytes[1], cudaMemcpyDeviceToHost, e->s_inv));
+            ok(cudaMemcpyAsync(host_snap, e->d_overflow, e->snap_bytes, cudaMemcpyDeviceToHost, e->s_inv));
+        }
         ok(cudaEventRecord(e->ev_cap[2], e->s_inv));
         ok(cudaStreamWaitEvent(e->stream, e->ev_cap[2], 0));
     }
@@ -2372,6 +2389,18 @@ static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const Un
     for (size_t i = 0; i < n; i++) {
         cudaGraphNodeType ty;
         CU(cudaGraphNodeGetType(nodes[i], &ty));
+        if (ty == cudaGraphNodeTypeMemcpy) {
+            cudaMemcpy3DParms mp;
+            CU(cudaGraphMemcpyNodeGetParams(nodes[i], &mp));
+            if (host_in != nullptr && mp.dstPtr.ptr == (void *)ua.raw_in) {
+                g.n_h2d = nodes[i];
+            } else if (host_out != nullptr && mp.srcPtr.ptr == (void *)ia.raw_out) {
+                g.n_d2h = nodes[i];
+            } else if (host_out != nullptr && mp.srcPtr.ptr == (void *)e->d_overflow) {
+                g.n_snap = nodes[i];
+            }
+            continue;
+        }
         if (ty != cudaGraphNodeTypeKernel) {
             continue;
         }
@@ -2386,7 +2415,9 @@ static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const Un
             g.p_mac = kp;
         }
     }
-    if (((mask & 4) && g.n_fwd == nullptr) || ((mask & 2) && g.n_mac == nullptr)) {
+    if (((mask & 4) && g.n_fwd == nullptr) || ((mask & 2) && g.n_mac == nullptr) ||
+        ((mask & 4) && host_in != nullptr && g.n_h2d == nullptr) ||
+        ((mask & 1) && host_out != nullptr && (g.n_d2h == nullptr || g.n_snap == nullptr))) {
         cudaGraphDestroy(graph);
         memset(&g, 0, sizeof(g));
         return fail(BFCUDA_ECUDA, "step graph: could not identify the forward / MAC kernel nodes");
@@ -2403,7 +2434,7 @@ static int capture_step_graph(bfcuda_engine *e, StepGraph &g, int mask, const Un
 // One tick of the skewed pipeline.  have_f: a new step enters (its raw input is in the device input buffer of this
 // tick's parity); the pending MAC / inverse stages of the two steps before it ride along.  Without have_f the tick only
 // drains.  host_out / call: destination and number of the host-buffer call that brought the new step.
-static int graph_tick(bfcuda_engine *e, bool have_f, void *host_out, unsigned int call)
+static int graph_tick(bfcuda_engine *e, bool have_f, void *host_out, unsigned int call, const void *host_in = nullptr)
 {
     const int nb = e->max_batch;
     const int mask = (have_f ? 4 : 0) | (e->pend_mac.valid ? 2 : 0) | (e->pend_inv.valid ? 1 : 0);
@@ -2411,9 +2442,10 @@ static int graph_tick(bfcuda_engine *e, bool have_f, void *host_out, unsigned in
         return 0;
     }
     const unsigned int k = have_f ? e->launch_no : (e->pend_mac.valid ? e->pend_mac.step + 1u : e->pend_inv.step + 2u);
-    const bool host = e->graph_host;
-    // the double-buffered operands (Y, unpacked samples) follow k & 1; a host-buffer pipeline keeps FOUR raw blocks
-    // per direction in flight (the copies of a 16 MiB step take longer than its kernels), so its graphs go by k & 3
+    const bool host = e->graph_host == 1;       // copies on the copy streams, around the graph
+    const bool inside = e->graph_host == 2;     // copies are nodes of the graph: one raw buffer per direction is enough
+    // the double-buffered operands (Y, unpacked samples) follow k & 1; a host-buffer pipeline with outside copies keeps
+    // FOUR raw blocks per direction in flight (the copies of a 16 MiB step take longer than its kernels): k & 3
     const int par = (int)(k & (host ? 3u : 1u));
     uint8_t *d_in = host ? raw_queue(e, 0, par) : e->d_raw[0];
     uint8_t *d_out = host ? raw_queue(e, 1, par) : e->d_raw[1];
@@ -2438,11 +2470,22 @@ static int graph_tick(bfcuda_engine *e, bool have_f, void *host_out, unsigned in
     if (mask & 1) {
         ia = make_inverse_args(e, nb, (int)(e->pend_inv.step & 1u), d_out);
     }
-    StepGraph &g = e->sg[host ? 1 : 0][mask][par];
+    StepGraph &g = e->sg[e->graph_host][mask][par];
+    const bool copy_out = inside && (mask & 1) && e->pend_inv.host_out != nullptr;
+    void *snap_dst = copy_out ? (void *)e->h_snap[e->pend_inv.call & 3u] : nullptr;
     if (g.exec == nullptr) {
-        int rc = capture_step_graph(e, g, mask, ua, fa, ma, ia);
+        int rc = capture_step_graph(e, g, mask, ua, fa, ma, ia, inside && have_f ? host_in : nullptr,
+                                    copy_out ? e->pend_inv.host_out : nullptr, snap_dst);
         if (rc != 0) return rc;
     } else {
+        if (inside && have_f) {
+            CU(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_h2d, d_in, host_in, (size_t)nb * e->n_bytes[0], cudaMemcpyHostToDevice));
+        }
+        if (copy_out) {
+            CU(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_d2h, e->pend_inv.host_out, d_out, (size_t)nb * e->n_bytes[1],
+                                                  cudaMemcpyDeviceToHost));
+            CU(cudaGraphExecMemcpyNodeSetParams1D(g.exec, g.n_snap, snap_dst, e->d_overflow, e->snap_bytes, cudaMemcpyDeviceToHost));
+        }
         if (mask & 4) {
             cudaKernelNodeParams kp = g.p_fwd;
             void *args[2] = { &fa, g.p_fwd.kernelParams[1] };
@@ -2474,10 +2517,16 @@ static int graph_tick(bfcuda_engine *e, bool have_f, void *host_out, unsigned in
         CU(cudaEventRecord(e->ev_call_done[c & 3u], e->s_out));
         CU(cudaEventRecord(e->ev_out_read[par], e->s_out));
         e->h_overflow_valid = e->n_ch[1] > 0;
-    } else {
+    } else if (copy_out) {
+        // the copies ran inside the graph: the call's output is complete when the graph is
+        CU(cudaEventRecord(e->ev_call_done[e->pend_inv.call & 3u], e->stream));
+        e->h_overflow_valid = e->n_ch[1] > 0;
+    } else if (!inside) {
         CU(cudaEventRecord(e->ev_g_done[par], e->stream));
     }
-    CU(cudaEventRecord(e->ev_inv, e->stream));
+    if (!inside) {
+        CU(cudaEventRecord(e->ev_inv, e->stream));
+    }
     // advance the pipeline
     e->pend_inv = e->pend_mac;
     e->pend_mac.valid = false;
@@ -2519,7 +2568,7 @@ static int leave_graph_mode(bfcuda_engine *e)
     return join_streams(e);
 }
 
-static int enter_graph_mode(bfcuda_engine *e, bool host)
+static int enter_graph_mode(bfcuda_engine *e, int host)
 {
     if (e->graph_mode && e->graph_host == host) {
         return 0;
@@ -2558,6 +2607,33 @@ static int wait_call(bfcuda_engine *e, unsigned int call)
     return 0;
 }
 
+// Copies as nodes of the step graph (mode 2): one launch per call and no event traffic around it.  Measured SLOWER than
+// the copies on their own streams (profiles/r2_graph_copies.txt: 2 x 64 K taps block by block x3600 against x4850
+// through host buffers, 8 blocks per call x22 700 against x32 200; only 32 x 256 K at 8 blocks gains 5 %): inside the
+// graph a copy's latency sits in its branch's dependency chain every tick, outside it overlaps the neighbouring ticks.
+// Kept opt-in (BFCUDA_GRAPH_COPIES=1); needs page-locked host memory and blocks up to 1 MiB per direction and call.
+static bool copies_fit_in_graph(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out)
+{
+    static const char *env = getenv("BFCUDA_GRAPH_COPIES");
+    if (env == nullptr || atoi(env) == 0) {
+        return false;
+    }
+    if ((size_t)n_blocks * e->n_bytes[0] > ((size_t)1 << 20) || (size_t)n_blocks * e->n_bytes[1] > ((size_t)1 << 20)) {
+        return false;
+    }
+    for (const void *p : { raw_in, (const void *)raw_out }) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        if (at.type != cudaMemoryTypeHost) {
+            return false;
+        }
+    }
+    return true;
+}
+
 static int process_blocks_host(bfcuda_engine *e, int n_blocks, const void *raw_in, void *raw_out, bool allow_graph)
 {
     if (e == nullptr || raw_in == nullptr || raw_out == nullptr) return fail(BFCUDA_EINVAL, "null argument");
@@ -2566,8 +2642,17 @@ static int process_blocks_host(bfcuda_engine *e, int n_blocks, const void *raw_i
     }
     CU(cudaSetDevice(e->device));
     const unsigned int call = e->io_count;
+    if (allow_graph && graph_eligible(e, n_blocks) && copies_fit_in_graph(e, n_blocks, raw_in, raw_out)) {
+        // small pinned blocks: the copies become nodes of the step graph (one launch per call and nothing around it)
+        int rc = enter_graph_mode(e, 2);
+        if (rc != 0) return rc;
+        rc = graph_tick(e, true, raw_out, call, raw_in);
+        if (rc != 0) return rc;
+        e->io_count++;
+        return 0;
+    }
     if (allow_graph && graph_eligible(e, n_blocks)) {
-        int rc = enter_graph_mode(e, true);
+        int rc = enter_graph_mode(e, 1);
         if (rc != 0) return rc;
         const int q = (int)(e->launch_no & 3u);
         uint8_t *d_in = raw_queue(e, 0, q);
@@ -2671,7 +2756,7 @@ int bfcuda_process_blocks_device(bfcuda_engine *e, int n_blocks)
     CU(cudaSetDevice(e->device));
     e->h_overflow_valid = false;        // no read-out follows a device-resident call
     if (graph_eligible(e, n_blocks)) {
-        int rc = enter_graph_mode(e, false);
+        int rc = enter_graph_mode(e, 0);
         if (rc != 0) return rc;
         return graph_tick(e, true, nullptr, 0);
     }

@@ -93,7 +93,10 @@ __device__ __forceinline__ void wait_twiddles(unsigned char *smem)
 // A warp moves a tile of 32 channels x RW samples; RW = 8 keeps every planar-side access a full 32-byte sector
 // (8 consecutive floats of one channel) while giving four times more warps than a square tile -- the quantiser is a
 // dependent double-precision chain per sample, so it is parallelism, not bytes, that the small launches lack.
-constexpr int RW = 8;           // samples per tile row group
+#ifndef BF_PACK_RW
+#define BF_PACK_RW 8
+#endif
+constexpr int RW = BF_PACK_RW;  // samples per tile row group
 constexpr int WPB = 8;          // warps per block
 constexpr int TS = RW + 1;      // padded row stride of the shared tile
 

@@ -428,10 +428,14 @@ __global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
 // k_split_reduce -- partial sums of a split partition range -> one spectrum per output, summed in range order
 // ======================================================================================================
 
+// Short spectra make this kernel latency: BASELINE config 4 (N = 512, 37 partials) is 128 vectors per output.  Blocks of
+// 64 threads spread them over the machine and twelve partials are in flight per thread (was: 256-thread blocks = one
+// block per output on 32 SMs, four in flight: 12.2 us for 2.4 MB, ncu profiles/r2_ncu_full_summary.json capture c4_mac).
 template <typename T>
-__global__ void __launch_bounds__(256) k_split_reduce(MacArgs a, int N)
+__global__ void __launch_bounds__(64) k_split_reduce(MacArgs a, int N)
 {
     constexpr int W = 16 / (int)sizeof(T);
+    constexpr int FL = 12;      // partials in flight
     typedef typename Vec16<T>::type V;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N / W) {
@@ -443,14 +447,14 @@ __global__ void __launch_bounds__(256) k_split_reduce(MacArgs a, int N)
     T *y0 = reinterpret_cast<T *>(a.Y) + ((size_t)b * a.n_slots + jb.out) * N + (size_t)v * W;
     Lanes<T, W> acc = as_lanes<T, W>(*reinterpret_cast<const V *>(y0));
     int z = 1;
-    for (; z + 4 <= a.split; z += 4) {      // four partials in flight; added in ascending order
-        V p[4];
+    for (; z + FL <= a.split; z += FL) {    // added in ascending order
+        V p[FL];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < FL; u++) {
             p[u] = ldg_stream(reinterpret_cast<const V *>(y0 + (size_t)(z + u) * zstride));
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < FL; u++) {
             const Lanes<T, W> q = as_lanes<T, W>(p[u]);
 #pragma unroll
             for (int l = 0; l < W; l++) {
@@ -458,11 +462,23 @@ __global__ void __launch_bounds__(256) k_split_reduce(MacArgs a, int N)
             }
         }
     }
-    for (; z < a.split; z++) {
-        const Lanes<T, W> q = as_lanes<T, W>(ldg_stream(reinterpret_cast<const V *>(y0 + (size_t)z * zstride)));
+    {
+        V p[FL];
 #pragma unroll
-        for (int l = 0; l < W; l++) {
-            acc.v[l] = add_rn(acc.v[l], q.v[l]);
+        for (int u = 0; u < FL; u++) {
+            if (z + u < a.split) {
+                p[u] = ldg_stream(reinterpret_cast<const V *>(y0 + (size_t)(z + u) * zstride));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FL; u++) {
+            if (z + u < a.split) {
+                const Lanes<T, W> q = as_lanes<T, W>(p[u]);
+#pragma unroll
+                for (int l = 0; l < W; l++) {
+                    acc.v[l] = add_rn(acc.v[l], q.v[l]);
+                }
+            }
         }
     }
     *reinterpret_cast<V *>(y0) = *reinterpret_cast<V *>(&acc);
@@ -1183,11 +1199,11 @@ cudaError_t launch_split_reduce(const FftPlan &plan, const MacArgs &a, cudaStrea
 {
     if (a.n_jobs == 0 || a.split <= 1) return cudaSuccess;
     const int W = 16 / plan.realsize;
-    dim3 grid((plan.N / W + 255) / 256, a.n_jobs, a.batch);
+    dim3 grid((plan.N / W + 63) / 64, a.n_jobs, a.batch);
     if (plan.realsize == 4) {
-        k_split_reduce<float><<<grid, 256, 0, s>>>(a, plan.N);
+        k_split_reduce<float><<<grid, 64, 0, s>>>(a, plan.N);
     } else {
-        k_split_reduce<double><<<grid, 256, 0, s>>>(a, plan.N);
+        k_split_reduce<double><<<grid, 64, 0, s>>>(a, plan.N);
     }
     return cudaGetLastError();
 }

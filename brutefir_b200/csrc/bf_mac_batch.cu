@@ -496,8 +496,10 @@ int mac_batch_lanes(int realsize, int batch, int n_jobs, int N)
         if (batch <= 4) return 4;
         static const int narrow_max = env_int("BFCUDA_MAC_NARROW_MAX_BINS", 8 * 8192);
         if (batch <= 8) return bins <= narrow_max ? 1 : 2;
+        // 16 blocks per launch: two bins per thread (241 registers, one 256-thread block per SM) measured faster than one
+        // bin per thread even at 8 filters (68 against 84 us per launch on a rank of an 8-GPU run)
         static const int narrow16 = env_int("BFCUDA_MAC_B16_NARROW", 0);
-        return (narrow16 || bins <= narrow_max) ? 1 : 2;
+        return narrow16 ? 1 : 2;
     }
     if (batch <= 2) return 2;
     return 1;
