@@ -282,14 +282,16 @@ __device__ __forceinline__ void load_frame(const ForwardArgs &a, int item, int t
     }
 }
 
-template <typename T, int LOG2M, bool SINGLE, bool TWS>
-__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_forward2(ForwardArgs a, const cpx<T> *__restrict__ tw_global)
+// MINB = 2 ("slim"): at most 64 registers per thread and no register prefetch of the next frame, so that a block fits
+// beside one resident block of the batched MAC (half an SM's registers) instead of waiting for an empty SM
+template <typename T, int LOG2M, bool SINGLE, bool TWS, int MINB = 1>
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_forward2(ForwardArgs a, const cpx<T> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, N = 2 * F::M;
     // holding the next frame in registers while the current one is stored: not with 1024 threads (64 registers each)
     // and not in double precision (the 16 points alone are 64 registers)
-    constexpr bool PREFETCH = F::NT < 1024 && sizeof(T) == 4;
+    constexpr bool PREFETCH = F::NT < 1024 && sizeof(T) == 4 && MINB == 1;
     extern __shared__ __align__(128) unsigned char smem2[];
     const int tid = threadIdx.x % F::NT, sub = threadIdx.x / F::NT;     // thread of its transform, transform of the block
     cpx<T> *s = reinterpret_cast<cpx<T> *>(smem2) + sub * F::SUB_STRIDE;
@@ -377,14 +379,14 @@ __global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_forward2(ForwardArgs a,
 // SIMPLE: every output is fed by exactly one filter, the partition sum is not split and no crossfade is pending
 // (the usual block): one scaled spectrum per transform, and the next transform's spectrum is fetched while this
 // one's samples are stored.
-template <typename T, int LOG2M, bool SIMPLE, bool TWS>
-__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, 1) k_inverse2(InverseArgs a, const cpx<T> *__restrict__ tw_global)
+template <typename T, int LOG2M, bool SIMPLE, bool TWS, int MINB = 1>
+__global__ void __launch_bounds__(Fft2<LOG2M>::CTA, MINB) k_inverse2(InverseArgs a, const cpx<T> *__restrict__ tw_global)
 {
     typedef Fft2<LOG2M> F;
     constexpr int M = F::M, L = F::M, N = 2 * F::M, NT = F::NT;
     constexpr int RL = F::radix(F::NP - 1);         // radix of the last pass
     constexpr int BPT = 16 / RL, HALF = RL / 2;      // butterflies per thread, valid outputs per butterfly
-    constexpr bool PREFETCH = F::NT < 1024 && sizeof(T) == 4;
+    constexpr bool PREFETCH = F::NT < 1024 && sizeof(T) == 4 && MINB == 1;
     extern __shared__ __align__(128) unsigned char smem2[];
     const int tid = threadIdx.x % NT, sub = threadIdx.x / NT;
     cpx<T> *s = reinterpret_cast<cpx<T> *>(smem2) + sub * F::SUB_STRIDE;
@@ -598,7 +600,7 @@ static cudaError_t persistent_grid(K kernel, int threads, size_t smem, int total
     return cudaSuccess;
 }
 
-template <typename T, int LOG2M, bool SINGLE, bool TWS>
+template <typename T, int LOG2M, bool SINGLE, bool TWS, int MINB = 1>
 static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
@@ -608,17 +610,17 @@ static cudaError_t launch_forward2_t(const FftPlan &plan, const ForwardArgs &a, 
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_forward2<T, LOG2M, SINGLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_forward2<T, LOG2M, SINGLE, TWS, MINB>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
     const int total = (a.n_in * a.batch + F::SUBS - 1) / F::SUBS;      // blocks needed: SUBS transforms each
     const int grid = total < resident[dev] ? total : resident[dev];
-    g_last_func = (const void *)k_forward2<T, LOG2M, SINGLE, TWS>;
-    k_forward2<T, LOG2M, SINGLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<T> *>(plan.tw2));
+    g_last_func = (const void *)k_forward2<T, LOG2M, SINGLE, TWS, MINB>;
+    k_forward2<T, LOG2M, SINGLE, TWS, MINB><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<T> *>(plan.tw2));
     return cudaGetLastError();
 }
 
-template <typename T, int LOG2M, bool SIMPLE, bool TWS>
+template <typename T, int LOG2M, bool SIMPLE, bool TWS, int MINB = 1>
 static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     typedef Fft2<LOG2M> F;
@@ -628,12 +630,12 @@ static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, 
     cudaGetDevice(&dev);
     dev = (dev >= 0 && dev < 64) ? dev : 0;
     if (resident[dev] == 0) {
-        cudaError_t err = persistent_grid(k_inverse2<T, LOG2M, SIMPLE, TWS>, F::CTA, smem, 1 << 30, &resident[dev]);
+        cudaError_t err = persistent_grid(k_inverse2<T, LOG2M, SIMPLE, TWS, MINB>, F::CTA, smem, 1 << 30, &resident[dev]);
         if (err != cudaSuccess) return err;
     }
     const int total = (a.n_out * a.batch + F::SUBS - 1) / F::SUBS;
     const int grid = total < resident[dev] ? total : resident[dev];
-    k_inverse2<T, LOG2M, SIMPLE, TWS><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<T> *>(plan.tw2));
+    k_inverse2<T, LOG2M, SIMPLE, TWS, MINB><<<grid, F::CTA, smem, s>>>(a, reinterpret_cast<const cpx<T> *>(plan.tw2));
     return cudaGetLastError();
 }
 
@@ -666,6 +668,12 @@ static cudaError_t launch_inverse2_t(const FftPlan &plan, const InverseArgs &a, 
     default: return cudaErrorInvalidValue;                                                    \
     }
 
+static bool fft2_slim()
+{
+    static const int v = [] { const char *e = getenv("BFCUDA_FFT_SLIM"); return e != nullptr ? atoi(e) : 0; }();
+    return v != 0;
+}
+
 cudaError_t launch_unpack(const FftPlan &plan, const UnpackArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
@@ -694,6 +702,10 @@ cudaError_t launch_pack(const FftPlan &plan, const InverseArgs &a, cudaStream_t 
 cudaError_t launch_forward2(const FftPlan &plan, const ForwardArgs &a, cudaStream_t s)
 {
     if (a.n_in == 0) return cudaSuccess;
+    if (fft2_slim() && plan.realsize == 4 && plan.N == 16384) {
+        return a.single_dest ? launch_forward2_t<float, 13, true, false, 2>(plan, a, s)
+                             : launch_forward2_t<float, 13, false, false, 2>(plan, a, s);
+    }
     if (a.single_dest) {
         BF_FFT2_SIZES(launch_forward2_t, true, plan, a, s)
     }
@@ -703,6 +715,10 @@ cudaError_t launch_forward2(const FftPlan &plan, const ForwardArgs &a, cudaStrea
 cudaError_t launch_inverse2(const FftPlan &plan, const InverseArgs &a, cudaStream_t s)
 {
     if (a.n_out == 0) return cudaSuccess;
+    if (fft2_slim() && plan.realsize == 4 && plan.N == 16384) {
+        return a.simple_mix ? launch_inverse2_t<float, 13, true, false, 2>(plan, a, s)
+                            : launch_inverse2_t<float, 13, false, false, 2>(plan, a, s);
+    }
     if (a.simple_mix) {
         BF_FFT2_SIZES(launch_inverse2_t, true, plan, a, s)
     }

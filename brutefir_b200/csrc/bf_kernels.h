@@ -202,6 +202,9 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 // The host stub of the kernel the most recent launch_forward / launch_mac call of this thread launched: how the engine
 // finds those two nodes in a captured step graph (their arguments carry the ring slot, which changes per launch).
 extern thread_local const void *g_last_func;
+// the batched MAC with block-cooperative, bulk-copy staged operands (bf_mac_tile.cu)
+bool mac_tile_applicable(const FftPlan &plan, const MacArgs &a);
+cudaError_t launch_mac_tile(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 // bins per thread the batched kernel will use for such a launch (bf_mac_batch.cu)
 int mac_batch_lanes(int realsize, int batch, int n_jobs, int N);
 // With split > 1 the MAC leaves `split` partial sums per output: add them, in order, into partial 0 (the consumers
