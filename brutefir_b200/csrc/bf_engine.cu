@@ -708,6 +708,12 @@ static int upload_tables(bfcuda_engine *e)
 
 static int choose_split(const bfcuda_engine *e, int requested)
 {
+    if (requested < 1) {
+        const char *env = getenv("BFCUDA_MAC_SPLIT");       // experiments: force the split of the automatic rule
+        if (env != nullptr && atoi(env) >= 1) {
+            requested = atoi(env);
+        }
+    }
     if (requested >= 1) {
         return std::min(requested, std::max(1, e->P));
     }
@@ -721,6 +727,12 @@ static int choose_split(const bfcuda_engine *e, int requested)
     }
     const long threads = (long)std::max(1, e->n_filters) * (e->N / 2 / lanes);
     long target = (long)e->sm_count * (e->max_batch > 1 ? 256 : 512);
+    if (e->max_batch > 1 && threads * 2 >= target) {
+        // at least four warps per SM of the batched kernel: keep the whole partition sum in one thread.  (The 8-filter
+        // shard of the headline job -- 32768 threads for 37888 slots -- was split three ways by the rule below: 45 us per
+        // launch against 37-39 us unsplit, profiles/r2_macsweep_w2split1.txt; and unsplit is the reference's summation order.)
+        return 1;
+    }
     if (e->max_batch > 1 && threads < target) {
         // once the sum has to be split anyway, split it far enough for ~4 warps per scheduler: the batched kernel's
         // throughput at low occupancy follows the warp count (32 x 256 bins x 1024 partitions: 62 us per 8 blocks with

@@ -204,6 +204,7 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 extern thread_local const void *g_last_func;
 // the batched MAC with block-cooperative, bulk-copy staged operands (bf_mac_tile.cu)
 bool mac_tile_applicable(const FftPlan &plan, const MacArgs &a);
+bool mac_coop_by_default(const FftPlan &plan, const MacArgs &a);
 cudaError_t launch_mac_tile(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 // bins per thread the batched kernel will use for such a launch (bf_mac_batch.cu)
 int mac_batch_lanes(int realsize, int batch, int n_jobs, int N);

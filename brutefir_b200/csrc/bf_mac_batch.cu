@@ -290,6 +290,17 @@ static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s, int group
                                   : launch_one_ps<T, W, B, S, REGS, MBT, false>(a, N, s, groups);
 }
 
+static int sm_count_cached()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        n = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+    }
+    return n;
+}
+
 // Instantiations: (lanes per thread W, batch B, ring stages S).  Larger batches use narrower vectors so that
 // B accumulators + the B-slot window stay within 128 registers (2 blocks of 256 threads per SM).  A batch smaller
 // than B leaves the surplus accumulators unused (their window slots are still read, always inside the ring).
@@ -311,7 +322,11 @@ int mac_batch_lanes(int realsize, int batch, int n_jobs, int N)
 #endif
     if (realsize == 4) {
         if (batch <= 4) return 4;
-        static const int narrow_max = env_int("BFCUDA_MAC_NARROW_MAX_BINS", 8 * 8192);
+        // 8 blocks per launch: two bins per thread at every size.  (Round 2 first ran shards of <= 8 filters with one bin
+        // per thread because the engine's split rule cut the two-bin kernel's partition sum three ways there; with the
+        // whole sum in one thread the two-bin kernel takes 37-39 us per launch on an 8-filter shard against 47 us --
+        // profiles/r2_macsweep_w2split1.txt.  BFCUDA_MAC_NARROW_MAX_BINS brings the old rule back for A/B runs.)
+        static const int narrow_max = env_int("BFCUDA_MAC_NARROW_MAX_BINS", 0);
         if (batch <= 8) return bins <= narrow_max ? 1 : 2;
         // 16 blocks per launch: two bins per thread (241 registers, one 256-thread block per SM) measured faster than one
         // bin per thread even at 8 filters (68 against 84 us per launch on a rank of an 8-GPU run)
@@ -325,8 +340,10 @@ int mac_batch_lanes(int realsize, int batch, int n_jobs, int N)
 cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
     const int lanes = mac_batch_lanes(plan.realsize, a.batch, a.n_jobs, plan.N);
-    static const int tile_mode = env_int("BFCUDA_MAC_TILE", 0);
-    if (tile_mode != 0 && mac_tile_applicable(plan, a)) {
+    // the shared-ring kernels (bf_mac_tile.cu): by default for 16-block launches of small shards; BFCUDA_MAC_TILE = 1 / 2
+    // forces the bulk-copy staged / the cooperative cp.async kernel wherever they apply, 0 turns them off
+    static const int tile_mode = env_int("BFCUDA_MAC_TILE", -1);
+    if ((tile_mode >= 1 && mac_tile_applicable(plan, a)) || mac_coop_by_default(plan, a)) {
         return launch_mac_tile(plan, a, s);
     }
     if (plan.realsize == 4) {
@@ -360,6 +377,15 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
             if (S == 8 && TPB == 256) return launch_one<float, 2, 8, 8>(a, plan.N, s);
             if (S == 8 && TPB == 128) return launch_one<float, 2, 8, 8, 128, 128>(a, plan.N, s);
             if (S == 8 && TPB == 224) return launch_one<float, 2, 8, 8, 128, 224>(a, plan.N, s);
+            if (S == 8 && TPB == 1256) return launch_one<float, 2, 8, 8, 255, 256>(a, plan.N, s);
+            if (S == 8 && TPB == 1224) return launch_one<float, 2, 8, 8, 255, 224>(a, plan.N, s);
+            if (S == 8 && TPB == 1192) return launch_one<float, 2, 8, 8, 255, 192>(a, plan.N, s);
+            if (S == 8 && TPB == 1160) return launch_one<float, 2, 8, 8, 255, 160>(a, plan.N, s);
+            if (S == 10 && TPB == 1224) return launch_one<float, 2, 8, 10, 255, 224>(a, plan.N, s);
+            if (S == 12 && TPB == 1224) return launch_one<float, 2, 8, 12, 255, 224>(a, plan.N, s);
+            if (S == 16 && TPB == 1224) return launch_one<float, 2, 8, 16, 255, 224>(a, plan.N, s);
+            if (S == 8 && TPB == 1128) return launch_one<float, 2, 8, 8, 255, 128>(a, plan.N, s);
+            if (S == 8 && TPB == 2256) return launch_one<float, 2, 8, 8, 168, 256>(a, plan.N, s);
             if (S == 8 && TPB == 192) return launch_one<float, 2, 8, 8, 128, 192>(a, plan.N, s);
             if (S == 8 && TPB == 160) return launch_one<float, 2, 8, 8, 128, 160>(a, plan.N, s);
             if (S == 8 && TPB == 96) return launch_one<float, 2, 8, 8, 128, 96>(a, plan.N, s);
@@ -372,7 +398,13 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
             if (S == 24 && TPB == 256) return launch_one<float, 2, 8, 24, 128, 256>(a, plan.N, s);
             return cudaErrorInvalidValue;
 #else
-            return lanes == 1 ? launch_one<float, 1, 8, 8, 96, 64>(a, plan.N, s) : launch_one<float, 2, 8, 8>(a, plan.N, s);
+            if (lanes == 1) return launch_one<float, 1, 8, 8, 96, 64>(a, plan.N, s);
+            // a grid of at most one 256-thread block per SM has the register file to itself: 154 registers instead of 128
+            // give the scheduler the temporaries to keep dependent FFMA2 / FADD2 pairs apart (37.0 against 38.8 us at 8 filters)
+            if ((long)a.n_jobs * (plan.N / 4) * a.split <= 256L * sm_count_cached()) {
+                return launch_one<float, 2, 8, 8, 255, 256>(a, plan.N, s);
+            }
+            return launch_one<float, 2, 8, 8>(a, plan.N, s);
 #endif
         }
         if (a.batch <= 16) {

@@ -574,21 +574,36 @@ static int tile_env(const char *name, int dflt)
     return v != nullptr ? atoi(v) : dflt;
 }
 
-// float_bits 32, no powersave flags, tiles of 2 * TPG bins must divide the spectrum
+// float_bits 32, no powersave flags, whole partition sums, tiles of 128 bins dividing the spectrum
 bool mac_tile_applicable(const FftPlan &plan, const MacArgs &a)
 {
-    return plan.realsize == 4 && a.slot_zero == nullptr && a.batch > 4 && a.batch <= 16 && (plan.N / 2) % 256 == 0 && plan.N >= 512 &&
-           a.head == 0 && a.z_count == 0;
+    return plan.realsize == 4 && a.slot_zero == nullptr && a.batch > 4 && a.batch <= 16 && (plan.N / 2) % 256 == 0 &&
+           plan.N >= 512 && a.head == 0 && a.z_count == 0;
+}
+
+// Which launches take a shared-ring kernel by default.  Measured (profiles/r2_macsweep_coop.txt, r2_coop_ab.txt, the
+// headline filter shape, 8 / 16 / 32 / 64 filters per GPU): at 8 blocks per launch k_mac_batch2 is as fast or faster
+// everywhere (46.9 / 66.5 / 120 / 201 us against 45-47 / 77 / 119-134 / 209-252 us); at 16 blocks per launch its
+// 241-register threads leave one block of 8 warps per SM, and k_mac_coop<2 groups x 8 blocks> wins up to 32 filters
+// (75 / 120 / 212 us against 97 / 134 / 227 us; at 64 filters 403 against 376 us).
+bool mac_coop_by_default(const FftPlan &plan, const MacArgs &a)
+{
+    static const int mode = tile_env("BFCUDA_MAC_TILE", -1);        // 0 forces k_mac_batch2
+    return mode != 0 && a.batch > 8 && mac_tile_applicable(plan, a) && (long)a.n_jobs * (plan.N / 2) <= 32L * 8192;
 }
 
 cudaError_t launch_mac_tile(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
     const int N = plan.N;
+    const int which = tile_env("BFCUDA_MAC_TILE", -1);      // -1: the default rule; 1: bulk-copy staged; 2: cooperative cp.async
+    if (which < 1) {
+        return launch_coop<2, 8, 64, 32, 2>(a, N, s);
+    }
     const int G = tile_env("BFCUDA_TILE_G", 2), TPG = tile_env("BFCUDA_TILE_TPG", 64);
-    if (tile_env("BFCUDA_MAC_TILE", 0) == 2) {
-        const int S = tile_env("BFCUDA_TILE_S", 16);
+    if (which == 2) {
         if (a.batch <= 8) {
 #ifdef BF_MAC_SWEEP
+            const int S = tile_env("BFCUDA_TILE_S", 16);
             const int mode = tile_env("BFCUDA_TILE_MODE", 0);
             if (mode == 1 && G == 2 && TPG == 32) return launch_coop<2, 4, 32, 16, 8, 1>(a, N, s);
             if (mode == 2 && G == 2 && TPG == 32) return launch_coop<2, 4, 32, 16, 8, 2>(a, N, s);
@@ -600,19 +615,19 @@ cudaError_t launch_mac_tile(const FftPlan &plan, const MacArgs &a, cudaStream_t 
             if (G == 2 && TPG == 64 && S == 32) return launch_coop<2, 4, 64, 32, 4>(a, N, s);
             if (G == 4 && TPG == 32 && S == 32) return launch_coop<4, 2, 32, 32, 4>(a, N, s);
             if (G == 1 && TPG == 32) return launch_coop<1, 8, 32, 16, 8>(a, N, s);
-            if (G == 1 && TPG == 64) return launch_coop<1, 8, 64, 16, 4>(a, N, s);
             if (G == 4 && TPG == 64) return launch_coop<4, 2, 64, 16, 2>(a, N, s);
-#endif
             if (G == 2 && TPG == 32) return launch_coop<2, 4, 32, 16, 8>(a, N, s);
-            if (G == 2 && TPG == 64) return launch_coop<2, 4, 64, 16, 4>(a, N, s);
             if (G == 4 && TPG == 32) return launch_coop<4, 2, 32, 16, 4>(a, N, s);
-            return cudaErrorInvalidValue;
+#endif
+            if (G == 1) return launch_coop<1, 8, 64, 16, 4>(a, N, s);
+            return launch_coop<2, 4, 64, 16, 4>(a, N, s);
         }
+#ifdef BF_MAC_SWEEP
         if (G == 2 && TPG == 32) return launch_coop<2, 8, 32, 32, 4>(a, N, s);
         if (G == 4 && TPG == 32) return launch_coop<4, 4, 32, 32, 4>(a, N, s);
-        if (G == 2 && TPG == 64) return launch_coop<2, 8, 64, 32, 2>(a, N, s);
         if (G == 4 && TPG == 64) return launch_coop<4, 4, 64, 32, 2>(a, N, s);
-        return cudaErrorInvalidValue;
+#endif
+        return launch_coop<2, 8, 64, 32, 2>(a, N, s);
     }
     if (a.batch <= 8) {
 #ifdef BF_MAC_SWEEP
@@ -621,20 +636,20 @@ cudaError_t launch_mac_tile(const FftPlan &plan, const MacArgs &a, cudaStream_t 
         if (mode == 2 && G == 2) return launch_tile<2, 4, 64, 16, 4, 2>(a, N, s);
         if (mode == 1 && G == 1) return launch_tile<1, 8, 64, 16, 4, 1>(a, N, s);
         if (mode == 2 && G == 1) return launch_tile<1, 8, 64, 16, 4, 2>(a, N, s);
-#endif
         if (G == 1 && TPG == 64) return launch_tile<1, 8, 64, 16, 4>(a, N, s);
-        if (G == 1 && TPG == 128) return launch_tile<1, 8, 128, 16, 2>(a, N, s);
         if (G == 2 && TPG == 32) return launch_tile<2, 4, 32, 16, 8>(a, N, s);
-        if (G == 2 && TPG == 64) return launch_tile<2, 4, 64, 16, 4>(a, N, s);
         if (G == 2 && TPG == 128) return launch_tile<2, 4, 128, 16, 2>(a, N, s);
         if (G == 4 && TPG == 32) return launch_tile<4, 2, 32, 32, 4>(a, N, s);
         if (G == 4 && TPG == 64) return launch_tile<4, 2, 64, 32, 2>(a, N, s);
-        return cudaErrorInvalidValue;
+#endif
+        if (G == 1) return launch_tile<1, 8, 128, 16, 2>(a, N, s);
+        return launch_tile<2, 4, 64, 16, 4>(a, N, s);
     }
-    if (G == 2 && TPG == 64) return launch_tile<2, 8, 64, 32, 2>(a, N, s);
+#ifdef BF_MAC_SWEEP
     if (G == 4 && TPG == 32) return launch_tile<4, 4, 32, 32, 4>(a, N, s);
     if (G == 4 && TPG == 64) return launch_tile<4, 4, 64, 32, 2>(a, N, s);
-    return cudaErrorInvalidValue;
+#endif
+    return launch_tile<2, 8, 64, 32, 2>(a, N, s);
 }
 
 }  // namespace bf

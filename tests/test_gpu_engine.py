@@ -754,6 +754,21 @@ def test_delay_lines_shared_across_filters(gpu_lib, oracle_libs, L, P, rs, B):
     assert_parity(g, shared, np.stack(want))
 
 
+@pytest.mark.parametrize("which", ["1", "2"])
+def test_shared_ring_mac_kernels_bit_identical(gpu_lib, oracle_libs, which):
+    """bf_mac_tile.cu: the batched MAC with a block-shared operand ring -- bulk-copy staged (BFCUDA_MAC_TILE=1) and
+    cooperative cp.async (=2; the default for 16-block launches of small shards).  The library reads the variable
+    once, so the batched == block-by-block test (control changes, crossfades, delays, split sums, ragged batches) and
+    the headline-size byte-identity test run in a child interpreter with the kernel forced wherever it applies."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(HERE, "test_gpu_engine.py"),
+                        os.path.join(HERE, "test_gpu_fullsize.py"), "-k",
+                        "batched_launches_are_bit_identical or c3_batched or c3_mac_stage"],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, BFCUDA_MAC_TILE=which))
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("calls,B", [(600, 1), (300, 4)])
 def test_pipelined_stages_equal_serialised_stages(gpu_lib, calls, B):
     """The engine overlaps the stages of consecutive launches on three streams (bf_engine.cu).  tests/checks/soak_pipeline.py
