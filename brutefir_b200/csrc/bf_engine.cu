@@ -1216,13 +1216,19 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     {
         const size_t N = e->N, L = e->L, F = std::max(1, e->n_filters);
         {
-            // the latency-bound FFT stages get the higher priority: their blocks take the SMs the MAC's retiring
-            // blocks free, instead of queueing behind its whole grid
+            // Stream priorities.  Round 1 gave the latency-bound FFT stages the higher priority (their blocks took the SMs
+            // the MAC's retiring blocks freed instead of queueing behind its whole grid).  With the batched MAC that is the
+            // wrong way round on small shards: a 128-block MAC launch that finds 64 + 64 transform blocks already holding
+            // whole SMs starts a third of its blocks late, and the step is the MAC plus that delay (8-filter shard:
+            // 57 us per step against 43 us with the MAC first; 16 / 32 filters 75-84 -> 72, 146 -> 133-135; the full job
+            // 270 -> 259-266, block by block 170 -> 164; profiles/r2_prio*.txt).  BFCUDA_MAC_PRIO=0 restores the old order.
             int lo = 0, hi = 0;
             TRYCU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            TRYCU(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, hi));
-            TRYCU(cudaStreamCreateWithPriority(&e->s_mac, cudaStreamNonBlocking, lo));
-            TRYCU(cudaStreamCreateWithPriority(&e->s_inv, cudaStreamNonBlocking, hi));
+            const char *pe = getenv("BFCUDA_MAC_PRIO");
+            const bool mac_first = pe == nullptr || atoi(pe) != 0;
+            TRYCU(cudaStreamCreateWithPriority(&e->stream, cudaStreamNonBlocking, mac_first ? lo : hi));
+            TRYCU(cudaStreamCreateWithPriority(&e->s_mac, cudaStreamNonBlocking, mac_first ? hi : lo));
+            TRYCU(cudaStreamCreateWithPriority(&e->s_inv, cudaStreamNonBlocking, mac_first ? lo : hi));
         }
         TRYCU(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
         TRYCU(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
