@@ -41,7 +41,10 @@ namespace bf {
 // waits with 2-3 warps per scheduler), two groups of four blocks per thread (twice the threads, 59 us), 128- or
 // 64-thread blocks of the two-bin kernel.
 // PS: powersave instantiation (zero delay-line slots are not read); kept apart so that the plain kernel carries none of it
-template <typename T, int W, int B, int S, int MINB, int MBT, bool PS>
+// PAIR = 2: two partition steps per wait -- one cp.async.wait_group, the shared loads of both steps, then the arithmetic
+// of both in one scheduling window (the wait is a compiler barrier: with one step per wait every step starts with an
+// exposed shared-memory load and ends with the tail of its dependent FFMA2 -> FADD2 -> FADD2 chains)
+template <typename T, int W, int B, int S, int MINB, int MBT, bool PS, int PAIR = 1>
 __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
 {
     static_assert(S >= 2, "at least one stage in flight");
@@ -201,11 +204,42 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
                 // (an S-fold unrolled body outgrew the instruction cache at S = 16 and 24).
                 int st_c = 1 % S;           // stage step j reads:    j % S
                 int st_p = 0;               // stage step j refills:  (j - 1) % S, consumed by the previous step
+                auto fp_step = [&](int u, const V &hr, const V &hi) {     // the arithmetic of a step whose rotation is u
+                    const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        acc[b].template step<true>(wr[(b - u + B) % B], wi[(b - u + B) % B], hr, hi, nz);
+                        if (DCNY) {
+                            const L br = *reinterpret_cast<const L *>(&wr[(b - u + B) % B]);
+                            const L bi = *reinterpret_cast<const L *>(&wi[(b - u + B) % B]);
+                            dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
+                            ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
+                        }
+                    }
+                };
                 for (int base = 1; base < n; base += B) {
 #pragma unroll
-                    for (int k = 0; k < B; k++) {
+                    for (int k = 0; k < B; k += PAIR) {
                         const int j = base + k;
-                        if (j < n) {
+                        if (PAIR == 2 && j + 1 < n) {
+                            const int u0 = (k + 1) % B, u1 = (k + 2) % B;
+                            const int st_n = st_c + 1 == S ? 0 : st_c + 1;
+                            cp_async_wait<S - 3>();         // the two oldest groups have landed
+                            const V hr0 = *stage_ptr(st_c, 0), hi0 = *stage_ptr(st_c, 1);
+                            const V xr0 = *stage_ptr(st_c, 2), xi0 = *stage_ptr(st_c, 3);
+                            const V hr1 = *stage_ptr(st_n, 0), hi1 = *stage_ptr(st_n, 1);
+                            const V xr1 = *stage_ptr(st_n, 2), xi1 = *stage_ptr(st_n, 3);
+                            issue(st_p);
+                            issue(st_c);
+                            st_p = st_n;
+                            st_c = st_n + 1 == S ? 0 : st_n + 1;
+                            wr[(B - u0) % B] = xr0;
+                            wi[(B - u0) % B] = xi0;
+                            fp_step(u0, hr0, hi0);
+                            wr[(B - u1) % B] = xr1;
+                            wi[(B - u1) % B] = xi1;
+                            fp_step(u1, hr1, hi1);
+                        } else if (j < n) {
                             const int u = (k + 1) % B;
                             cp_async_wait<S - 2>();
                             const V hr = *stage_ptr(st_c, 0), hi = *stage_ptr(st_c, 1);
@@ -215,17 +249,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
                             issue(st_p);
                             st_p = st_c;
                             st_c = st_c + 1 == S ? 0 : st_c + 1;
-                            const L cr = *reinterpret_cast<const L *>(&hr), ci = *reinterpret_cast<const L *>(&hi);
-#pragma unroll
-                            for (int b = 0; b < B; b++) {
-                                acc[b].template step<true>(wr[(b - u + B) % B], wi[(b - u + B) % B], hr, hi, nz);
-                                if (DCNY) {
-                                    const L br = *reinterpret_cast<const L *>(&wr[(b - u + B) % B]);
-                                    const L bi = *reinterpret_cast<const L *>(&wi[(b - u + B) % B]);
-                                    dc[b] = add_rn(dc[b], mul_rn(br.v[0], cr.v[0]));
-                                    ny[b] = add_rn(ny[b], mul_rn(bi.v[0], ci.v[0]));
-                                }
-                            }
+                            fp_step(u, hr, hi);
                         }
                     }
                 }
@@ -256,7 +280,7 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
     }
 }
 
-template <typename T, int W, int B, int S, int REGS, int MBT, bool PS>
+template <typename T, int W, int B, int S, int REGS, int MBT, bool PS, int PAIR = 1>
 static cudaError_t launch_one_ps(const MacArgs &a, int N, cudaStream_t s, int groups)
 {
     constexpr size_t smem = (size_t)S * 4 * MBT * W * sizeof(T);
@@ -265,7 +289,7 @@ static cudaError_t launch_one_ps(const MacArgs &a, int N, cudaStream_t s, int gr
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, MINB, MBT, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t err = cudaFuncSetAttribute(k_mac_batch2<T, W, B, S, MINB, MBT, PS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem);
         if (err != cudaSuccess) {
             return err;
@@ -278,16 +302,16 @@ static cudaError_t launch_one_ps(const MacArgs &a, int N, cudaStream_t s, int gr
     dim3 grid((unsigned int)((threads + MBT - 1) / MBT), a.split, groups);
     MacArgs args = a;
     args.neg_zero2 = 0x8000000080000000ull;     // (-0.0f, -0.0f): see BinPairAcc
-    g_last_func = (const void *)k_mac_batch2<T, W, B, S, MINB, MBT, PS>;
-    k_mac_batch2<T, W, B, S, MINB, MBT, PS><<<grid, MBT, smem, s>>>(args, N);
+    g_last_func = (const void *)k_mac_batch2<T, W, B, S, MINB, MBT, PS, PAIR>;
+    k_mac_batch2<T, W, B, S, MINB, MBT, PS, PAIR><<<grid, MBT, smem, s>>>(args, N);
     return cudaGetLastError();
 }
 
-template <typename T, int W, int B, int S, int REGS = 128, int MBT = 256>
+template <typename T, int W, int B, int S, int REGS = 128, int MBT = 256, int PAIR = 1>
 static cudaError_t launch_one(const MacArgs &a, int N, cudaStream_t s, int groups = 1)
 {
-    return a.slot_zero != nullptr ? launch_one_ps<T, W, B, S, REGS, MBT, true>(a, N, s, groups)
-                                  : launch_one_ps<T, W, B, S, REGS, MBT, false>(a, N, s, groups);
+    return a.slot_zero != nullptr ? launch_one_ps<T, W, B, S, REGS, MBT, true, PAIR>(a, N, s, groups)
+                                  : launch_one_ps<T, W, B, S, REGS, MBT, false, PAIR>(a, N, s, groups);
 }
 
 static int sm_count_cached()
@@ -378,6 +402,9 @@ cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_
             if (S == 8 && TPB == 128) return launch_one<float, 2, 8, 8, 128, 128>(a, plan.N, s);
             if (S == 8 && TPB == 224) return launch_one<float, 2, 8, 8, 128, 224>(a, plan.N, s);
             if (S == 8 && TPB == 1256) return launch_one<float, 2, 8, 8, 255, 256>(a, plan.N, s);
+            if (S == 8 && TPB == 3256) return launch_one<float, 2, 8, 8, 255, 256, 2>(a, plan.N, s);
+            if (S == 8 && TPB == 4256) return launch_one<float, 2, 8, 8, 128, 256, 2>(a, plan.N, s);
+            if (S == 12 && TPB == 3256) return launch_one<float, 2, 8, 12, 255, 256, 2>(a, plan.N, s);
             if (S == 8 && TPB == 1224) return launch_one<float, 2, 8, 8, 255, 224>(a, plan.N, s);
             if (S == 8 && TPB == 1192) return launch_one<float, 2, 8, 8, 255, 192>(a, plan.N, s);
             if (S == 8 && TPB == 1160) return launch_one<float, 2, 8, 8, 255, 160>(a, plan.N, s);
