@@ -280,10 +280,19 @@ __global__ void __launch_bounds__(MBT, MINB) k_mac_batch2(MacArgs a, int N)
     }
 }
 
+static int env_int_early(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v != nullptr ? atoi(v) : dflt;
+}
+
 template <typename T, int W, int B, int S, int REGS, int MBT, bool PS, int PAIR = 1>
 static cudaError_t launch_one_ps(const MacArgs &a, int N, cudaStream_t s, int groups)
 {
-    constexpr size_t smem = (size_t)S * 4 * MBT * W * sizeof(T);
+    // BFCUDA_MAC_SMEM_PAD (experiments): extra dynamic shared memory per block, i.e. fewer resident blocks per SM -- room
+    // for the FFT-side kernels to run beside the MAC instead of after it
+    static const size_t pad = (size_t)env_int_early("BFCUDA_MAC_SMEM_PAD", 0);
+    const size_t smem = (size_t)S * 4 * MBT * W * sizeof(T) + pad;
     constexpr int MINB = 65536 / REGS / MBT;    // 512 threads per SM at 128 registers, 256 at 255
     static bool configured[64];
     int dev = 0;
