@@ -184,6 +184,30 @@ BF_HD int32_t real_to_int(T sample, double rmin, double rmax, int32_t imin, int3
 }
 
 // float output formats: REAL_OVERFLOW_UPDATE (real2raw.h:44-59) with rmin = (T)-max, rmax = (T)max
+// The same quantiser for float samples well inside the clip range, in single precision and without the sum x + 0.5
+// (which is NOT exact in float for small x): with fl = floor(x) and fr = x - fl (exact), y = x + 0.5 has
+// floor(y) = fl + (fr >= 0.5), y < 0 <=> x < -0.5, and y is an integer <=> fr == 0.5.  The double chain of
+// dither_funs.h:70-114 gives y >= 0 -> (int32)y = floor(y); y < 0 -> (int32)y - 1 = floor(y), or y - 1 where y is an
+// integer (the reference's off-by-one for negative exact integers).  `cand` is what the branch taken would compare with
+// intlargest (q, or -q on the negative side).  Returns false where the full chain must run (near or beyond full scale,
+// non-finite).  thr = min(2^22 - 1, imax - 1).
+BF_HD bool real_to_int_fast(float x, float thr, int32_t &q, int32_t &cand)
+{
+    if (!(fabsf(x) <= thr)) {
+        return false;
+    }
+    const float fl = floorf(x);
+    const float fr = x - fl;
+    q = (int32_t)fl + (fr >= 0.5f ? 1 : 0);
+    const bool neg = x < -0.5f;
+    if (neg && fr == 0.5f) {
+        q--;
+    }
+    cand = neg ? -q : q;
+    return true;
+}
+BF_HD bool real_to_int_fast(double, float, int32_t &, int32_t &) { return false; }
+
 template <typename T>
 BF_HD void float_overflow_update(T v, T rmin, T rmax, QuantStats &s)
 {

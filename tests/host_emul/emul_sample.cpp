@@ -95,10 +95,62 @@ static int run(int L)
     return bad;
 }
 
+// the single-precision form of the quantiser (k_pack's 4-byte integer path) against the full double chain:
+// every float in a dense sweep around the integers and halves, random values over the whole fast range and beyond it
+static int fast_path()
+{
+    int bad = 0;
+    long n_fast = 0;
+    for (int sbytes = 3; sbytes <= 4; sbytes++) {
+        const int bits_n = sbytes << 3;
+        const int32_t imin = (int32_t)(-((uint64_t)1 << (bits_n - 1)));
+        const int32_t imax = (int32_t)(((uint64_t)1 << (bits_n - 1)) - 1);
+        const double rmin = (double)(float)imin, rmax = (double)(float)imax;
+        const float thr = fminf(4194303.0f, (float)(imax - 1));
+        auto check = [&](float x) {
+            int32_t q, cand;
+            if (!real_to_int_fast(x, thr, q, cand)) {
+                return;
+            }
+            n_fast++;
+            QuantStats st;
+            quant_stats_init(st);
+            const int32_t want = real_to_int<float>(x, rmin, rmax, imin, imax, st);
+            if (q != want || cand != st.intlargest || st.n_overflows != 0 || st.largest != 0.0) {
+                if (bad < 10) printf("fast path: x = %.9g -> %d (cand %d), full chain %d (intlargest %d)\n", x, q, cand, want, st.intlargest);
+                bad++;
+            }
+        };
+        for (int k = -5000; k <= 5000; k++) {           // integers, halves, quarters and their float neighbours
+            for (int f4 = 0; f4 < 4; f4++) {
+                const float c = (float)k + 0.25f * f4;
+                check(c);
+                check(nextafterf(c, 1e30f));
+                check(nextafterf(c, -1e30f));
+                check(-c);
+            }
+        }
+        const float edges[] = { 4194303.0f, 4194302.75f, 4194302.5f, 4194303.25f, 4194304.0f, 8388606.0f, 8388607.0f, 0.0f, -0.0f,
+                                -0.5f, 0.5f, -1.0f, -1.5f, 1e-30f, -1e-30f, 2097151.75f, -2097152.0f, INFINITY, -INFINITY, NAN };
+        for (float e : edges) {
+            check(e);
+            check(-e);
+        }
+        for (int i = 0; i < 4000000; i++) {
+            const double u = (double)rand() / RAND_MAX - 0.5;
+            const int sh = rand() % 24;
+            check((float)(u * 2.2 * (double)(1 << sh)));
+            check((float)(floor(u * (double)(1 << sh)) + ((rand() & 1) ? 0.5 : 0.0)));
+        }
+    }
+    printf("fast path: %ld values checked, %d mismatches\n", n_fast, bad);
+    return bad;
+}
+
 int main()
 {
     srand(12345);
-    int bad = run<float>(256) + run<double>(256);
+    int bad = run<float>(256) + run<double>(256) + fast_path();
     printf("%s\n", bad ? "FAIL" : "emul_sample ok");
     return bad;
 }
