@@ -2324,8 +2324,13 @@ static bool graph_preferred(const bfcuda_engine *e)
     if (env != nullptr) {
         return atoi(env) != 0;
     }
-    const size_t bytes = e->max_batch > 1 ? e->mac_bytes_batch : e->mac_bytes;
-    return bytes <= (size_t)136500000;
+    // block by block the graphs win at every size measured since the MAC stream has the higher priority (the full job
+    // 163.6 -> 159.3 us per block, shards of 2 / 4 / 8 ranks 87.8 -> 86.2, 55.3 -> 53.4, 34.9 -> 32.9; host-buffer figures
+    // within +-1-3 %; profiles/r2_graph_b1.txt); batched calls keep the size rule
+    if (e->max_batch == 1) {
+        return true;
+    }
+    return e->mac_bytes_batch <= (size_t)136500000;
 }
 
 static bool graph_eligible(const bfcuda_engine *e, int n_blocks)
