@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "m8", "c3f64"],
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "m8", "c3f64", "c3s24le"],
                     help="c3 = the headline configuration; c2 / c4 = BASELINE configs[1] / [3]; m8 = 8 x 8 matrix of the "
                          "headline filter shape (64 filters, every input feeds 8 of them: shared delay lines); c3f64 = "
                          "the headline shape at float_bits 64")
@@ -74,7 +74,7 @@ def parse_args():
 def workload_graph(name):
     from brutefir_b200 import configs
     return {"c2": configs.config_c2, "c3": configs.config_c3, "c4": configs.config_c4, "m8": configs.config_matrix,
-            "c3f64": lambda: configs.config_c3(realsize=8)}[name]()
+            "c3f64": lambda: configs.config_c3(realsize=8), "c3s24le": lambda: configs.config_c3(fmt="S24_LE")}[name]()
 
 
 def workload_config(name, graph, n_gpus):
@@ -502,6 +502,20 @@ def sub_records(ctx, steps, warmup):
         out["c3_f64"] = rec
     except Exception as exc:
         out["c3_f64"] = {"error": repr(exc)}
+    try:
+        # the headline shape in massive_config's OWN sample format (/root/reference/massive_config:11,17: "S24_LE", packed
+        # three-byte samples): 12 MiB instead of 16 MiB each way per 8-block step -- what the host-buffer figure, bound by
+        # the box's PCIe copies, gains from a quarter fewer bytes
+        g = configs.config_c3(fmt="S24_LE")
+        taps = fast_filters(g, 2003)
+        sh = shard_graph(g, 1)[0]
+        rec = {"workload": workload_config("c3 (S24_LE I/O)", g, 1)["workload"],
+               "batch8": summary(measure(one, g, sh, taps, 3, 8, max(20, steps // 2), warmup, tag="c3s24le", light=True))}
+        rec["batch8"]["h2d_bytes_per_step"] = 8 * g.in_bytes
+        rec["batch8"]["d2h_bytes_per_step"] = 8 * g.out_bytes
+        out["c3_s24le"] = rec
+    except Exception as exc:
+        out["c3_s24le"] = {"error": repr(exc)}
     return out
 
 

@@ -1147,6 +1147,21 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
                 fast = 0;
             }
         }
+        if (fast == 0 && e->n_ch[io] > 0 && e->n_ch[io] % 32 == 0) {
+            // packed 24-bit little-endian, all channels interleaved in channel order (massive_config's / xtc_config's
+            // "S24_LE"): whole 32-channel tiles of 96 contiguous, 4-byte aligned bytes per sample time
+            bool packed = e->n_bytes[io] % 4 == 0;
+            for (int ch = 0; ch < e->n_ch[io]; ch++) {
+                const bfcuda_buffer_format &b = e->fmt[io][(size_t)ch];
+                if (b.sf.isfloat || b.sf.swap || b.sf.bytes != 3 || b.sf.sbytes != 3 || b.sample_spacing != e->n_ch[io] ||
+                    b.byte_offset != 3 * ch) {
+                    packed = false;
+                }
+            }
+            if (packed) {
+                fast = 3;
+            }
+        }
         e->fast_fmt[io] = fast;
     }
     e->filters.resize(e->n_filters);
@@ -1839,6 +1854,19 @@ static InverseArgs make_inverse_args(const bfcuda_engine *e, int nb, int y_gen, 
     ia.out_stride = (size_t)e->n_bytes[1];
     ia.safety_limit = e->safety_limit;
     ia.fast_fmt = e->fast_fmt[1];
+    if (ia.fast_fmt == 3) {
+        // the packed path shuffles across all 32 lanes of a tile: not with outputs k_pack leaves out (dither, virtual groups)
+        bool whole = true;
+        for (size_t o = 0; o < e->out_rep.size(); o++) {
+            whole = whole && e->out_rep[o] == (int)o;
+        }
+        for (int d : e->dither_of_out) {
+            whole = whole && d < 0;
+        }
+        if (!whole) {
+            ia.fast_fmt = 0;
+        }
+    }
     ia.simple_mix = e->simple_mix ? 1 : 0;
     ia.any_xfade = e->xfade_active ? 1 : 0;
     return ia;

@@ -112,7 +112,7 @@ struct ForwardArgs {
     int t;
     int batch;
     size_t in_stride;
-    int fast_fmt;               // 1: every input is an aligned 4-byte LE integer, 2: FLOAT_LE, 0: per-sample generic decode
+    int fast_fmt;               // 1: every input is an aligned 4-byte LE integer, 2: FLOAT_LE, 3: packed S24_LE in whole 32-channel tiles, 0: per-sample generic decode
     // size-specialised path (bf_fft2_kernels.cu): the samples arrive unpacked
     const void *xt_cur;         // [batch][n_in][L] reals, this launch's blocks
     const void *xt_prev;        // [n_in][L] reals, the block before the first one

@@ -13,7 +13,7 @@ import pytest
 
 from brutefir_b200 import _abi, configs
 from brutefir_b200.engine import Engine
-from brutefir_b200.formats import BufferFormat, interleaved_layout, pack_block, parse_sample_format, planar_layout
+from brutefir_b200.formats import BufferFormat, interleaved_layout, pack_block, parse_sample_format, planar_layout, unpack_block
 from brutefir_b200.graph import Filter, FilterGraph
 from oracle import pyoracle as po
 from helpers import unpack_run
@@ -752,6 +752,35 @@ def test_delay_lines_shared_across_filters(gpu_lib, oracle_libs, L, P, rs, B):
         want.append(d.process_block(sig[b]))
     d.close()
     assert_parity(g, shared, np.stack(want))
+
+
+@pytest.mark.parametrize("B", [1, 4])
+def test_packed_s24_tiles_equal_the_4_byte_layout(gpu_lib, B):
+    """massive_config's own sample format, packed "S24_LE" on 64 interleaved channels, takes a tile path of its own in
+    k_unpack / k_pack (24 lanes move the 96 bytes of a 32-channel row, shuffles pick the three bytes): the same samples in
+    the S24_4LE layout (pinned against the oracle elsewhere) must come out as the same integers, overflow counters
+    included -- loud enough to clip."""
+    L, P, nb = 256, 3, 9
+    outs, stats = [], []
+    for fmt in ("S24_4LE", "S24_LE"):
+        g = configs.diagonal_graph(64, L, P, 4, fmt)
+        taps = configs.synthetic_filters(g, 31)
+        sig = configs.synthetic_signal(g, 31, nb, sigma=0.4)
+        with Engine(g, max_batch=B) as e:
+            assert e.lib is not None
+            for c, h in enumerate(taps):
+                e.coeff_from_taps(c, h, 3.0)
+            out = np.zeros((nb, g.out_bytes), np.uint8)
+            b = 0
+            while b < nb:
+                n = min(B, nb - b)
+                e.process_blocks_async(sig[b:b + n], out[b:b + n], n)
+                b += n
+            e.synchronize()
+            stats.append([(e.overflow(o).n_overflows, e.overflow(o).intlargest, e.overflow(o).largest) for o in range(64)])
+        outs.append(np.stack([unpack_block(blk, g.out_formats, L) for blk in out]))
+    assert np.array_equal(outs[0], outs[1])
+    assert stats[0] == stats[1] and sum(s[0] for s in stats[0]) > 0 and np.abs(outs[0]).max() == 2 ** 23
 
 
 @pytest.mark.parametrize("which", ["1", "2"])
