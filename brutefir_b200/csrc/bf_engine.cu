@@ -264,7 +264,6 @@ struct bfcuda_engine {
     unsigned int *d_amax[2];            // [max_batch][n_in] block peaks, by the generation of d_xt
     float *d_ps_thr;                    // [n_in]
     uint8_t *d_slot_zero;               // [F][ring]
-    unsigned int *d_split_cnt;          // k_mac's per-column arrival counters (the last partial's block adds the partials)
     long ps_hold_until;                 // block count until which the MAC ignores the flags (after a delay transition)
     // virtual -> physical outputs, mute, sub-sample delay (bfrun.c:1503-1526, 1918-2002)
     std::vector<int> out_rep;           // per output: the member of its physical channel that is quantised (itself: alone)
@@ -890,7 +889,7 @@ void bfcuda_destroy(bfcuda_engine *e)
         g_nccl.CommDestroy(e->comm);
     }
     void *ptrs[] = { e->d_groups, e->d_members, e->d_muted[0], e->d_muted[1], e->d_sd_chans[0], e->d_sd_chans[1], e->d_sd_taps[0],
-                     e->d_sd_taps[1], e->d_sd_hist[0], e->d_sd_hist[1], e->d_amax[0], e->d_amax[1], e->d_ps_thr, e->d_slot_zero, e->d_split_cnt, e->d_raw34[0][0], e->d_raw34[0][1], e->d_raw34[1][0], e->d_raw34[1][1], e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
+                     e->d_sd_taps[1], e->d_sd_hist[0], e->d_sd_hist[1], e->d_amax[0], e->d_amax[1], e->d_ps_thr, e->d_slot_zero, e->d_raw34[0][0], e->d_raw34[0][1], e->d_raw34[1][0], e->d_raw34[1][1], e->d_xt[0], e->d_xt[1], e->d_raw[0], e->d_raw[1], e->d_raw2[0], e->d_raw2[1], e->d_fmt[0], e->d_fmt[1], e->d_prev[0], e->d_prev[1], e->d_fdl, e->d_xin, e->d_H,
                      e->d_Y, e->d_out_time, e->d_scratch, e->d_overflow, e->d_dests, e->d_dest_first,
                      e->d_need_xin, e->d_mix_streams, e->d_mix_terms, e->d_jobs, e->d_chans, e->d_out_terms,
                      e->d_keep, e->d_eval_entries, e->d_eval_terms, e->d_mixes, e->dither.chans, (void *)e->dither.randtab,
@@ -1109,7 +1108,6 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
     e->d_amax[0] = e->d_amax[1] = nullptr;
     e->d_ps_thr = nullptr;
     e->d_slot_zero = nullptr;
-    e->d_split_cnt = nullptr;
     e->ps_hold_until = -1;
     e->pend_mac.valid = e->pend_inv.valid = false;
     e->h_overflow_valid = false;
@@ -1356,11 +1354,6 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
             TRY(dev_alloc(e, &e->d_out_terms, sizeof(MixTerm) * terms));
         }
         TRY(dev_alloc(e, &e->d_jobs, sizeof(MacJob) * 2 * F));
-        if (e->split > 1) {
-            // one counter per 256-thread column of k_mac (16-byte vectors per half spectrum: N / 2 / (16 / rs) per job)
-            const size_t cols = (2 * F * (N / 2 / (16 / (size_t)e->rs)) + 255) / 256 + 1;
-            TRY(dev_alloc(e, &e->d_split_cnt, sizeof(unsigned int) * cols));
-        }
         TRY(dev_alloc(e, &e->d_chans, sizeof(OutChan) * std::max(1, e->n_ch[1])));
         TRY(dev_alloc(e, &e->d_mixes, sizeof(OutChan) * std::max(1, e->n_ch[1])));
         e->h_dest_first.assign(e->n_ch[0] + 1, 0);
@@ -1832,7 +1825,6 @@ static MacArgs make_mac_args(const bfcuda_engine *e, int nb, int slot_t, int y_g
     // powersave: zero slots are skipped -- unless a delay transition has been rewriting slots behind the flags' back
     ma.slot_zero = (e->powersave && !in_transition(e) && (long)e->t >= e->ps_hold_until) ? e->d_slot_zero : nullptr;
     ma.neg_zero2 = 0x8000000080000000ull;   // two packed -0.0f (bf_mac_batch.cu, BinPairAcc): the launcher sets the same
-    ma.split_cnt = e->d_split_cnt;
     return ma;
 }
 
@@ -2011,7 +2003,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
     e->launches += ma.n_jobs > 0;
     if (e->split > 1) {
         CU(launch_split_reduce(e->plan, ma, e->s_mac));
-        e->launches += ma.n_jobs > 0 && !mac_reduces_inline(e->plan, ma);
+        e->launches += ma.n_jobs > 0;
     }
     for (int level = 1; level < e->n_levels; level++) {
         // filter -> filter chaining (bfrun.c:1603-1660): evaluate the finished source outputs, mix them with the
@@ -2042,7 +2034,7 @@ static int enqueue_batch(bfcuda_engine *e, int nb, uint8_t *raw_in, uint8_t *raw
         e->launches += 3;
         if (e->split > 1) {
             CU(launch_split_reduce(e->plan, ma, e->s_mac));
-            e->launches += !mac_reduces_inline(e->plan, ma);
+            e->launches++;
         }
     }
     if (timing) CU(cudaEventRecord(ev[3], e->s_mac));

@@ -305,14 +305,19 @@ __device__ __forceinline__ Lanes<T, W> as_lanes(const V &x)
 }
 
 template <typename T, int UNROLL>
-__device__ __forceinline__ void mac_thread(const MacArgs &a, int N, long g, int z)
+__global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
 {
     constexpr int W = 16 / (int)sizeof(T);
     typedef typename Vec16<T>::type V;
     const int M = N >> 1;
     const int vecs = M / W;     // 16-byte vectors per half spectrum
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long)a.n_jobs * vecs) {
+        return;
+    }
     const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
     const MacJob jb = a.jobs[job];
+    const int z = (int)blockIdx.y + a.z_first;
     const int P = a.ring;       // ring slots per stream
     T *out = reinterpret_cast<T *>(a.Y) + ((size_t)z * a.n_slots + jb.out) * N + (size_t)v * W;
     const T *X = reinterpret_cast<const T *>(a.fdl) + (size_t)jb.stream * P * N + (size_t)v * W;
@@ -417,81 +422,6 @@ __device__ __forceinline__ void mac_thread(const MacArgs &a, int N, long g, int 
     }
     *reinterpret_cast<V *>(out) = *reinterpret_cast<V *>(&are);
     *reinterpret_cast<V *>(out + M) = *reinterpret_cast<V *>(&aim);
-}
-
-// Loads that must see what OTHER blocks of the running kernel have just written (L1 is not coherent): ld.global.cg
-template <typename V>
-__device__ __forceinline__ V ldg_l2(const V *p)
-{
-    uint4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return *reinterpret_cast<V *>(&r);
-}
-
-// With a split partition sum every (job, bin) has `split` partial sums, written by the `split` blocks that share a
-// blockIdx.x.  split_cnt != NULL: the block that finishes LAST among them adds the partials in range order into partial 0
-// -- k_split_reduce's sum, bit for bit, without a second launch behind the MAC (BASELINE config 4 block by block is
-// three kernels of a few microseconds per stage; the counters reset themselves for the next launch).
-template <typename T, int UNROLL>
-__global__ void __launch_bounds__(256) k_mac(MacArgs a, int N)
-{
-    constexpr int W = 16 / (int)sizeof(T);
-    typedef typename Vec16<T>::type V;
-    const int vecs = (N >> 1) / W;
-    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = g < (long)a.n_jobs * vecs;
-    if (active) {
-        mac_thread<T, UNROLL>(a, N, g, (int)blockIdx.y + a.z_first);
-    }
-    if (a.split_cnt == nullptr) {
-        return;
-    }
-    __shared__ int is_last;
-    __threadfence();            // this thread's partial is visible device-wide before the block is counted
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int done = atomicAdd(&a.split_cnt[blockIdx.x], 1u);
-        is_last = done == (unsigned int)a.split - 1u;
-        if (is_last) {
-            a.split_cnt[blockIdx.x] = 0;        // every block of this column has arrived: ready for the next launch
-        }
-    }
-    __syncthreads();
-    if (!is_last || !active) {
-        return;
-    }
-    __threadfence();
-    constexpr int FL = 12;      // partials in flight
-    const int job = (int)(g / vecs), v = (int)(g - (long)job * vecs);
-    const MacJob jb = a.jobs[job];
-    const size_t zstride = (size_t)a.batch * a.n_slots * N;
-    T *y0 = reinterpret_cast<T *>(a.Y) + (size_t)jb.out * N + (size_t)v * W;
-    const int M = N >> 1;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        T *yp = y0 + half * M;
-        Lanes<T, W> acc = as_lanes<T, W>(ldg_l2(reinterpret_cast<const V *>(yp)));
-        for (int z = 1; z < a.split; z += FL) {     // added in ascending order
-            V p[FL];
-#pragma unroll
-            for (int u = 0; u < FL; u++) {
-                if (z + u < a.split) {
-                    p[u] = ldg_l2(reinterpret_cast<const V *>(yp + (size_t)(z + u) * zstride));
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < FL; u++) {
-                if (z + u < a.split) {
-                    const Lanes<T, W> q = as_lanes<T, W>(p[u]);
-#pragma unroll
-                    for (int l = 0; l < W; l++) {
-                        acc.v[l] = add_rn(acc.v[l], q.v[l]);
-                    }
-                }
-            }
-        }
-        *reinterpret_cast<V *>(yp) = *reinterpret_cast<V *>(&acc);
-    }
 }
 
 // ======================================================================================================
@@ -1240,14 +1170,6 @@ cudaError_t launch_stream_mix(const FftPlan &plan, const StreamMixArgs &a, cudaS
 cudaError_t launch_mac_tma(const FftPlan &plan, const MacArgs &a, cudaStream_t s);   // bf_mac_tma.cu
 cudaError_t launch_mac_batch2(const FftPlan &plan, const MacArgs &a, cudaStream_t s); // bf_mac_batch.cu
 
-// does launch_mac's kernel add the partial sums of a split itself (no launch_split_reduce needed)?
-bool mac_reduces_inline(const FftPlan &plan, const MacArgs &a)
-{
-    static const int off = [] { const char *e = getenv("BFCUDA_MAC_INLINE_REDUCE"); return e != nullptr && atoi(e) == 0; }();
-    return !off && a.split_cnt != nullptr && a.split > 1 && a.batch == 1 && a.head == 0 && a.z_count == 0 &&
-           !(a.variant == 1);
-}
-
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
     if (a.n_jobs == 0) return cudaSuccess;
@@ -1261,25 +1183,21 @@ cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
         if (a.head > 0 || a.z_count > 0) return cudaErrorInvalidValue;     // block-by-block schedule only
         return launch_mac_batch2(plan, a, s);      // bf_mac_batch.cu
     }
-    MacArgs k = a;
-    if (!mac_reduces_inline(plan, a)) {
-        k.split_cnt = nullptr;
-    }
     // (the cp.async ring kernel was tried for single blocks as well -- BASELINE config 4, 28 partitions per thread after
     // the split: 36.8 us against 32.0 us for this kernel, profiles/r2_macsweep_groups_b1ring.txt)
     if (plan.realsize == 4) {
         g_last_func = (const void *)k_mac<float, 4>;
-        k_mac<float, 4><<<grid, 256, 0, s>>>(k, plan.N);
+        k_mac<float, 4><<<grid, 256, 0, s>>>(a, plan.N);
     } else {
         g_last_func = (const void *)k_mac<double, 4>;
-        k_mac<double, 4><<<grid, 256, 0, s>>>(k, plan.N);
+        k_mac<double, 4><<<grid, 256, 0, s>>>(a, plan.N);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_split_reduce(const FftPlan &plan, const MacArgs &a, cudaStream_t s)
 {
-    if (a.n_jobs == 0 || a.split <= 1 || mac_reduces_inline(plan, a)) return cudaSuccess;
+    if (a.n_jobs == 0 || a.split <= 1) return cudaSuccess;
     const int W = 16 / plan.realsize;
     dim3 grid((plan.N / W + 63) / 64, a.n_jobs, a.batch);
     if (plan.realsize == 4) {

@@ -197,7 +197,6 @@ struct MacArgs {
     // z_count - 1 (the "rest" is computed one block ahead, bf_engine.cu).
     int head, z_first, z_count;
     const uint8_t *slot_zero;   // [U][ring] powersave: slots flagged 1 are not read (nor the coefficients they meet), or NULL
-    unsigned int *split_cnt;    // one zeroed counter per blockIdx.x of k_mac: the last partial's block adds the partials (or NULL)
 };
 cudaError_t launch_mac(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
 // The host stub of the kernel the most recent launch_forward / launch_mac call of this thread launched: how the engine
@@ -212,7 +211,6 @@ int mac_batch_lanes(int realsize, int batch, int n_jobs, int N);
 // With split > 1 the MAC leaves `split` partial sums per output: add them, in order, into partial 0 (the consumers
 // -- inverse stage, chaining evaluation -- then read one complete spectrum per filter).
 cudaError_t launch_split_reduce(const FftPlan &plan, const MacArgs &a, cudaStream_t s);
-bool mac_reduces_inline(const FftPlan &plan, const MacArgs &a);
 
 struct InverseArgs {
     const void *Y;              // [split][batch][n_slots][N]
