@@ -1145,9 +1145,9 @@ int bfcuda_create(const struct bfcuda_config *c, bfcuda_engine **out)
                 fast = 0;
             }
         }
-        if (fast == 0 && e->n_ch[io] > 0 && e->n_ch[io] % 32 == 0) {
+        if (fast == 0 && e->n_ch[io] > 0 && e->n_ch[io] % 4 == 0) {
             // packed 24-bit little-endian, all channels interleaved in channel order (massive_config's / xtc_config's
-            // "S24_LE"): whole 32-channel tiles of 96 contiguous, 4-byte aligned bytes per sample time
+            // "S24_LE"): tiles of up to 32 channels, 3 nc contiguous and 4-byte aligned bytes per sample time (nc % 4 == 0)
             bool packed = e->n_bytes[io] % 4 == 0;
             for (int ch = 0; ch < e->n_ch[io]; ch++) {
                 const bfcuda_buffer_format &b = e->fmt[io][(size_t)ch];

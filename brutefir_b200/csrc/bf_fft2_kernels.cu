@@ -113,6 +113,24 @@ __global__ void __launch_bounds__(32 * WPB) k_unpack(UnpackArgs a)
         return;
     }
     const uint8_t *raw = a.raw_in + (size_t)blk * a.in_stride;
+    if (a.fast_fmt == 3) {
+        // packed 24-bit little-endian, all channels interleaved (massive_config's own format): a tile row is 3 * nc
+        // contiguous bytes (nc = channels of this tile, a multiple of 4); 3 nc / 4 lanes fetch the words, every lane picks
+        // its three bytes out of two of them (raw2real.h:106-142: into the top of an int32, arithmetic shift down).
+        // All 32 lanes take part in the shuffles, whatever nc is.
+        const int nc = min(32, a.n_in - c0);
+        const size_t stride = (size_t)a.n_in * 3;
+        const int w0 = (3 * lane) >> 2, sh = ((3 * lane) & 3) * 8;
+        const uint8_t *rowp = raw + (size_t)n0 * stride + (size_t)c0 * 3;
+        T *row = &tile[w][lane * TS];
+#pragma unroll
+        for (int r = 0; r < RW; r++) {
+            const uint32_t wv = 4 * lane < 3 * nc ? reinterpret_cast<const uint32_t *>(rowp + r * stride)[lane] : 0u;
+            const uint32_t lo = __shfl_sync(0xffffffffu, wv, w0), hi = __shfl_sync(0xffffffffu, wv, (w0 + 1) & 31);
+            const uint32_t v3 = __funnelshift_r(lo, hi, sh);
+            row[r] = (T)((int32_t)(v3 << 8) >> 8);
+        }
+    }
     {
         const int c = c0 + lane;
         if (c < a.n_in) {
@@ -130,20 +148,7 @@ __global__ void __launch_bounds__(32 * WPB) k_unpack(UnpackArgs a)
                 for (int r = 0; r < RW; r++) {
                     row[r] = (T)*reinterpret_cast<const float *>(p + r * stride);
                 }
-            } else if (a.fast_fmt == 3) {
-                // packed 24-bit little-endian, 32 channels = 96 contiguous bytes per sample time (massive_config's own
-                // format): 24 lanes fetch the words, every lane picks its three bytes out of two of them
-                // (raw2real.h:106-142: into the top of an int32, arithmetic shift down)
-                const int w0 = (3 * lane) >> 2, sh = ((3 * lane) & 3) * 8;
-                const uint8_t *rowp = raw + (size_t)n0 * stride + (size_t)c0 * 3;
-#pragma unroll
-                for (int r = 0; r < RW; r++) {
-                    const uint32_t wv = lane < 24 ? reinterpret_cast<const uint32_t *>(rowp + r * stride)[lane] : 0u;
-                    const uint32_t lo = __shfl_sync(0xffffffffu, wv, w0), hi = __shfl_sync(0xffffffffu, wv, (w0 + 1) & 31);
-                    const uint32_t v3 = __funnelshift_r(lo, hi, sh);
-                    row[r] = (T)((int32_t)(v3 << 8) >> 8);
-                }
-            } else {
+            } else if (a.fast_fmt != 3) {
                 for (int r = 0; r < RW; r++) {
                     row[r] = decode_sample<T>(load_raw_le(p + r * stride, f.bytes), f.bytes, f.isfloat, f.swap);
                 }
@@ -205,7 +210,37 @@ __global__ void __launch_bounds__(32 * WPB) k_pack(InverseArgs a, int L)
         }
         __syncwarp();
         const int c = c0 + lane;
-        if (c < a.n_out && !(a.chans[c].shared & 6)) {      // dithered outputs are k_dither's; bit 2: mixed into another channel
+        if (a.fast_fmt == 3) {
+            // packed 24-bit little-endian on all (undithered, ungrouped) outputs: quantise per lane, then 3 nc / 4 lanes
+            // assemble and store the tile row -- word w holds the tail of channel 4w/3 and the head of the next one.
+            // All 32 lanes take part in the shuffles; lanes beyond the last channel carry zeros.
+            const bool live = c < a.n_out;
+            const int32_t imin = -(1 << 23), imax = (1 << 23) - 1;
+            const double rmin = (double)(T)imin, rmax = (double)(T)imax;
+            const double of_max = live ? a.overflow[c].max : 1.0;
+            const float thr = 4194303.0f;
+            const bool limit = a.safety_limit != 0.0;
+            const int ca = (4 * lane) / 3, sh = ((4 * lane) % 3) * 8;
+            const size_t stride = (size_t)a.n_out * 3;
+            uint8_t *rowp = a.raw_out + (size_t)blk * a.out_stride + (size_t)n0 * stride + (size_t)c0 * 3;
+            const T *row = &tile[w][lane * TS];
+#pragma unroll
+            for (int r = 0; r < RW; r++) {
+                const T y = live ? row[r] : (T)0;
+                int32_t q, cand;
+                if (!limit && real_to_int_fast(y, thr, q, cand)) {
+                    st.intlargest = max(st.intlargest, cand);
+                } else {
+                    sample_test<T>(y, a.safety_limit, of_max, st);
+                    q = real_to_int<T>(y, rmin, rmax, imin, imax, st);
+                }
+                const uint32_t q24 = (uint32_t)q & 0xffffffu;
+                const uint32_t qa = __shfl_sync(0xffffffffu, q24, ca & 31), qb = __shfl_sync(0xffffffffu, q24, (ca + 1) & 31);
+                if (4 * lane < 3 * nc) {        // bytes [o, o + 4) of (qa's three bytes | qb's three bytes), o = sh / 8
+                    reinterpret_cast<uint32_t *>(rowp + r * stride)[lane] = (qa >> sh) | (qb << (24 - sh));
+                }
+            }
+        } else if (c < a.n_out && !(a.chans[c].shared & 6)) {      // dithered outputs are k_dither's; bit 2: mixed into another channel
             const SampleFormat f = a.fmt[c];
             const size_t stride = (size_t)f.sample_spacing * f.bytes;
             uint8_t *p = a.raw_out + (size_t)blk * a.out_stride + f.byte_offset + (size_t)n0 * stride;
@@ -232,31 +267,6 @@ __global__ void __launch_bounds__(32 * WPB) k_pack(InverseArgs a, int L)
                         q = real_to_int<T>(y, rmin, rmax, imin, imax, st);
                     }
                     *reinterpret_cast<int32_t *>(p + r * stride) = q;
-                }
-            } else if (a.fast_fmt == 3) {
-                // packed 24-bit little-endian: quantise per lane, then 24 lanes assemble and store the 96 bytes of the
-                // tile row -- word w holds the tail of channel 4w/3 and the head of the next one
-                const int32_t imin = -(1 << 23), imax = (1 << 23) - 1;
-                const double rmin = (double)(T)imin, rmax = (double)(T)imax;
-                const float thr = 4194303.0f;
-                const bool limit = a.safety_limit != 0.0;
-                const int ca = (4 * lane) / 3, sh = ((4 * lane) % 3) * 8;
-                uint8_t *rowp = a.raw_out + (size_t)blk * a.out_stride + (size_t)n0 * stride + (size_t)c0 * 3;
-#pragma unroll
-                for (int r = 0; r < RW; r++) {
-                    const T y = row[r];
-                    int32_t q, cand;
-                    if (!limit && real_to_int_fast(y, thr, q, cand)) {
-                        st.intlargest = max(st.intlargest, cand);
-                    } else {
-                        sample_test<T>(y, a.safety_limit, of_max, st);
-                        q = real_to_int<T>(y, rmin, rmax, imin, imax, st);
-                    }
-                    const uint32_t q24 = (uint32_t)q & 0xffffffu;
-                    const uint32_t qa = __shfl_sync(0xffffffffu, q24, ca & 31), qb = __shfl_sync(0xffffffffu, q24, (ca + 1) & 31);
-                    if (lane < 24) {        // bytes [o, o + 4) of (qa's three bytes | qb's three bytes), o = sh / 8
-                        reinterpret_cast<uint32_t *>(rowp + r * stride)[lane] = (qa >> sh) | (qb << (24 - sh));
-                    }
                 }
             } else if (a.fast_fmt == 2) {
 #pragma unroll

@@ -754,16 +754,16 @@ def test_delay_lines_shared_across_filters(gpu_lib, oracle_libs, L, P, rs, B):
     assert_parity(g, shared, np.stack(want))
 
 
-@pytest.mark.parametrize("B", [1, 4])
-def test_packed_s24_tiles_equal_the_4_byte_layout(gpu_lib, B):
-    """massive_config's own sample format, packed "S24_LE" on 64 interleaved channels, takes a tile path of its own in
-    k_unpack / k_pack (24 lanes move the 96 bytes of a 32-channel row, shuffles pick the three bytes): the same samples in
-    the S24_4LE layout (pinned against the oracle elsewhere) must come out as the same integers, overflow counters
-    included -- loud enough to clip."""
+@pytest.mark.parametrize("n_ch,B", [(64, 1), (64, 4), (8, 4), (40, 2), (4, 1)])
+def test_packed_s24_tiles_equal_the_4_byte_layout(gpu_lib, n_ch, B):
+    """massive_config's own sample format, packed "S24_LE" on interleaved channels (a multiple of four of them), takes a
+    tile path of its own in k_unpack / k_pack (24 lanes move the 96 bytes of a 32-channel row, shuffles pick the three
+    bytes; ragged last tiles and shards of 8 channels included): the same samples in the S24_4LE layout (pinned against
+    the oracle elsewhere) must come out as the same integers, overflow counters included -- loud enough to clip."""
     L, P, nb = 256, 3, 9
     outs, stats = [], []
     for fmt in ("S24_4LE", "S24_LE"):
-        g = configs.diagonal_graph(64, L, P, 4, fmt)
+        g = configs.diagonal_graph(n_ch, L, P, 4, fmt)
         taps = configs.synthetic_filters(g, 31)
         sig = configs.synthetic_signal(g, 31, nb, sigma=0.4)
         with Engine(g, max_batch=B) as e:
@@ -777,7 +777,7 @@ def test_packed_s24_tiles_equal_the_4_byte_layout(gpu_lib, B):
                 e.process_blocks_async(sig[b:b + n], out[b:b + n], n)
                 b += n
             e.synchronize()
-            stats.append([(e.overflow(o).n_overflows, e.overflow(o).intlargest, e.overflow(o).largest) for o in range(64)])
+            stats.append([(e.overflow(o).n_overflows, e.overflow(o).intlargest, e.overflow(o).largest) for o in range(n_ch)])
         outs.append(np.stack([unpack_block(blk, g.out_formats, L) for blk in out]))
     assert np.array_equal(outs[0], outs[1])
     assert stats[0] == stats[1] and sum(s[0] for s in stats[0]) > 0 and np.abs(outs[0]).max() == 2 ** 23
