@@ -153,3 +153,24 @@ def test_c3_batched_pipeline_equals_block_by_block_at_full_size(gpu_lib):
             outs.append(out)
     assert np.array_equal(outs[0], outs[1])
     assert np.abs(unpack_run(outs[0], g.out_formats, L)).max() > 1e4
+
+
+def test_c3_packed_s24_io_equals_the_4_byte_layout_at_the_headline_partition_size(gpu_lib):
+    """The headline shape's channels and partition size (64 x 8192) in massive_config's own sample format, packed S24_LE
+    (massive_config:11,17), 8 blocks per call: the same integers as the S24_4LE layout, byte for byte after unpacking
+    (the 4-byte layout is the one the full-size parity tests pin against the reference build)."""
+    L, P, nb, B = 8192, 4, 16, 8
+    outs = []
+    for fmt in ("S24_4LE", "S24_LE"):
+        g = configs.config_c3(fmt=fmt, P=P)
+        taps = configs.synthetic_filters(g, 3)
+        sig = configs.synthetic_signal(g, 3, nb, sigma=0.1)
+        with Engine(g, max_batch=B) as e:
+            for c, h in enumerate(taps):
+                e.coeff_from_taps(c, h)
+            out = np.zeros((nb, g.out_bytes), np.uint8)
+            for b in range(0, nb, B):
+                e.process_blocks_async(sig[b:b + B], out[b:b + B], B)
+            e.synchronize()
+        outs.append(unpack_run(out, g.out_formats, L))
+    assert np.array_equal(outs[0], outs[1]) and np.abs(outs[0]).max() > 2 ** 20
