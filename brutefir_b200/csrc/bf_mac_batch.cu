@@ -30,16 +30,16 @@ namespace bf {
 // slots are 3.46 "waves" at the headline shape.  Measured: 64, 128 and 256 threads per block take the same time -- the
 // blocks of the partial last wave run alone on their SMs and correspondingly faster.)
 //
-// Small shards (8 filters of a 64-filter job per GPU) do not have a power of two of 256-thread blocks to spread:
-// 8 filters x 4096 bin pairs are 128 blocks for 148 SMs, and the engine's split heuristic would cut the partition sum in
-// two (a different summation tree) to fill the machine.  They run one bin per thread instead (W = 1: twice the threads,
-// the (re, im)-pair accumulators PairAcc, scalar products cost the FP32 pipe the same cycles as packed ones) in blocks
-// of 64 threads, which deal out evenly (1024 blocks = 6.9 per SM): the same 44-45 us per 8-block launch as the split
-// two-bin kernel, in the reference's summation order.  mac_batch_lanes() is the one place that decides.
-// What did NOT help at that size (profiles/r2_macsweep_*.txt, ncu profiles/r2_shard8_mac_summary.txt): deeper rings
-// (S = 12 .. 24: slower -- the kernel is not waiting for memory, its stalls are math-pipe throttle and fixed-latency
-// waits with 2-3 warps per scheduler), two groups of four blocks per thread (twice the threads, 59 us), 128- or
-// 64-thread blocks of the two-bin kernel.
+// Small shards (8 filters of a 64-filter job per GPU: 128 blocks of 256 threads for 148 SMs).  The first half of round 2 ran
+// them one bin per thread (W = 1, PairAcc) in 64-thread blocks, because the engine's split heuristic cut the two-bin
+// kernel's partition sum three ways there: 44-47 us per 8-block launch either way.  With the WHOLE sum in one thread (no
+// split from four warps per SM up, choose_split in bf_engine.cu) the two-bin kernel takes 38.8 us, and 37.0 us in the
+// 154-register build below -- a grid of at most one block per SM has the register file to itself -- in the reference's
+// summation order.  mac_batch_lanes() is the one place that decides the lanes.
+// What did NOT help at that size (profiles/r2_macsweep_*.txt, r2s_shard8_*): deeper rings (S = 12 .. 24: the kernel is
+// not waiting for memory, its stalls are fixed-latency waits and math-pipe throttle with two warps per scheduler), block
+// sizes that fill 148 SMs evenly (224 threads: the two-warp schedulers bound it, not the idle SMs), two steps per wait
+// (PAIR = 2), two groups of four blocks per thread (59 us), the shared-ring kernels of bf_mac_tile.cu at 8 blocks per launch.
 // PS: powersave instantiation (zero delay-line slots are not read); kept apart so that the plain kernel carries none of it
 // PAIR = 2: two partition steps per wait -- one cp.async.wait_group, the shared loads of both steps, then the arithmetic
 // of both in one scheduling window (the wait is a compiler barrier: with one step per wait every step starts with an
