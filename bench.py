@@ -83,7 +83,8 @@ def workload_config(name, graph, n_gpus):
                         f"float_bits {graph.realsize * 8}, {graph.in_formats[0].sf.name} I/O, dither off",
             "n_filters": len(graph.filters), "filter_length": graph.filter_length, "n_blocks": graph.n_blocks,
             "sampling_rate": graph.sampling_rate, "parallelism": f"filters sharded over {n_gpus} GPU(s), no collective; every rank is handed and returns "
-                           "only its own channels' interleaved blocks",
+                           "only its own channels' interleaved blocks; ranks on every (visible GPUs / ranks)-th device, i.e. one PCIe switch "
+                           "uplink each where the box shows more GPUs than the run uses",
             "l2": "per-block working set (coefficients + delay lines) exceeds L2 many times over; nothing is re-read "
                   "from L2 between steps"}
 
@@ -667,10 +668,27 @@ def nccl_xtc(ctx):
     return res
 
 
+def spread_device(local_rank, world):
+    """The GPUs of the box hang in PAIRS off one PCIe switch uplink: two ranks copying on neighbouring devices get half the
+    host bandwidth each (profiles/r2_copy_skew_n8.txt: ranks 0-3 at once 15-17 GB/s per direction each, ranks 0/2/4/6 at
+    once 32-33 GB/s each, one rank alone 39-41 GB/s).  A run on fewer ranks than the box shows GPUs therefore takes every
+    (count // world)-th device, so that each rank has an uplink of its own.  BENCH_NO_SPREAD=1 keeps device = LOCAL_RANK."""
+    if world < 2 or os.environ.get("BENCH_NO_SPREAD"):
+        return local_rank, 1
+    try:
+        import torch
+        count = torch.cuda.device_count()
+    except Exception:
+        return local_rank, 1
+    if count >= 2 * world and count % world == 0:
+        return local_rank * (count // world), count // world
+    return local_rank, 1
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_rank, device_stride = spread_device(int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from brutefir_b200 import configs
 
@@ -742,6 +760,8 @@ def main():
                              "'streaming'")}
     if n_shards != world:
         schedule["shard_of"] = n_shards
+    if device_stride > 1:
+        schedule["device_stride"] = device_stride
     line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if graph.realsize == 4 else "f64", "data": "synthetic", "config": cfg,
