@@ -158,3 +158,19 @@ def test_world_size_2_gloo(tmp_path):
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "DIST_OK" in r.stdout
+
+
+@pytest.mark.parametrize("count,world,want", [(8, 1, (0,)), (8, 2, (0, 4)), (8, 4, (0, 2, 4, 6)), (8, 8, tuple(range(8))),
+                                              (2, 2, (0, 1)), (4, 2, (0, 2)), (6, 4, (0, 1, 2, 3)), (0, 2, (0, 1))])
+def test_bench_spreads_ranks_over_the_visible_gpus(monkeypatch, count, world, want):
+    """bench.py: a run on fewer ranks than the box shows GPUs takes every (count // world)-th device (the GPUs of an HGX
+    box share PCIe switch uplinks in pairs, profiles/r2_copy_skew_n8.txt); otherwise device = LOCAL_RANK."""
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: count)
+    monkeypatch.delenv("BENCH_NO_SPREAD", raising=False)
+    got = tuple(bench.spread_device(r, world)[0] for r in range(max(world, len(want))))[:len(want)]
+    assert got == want
+    monkeypatch.setenv("BENCH_NO_SPREAD", "1")
+    assert all(bench.spread_device(r, world)[0] == r for r in range(world))
