@@ -11,7 +11,8 @@
  * (diagonal graphs and per-output groups of a matrix need no collective).
  *
  *   bfcuda_multi -g 4 -n 64 -L 8192 -P 128 [-m] [-c taps.f32|dirac] [-B 8] [-r 32|64] [-i fmt] [-o fmt] in.raw out.raw
- *     -g gpus : engines; engine k runs on CUDA device k modulo the number of devices present
+ *     -g gpus : engines; engine k runs on CUDA device k modulo the number of devices present (spread over every
+ *               (devices / gpus)-th device when the box has at least twice as many)
  *     -m      : n x n matrix (output o = sum over inputs i of filter o*n+i, each scaled 1/n) instead of the diagonal
  *     -B      : audio blocks per call (file-to-file mode); four calls are kept in flight per engine
  *   Output is byte-identical to bfcuda_run's for the same arguments (tests/test_gpu_host.py).
@@ -216,7 +217,10 @@ main(int argc, char *argv[])
         cfg.filters = filters;
         cfg.n_coeffs = s->n_filters;
         cfg.coeff_n_blocks = cb;
-        cfg.device = g % n_dev;
+        /* The GPUs of an HGX box share PCIe switch uplinks in pairs (profiles/r2_copy_skew_n8.txt): with fewer engines than
+         * devices take every (n_dev / gpus)-th device, one uplink per engine; otherwise engine k runs on device k modulo the
+         * number of devices. */
+        cfg.device = (gpus > 1 && n_dev >= 2 * gpus && n_dev % gpus == 0) ? g * (n_dev / gpus) : g % n_dev;
         cfg.max_batch = batch;
         CHECK(bfcuda_create(&cfg, &s->eng));
         s->in_bytes = (size_t)cfg.n_bytes[BFCUDA_IN];
