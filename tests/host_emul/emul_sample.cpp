@@ -147,10 +147,55 @@ static int fast_path()
     return bad;
 }
 
+// the packed S24_LE tile path of k_unpack / k_pack (bf_fft2_kernels.cu), one warp emulated lane by lane: 3 nc / 4 lanes
+// hold the words of a tile row, shuffles + a funnel shift pick (or place) every channel's three bytes -- against the
+// generic per-sample routines, for every tile width nc = 4 .. 32
+static uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return sh == 0 ? lo : (uint32_t)((((uint64_t)hi << 32) | lo) >> sh); }
+static int packed_tiles()
+{
+    int bad = 0;
+    for (int nc = 4; nc <= 32; nc += 4) {
+        for (int trial = 0; trial < 200; trial++) {
+            uint8_t rowb[96 + 8] = {0}, outb[96 + 8];
+            for (int i = 0; i < 3 * nc; i++) rowb[i] = (uint8_t)(rand() & 0xff);
+            uint32_t wv[32];
+            for (int lane = 0; lane < 32; lane++) {
+                wv[lane] = 0;
+                if (4 * lane < 3 * nc) memcpy(&wv[lane], rowb + 4 * lane, 4);
+            }
+            int32_t q[32];
+            for (int lane = 0; lane < 32; lane++) {             // unpack
+                const int w0 = (3 * lane) >> 2, sh = ((3 * lane) & 3) * 8;
+                const uint32_t v3 = funnel_r(wv[w0], wv[(w0 + 1) & 31], sh);
+                const float got = (float)((int32_t)(v3 << 8) >> 8);
+                q[lane] = (int32_t)got;
+                if (lane < nc) {
+                    const float want = raw_to_real<float>(rowb + 3 * lane, 3, 0, 0);
+                    if (got != want) bad++;
+                } else {
+                    q[lane] = 0;
+                }
+            }
+            memset(outb, 0xaa, sizeof(outb));
+            for (int lane = 0; lane < 32; lane++) {             // pack
+                const int ca = (4 * lane) / 3, sh = ((4 * lane) % 3) * 8;
+                const uint32_t qa = (uint32_t)q[ca & 31] & 0xffffffu, qb = (uint32_t)q[(ca + 1) & 31] & 0xffffffu;
+                if (4 * lane < 3 * nc) {
+                    const uint32_t word = (qa >> sh) | (qb << (24 - sh));
+                    memcpy(outb + 4 * lane, &word, 4);
+                }
+            }
+            if (memcmp(outb, rowb, 3 * nc) != 0 || outb[3 * nc] != 0xaa) bad++;
+        }
+    }
+    printf("packed S24_LE tiles: %d mismatches\n", bad);
+    return bad;
+}
+
 int main()
 {
     srand(12345);
-    int bad = run<float>(256) + run<double>(256) + fast_path();
+    int bad = run<float>(256) + run<double>(256) + fast_path() + packed_tiles();
     printf("%s\n", bad ? "FAIL" : "emul_sample ok");
     return bad;
 }
